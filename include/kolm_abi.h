@@ -1,0 +1,98 @@
+/* kolm_abi.h — C ABI of libkolm_b200.so: the B200-native (sm_100a) per-block transform
+ * encode/decode hot path of KolmogorovLike-DataCompressor.
+ *
+ * The reference has no FFI layer; its de-facto operator API is the set of pure per-block
+ * functions listed below.  Each entry point replaces the named reference
+ * function(s) for a *batch* of independent blocks:
+ *
+ *   KF  = final/kolm_final.py                              ('KOLM' container)
+ *   V22 = final_researched/kolm_final_researched_v2-2.py   ('KOLR' container)
+ *
+ * Conventions
+ *   - `in`, `out`, payload buffers: raw DEVICE pointers owned by the caller.
+ *   - `off`: HOST array of nblocks+1 byte offsets (off[0]=0 is not required; block b is
+ *     bytes [off[b], off[b+1]) of every per-byte buffer of the call).
+ *   - every call is asynchronous on `stream` except where it returns host scalars
+ *     (those calls synchronise `stream` before returning).
+ *   - return value: 0 = ok, <0 = KOLM_E_* (kolm_strerror()).  No exceptions, no allocation
+ *     in the hot path; all scratch lives in the context.
+ *   - a context is bound to one device and must not be used from two threads at once;
+ *     distinct contexts are independent.
+ */
+#ifndef KOLM_ABI_H
+#define KOLM_ABI_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kolm_ctx kolm_ctx;
+typedef void* kolm_stream_t; /* cudaStream_t */
+
+#define KOLM_PROFILE_KOLM 1 /* kolm_final.py: models 0..3 */
+#define KOLM_PROFILE_KOLR 2 /* kolm_final_researched_v2-2.py: models 0..10 */
+
+/* error codes */
+#define KOLM_OK 0
+#define KOLM_E_CUDA (-1)
+#define KOLM_E_ARG (-2)
+#define KOLM_E_CAPACITY (-3)
+#define KOLM_E_TRUNCATED (-4)   /* reference raises EOFError   */
+#define KOLM_E_CORRUPT (-5)     /* reference raises ValueError */
+#define KOLM_E_UNSUPPORTED (-6)
+#define KOLM_E_INDEX (-7)       /* reference raises IndexError */
+
+int kolm_abi_version(void);
+const char* kolm_strerror(int code);
+const char* kolm_last_cuda_error(void);
+
+/* context: scratch for batches of up to max_batch_bytes bytes in up to max_blocks blocks */
+size_t kolm_scratch_bytes(size_t max_batch_bytes, int max_blocks);
+int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** out);
+void kolm_destroy(kolm_ctx* ctx);
+
+/* ---- stage operators (batched) ------------------------------------------------------------- */
+
+/* duval_lyndon  KF.py:200-225 == V22.py:326-349.
+ * start_flags[i] = 1 iff a Lyndon factor starts at byte i (same indexing as `in`). */
+int kolm_lyndon(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* start_flags, kolm_stream_t stream);
+
+/* bbwt_forward  KF.py:227-325 == V22.py:351-423 */
+int kolm_bbwt_fwd(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream);
+/* bbwt_inverse  KF.py:327-369 == V22.py:425-454 */
+int kolm_bbwt_inv(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream);
+
+/* mtf_encode / mtf_decode  KF.py:375-405 == V22.py:460-478 */
+int kolm_mtf_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream);
+int kolm_mtf_dec(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream);
+
+/* KF model-2 token coder on an MTF sequence: choose_rice_grid/cost_gamma + BitWriter pack
+ * (KF.py:499-529, 636-691).  Payload b is written at out + out_off[b]; out_off (HOST, nblocks+1)
+ * receives the exclusive prefix sums of the payload sizes.  `out` must hold out_cap bytes.
+ * params (HOST, 4*nblocks ints, may be NULL): k0, k1, use_rice_zero, use_rice_nz per block. */
+int kolm_rice_kf_enc(kolm_ctx* ctx, const uint8_t* mtf, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap,
+                     int64_t* out_off, int* params, kolm_stream_t stream);
+/* decode_model_bbwt_mtf's bit parser (KF.py:771-794): payloads -> MTF sequences of orig length */
+int kolm_rice_kf_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks,
+                     uint8_t* mtf_out, kolm_stream_t stream);
+
+/* V22 models 2-6: byte transform (flags 0,1,4,8,16 = none, 8x8 bit-plane, nibble swap, bit reverse,
+ * Gray) + rice_encode(k=2)  (V22.py:1100-1120, 1413-1421, 1650-1680, 2044-2065).
+ * sizes (HOST, 5*nblocks int64, may be NULL) receives every variant's exact payload size in the
+ * order flags {0,1,4,8,16}; the variant `flags` is packed. */
+int kolm_rice_k2_enc(kolm_ctx* ctx, const uint8_t* mtf, const int64_t* off, int nblocks, int flags, uint8_t* out, size_t out_cap,
+                     int64_t* out_off, int64_t* sizes, kolm_stream_t stream);
+int kolm_rice_k2_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int flags,
+                     uint8_t* mtf_out, kolm_stream_t stream);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+/* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
+ * rounds, [2] kernels launched, [3] Lyndon factors (sum over blocks, saturating) */
+int kolm_last_counters(kolm_ctx* ctx, int64_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,69 @@
+"""ctypes loader of libkolm_b200.so (the C-ABI in include/kolm_abi.h).  Fails loudly when the CUDA
+library is missing: there is no CPU fallback in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+KOLM_PROFILE_KOLM = 1
+KOLM_PROFILE_KOLR = 2
+
+EXPORTS = [
+    "kolm_abi_version", "kolm_strerror", "kolm_last_cuda_error", "kolm_scratch_bytes", "kolm_create", "kolm_destroy",
+    "kolm_lyndon", "kolm_bbwt_fwd", "kolm_bbwt_inv", "kolm_mtf_enc", "kolm_mtf_dec",
+    "kolm_rice_kf_enc", "kolm_rice_kf_dec", "kolm_rice_k2_enc", "kolm_rice_k2_dec", "kolm_last_counters",
+]
+
+
+class KolmError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        msg = lib().kolm_strerror(code).decode()
+        if code == -1:
+            msg += ": " + lib().kolm_last_cuda_error().decode()
+        super().__init__(f"libkolm_b200: {msg} ({code}) {detail}")
+
+
+def so_path() -> str:
+    return _build.SO
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = so_path()
+    if not os.path.exists(path) or _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc / compile error: refuse to run
+            if not os.path.exists(path):
+                raise RuntimeError(f"libkolm_b200.so is missing and could not be built ({e}); "
+                                   "the GPU path has no fallback — run `python -m kolmogorovlike_datacompressor_b200.build`") from e
+    L = C.CDLL(path)
+    L.kolm_strerror.restype = C.c_char_p
+    L.kolm_last_cuda_error.restype = C.c_char_p
+    L.kolm_scratch_bytes.restype = C.c_size_t
+    L.kolm_scratch_bytes.argtypes = [C.c_size_t, C.c_int]
+    L.kolm_create.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.kolm_destroy.argtypes = [C.c_void_p]
+    p, i64p, ip = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int)
+    L.kolm_lyndon.argtypes = [p, p, i64p, C.c_int, p, p]
+    for f in ("kolm_bbwt_fwd", "kolm_bbwt_inv", "kolm_mtf_enc", "kolm_mtf_dec"):
+        getattr(L, f).argtypes = [p, p, i64p, C.c_int, p, p]
+    L.kolm_rice_kf_enc.argtypes = [p, p, i64p, C.c_int, p, C.c_size_t, i64p, ip, p]
+    L.kolm_rice_kf_dec.argtypes = [p, p, i64p, i64p, C.c_int, p, p]
+    L.kolm_rice_k2_enc.argtypes = [p, p, i64p, C.c_int, C.c_int, p, C.c_size_t, i64p, i64p, p]
+    L.kolm_rice_k2_dec.argtypes = [p, p, i64p, i64p, C.c_int, C.c_int, p, p]
+    L.kolm_last_counters.argtypes = [p, i64p]
+    _LIB = L
+    return L
+
+
+def check(code: int, detail: str = ""):
+    if code != 0:
+        raise KolmError(code, detail)

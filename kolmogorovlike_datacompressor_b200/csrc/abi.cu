@@ -1,0 +1,202 @@
+// abi.cu — extern "C" surface of libkolm_b200.so (include/kolm_abi.h), context and batch setup.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_cuda_err[512] = "";
+void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+}
+
+// single translation unit: the stage files are included here (no -rdc needed)
+#include "bbwt_fwd.cu"
+#include "bbwt_inv.cu"
+#include "mtf.cu"
+#include "rice.cu"
+
+static size_t padded_capacity(size_t max_batch_bytes, int max_blocks) {
+    return max_batch_bytes + (size_t)KOLM_PAD * (size_t)max_blocks + 4 * KOLM_PAD;
+}
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+extern "C" {
+
+int kolm_abi_version(void) { return 1; }
+
+const char* kolm_strerror(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case KOLM_E_CUDA: return "CUDA error";
+        case KOLM_E_ARG: return "bad argument";
+        case KOLM_E_CAPACITY: return "batch exceeds context capacity";
+        case KOLM_E_TRUNCATED: return "truncated payload";
+        case KOLM_E_CORRUPT: return "corrupt payload";
+        case KOLM_E_UNSUPPORTED: return "unsupported";
+        case KOLM_E_INDEX: return "index error (reference decoder bug reproduced)";
+    }
+    return "unknown";
+}
+const char* kolm_last_cuda_error(void) { return g_cuda_err; }
+
+size_t kolm_scratch_bytes(size_t max_batch_bytes, int max_blocks) {
+    size_t e = padded_capacity(max_batch_bytes, max_blocks);
+    size_t tiles = e / KOLM_TILE + max_blocks + 2;
+    return e * (4 * 8 + 4 / 8 + 2) + tiles * (sizeof(TileDesc) * 2 + 16 + 1024) + (size_t)max_blocks * (sizeof(BlockInfo) + 4 * 9 + 64 * 8);
+}
+
+int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** out) {
+    if (!out || max_blocks < 1 || max_batch_bytes < 1) return KOLM_E_ARG;
+    size_t e = padded_capacity(max_batch_bytes, max_blocks);
+    if (e >= (1ull << 31)) return KOLM_E_ARG;     // 31-bit positions / ranks
+    CUDA_TRY(cudaSetDevice(device));
+    kolm_ctx* c = new kolm_ctx();
+    memset(c, 0, sizeof *c);
+    c->device = device; c->max_elems = e; c->max_blocks = max_blocks;
+    c->max_tiles = (int)(e / KOLM_TILE) + max_blocks + 2;
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    size_t nb = (size_t)max_blocks, nt = (size_t)c->max_tiles;
+    CUDA_TRY(dalloc(&c->d_binfo, nb)); CUDA_TRY(dalloc(&c->d_btile0, nb)); CUDA_TRY(dalloc(&c->d_btilen, nb));
+    CUDA_TRY(dalloc(&c->d_atile0, nb)); CUDA_TRY(dalloc(&c->d_atilen, nb)); CUDA_TRY(dalloc(&c->d_active, nb));
+    CUDA_TRY(dalloc(&c->d_newcls, nb)); CUDA_TRY(dalloc(&c->d_done, nb)); CUDA_TRY(dalloc(&c->d_nfac, nb));
+    CUDA_TRY(dalloc(&c->d_stats, 16)); CUDA_TRY(dalloc(&c->d_bacc, nb * 64));
+    CUDA_TRY(dalloc(&c->d_tiles, nt)); CUDA_TRY(dalloc(&c->d_atiles, nt));
+    CUDA_TRY(dalloc(&c->d_lb, 16 + 2 * nt)); CUDA_TRY(dalloc(&c->d_thist, nt * 256));
+    CUDA_TRY(dalloc(&c->d_k0, e)); CUDA_TRY(dalloc(&c->d_v0, e)); CUDA_TRY(dalloc(&c->d_k1, e)); CUDA_TRY(dalloc(&c->d_v1, e));
+    CUDA_TRY(dalloc(&c->d_sa, e)); CUDA_TRY(dalloc(&c->d_rank, e)); CUDA_TRY(dalloc(&c->d_nr, e));
+    CUDA_TRY(dalloc(&c->d_single, e / 32 + 8)); CUDA_TRY(dalloc(&c->d_fstart, e));
+    CUDA_TRY(dalloc(&c->d_tmp8a, e)); CUDA_TRY(dalloc(&c->d_tmp8b, e));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_binfo, nb * sizeof(BlockInfo)));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_u32, nb * 4 * sizeof(u32)));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_stats, 16 * sizeof(u32)));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_bacc, nb * 64 * sizeof(u64)));
+    *out = c;
+    return KOLM_OK;
+}
+
+void kolm_destroy(kolm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    void* dptrs[] = {c->d_binfo, c->d_btile0, c->d_btilen, c->d_atile0, c->d_atilen, c->d_active, c->d_newcls, c->d_done, c->d_nfac,
+                     c->d_stats, c->d_bacc, c->d_tiles, c->d_atiles, c->d_lb, c->d_thist, c->d_k0, c->d_v0, c->d_k1, c->d_v1,
+                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b};
+    for (void* p : dptrs) if (p) cudaFree(p);
+    if (c->h_binfo) cudaFreeHost(c->h_binfo);
+    if (c->h_u32) cudaFreeHost(c->h_u32);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->h_bacc) cudaFreeHost(c->h_bacc);
+    delete c;
+}
+
+}  // extern "C"
+
+// Describe the batch: block table, padded index space, static tile map.
+int kolm_set_batch(kolm_ctx* c, const i64* off, int nblocks, cudaStream_t s) {
+    if (!c || !off || nblocks < 0) return KOLM_E_ARG;
+    if (nblocks > c->max_blocks) return KOLM_E_CAPACITY;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(s));           // pinned staging below may still be in flight from the previous call
+    u64 p = 0; u32 t = 0, maxlen = 0;
+    u32* bt0 = c->h_u32; u32* btn = c->h_u32 + nblocks;
+    for (int b = 0; b < nblocks; ++b) {
+        i64 len = off[b + 1] - off[b];
+        if (len < 0 || len >= (1ll << 30)) return KOLM_E_ARG;
+        c->h_binfo[b].ioff = off[b]; c->h_binfo[b].pbase = (u32)p; c->h_binfo[b].len = (u32)len;
+        bt0[b] = t; btn[b] = (u32)((len + KOLM_TILE - 1) / KOLM_TILE); t += btn[b];
+        p += ((u64)len + KOLM_PAD - 1) / KOLM_PAD * KOLM_PAD;
+        if ((u32)len > maxlen) maxlen = (u32)len;
+        if (p + 2 * KOLM_PAD > c->max_elems) return KOLM_E_CAPACITY;
+    }
+    if ((int)t > c->max_tiles) return KOLM_E_CAPACITY;
+    c->nblocks = nblocks; c->total_elems = (u32)p; c->ntiles = (int)t; c->max_len = maxlen;
+    c->total_bytes = nblocks ? off[nblocks] - off[0] : 0;
+    if (!nblocks) return KOLM_OK;
+    CUDA_TRY(cudaMemcpyAsync(c->d_binfo, c->h_binfo, (size_t)nblocks * sizeof(BlockInfo), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->d_btile0, bt0, (size_t)nblocks * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(c->d_btilen, btn, (size_t)nblocks * 4, cudaMemcpyHostToDevice, s));
+    if (t) {
+        int g = nblocks < 1024 ? nblocks : 1024;
+        k_build_tiles<<<g, 128, 0, s>>>(c->d_binfo, c->d_btile0, c->d_btilen, nullptr, c->d_tiles, nblocks);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return KOLM_OK;
+}
+
+static thread_local i64 g_counters[4];
+
+extern "C" {
+
+int kolm_lyndon(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* start_flags, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    int r = 0;
+    KOLM_TRY(kolm_lyndon_impl(c, in, start_flags, &r, s));
+    g_counters[0] = r; g_counters[1] = 0;
+    return KOLM_OK;
+}
+
+int kolm_bbwt_fwd(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    int rp = 0, rc = 0;
+    KOLM_TRY(kolm_bbwt_fwd_impl(c, in, out, &rp, &rc, s));
+    g_counters[0] = rp; g_counters[1] = rc;
+    return KOLM_OK;
+}
+
+int kolm_bbwt_inv(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_bbwt_inv_impl(c, in, out, s);
+}
+
+int kolm_mtf_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_mtf_impl(c, in, out, false, s);
+}
+
+int kolm_mtf_dec(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_mtf_impl(c, in, out, true, s);
+}
+
+int kolm_rice_kf_enc(kolm_ctx* c, const uint8_t* mtf, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
+                     int* params, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_rice_kf_enc_impl(c, mtf, out, out_cap, out_off, params, s);
+}
+
+int kolm_rice_kf_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* mtf_out,
+                     kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_rice_kf_dec_impl(c, payload, pay_off, mtf_out, s);
+}
+
+int kolm_rice_k2_enc(kolm_ctx* c, const uint8_t* mtf, const int64_t* off, int nblocks, int flags, uint8_t* out, size_t out_cap,
+                     int64_t* out_off, int64_t* sizes, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_rice_k2_enc_impl(c, mtf, flags, out, out_cap, out_off, sizes, s);
+}
+
+int kolm_rice_k2_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int flags,
+                     uint8_t* mtf_out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_rice_k2_dec_impl(c, payload, pay_off, flags, mtf_out, s);
+}
+
+int kolm_last_counters(kolm_ctx* c, int64_t* out4) {
+    (void)c;
+    for (int i = 0; i < 4; ++i) out4[i] = g_counters[i];
+    return KOLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,601 @@
+// bbwt_fwd.cu — Lyndon factorisation + bijective-BWT rotation sort.
+//
+// Replaces  duval_lyndon  (kolm_final.py:200-225 == kolm_final_researched_v2-2.py:326-349) and
+//           bbwt_forward  (kolm_final.py:227-325 == kolm_final_researched_v2-2.py:351-423).
+//
+// One engine, two successor functions:
+//   plain  : succ_h(i) = i+h (end of block = smallest)      -> suffix ranks (ISA) -> Lyndon starts
+//            = strict prefix minima of the ISA, found by a look-back min-scan.
+//   cyclic : succ_h(i) = rotate by h inside i's Lyndon factor -> ω-order of all rotations -> BBWT.
+//
+// Prefix doubling in the Manber–Myers form with Larsson–Sadakane pruning:
+//   round(h): stream the current order `sa`; for every j emit pred_h(sa[j]) if its rank is not yet
+//   final ("active").  The emitted list is already ordered by the *second* key, so one stable LSD
+//   radix sort by the *first* key (the element's current group start, <= ceil(log2 n) bits) yields
+//   the 2h-order of every non-singleton group.  Only active records are sorted; settled suffixes
+//   are never touched again.  All blocks of the batch advance in the same launches.
+//
+// Radix passes: per-tile digit histogram -> per-block scan -> scatter.  The scatter kernel stages its
+// tile of keys/values in shared memory with 1-D TMA (cp.async.bulk + mbarrier), ranks with
+// __match_any_sync into warp-private histograms, reorders inside shared memory and writes digit runs
+// back coalesced.
+#include "common.cuh"
+
+#define NWARPS (KOLM_THREADS / 32)
+#define FULL 0xffffffffu
+#define SIDX(x) ((x) + ((x) >> 4))                    // smem padding: 1 word per 16 (IPT) -> conflict-free blocked access
+#define SPAD (KOLM_TILE + 2 + ((KOLM_TILE + 2) >> 4) + 1)
+
+// ------------------------------------------------------------------------------------------------
+// tile maps
+// ------------------------------------------------------------------------------------------------
+__global__ void k_build_tiles(const BlockInfo* __restrict__ binfo, const u32* __restrict__ tile0, const u32* __restrict__ tilen,
+                              const u32* __restrict__ lens /*null -> binfo.len*/, TileDesc* __restrict__ tiles, int nblocks) {
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        u32 nt = tilen[b];
+        if (!nt) continue;
+        u32 t0 = tile0[b], len = lens ? lens[b] : binfo[b].len, pb = binfo[b].pbase;
+        for (u32 k = threadIdx.x; k < nt; k += blockDim.x) {
+            TileDesc td;
+            td.start = pb + k * KOLM_TILE;
+            u32 rem = len - k * KOLM_TILE;
+            td.count = rem < KOLM_TILE ? rem : KOLM_TILE;
+            td.block = b;
+            td.flags = (k == 0 ? 1u : 0u) | (k == nt - 1 ? 2u : 0u);
+            tiles[t0 + k] = td;
+        }
+    }
+}
+
+// single CTA: active tile ranges per block + totals.  stats[0]=active tiles, stats[1]=active records (saturating)
+__global__ void k_plan_active(const u32* __restrict__ active, const u32* __restrict__ done, u32* __restrict__ atile0,
+                              u32* __restrict__ atilen, u32* __restrict__ stats, int nblocks) {
+    __shared__ u32 s_w[32];
+    __shared__ u32 s_carry, s_rec;
+    if (threadIdx.x == 0) { s_carry = 0; s_rec = 0; }
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        int b = base + threadIdx.x;
+        u32 a = (b < nblocks && !done[b]) ? active[b] : 0;
+        u32 nt = (a + KOLM_TILE - 1) / KOLM_TILE;
+        u32 v = nt;
+        for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(FULL, v, o); if (lane_id() >= (u32)o) v += n; }
+        if (lane_id() == 31) s_w[threadIdx.x >> 5] = v;
+        u32 ra = a;
+        for (int o = 16; o > 0; o >>= 1) ra += __shfl_xor_sync(FULL, ra, o);
+        __syncthreads();
+        u32 pre = 0;
+        for (u32 i = 0; i < (threadIdx.x >> 5); ++i) pre += s_w[i];
+        u32 carry = s_carry;
+        if (b < nblocks) { atile0[b] = carry + pre + v - nt; atilen[b] = nt; }
+        __syncthreads();
+        if (lane_id() == 0) atomicAdd(&s_rec, ra);
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + pre + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[0] = s_carry; stats[1] = s_rec; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lyndon factor lookup (cyclic successor / predecessor)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void find_factor(const u32* __restrict__ fst, u32 nfac, u32 len, u32 lp, u32& fs, u32& fl) {
+    u32 lo = 0, hi = nfac;
+    if (lp >= fst[nfac - 1]) lo = nfac - 1;
+    else while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (__ldg(fst + mid) <= lp) lo = mid; else hi = mid; }
+    fs = __ldg(fst + lo);
+    u32 fe = (lo + 1 < nfac) ? __ldg(fst + lo + 1) : len;
+    fl = fe - fs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bootstrap keys
+//   plain : 3 bytes (zero padded) + 3-bit length code min(len-lp,4)   -> 27-bit key, h0 = 3
+//           (every suffix of length <= 3 gets a unique key, so successor-less elements are settled)
+//   cyclic: 4 bytes of the rotation (infinite power of the factor)     -> 32-bit key, h0 = 4
+// ------------------------------------------------------------------------------------------------
+template <bool CYCLIC>
+__global__ void __launch_bounds__(KOLM_THREADS) k_boot_keys(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo,
+                                                            const TileDesc* __restrict__ tiles, const u32* __restrict__ fstart,
+                                                            const u32* __restrict__ nfac, u32* __restrict__ K, u32* __restrict__ V) {
+    TileDesc td = tiles[blockIdx.x];
+    BlockInfo bi = binfo[td.block];
+    const u8* src = in + bi.ioff;
+    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
+        u32 pg = td.start + x, lp = pg - bi.pbase, key;
+        if (CYCLIC) {
+            u32 fs, fl; find_factor(fstart + bi.pbase, nfac[td.block], bi.len, lp, fs, fl);
+            u32 o = lp - fs; key = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { key = (key << 8) | src[fs + o]; if (++o == fl) o = 0; }
+        } else {
+            u32 rem = bi.len - lp;
+            u32 b0 = src[lp], b1 = rem > 1 ? src[lp + 1] : 0, b2 = rem > 2 ? src[lp + 2] : 0;
+            key = (((b0 << 16) | (b1 << 8) | b2) << 3) | (rem < 4 ? rem : 4);
+        }
+        K[pg] = key; V[pg] = pg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix pass 1/3: per-tile digit histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KOLM_THREADS) k_radix_hist(const u32* __restrict__ K, const TileDesc* __restrict__ tiles,
+                                                             u32* __restrict__ thist, int shift, u32 mask) {
+    __shared__ u32 h[256];
+    TileDesc td = tiles[blockIdx.x];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const u32* k = K + td.start;
+    for (u32 x0 = 0; x0 < td.count; x0 += KOLM_THREADS) {
+        u32 x = x0 + threadIdx.x;
+        u32 d = x < td.count ? ((k[x] >> shift) & mask) : 0xffffffffu;
+        u32 peers = __match_any_sync(FULL, d);
+        if (x < td.count && (peers & lanemask_lt()) == 0) atomicAdd(&h[d], __popc(peers));
+    }
+    __syncthreads();
+    thist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// radix pass 2/3: per block, turn tile histograms into block-relative scatter bases (digit-major, tile-minor)
+__global__ void __launch_bounds__(256) k_radix_scan(u32* __restrict__ thist, const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks) {
+    __shared__ u32 tot[256];
+    __shared__ u32 excl[256];
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        u32 nt = tilen[b];
+        if (!nt) continue;
+        u32* base = thist + (size_t)tile0[b] * 256 + threadIdx.x;
+        u32 run = 0;
+        for (u32 t = 0; t < nt; ++t) { u32 v = base[(size_t)t * 256]; base[(size_t)t * 256] = run; run += v; }
+        tot[threadIdx.x] = run;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            u32 s = 0, loc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { loc[i] = s; s += tot[threadIdx.x * 8 + i]; }
+            u32 v = s;
+            for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(FULL, v, o); if (threadIdx.x >= (u32)o) v += n; }
+            u32 pre = v - s;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) excl[threadIdx.x * 8 + i] = pre + loc[i];
+        }
+        __syncthreads();
+        u32 db = excl[threadIdx.x];
+        if (db) for (u32 t = 0; t < nt; ++t) base[(size_t)t * 256] += db;
+        __syncthreads();
+    }
+}
+
+// radix pass 3/3: stable scatter of one tile.  Keys/values staged with 1-D TMA into shared memory.
+__global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __restrict__ Kin, const u32* __restrict__ Vin,
+                                                                u32* __restrict__ Kout, u32* __restrict__ Vout,
+                                                                const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
+                                                                const u32* __restrict__ thist, int shift, u32 mask) {
+    __shared__ __align__(128) u32 sk[KOLM_TILE];
+    __shared__ __align__(128) u32 sv[KOLM_TILE];
+    __shared__ u32 whist[NWARPS][256];
+    __shared__ u32 dstart[256];
+    __shared__ u32 gbase[256];
+    __shared__ __align__(8) u64 bar;
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    TileDesc td = tiles[blockIdx.x];
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (u32 i = tid; i < NWARPS * 256; i += KOLM_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        u32 bytes = ((td.count + 3u) & ~3u) * 4u;       // 16-byte granules; block bases are padded so the over-read stays in scratch
+        mbar_expect_tx(&bar, 2 * bytes);
+        tma_load_1d(sk, Kin + td.start, bytes, &bar);
+        tma_load_1d(sv, Vin + td.start, bytes, &bar);
+    }
+    gbase[tid] = thist[(size_t)blockIdx.x * 256 + tid] + binfo[td.block].pbase;
+    mbar_wait(&bar, 0);
+    // ---- rank: warp w owns elements [w*IPT*32, (w+1)*IPT*32), iteration k covers 32 consecutive ones
+    u32 key[KOLM_IPT], val[KOLM_IPT]; u16 off[KOLM_IPT];
+#pragma unroll
+    for (int k = 0; k < KOLM_IPT; ++k) {
+        u32 idx = w * (KOLM_IPT * 32) + k * 32 + lane;
+        bool valid = idx < td.count;
+        key[k] = valid ? sk[idx] : 0; val[k] = valid ? sv[idx] : 0;
+        u32 d = valid ? ((key[k] >> shift) & mask) : 0xffffffffu;
+        u32 peers = __match_any_sync(FULL, d);
+        u32 lt = __popc(peers & lanemask_lt());
+        u32 old = 0;
+        if (valid && lt == 0) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
+        old = __shfl_sync(FULL, old, __ffs(peers) - 1);
+        off[k] = (u16)(old + lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- per digit: exclusive scan over warps, then over digits
+    {
+        u32 run = 0;
+#pragma unroll
+        for (int i = 0; i < NWARPS; ++i) { u32 t = whist[i][tid]; whist[i][tid] = run; run += t; }
+        dstart[tid] = run;     // total for digit tid (scanned below)
+    }
+    __syncthreads();
+    if (tid < 32) {
+        u32 s = 0, loc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = s; s += dstart[tid * 8 + i]; }
+        u32 v = s;
+        for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(FULL, v, o); if (tid >= (u32)o) v += n; }
+        u32 pre = v - s;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dstart[tid * 8 + i] = pre + loc[i];
+    }
+    __syncthreads();
+    // ---- reorder inside shared memory (everything is in registers now)
+#pragma unroll
+    for (int k = 0; k < KOLM_IPT; ++k) {
+        u32 idx = w * (KOLM_IPT * 32) + k * 32 + lane;
+        if (idx < td.count) {
+            u32 d = (key[k] >> shift) & mask;
+            u32 pos = dstart[d] + whist[w][d] + off[k];
+            sk[pos] = key[k]; sv[pos] = val[k];
+        }
+    }
+    __syncthreads();
+    // ---- coalesced digit runs to global
+    for (u32 s = tid; s < td.count; s += KOLM_THREADS) {
+        u32 kk = sk[s];
+        u32 d = (kk >> shift) & mask;
+        u32 g = gbase[d] + (s - dstart[d]);
+        Kout[g] = kk; Vout[g] = sv[s];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rerank: group heads, new ranks, new order.  BOOT: records are (key32, pos) of whole blocks.
+// round : records are (group start, pos) of active elements; second key = rank[succ_h(pos)].
+// ------------------------------------------------------------------------------------------------
+struct RerankArgs {
+    const u32* K; const u32* V; const TileDesc* tiles; const BlockInfo* binfo; const u32* active;
+    const u32* fstart; const u32* nfac; u64* lb;
+    u32* sa; u32* rank; u32* nr; u32* single; u32* newcls; u32 h;
+};
+
+template <bool BOOT, bool CYCLIC>
+__global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
+    __shared__ u32 sk[SPAD];
+    __shared__ u32 sk2[SPAD];
+    __shared__ u64 s_warp[NWARPS];
+    __shared__ u64 s_excl;
+    __shared__ u32 s_cnt;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(a.lb);
+    const TileDesc td = a.tiles[tile];
+    const BlockInfo bi = a.binfo[td.block];
+    const u32 nrec = BOOT ? bi.len : a.active[td.block];
+    const u32 t0 = td.start - bi.pbase;
+    if (tid == 0) s_cnt = 0;
+    // stage (key, key2) of records t0-1 .. t0+count into smem slots 0 .. count+1
+    for (u32 x = tid; x < td.count + 2; x += KOLM_THREADS) {
+        i64 tl = (i64)t0 + x - 1;
+        u32 k = 0xffffffffu, k2 = 0xffffffffu;
+        if (tl >= 0 && tl < (i64)nrec) {
+            u32 g = bi.pbase + (u32)tl;
+            if (BOOT) { k = 0; k2 = a.K[g]; }
+            else {
+                k = a.K[g];
+                u32 lp = a.V[g] - bi.pbase, sp;
+                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, a.nfac[td.block], bi.len, lp, fs, fl); sp = fs + (u32)(((u64)(lp - fs) + a.h) % fl); }
+                else sp = lp + a.h;                    // active plain elements always have a successor (see boot keys)
+                k2 = a.rank[bi.pbase + sp];
+            }
+        }
+        sk[SIDX(x)] = k; sk2[SIDX(x)] = k2;
+    }
+    __syncthreads();
+    // per-thread blocked scan: 1-based local record index of the last group-first / last head
+    u32 lf = 0, lh = 0, nh = 0;
+    u32 firstbits = 0, headbits = 0, nextbits = 0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        if (r < td.count) {
+            u32 x = r + 1;
+            u32 kp = sk[SIDX(x - 1)], kc = sk[SIDX(x)], kn = sk[SIDX(x + 1)];
+            u32 qp = sk2[SIDX(x - 1)], qc = sk2[SIDX(x)], qn = sk2[SIDX(x + 1)];
+            bool first = kc != kp, head = first || qc != qp, nxt = (kn != kc) || (qn != qc);
+            if (first) { lf = t0 + r + 1; firstbits |= 1u << i; }
+            if (head) { lh = t0 + r + 1; headbits |= 1u << i; nh += first ? (BOOT ? 1u : 0u) : 1u; }
+            if (nxt) nextbits |= 1u << i;
+        }
+    }
+    u64 agg = ((u64)lf << 31) | lh, tot;
+    u64 incl = block_scan_incl(agg, 0ull, OpMax2(), s_warp, &tot);
+    // exclusive for this thread = scan of preceding threads
+    u64 prev = __shfl_up_sync(FULL, incl, 1);
+    __shared__ u64 s_last[NWARPS];
+    if ((tid & 31) == 31) s_last[tid >> 5] = incl;
+    __syncthreads();
+    if ((tid & 31) == 0) prev = (tid >> 5) ? s_last[(tid >> 5) - 1] : 0ull;
+    if (tid < 32) {
+        u64 e = lb_exclusive(a.lb, tile, (td.flags & 1u) != 0, tot, 0ull, OpMax2());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u64 ex = OpMax2()(s_excl, prev);
+    u32 cf = (u32)(ex >> 31), ch = (u32)(ex & 0x7fffffffu);
+    const u32* Vt = a.V + td.start;
+    const u32* Kt = a.K + td.start;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        if (r < td.count) {
+            u32 tl1 = t0 + r + 1;
+            if ((firstbits >> i) & 1u) cf = tl1;
+            if ((headbits >> i) & 1u) ch = tl1;
+            u32 key = BOOT ? 0u : Kt[r];
+            u32 val = Vt[r];
+            u32 pos = key + (tl1 - cf);
+            u32 nrk = key + (ch - cf);
+            bool single = ((headbits >> i) & 1u) && ((nextbits >> i) & 1u);
+            a.sa[bi.pbase + pos] = val;
+            if (BOOT) {
+                a.rank[val] = nrk;
+                if (single) atomicOr(a.single + (val >> 5), 1u << (val & 31));
+            } else a.nr[td.start + r] = nrk | (single ? 0x80000000u : 0u);
+        }
+    }
+    // classes created in this tile
+    for (int o = 16; o > 0; o >>= 1) nh += __shfl_xor_sync(FULL, nh, o);
+    if ((tid & 31) == 0 && nh) atomicAdd(&s_cnt, nh);
+    __syncthreads();
+    if (tid == 0 && s_cnt) atomicAdd(a.newcls + td.block, s_cnt);
+}
+
+__global__ void __launch_bounds__(KOLM_THREADS) k_apply(const u32* __restrict__ V, const u32* __restrict__ nr, const TileDesc* __restrict__ tiles,
+                                                        u32* __restrict__ rank, u32* __restrict__ single) {
+    TileDesc td = tiles[blockIdx.x];
+    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
+        u32 v = V[td.start + x], r = nr[td.start + x];
+        rank[v] = r & 0x7fffffffu;
+        if (r >> 31) atomicOr(single + (v >> 5), 1u << (v & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather (Manber–Myers step): stream sa, emit active predecessors in order, compacted per block
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    const u32* sa; const u32* rank; const u32* single; const TileDesc* tiles; const BlockInfo* binfo;
+    const u32* fstart; const u32* nfac; const u32* done; u64* lb; u32* K; u32* V; u32* active; u32 h;
+};
+
+template <bool CYCLIC>
+__global__ void __launch_bounds__(KOLM_THREADS) k_gather(GatherArgs a) {
+    __shared__ u64 s_warp[NWARPS];
+    __shared__ u64 s_excl;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(a.lb);
+    const TileDesc td = a.tiles[tile];
+    const BlockInfo bi = a.binfo[td.block];
+    const bool done = a.done[td.block] != 0;
+    u32 pk[KOLM_IPT], pv[KOLM_IPT];
+    u32 amask = 0;
+    if (!done) {
+        u32 nf = CYCLIC ? a.nfac[td.block] : 0;
+        const u32* fst = a.fstart + bi.pbase;
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) {
+            u32 r = tid * KOLM_IPT + i;
+            pk[i] = 0; pv[i] = 0;
+            if (r < td.count) {
+                u32 lp = a.sa[td.start + r] - bi.pbase, pp; bool ok = true;
+                if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); u32 hm = a.h % fl; u32 o = lp - fs; pp = fs + (o >= hm ? o - hm : o + fl - hm); }
+                else { ok = lp >= a.h; pp = lp - a.h; }
+                if (ok) {
+                    u32 pg = bi.pbase + pp;
+                    if (!((a.single[pg >> 5] >> (pg & 31)) & 1u)) { pk[i] = a.rank[pg]; pv[i] = pg; amask |= 1u << i; }
+                }
+            }
+        }
+    }
+    const u32 cnt = __popc(amask);
+    u64 tot;
+    u64 incl = block_scan_incl((u64)cnt, 0ull, OpAdd(), s_warp, &tot);
+    if (tid < 32) {
+        u64 e = lb_exclusive(a.lb, tile, (td.flags & 1u) != 0, tot, 0ull, OpAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 o = bi.pbase + (u32)s_excl + (u32)(incl - cnt);
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) if ((amask >> i) & 1u) { u32 d = o + __popc(amask & ((1u << i) - 1u)); a.K[d] = pk[i]; a.V[d] = pv[i]; }
+    if (tid == 0 && (td.flags & 2u)) a.active[td.block] = (u32)(s_excl + tot);
+}
+
+__global__ void k_round_end(u32* __restrict__ newcls, u32* __restrict__ done, const u32* __restrict__ active, int nblocks, int cyclic) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    if (cyclic && !done[b] && active[b] && newcls[b] == 0) done[b] = 1;   // partition stable: equal rotations remain
+    newcls[b] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lyndon starts = strict prefix minima of the ISA (a1).  Emits the compacted factor-start list per
+// block (block-local positions), the factor count, and optionally one flag byte per position.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KOLM_THREADS) k_lyndon(const u32* __restrict__ rank, const TileDesc* __restrict__ tiles,
+                                                         const BlockInfo* __restrict__ binfo, u64* lb, u32* __restrict__ fstart,
+                                                         u32* __restrict__ nfac, u8* __restrict__ flags_out) {
+    __shared__ u64 s_warp[NWARPS];
+    __shared__ u64 s_last[NWARPS];
+    __shared__ u64 s_excl;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(lb);
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u64 IDENT = 0x7fffffffull << 31;
+    u32 rk[KOLM_IPT];
+    u32 mn = 0x7fffffffu;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        rk[i] = r < td.count ? rank[td.start + r] : 0x7fffffffu;
+        mn = min(mn, rk[i]);
+    }
+    // pass 1: prefix minimum only (count lane 0)
+    u64 tot;
+    u64 incl = block_scan_incl((u64)mn << 31, IDENT, OpMinAdd(), s_warp, &tot);
+    u64 prev = __shfl_up_sync(FULL, incl, 1);
+    if ((tid & 31) == 31) s_last[tid >> 5] = incl;
+    __syncthreads();
+    if ((tid & 31) == 0) prev = (tid >> 5) ? s_last[(tid >> 5) - 1] : IDENT;
+    // tile-local start candidates need the exclusive min from previous tiles first: do the look-back
+    // on (min, 0), then a second block scan for the count and a second look-back for the offsets.
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb, tile, (td.flags & 1u) != 0, tot, IDENT, OpMinAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 run = min((u32)(s_excl >> 31), (u32)(prev >> 31));
+    u32 startbits = 0, cnt = 0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        if (r < td.count && rk[i] < run) { startbits |= 1u << i; ++cnt; run = rk[i]; }
+    }
+    __syncthreads();
+    // second scan: counts.  A separate look-back array region (lb2 = lb + 8 + gridDim.x) keeps the two scans apart.
+    u64* lb2 = lb + 8 + gridDim.x;
+    u64 ctot;
+    u64 cincl = block_scan_incl((u64)cnt, 0ull, OpAdd(), s_warp, &ctot);
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb2 - 8, tile, (td.flags & 1u) != 0, ctot, 0ull, OpAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 o = bi.pbase + (u32)s_excl + (u32)(cincl - cnt);
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        if (r < td.count) {
+            bool st = (startbits >> i) & 1u;
+            if (st) fstart[o++] = td.start + r - bi.pbase;
+            if (flags_out) flags_out[bi.ioff + (td.start + r - bi.pbase)] = st ? 1 : 0;
+        }
+    }
+    if (tid == 0 && (td.flags & 2u)) nfac[td.block] = (u32)(s_excl + ctot);
+}
+
+// out[j] = byte preceding rotation sa[j] inside its factor  (kolm_final.py:321)
+__global__ void __launch_bounds__(KOLM_THREADS) k_bbwt_emit(const u8* __restrict__ in, u8* __restrict__ out, const u32* __restrict__ sa,
+                                                            const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
+                                                            const u32* __restrict__ fstart, const u32* __restrict__ nfac) {
+    TileDesc td = tiles[blockIdx.x];
+    BlockInfo bi = binfo[td.block];
+    const u8* src = in + bi.ioff;
+    u32 nf = nfac[td.block];
+    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
+        u32 lp = sa[td.start + x] - bi.pbase, fs, fl;
+        find_factor(fstart + bi.pbase, nf, bi.len, lp, fs, fl);
+        u32 pp = (lp == fs) ? fs + fl - 1 : lp - 1;
+        out[bi.ioff + (td.start + x - bi.pbase)] = src[pp];
+    }
+}
+
+// ================================================================================================
+// host drivers
+// ================================================================================================
+static inline int ceil_log2_u32(u32 v) { int b = 0; while ((1ull << b) < v) ++b; return b; }
+
+// stable LSD radix sort of (K,V) records over `ntiles` tiles; result pointers returned in *Kr,*Vr.
+static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, const u32* tile0, const u32* tilen, int bits,
+                      u32* Ka, u32* Va, u32* Kb, u32* Vb, u32** Kr, u32** Vr, cudaStream_t s) {
+    int passes = (bits + 7) / 8; if (passes < 1) passes = 1;
+    int dbits = (bits + passes - 1) / passes; if (dbits < 1) dbits = 1;
+    u32 mask = (1u << dbits) - 1;
+    int sgrid = c->nblocks < 4 * c->sm_count ? c->nblocks : 4 * c->sm_count;
+    for (int p = 0; p < passes; ++p) {
+        int shift = p * dbits;
+        k_radix_hist<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, tiles, c->d_thist, shift, mask);
+        k_radix_scan<<<sgrid, 256, 0, s>>>(c->d_thist, tile0, tilen, c->nblocks);
+        k_radix_scatter<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, Va, Kb, Vb, tiles, c->d_binfo, c->d_thist, shift, mask);
+        u32* t = Ka; Ka = Kb; Kb = t; t = Va; Va = Vb; Vb = t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    *Kr = Ka; *Vr = Va;
+    return KOLM_OK;
+}
+
+int kolm_lb_reset(kolm_ctx* c, int ntiles, cudaStream_t s) {
+    CUDA_TRY(cudaMemsetAsync(c->d_lb, 0, (size_t)(16 + 2 * (size_t)ntiles) * sizeof(u64), s));
+    return KOLM_OK;
+}
+
+// Sort all suffixes (plain) or all rotations (cyclic) of every block of the current batch.
+// On return c->d_sa holds the order and c->d_rank the (group-start) ranks.  *rounds_out = doubling rounds run.
+static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, cudaStream_t s) {
+    const int nb = c->nblocks, nt = c->ntiles;
+    if (!nt) { if (rounds_out) *rounds_out = 0; return KOLM_OK; }
+    const size_t words = (c->total_elems + 31) / 32 + 1;
+    CUDA_TRY(cudaMemsetAsync(c->d_single, 0, words * 4, s));
+    CUDA_TRY(cudaMemsetAsync(c->d_done, 0, (size_t)nb * 4, s));
+    CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
+    int bgrid = nb < 1024 ? nb : 1024;
+    // ---- bootstrap
+    if (cyclic) k_boot_keys<true><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0);
+    else k_boot_keys<false><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0);
+    u32 *K, *V;
+    KOLM_TRY(radix_sort(c, c->d_tiles, nt, c->d_btile0, c->d_btilen, cyclic ? 32 : 27, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
+    KOLM_TRY(kolm_lb_reset(c, nt, s));
+    RerankArgs ra;
+    ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
+    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = 0;
+    if (cyclic) k_rerank<true, true><<<nt, KOLM_THREADS, 0, s>>>(ra); else k_rerank<true, false><<<nt, KOLM_THREADS, 0, s>>>(ra);
+    CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
+    CUDA_TRY(cudaGetLastError());
+    const int kbits = ceil_log2_u32(c->max_len > 1 ? c->max_len : 2);
+    int rounds = 0;
+    for (u64 h = cyclic ? 4 : 3; rounds < 40; h <<= 1) {
+        if (h > 0x7fffffffull) h = 0x7fffffffull;
+        // ---- gather active predecessors
+        KOLM_TRY(kolm_lb_reset(c, nt, s));
+        GatherArgs ga;
+        ga.sa = c->d_sa; ga.rank = c->d_rank; ga.single = c->d_single; ga.tiles = c->d_tiles; ga.binfo = c->d_binfo; ga.fstart = c->d_fstart;
+        ga.nfac = c->d_nfac; ga.done = c->d_done; ga.lb = c->d_lb; ga.K = c->d_k0; ga.V = c->d_v0; ga.active = c->d_active; ga.h = (u32)h;
+        if (cyclic) k_gather<true><<<nt, KOLM_THREADS, 0, s>>>(ga); else k_gather<false><<<nt, KOLM_THREADS, 0, s>>>(ga);
+        k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb);
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        int ant = (int)c->h_stats[0];
+        if (ant == 0) break;
+        ++rounds;
+        k_build_tiles<<<bgrid, 128, 0, s>>>(c->d_binfo, c->d_atile0, c->d_atilen, c->d_active, c->d_atiles, nb);
+        KOLM_TRY(radix_sort(c, c->d_atiles, ant, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
+        KOLM_TRY(kolm_lb_reset(c, ant, s));
+        ra.K = K; ra.V = V; ra.tiles = c->d_atiles; ra.h = (u32)h;
+        if (cyclic) k_rerank<false, true><<<ant, KOLM_THREADS, 0, s>>>(ra); else k_rerank<false, false><<<ant, KOLM_THREADS, 0, s>>>(ra);
+        k_apply<<<ant, KOLM_THREADS, 0, s>>>(V, c->d_nr, c->d_atiles, c->d_rank, c->d_single);
+        k_round_end<<<(nb + 255) / 256, 256, 0, s>>>(c->d_newcls, c->d_done, c->d_active, nb, cyclic ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        if (h >= 0x7fffffffull) break;
+    }
+    if (rounds_out) *rounds_out = rounds;
+    return KOLM_OK;
+}
+
+// a1: Lyndon factorisation of every block.  Leaves factor lists in the context for the cyclic sort.
+int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, cudaStream_t s) {
+    if (!c->ntiles) return KOLM_OK;
+    KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
+    KOLM_TRY(kolm_lb_reset(c, c->ntiles, s));
+    k_lyndon<<<c->ntiles, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out);
+    CUDA_TRY(cudaGetLastError());
+    return KOLM_OK;
+}
+
+// a2: BBWT of every block
+int kolm_bbwt_fwd_impl(kolm_ctx* c, const u8* in, u8* out, int* rounds_plain, int* rounds_cyclic, cudaStream_t s) {
+    if (!c->ntiles) return KOLM_OK;
+    KOLM_TRY(kolm_lyndon_impl(c, in, nullptr, rounds_plain, s));
+    KOLM_TRY(sort_batch(c, in, true, rounds_cyclic, s));
+    k_bbwt_emit<<<c->ntiles, KOLM_THREADS, 0, s>>>(in, out, c->d_sa, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac);
+    CUDA_TRY(cudaGetLastError());
+    return KOLM_OK;
+}

@@ -1,0 +1,126 @@
+"""Batched stage operators on torch CUDA uint8 tensors — thin wrappers over the C-ABI.
+
+A batch is a 1-D uint8 CUDA tensor holding nblocks blocks back to back plus a Python/numpy list of
+nblocks+1 offsets.  Function names follow the reference's stage functions:
+bbwt_forward, bbwt_inverse, mtf_encode, mtf_decode, duval_lyndon, ...
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _offsets(off: Sequence[int]):
+    a = np.ascontiguousarray(np.asarray(off, dtype=np.int64))
+    return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+class Context:
+    """Owns the device scratch for batches up to (max_batch_bytes, max_blocks) on one device."""
+
+    def __init__(self, max_batch_bytes: int, max_blocks: int, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("kolmogorovlike_datacompressor_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.max_batch_bytes = int(max_batch_bytes)
+        self.max_blocks = int(max_blocks)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().kolm_create(self.device, max(1, self.max_batch_bytes), max(1, self.max_blocks), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().kolm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _n2n(self, fn: str, x: torch.Tensor, off, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()
+        oa, op = _offsets(off)
+        assert int(oa[-1]) <= x.numel()
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(getattr(_lib.lib(), fn)(self._h, C.c_void_p(x.data_ptr()), op, len(oa) - 1, C.c_void_p(out.data_ptr()), self._stream()), fn)
+        return out
+
+    def duval_lyndon_flags(self, x, off):
+        """1 where a Lyndon factor starts (kolm_final.py:200-225)."""
+        return self._n2n("kolm_lyndon", x, off)
+
+    def bbwt_forward(self, x, off, out=None):
+        return self._n2n("kolm_bbwt_fwd", x, off, out)
+
+    def bbwt_inverse(self, x, off, out=None):
+        return self._n2n("kolm_bbwt_inv", x, off, out)
+
+    def mtf_encode(self, x, off, out=None):
+        return self._n2n("kolm_mtf_enc", x, off, out)
+
+    def mtf_decode(self, x, off, out=None):
+        return self._n2n("kolm_mtf_dec", x, off, out)
+
+    def counters(self):
+        a = (C.c_int64 * 4)()
+        _lib.lib().kolm_last_counters(self._h, a)
+        return dict(rounds_plain=a[0], rounds_cyclic=a[1], launches=a[2], factors=a[3])
+
+    # ---- entropy coders -------------------------------------------------
+    def rice_kf_encode(self, mtf, off, out: Optional[torch.Tensor] = None, want_params=False):
+        """KF model-2 token stream of each block's MTF sequence -> (payload tensor, out_off ndarray[, params])."""
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        if out is None:
+            out = torch.empty(int(oa[-1] - oa[0]) * 2 + 16 * nb + 64, dtype=torch.uint8, device=mtf.device)
+        out_off = np.zeros(nb + 1, dtype=np.int64)
+        params = np.zeros(4 * max(1, nb), dtype=np.int32)
+        _lib.check(_lib.lib().kolm_rice_kf_enc(self._h, C.c_void_p(mtf.data_ptr()), op, nb, C.c_void_p(out.data_ptr()), out.numel(),
+                                               out_off.ctypes.data_as(C.POINTER(C.c_int64)), params.ctypes.data_as(C.POINTER(C.c_int)),
+                                               self._stream()), "kolm_rice_kf_enc")
+        return (out, out_off, params.reshape(-1, 4)[:nb]) if want_params else (out, out_off)
+
+    def rice_kf_decode(self, payload, pay_off, off, out=None):
+        pa, pp = _offsets(pay_off)
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        if out is None:
+            out = torch.empty(int(oa[-1]), dtype=torch.uint8, device=payload.device)
+        _lib.check(_lib.lib().kolm_rice_kf_dec(self._h, C.c_void_p(payload.data_ptr()), pp, op, nb, C.c_void_p(out.data_ptr()), self._stream()),
+                   "kolm_rice_kf_dec")
+        return out
+
+    def rice_k2_encode(self, mtf, off, flags: int, out: Optional[torch.Tensor] = None):
+        """V22 models 2-6 -> (payload tensor, out_off ndarray, sizes ndarray[nb,5])."""
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        if out is None:
+            out = torch.empty(int(oa[-1] - oa[0]) * 9 + 16 * nb + 64, dtype=torch.uint8, device=mtf.device)
+        out_off = np.zeros(nb + 1, dtype=np.int64)
+        sizes = np.zeros(5 * max(1, nb), dtype=np.int64)
+        _lib.check(_lib.lib().kolm_rice_k2_enc(self._h, C.c_void_p(mtf.data_ptr()), op, nb, int(flags), C.c_void_p(out.data_ptr()), out.numel(),
+                                               out_off.ctypes.data_as(C.POINTER(C.c_int64)), sizes.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               self._stream()), "kolm_rice_k2_enc")
+        return out, out_off, sizes.reshape(-1, 5)[:nb]
+
+    def rice_k2_decode(self, payload, pay_off, off, flags: int, out=None):
+        pa, pp = _offsets(pay_off)
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        if out is None:
+            out = torch.empty(int(oa[-1]), dtype=torch.uint8, device=payload.device)
+        _lib.check(_lib.lib().kolm_rice_k2_dec(self._h, C.c_void_p(payload.data_ptr()), pp, op, nb, int(flags), C.c_void_p(out.data_ptr()),
+                                               self._stream()), "kolm_rice_k2_dec")
+        return out
