@@ -73,6 +73,10 @@ int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** o
     CUDA_TRY(cudaMallocHost((void**)&c->h_u32, nb * 4 * sizeof(u32)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_stats, 16 * sizeof(u32)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_bacc, nb * 64 * sizeof(u64)));
+    CUDA_TRY(dalloc(&c->d_poff, nb + 1)); CUDA_TRY(dalloc(&c->d_params, nb * 4)); CUDA_TRY(dalloc(&c->d_sizes, nb * 5));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_poff, (nb + 1) * sizeof(i64)));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_params, nb * 4 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_sizes, nb * 5 * sizeof(i64)));
     *out = c;
     return KOLM_OK;
 }
@@ -82,12 +86,15 @@ void kolm_destroy(kolm_ctx* c) {
     cudaSetDevice(c->device);
     void* dptrs[] = {c->d_binfo, c->d_btile0, c->d_btilen, c->d_atile0, c->d_atilen, c->d_active, c->d_newcls, c->d_done, c->d_nfac,
                      c->d_stats, c->d_bacc, c->d_tiles, c->d_atiles, c->d_lb, c->d_thist, c->d_k0, c->d_v0, c->d_k1, c->d_v1,
-                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b};
+                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes};
     for (void* p : dptrs) if (p) cudaFree(p);
     if (c->h_binfo) cudaFreeHost(c->h_binfo);
     if (c->h_u32) cudaFreeHost(c->h_u32);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_bacc) cudaFreeHost(c->h_bacc);
+    if (c->h_poff) cudaFreeHost(c->h_poff);
+    if (c->h_params) cudaFreeHost(c->h_params);
+    if (c->h_sizes) cudaFreeHost(c->h_sizes);
     delete c;
 }
 

@@ -66,6 +66,9 @@ struct kolm_ctx {
     u32* h_stats;            // pinned mirror
     u64* d_bacc;             // [max_blocks*64] per-block 64-bit accumulators (Rice cost sums, ...)
     u64* h_bacc;             // pinned mirror
+    i64* d_poff; i64* h_poff;      // [max_blocks+1] payload offsets
+    int* d_params; int* h_params;  // [4*max_blocks]
+    i64* d_sizes; i64* h_sizes;    // [5*max_blocks]
     // tiles
     TileDesc* d_tiles;       // static tiles
     TileDesc* d_atiles;      // active tiles

@@ -1,6 +1,419 @@
-// rice.cu — placeholder
+// rice.cu — entropy-coder stage.
+//
+//   KF model 2  (kolm_final.py:499-529 cost_gamma/cost_rice/choose_rice_grid, :636-691 pack, :762-798 unpack):
+//       tokens = zero runs r>=1 (tag 0) and non-zeros x=v-1 (tag 1); k0,k1 = argmin over k in 0..6,
+//       Rice vs Elias-gamma per class; stream = 2b flags, 4b k0, 4b k1, then tag + code per token.
+//   V22 models 2-6 (kolm_final_researched_v2-2.py:1100-1120 bit-plane, :1413-1421 rice_encode,
+//       :1650-1680 nibble/bit-reverse/Gray, :2044-2065): Rice(k=2) of every transformed MTF byte.
+//
+// Encode = cost pass (all candidate parameterisations in one read, per-block 64-bit sums)
+//        -> device-side parameter choice + payload offsets (exclusive scan over blocks)
+//        -> pack pass: per-position bit length, block-wide exclusive prefix sum with a look-back
+//           across tiles, MSB-first bit scatter.
+// Bitstreams are MSB-first, zero padded to a byte (BitWriter.getbytes / _BitWriter.pad_to_byte).
 #include "common.cuh"
-int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i64* out_off, int* params, cudaStream_t s) { return KOLM_E_UNSUPPORTED; }
+
+#define RB_STRIDE 64
+// per-block accumulator slots (u64)
+#define RB_KF_Z 0      // [0..6] rice cost of zero runs for k, [7] gamma cost
+#define RB_KF_N 8      // [8..14] rice cost of non-zeros,      [15] gamma cost
+#define RB_KF_NZ 16    // number of zero-run tokens
+#define RB_KF_NN 17    // number of non-zero tokens
+#define RB_K2 20       // [20..24] Rice(k=2) bit sums for flags {0,1,4,8,16}
+#define RB_BYTES 32    // chosen payload size in bytes
+#define RB_OFF 33      // exclusive byte offset of the payload
+#define RB_PARAM 34    // KF: k0 | k1<<8 | urz<<16 | urn<<17
+
+__device__ __forceinline__ u32 bitlen32(u32 v) { return 32u - __clz(v); }
+__device__ __forceinline__ u8 dev_bitrev8(u32 b) { return (u8)(__brev(b) >> 24); }
+
+// 8x8 bit transpose of one group: out byte `bit` collects bit (7-bit) of every input byte, input i -> bit (7-i)
+__device__ __forceinline__ u64 bitplane8(u64 g /* byte i of the group in bits [8i, 8i+8) */) {
+    u64 r = 0;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        u32 v = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v |= (u32)((g >> (8 * i + (7 - bit))) & 1ull) << (7 - i);
+        r |= (u64)v << (8 * bit);
+    }
+    return r;
+}
+__device__ __forceinline__ u32 v22_xform(u32 b, int flags) {
+    if (flags & 4) b = ((b & 0x0F) << 4) | ((b & 0xF0) >> 4);
+    if (flags & 8) b = dev_bitrev8(b);
+    if (flags & 16) b = (b ^ (b >> 1)) & 0xFF;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSB-first bit scatter into 32-bit words (output region must be zero).  `base` is 4-byte aligned;
+// bit 0 of the stream is the MSB of byte 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_word(u32* base, u64 word, u32 be_bits) {
+    if (be_bits) atomicOr(base + word, __byte_perm(be_bits, 0, 0x0123));
+}
+__device__ __forceinline__ void put_bits(u32* base, u64 bitpos, u32 value, u32 n) {   // n in 1..32, value < 2^n
+    u64 w = bitpos >> 5; u32 o = (u32)bitpos & 31;
+    u64 v = (u64)value << (64 - n - o);                   // left-aligned at bit offset o of a 64-bit window
+    put_word(base, w, (u32)(v >> 32));
+    put_word(base, w + 1, (u32)v);
+}
+__device__ __forceinline__ void put_ones(u32* base, u64 bitpos, u64 q) {
+    while (q >= 32) { put_bits(base, bitpos, 0xffffffffu, 32); bitpos += 32; q -= 32; }
+    if (q) put_bits(base, bitpos, (1u << q) - 1u, (u32)q);
+}
+__device__ __forceinline__ void put_rice(u32* base, u64 bitpos, u64 x, u32 k) {        // q ones, 0, k bits
+    u64 q = x >> k;
+    put_ones(base, bitpos, q);
+    if (k) put_bits(base, bitpos + q + 1, (u32)(x & ((1u << k) - 1u)), k);
+}
+__device__ __forceinline__ void put_gamma(u32* base, u64 bitpos, u32 x) {              // (b-1) zeros then b bits
+    u32 b = bitlen32(x);
+    put_bits(base, bitpos + (b - 1), x, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared tile prologue: symbols of my IPT items plus the one after (run-end detection)
+// ---------------------------------------------------------------------------------------------
+#define V_END 0x100u      // beyond the end of the block
+__device__ __forceinline__ void load_items(const u8* __restrict__ src, u32 t0, u32 count, u32 blen, u32 (&v)[KOLM_IPT + 1]) {
+#pragma unroll
+    for (int i = 0; i <= KOLM_IPT; ++i) {
+        u32 r = threadIdx.x * KOLM_IPT + i;
+        v[i] = (r < count || (r == count && t0 + r < blen)) ? (u32)src[r] : V_END;
+    }
+}
+// exclusive "last non-zero position (1-based, block-local)" for this thread: block scan + look-back
+__device__ __forceinline__ u32 scan_last_nonzero(u32 mine, u64* lb, u32 tile, bool first, u64* s_warp, u64* s_last, u64* s_excl) {
+    const u32 tid = threadIdx.x;
+    u64 tot;
+    u64 incl = block_scan_incl((u64)mine, 0ull, OpMax(), s_warp, &tot);
+    u64 prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if ((tid & 31) == 31) s_last[tid >> 5] = incl;
+    __syncthreads();
+    if ((tid & 31) == 0) prev = (tid >> 5) ? s_last[(tid >> 5) - 1] : 0ull;
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb, tile, first, tot, 0ull, OpMax());
+        if (tid == 0) *s_excl = e;
+    }
+    __syncthreads();
+    u32 r = (u32)max(*s_excl, prev);
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cost pass: every candidate parameterisation in one read of the MTF bytes
+// ---------------------------------------------------------------------------------------------
+template <bool KF, bool K2>
+__global__ void __launch_bounds__(KOLM_THREADS) k_rice_cost(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+                                                            const BlockInfo* __restrict__ binfo, u64* lb, u64* __restrict__ bacc) {
+    __shared__ u64 s_warp[KOLM_THREADS / 32];
+    __shared__ u64 s_last[KOLM_THREADS / 32];
+    __shared__ u64 s_excl;
+    __shared__ unsigned long long s_acc[25];
+    const u32 tid = threadIdx.x;
+    const u32 tile = KF ? lb_take_ticket(lb) : blockIdx.x;
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u32 t0 = td.start - bi.pbase;
+    const u8* src = mtf + bi.ioff + t0;
+    if (tid < 25) s_acc[tid] = 0;
+    u32 v[KOLM_IPT + 1];
+    load_items(src, t0, td.count, bi.len, v);
+    u64 accz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 accn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 nzt = 0, nnt = 0;
+    u32 k2[5] = {0, 0, 0, 0, 0};
+    if (KF) {
+        u32 lastnz = 0;
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
+        u32 ln = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) {
+            u32 r = tid * KOLM_IPT + i;
+            if (r < td.count) {
+                u32 pos1 = t0 + r + 1;
+                if (v[i]) {
+                    ln = pos1;
+                    u32 x = v[i] - 1;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) accn[k] += (x >> k) + 1 + k;
+                    accn[7] += 2 * bitlen32(v[i]) - 1;
+                    ++nnt;
+                } else if (v[i + 1] != 0) {                 // zero run ends here (next is non-zero or end of block)
+                    u32 run = pos1 - ln;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) accz[k] += (u64)(run >> k) + 1 + k;
+                    accz[7] += 2 * bitlen32(run) - 1;
+                    ++nzt;
+                }
+            }
+        }
+    }
+    if (K2) {
+#pragma unroll
+        for (int gi = 0; gi < KOLM_IPT / 8; ++gi) {
+            u32 r0 = tid * KOLM_IPT + gi * 8;
+            if (r0 < td.count) {
+                u64 g = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (r0 + i < td.count) g |= (u64)v[gi * 8 + i] << (8 * i);
+                u64 tp = bitplane8(g);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    u32 b = (u32)(g >> (8 * i)) & 0xFF, t = (u32)(tp >> (8 * i)) & 0xFF;
+                    if (r0 + i < td.count) {
+                        k2[0] += (b >> 2) + 3;
+                        k2[2] += (v22_xform(b, 4) >> 2) + 3;
+                        k2[3] += (v22_xform(b, 8) >> 2) + 3;
+                        k2[4] += (v22_xform(b, 16) >> 2) + 3;
+                    }
+                    k2[1] += (t >> 2) + 3;                  // bit-plane variant codes the zero-padded group (V22.py:1112-1113)
+                }
+            }
+        }
+    }
+    __syncthreads();
+    auto red = [&](u64 x, int slot) {
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((tid & 31) == 0 && x) atomicAdd(&s_acc[slot], (unsigned long long)x);
+    };
+    if (KF) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { red(accz[k], k); red(accn[k], 8 + k); }
+        red(nzt, 16); red(nnt, 17);
+    }
+    if (K2) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) red(k2[k], 20 + k);
+    }
+    __syncthreads();
+    if (tid < 25 && s_acc[tid]) atomicAdd((unsigned long long*)(bacc + (size_t)td.block * RB_STRIDE + tid), s_acc[tid]);
+}
+
+// single CTA: per-block parameter choice, payload size, exclusive offsets.  mode 1 = KF, 2 = K2 (slot)
+__global__ void k_rice_plan(u64* __restrict__ bacc, const BlockInfo* __restrict__ binfo, i64* __restrict__ poff, int* __restrict__ params,
+                            i64* __restrict__ sizes5, int nblocks, int mode, int k2slot) {
+    __shared__ u64 s_w[32];
+    __shared__ u64 s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        int b = base + threadIdx.x;
+        u64 bytes = 0;
+        if (b < nblocks) {
+            u64* a = bacc + (size_t)b * RB_STRIDE;
+            if (mode == 1) {
+                int k0 = 0, k1 = 0; u64 c0 = 0, c1 = 0;
+                if (a[RB_KF_NZ]) { c0 = a[RB_KF_Z]; for (int k = 1; k < 7; ++k) if (a[RB_KF_Z + k] < c0) { c0 = a[RB_KF_Z + k]; k0 = k; } }
+                if (a[RB_KF_NN]) { c1 = a[RB_KF_N]; for (int k = 1; k < 7; ++k) if (a[RB_KF_N + k] < c1) { c1 = a[RB_KF_N + k]; k1 = k; } }
+                u64 g0 = a[RB_KF_Z + 7], g1 = a[RB_KF_N + 7];
+                int urz = c0 < g0, urn = c1 < g1;
+                u64 bits = 10 + a[RB_KF_NZ] + a[RB_KF_NN] + (urz ? c0 : g0) + (urn ? c1 : g1);
+                bytes = (bits + 7) >> 3;
+                a[RB_PARAM] = (u64)k0 | ((u64)k1 << 8) | ((u64)urz << 16) | ((u64)urn << 17);
+                params[4 * b] = k0; params[4 * b + 1] = k1; params[4 * b + 2] = urz; params[4 * b + 3] = urn;
+            } else {
+                bytes = (a[RB_K2 + k2slot] + 7) >> 3;
+                for (int k = 0; k < 5; ++k) sizes5[5 * (size_t)b + k] = (i64)((a[RB_K2 + k] + 7) >> 3);
+            }
+            a[RB_BYTES] = bytes;
+        }
+        u64 v = bytes;
+        for (int o = 1; o < 32; o <<= 1) { u64 n = __shfl_up_sync(0xffffffffu, v, o); if (lane_id() >= (u32)o) v += n; }
+        if (lane_id() == 31) s_w[threadIdx.x >> 5] = v;
+        __syncthreads();
+        u64 pre = 0;
+        for (u32 i = 0; i < (threadIdx.x >> 5); ++i) pre += s_w[i];
+        u64 carry = s_carry;
+        if (b < nblocks) { poff[b] = (i64)(carry + pre + v - bytes); bacc[(size_t)b * RB_STRIDE + RB_OFF] = carry + pre + v - bytes; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + pre + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) poff[nblocks] = (i64)s_carry;
+}
+
+__global__ void k_zero_words(u32* __restrict__ out, const i64* __restrict__ total_bytes, size_t cap_words) {
+    size_t n = ((size_t)*total_bytes + 3) / 4 + 1;
+    if (n > cap_words) n = cap_words;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KF pack (KF.py:662-684)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KOLM_THREADS) k_rice_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+                                                               const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
+                                                               u32* __restrict__ out) {
+    __shared__ u64 s_warp[KOLM_THREADS / 32];
+    __shared__ u64 s_last[KOLM_THREADS / 32];
+    __shared__ u64 s_excl;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(lb);
+    u64* lb2 = lb + gridDim.x;                              // second look-back (bit offsets)
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u64* a = bacc + (size_t)td.block * RB_STRIDE;
+    const u32 prm = (u32)a[RB_PARAM];
+    const u32 k0 = prm & 0xff, k1 = (prm >> 8) & 0xff; const bool urz = (prm >> 16) & 1, urn = (prm >> 17) & 1;
+    const u64 bitbase = a[RB_OFF] * 8;
+    const u32 t0 = td.start - bi.pbase;
+    u32 v[KOLM_IPT + 1];
+    load_items(mtf + bi.ioff + t0, t0, td.count, bi.len, v);
+    u32 lastnz = 0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
+    const u32 ln0 = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
+    // token bit lengths of my items
+    u64 mybits = 0; u32 ln = ln0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        if (r < td.count) {
+            u32 pos1 = t0 + r + 1;
+            if (v[i]) { ln = pos1; u32 x = v[i] - 1; mybits += 1 + (urn ? (u64)(x >> k1) + 1 + k1 : (u64)(2 * bitlen32(v[i]) - 1)); }
+            else if (v[i + 1] != 0) { u32 run = pos1 - ln; mybits += 1 + (urz ? (u64)(run >> k0) + 1 + k0 : (u64)(2 * bitlen32(run) - 1)); }
+        }
+    }
+    u64 btot;
+    u64 bincl = block_scan_incl(mybits, 0ull, OpAdd(), s_warp, &btot);
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb2, tile, (td.flags & 1u) != 0, btot, 0ull, OpAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u64 bp = bitbase + 10 + s_excl + (bincl - mybits);
+    if ((td.flags & 1u) && tid == 0) put_bits(out, bitbase, (((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1, 10);   // KF.py:664-668
+    ln = ln0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        if (r < td.count) {
+            u32 pos1 = t0 + r + 1;
+            if (v[i]) {
+                ln = pos1;
+                u32 x = v[i] - 1;
+                put_bits(out, bp, 1, 1);
+                if (urn) { put_rice(out, bp + 1, x, k1); bp += 1 + (u64)(x >> k1) + 1 + k1; }
+                else { put_gamma(out, bp + 1, v[i]); bp += 1 + 2 * bitlen32(v[i]) - 1; }
+            } else if (v[i + 1] != 0) {
+                u32 run = pos1 - ln;                         // tag bit 0: nothing to write
+                if (urz) { put_rice(out, bp + 1, run, k0); bp += 1 + (u64)(run >> k0) + 1 + k0; }
+                else { put_gamma(out, bp + 1, run); bp += 1 + 2 * bitlen32(run) - 1; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// V22 Rice(k=2) pack of T_flags(mtf)  (V22.py:1413-1421)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KOLM_THREADS) k_rice_k2_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+                                                               const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
+                                                               u32* __restrict__ out, int flags) {
+    __shared__ u64 s_warp[KOLM_THREADS / 32];
+    __shared__ u64 s_excl;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(lb);
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u64 bitbase = bacc[(size_t)td.block * RB_STRIDE + RB_OFF] * 8;
+    const u32 t0 = td.start - bi.pbase;
+    u32 v[KOLM_IPT + 1];
+    load_items(mtf + bi.ioff + t0, t0, td.count, bi.len, v);
+    u32 sym[KOLM_IPT]; u32 nsym_mask = 0;
+    u64 mybits = 0;
+#pragma unroll
+    for (int gi = 0; gi < KOLM_IPT / 8; ++gi) {
+        u32 r0 = tid * KOLM_IPT + gi * 8;
+        u64 g = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (r0 + i < td.count) g |= (u64)v[gi * 8 + i] << (8 * i);
+        if (flags & 1) g = bitplane8(g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            bool coded = (flags & 1) ? (r0 < td.count) : (r0 + i < td.count);
+            u32 t = v22_xform((u32)(g >> (8 * i)) & 0xFF, flags);
+            sym[gi * 8 + i] = t;
+            if (coded) { nsym_mask |= 1u << (gi * 8 + i); mybits += (t >> 2) + 3; }
+        }
+    }
+    u64 btot;
+    u64 bincl = block_scan_incl(mybits, 0ull, OpAdd(), s_warp, &btot);
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb, tile, (td.flags & 1u) != 0, btot, 0ull, OpAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u64 bp = bitbase + s_excl + (bincl - mybits);
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        if ((nsym_mask >> i) & 1u) {
+            u32 t = sym[i], q = t >> 2;
+            put_ones(out, bp, q);
+            put_bits(out, bp + q, t & 3u, 3);               // the terminating 0 and the 2 remainder bits
+            bp += q + 3;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+static int rice_finish(kolm_ctx* c, i64* out_off, int* params, i64* sizes, size_t out_cap, cudaStream_t s) {
+    const int nb = c->nblocks;
+    CUDA_TRY(cudaMemcpyAsync(c->h_poff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (params) CUDA_TRY(cudaMemcpyAsync(c->h_params, c->d_params, (size_t)nb * 16, cudaMemcpyDeviceToHost, s));
+    if (sizes) CUDA_TRY(cudaMemcpyAsync(c->h_sizes, c->d_sizes, (size_t)nb * 40, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(out_off, c->h_poff, (size_t)(nb + 1) * 8);
+    if (params) memcpy(params, c->h_params, (size_t)nb * 16);
+    if (sizes) memcpy(sizes, c->h_sizes, (size_t)nb * 40);
+    if ((size_t)out_off[nb] > out_cap) return KOLM_E_CAPACITY;
+    return KOLM_OK;
+}
+
+int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i64* out_off, int* params, cudaStream_t s) {
+    const int nb = c->nblocks, nt = c->ntiles;
+    if (((uintptr_t)out & 3) != 0) return KOLM_E_ARG;
+    if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
+    CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
+    if (nt) {
+        KOLM_TRY(kolm_lb_reset(c, nt, s));
+        k_rice_cost<true, false><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc);
+    }
+    k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0);
+    k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4);
+    if (nt) {
+        KOLM_TRY(kolm_lb_reset(c, nt, s));
+        k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return rice_finish(c, out_off, params, nullptr, out_cap, s);
+}
+
+static int k2_slot(int flags) { switch (flags) { case 0: return 0; case 1: return 1; case 4: return 2; case 8: return 3; case 16: return 4; } return -1; }
+
+int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t out_cap, i64* out_off, i64* sizes, cudaStream_t s) {
+    const int nb = c->nblocks, nt = c->ntiles;
+    int slot = k2_slot(flags);
+    if (slot < 0 || ((uintptr_t)out & 3) != 0) return KOLM_E_ARG;
+    if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
+    CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
+    if (nt) k_rice_cost<false, true><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc);
+    k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 2, slot);
+    k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4);
+    if (nt) {
+        KOLM_TRY(kolm_lb_reset(c, nt, s));
+        k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return rice_finish(c, out_off, nullptr, sizes, out_cap, s);
+}
+
 int kolm_rice_kf_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u8* mtf_out, cudaStream_t s) { return KOLM_E_UNSUPPORTED; }
-int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t out_cap, i64* out_off, i64* sizes, cudaStream_t s) { return KOLM_E_UNSUPPORTED; }
 int kolm_rice_k2_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, int flags, u8* mtf_out, cudaStream_t s) { return KOLM_E_UNSUPPORTED; }
