@@ -89,8 +89,18 @@ int kolm_rice_k2_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_o
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
- * rounds, [2] kernels launched, [3] Lyndon factors (sum over blocks, saturating) */
+ * rounds, [2] kernels launched since the last profile reset, [3] records sorted (sum over rounds) */
 int kolm_last_counters(kolm_ctx* ctx, int64_t* out4);
+
+/* launch accounting and optional CUDA-event timing per kernel category (used by bench.py):
+ * enable(1) brackets every kernel launch with events on the launching stream; read() synchronises
+ * the device and returns, per category, summed milliseconds, launch count and algorithmic bytes
+ * since the last reset(). */
+int kolm_profile_categories(void);
+const char* kolm_profile_name(int cat);
+int kolm_profile_enable(kolm_ctx* ctx, int on);
+int kolm_profile_reset(kolm_ctx* ctx);
+int kolm_profile_read(kolm_ctx* ctx, double* ms, int64_t* launches, int64_t* algbytes);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ EXPORTS = [
     "kolm_abi_version", "kolm_strerror", "kolm_last_cuda_error", "kolm_scratch_bytes", "kolm_create", "kolm_destroy",
     "kolm_lyndon", "kolm_bbwt_fwd", "kolm_bbwt_inv", "kolm_mtf_enc", "kolm_mtf_dec",
     "kolm_rice_kf_enc", "kolm_rice_kf_dec", "kolm_rice_k2_enc", "kolm_rice_k2_dec", "kolm_last_counters",
+    "kolm_profile_categories", "kolm_profile_name", "kolm_profile_enable", "kolm_profile_reset", "kolm_profile_read",
 ]
 
 
@@ -60,6 +61,11 @@ def lib():
     L.kolm_rice_k2_enc.argtypes = [p, p, i64p, C.c_int, C.c_int, p, C.c_size_t, i64p, i64p, p]
     L.kolm_rice_k2_dec.argtypes = [p, p, i64p, i64p, C.c_int, C.c_int, p, p]
     L.kolm_last_counters.argtypes = [p, i64p]
+    L.kolm_profile_name.restype = C.c_char_p
+    L.kolm_profile_name.argtypes = [C.c_int]
+    L.kolm_profile_enable.argtypes = [p, C.c_int]
+    L.kolm_profile_reset.argtypes = [p]
+    L.kolm_profile_read.argtypes = [p, C.POINTER(C.c_double), i64p, i64p]
     _LIB = L
     return L
 

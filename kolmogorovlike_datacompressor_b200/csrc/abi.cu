@@ -77,6 +77,8 @@ int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** o
     CUDA_TRY(cudaMallocHost((void**)&c->h_poff, (nb + 1) * sizeof(i64)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_params, nb * 4 * sizeof(int)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_sizes, nb * 5 * sizeof(i64)));
+    c->prof_ev = new cudaEvent_t[2 * KOLM_PROF_MAX];
+    for (int i = 0; i < 2 * KOLM_PROF_MAX; ++i) CUDA_TRY(cudaEventCreate(&c->prof_ev[i]));
     *out = c;
     return KOLM_OK;
 }
@@ -88,6 +90,7 @@ void kolm_destroy(kolm_ctx* c) {
                      c->d_stats, c->d_bacc, c->d_tiles, c->d_atiles, c->d_lb, c->d_thist, c->d_k0, c->d_v0, c->d_k1, c->d_v1,
                      c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes};
     for (void* p : dptrs) if (p) cudaFree(p);
+    if (c->prof_ev) { for (int i = 0; i < 2 * KOLM_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]); delete[] c->prof_ev; }
     if (c->h_binfo) cudaFreeHost(c->h_binfo);
     if (c->h_u32) cudaFreeHost(c->h_u32);
     if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -126,13 +129,15 @@ int kolm_set_batch(kolm_ctx* c, const i64* off, int nblocks, cudaStream_t s) {
     CUDA_TRY(cudaMemcpyAsync(c->d_btilen, btn, (size_t)nblocks * 4, cudaMemcpyHostToDevice, s));
     if (t) {
         int g = nblocks < 1024 ? nblocks : 1024;
-        k_build_tiles<<<g, 128, 0, s>>>(c->d_binfo, c->d_btile0, c->d_btilen, nullptr, c->d_tiles, nblocks);
+        KL(c, KC_TILES, (i64)t * 16, s, k_build_tiles<<<g, 128, 0, s>>>(c->d_binfo, c->d_btile0, c->d_btilen, nullptr, c->d_tiles, nblocks));
         CUDA_TRY(cudaGetLastError());
     }
     return KOLM_OK;
 }
 
-static thread_local i64 g_counters[4];
+static const char* KC_NAMES[KC_COUNT] = {"build_tiles", "boot_keys", "radix_hist", "radix_scan", "radix_scatter", "rerank", "apply_ranks",
+                                        "gather", "plan", "lyndon_scan", "bbwt_emit", "mtf_pre", "mtf_scan", "mtf_main", "rice_cost",
+                                        "rice_plan", "rice_pack", "zero_fill", "bbwt_inverse", "misc"};
 
 extern "C" {
 
@@ -141,7 +146,7 @@ int kolm_lyndon(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks,
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
     int r = 0;
     KOLM_TRY(kolm_lyndon_impl(c, in, start_flags, &r, s));
-    g_counters[0] = r; g_counters[1] = 0;
+    c->counters[0] = r; c->counters[1] = 0;
     return KOLM_OK;
 }
 
@@ -150,7 +155,7 @@ int kolm_bbwt_fwd(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblock
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
     int rp = 0, rc = 0;
     KOLM_TRY(kolm_bbwt_fwd_impl(c, in, out, &rp, &rc, s));
-    g_counters[0] = rp; g_counters[1] = rc;
+    c->counters[0] = rp; c->counters[1] = rc;
     return KOLM_OK;
 }
 
@@ -201,8 +206,28 @@ int kolm_rice_k2_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off
 }
 
 int kolm_last_counters(kolm_ctx* c, int64_t* out4) {
-    (void)c;
-    for (int i = 0; i < 4; ++i) out4[i] = g_counters[i];
+    i64 total = 0;
+    for (int i = 0; i < KC_COUNT; ++i) total += c->launches[i];
+    out4[0] = c->counters[0]; out4[1] = c->counters[1]; out4[2] = total; out4[3] = c->counters[4];
+    return KOLM_OK;
+}
+
+int kolm_profile_categories(void) { return KC_COUNT; }
+const char* kolm_profile_name(int cat) { return (cat >= 0 && cat < KC_COUNT) ? KC_NAMES[cat] : ""; }
+int kolm_profile_enable(kolm_ctx* c, int on) { c->prof_on = on; return KOLM_OK; }
+int kolm_profile_reset(kolm_ctx* c) {
+    memset(c->launches, 0, sizeof c->launches); memset(c->algbytes, 0, sizeof c->algbytes); memset(c->counters, 0, sizeof c->counters);
+    c->prof_n = 0;
+    return KOLM_OK;
+}
+int kolm_profile_read(kolm_ctx* c, double* ms, int64_t* launches, int64_t* algbytes) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = c->launches[i]; algbytes[i] = c->algbytes[i]; }
+    for (int i = 0; i < c->prof_n; ++i) {
+        float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        ms[c->prof_cat[i]] += t;
+    }
     return KOLM_OK;
 }
 

@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_bbwt_emit(const u8* __restrict
 static inline int ceil_log2_u32(u32 v) { int b = 0; while ((1ull << b) < v) ++b; return b; }
 
 // stable LSD radix sort of (K,V) records over `ntiles` tiles; result pointers returned in *Kr,*Vr.
-static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, const u32* tile0, const u32* tilen, int bits,
+static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, i64 nrec, const u32* tile0, const u32* tilen, int bits,
                       u32* Ka, u32* Va, u32* Kb, u32* Vb, u32** Kr, u32** Vr, cudaStream_t s) {
     int passes = (bits + 7) / 8; if (passes < 1) passes = 1;
     int dbits = (bits + passes - 1) / passes; if (dbits < 1) dbits = 1;
@@ -513,9 +513,9 @@ static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, const u32*
     int sgrid = c->nblocks < 4 * c->sm_count ? c->nblocks : 4 * c->sm_count;
     for (int p = 0; p < passes; ++p) {
         int shift = p * dbits;
-        k_radix_hist<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, tiles, c->d_thist, shift, mask);
-        k_radix_scan<<<sgrid, 256, 0, s>>>(c->d_thist, tile0, tilen, c->nblocks);
-        k_radix_scatter<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, Va, Kb, Vb, tiles, c->d_binfo, c->d_thist, shift, mask);
+        KL(c, KC_HIST, nrec * 4 + (i64)ntiles * 1024, s, k_radix_hist<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, tiles, c->d_thist, shift, mask));
+        KL(c, KC_SCAN, (i64)ntiles * 2048, s, k_radix_scan<<<sgrid, 256, 0, s>>>(c->d_thist, tile0, tilen, c->nblocks));
+        KL(c, KC_SCATTER, nrec * 16 + (i64)ntiles * 1024, s, k_radix_scatter<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, Va, Kb, Vb, tiles, c->d_binfo, c->d_thist, shift, mask));
         u32* t = Ka; Ka = Kb; Kb = t; t = Va; Va = Vb; Vb = t;
     }
     CUDA_TRY(cudaGetLastError());
@@ -539,15 +539,17 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
     int bgrid = nb < 1024 ? nb : 1024;
     // ---- bootstrap
-    if (cyclic) k_boot_keys<true><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0);
-    else k_boot_keys<false><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0);
+    const i64 N = c->total_bytes;
+    if (cyclic) KL(c, KC_BOOT, N * 9, s, k_boot_keys<true><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
+    else KL(c, KC_BOOT, N * 9, s, k_boot_keys<false><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
     u32 *K, *V;
-    KOLM_TRY(radix_sort(c, c->d_tiles, nt, c->d_btile0, c->d_btilen, cyclic ? 32 : 27, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
+    KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, cyclic ? 32 : 27, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
     KOLM_TRY(kolm_lb_reset(c, nt, s));
     RerankArgs ra;
     ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
     ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = 0;
-    if (cyclic) k_rerank<true, true><<<nt, KOLM_THREADS, 0, s>>>(ra); else k_rerank<true, false><<<nt, KOLM_THREADS, 0, s>>>(ra);
+    if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<true, true><<<nt, KOLM_THREADS, 0, s>>>(ra));
+    else KL(c, KC_RERANK, N * 16, s, k_rerank<true, false><<<nt, KOLM_THREADS, 0, s>>>(ra));
     CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
     CUDA_TRY(cudaGetLastError());
     const int kbits = ceil_log2_u32(c->max_len > 1 ? c->max_len : 2);
@@ -559,20 +561,24 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         GatherArgs ga;
         ga.sa = c->d_sa; ga.rank = c->d_rank; ga.single = c->d_single; ga.tiles = c->d_tiles; ga.binfo = c->d_binfo; ga.fstart = c->d_fstart;
         ga.nfac = c->d_nfac; ga.done = c->d_done; ga.lb = c->d_lb; ga.K = c->d_k0; ga.V = c->d_v0; ga.active = c->d_active; ga.h = (u32)h;
-        if (cyclic) k_gather<true><<<nt, KOLM_THREADS, 0, s>>>(ga); else k_gather<false><<<nt, KOLM_THREADS, 0, s>>>(ga);
-        k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb);
+        if (cyclic) KL(c, KC_GATHER, N * 4, s, k_gather<true><<<nt, KOLM_THREADS, 0, s>>>(ga));
+        else KL(c, KC_GATHER, N * 4, s, k_gather<false><<<nt, KOLM_THREADS, 0, s>>>(ga));
+        KL(c, KC_PLAN, (i64)nb * 16, s, k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb));
         CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 8, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         int ant = (int)c->h_stats[0];
+        const i64 M = (i64)c->h_stats[1];
         if (ant == 0) break;
         ++rounds;
-        k_build_tiles<<<bgrid, 128, 0, s>>>(c->d_binfo, c->d_atile0, c->d_atilen, c->d_active, c->d_atiles, nb);
-        KOLM_TRY(radix_sort(c, c->d_atiles, ant, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
+        c->counters[4] += M;                                  // active records summed over rounds
+        KL(c, KC_TILES, (i64)ant * 16, s, k_build_tiles<<<bgrid, 128, 0, s>>>(c->d_binfo, c->d_atile0, c->d_atilen, c->d_active, c->d_atiles, nb));
+        KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
         KOLM_TRY(kolm_lb_reset(c, ant, s));
         ra.K = K; ra.V = V; ra.tiles = c->d_atiles; ra.h = (u32)h;
-        if (cyclic) k_rerank<false, true><<<ant, KOLM_THREADS, 0, s>>>(ra); else k_rerank<false, false><<<ant, KOLM_THREADS, 0, s>>>(ra);
-        k_apply<<<ant, KOLM_THREADS, 0, s>>>(V, c->d_nr, c->d_atiles, c->d_rank, c->d_single);
-        k_round_end<<<(nb + 255) / 256, 256, 0, s>>>(c->d_newcls, c->d_done, c->d_active, nb, cyclic ? 1 : 0);
+        if (cyclic) KL(c, KC_RERANK, M * 20, s, k_rerank<false, true><<<ant, KOLM_THREADS, 0, s>>>(ra));
+        else KL(c, KC_RERANK, M * 20, s, k_rerank<false, false><<<ant, KOLM_THREADS, 0, s>>>(ra));
+        KL(c, KC_APPLY, M * 12, s, k_apply<<<ant, KOLM_THREADS, 0, s>>>(V, c->d_nr, c->d_atiles, c->d_rank, c->d_single));
+        KL(c, KC_PLAN, (i64)nb * 12, s, k_round_end<<<(nb + 255) / 256, 256, 0, s>>>(c->d_newcls, c->d_done, c->d_active, nb, cyclic ? 1 : 0));
         CUDA_TRY(cudaGetLastError());
         if (h >= 0x7fffffffull) break;
     }
@@ -585,7 +591,7 @@ int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, 
     if (!c->ntiles) return KOLM_OK;
     KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
     KOLM_TRY(kolm_lb_reset(c, c->ntiles, s));
-    k_lyndon<<<c->ntiles, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out);
+    KL(c, KC_LYNDON, c->total_bytes * 4, s, k_lyndon<<<c->ntiles, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out));
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;
 }
@@ -595,7 +601,7 @@ int kolm_bbwt_fwd_impl(kolm_ctx* c, const u8* in, u8* out, int* rounds_plain, in
     if (!c->ntiles) return KOLM_OK;
     KOLM_TRY(kolm_lyndon_impl(c, in, nullptr, rounds_plain, s));
     KOLM_TRY(sort_batch(c, in, true, rounds_cyclic, s));
-    k_bbwt_emit<<<c->ntiles, KOLM_THREADS, 0, s>>>(in, out, c->d_sa, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac);
+    KL(c, KC_EMIT, c->total_bytes * 6, s, k_bbwt_emit<<<c->ntiles, KOLM_THREADS, 0, s>>>(in, out, c->d_sa, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac));
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;
 }

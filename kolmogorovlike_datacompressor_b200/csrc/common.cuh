@@ -87,6 +87,10 @@ struct kolm_ctx {
     u32* h_u32;              // pinned scratch [4*max_blocks]
     int nblocks; u32 total_elems; u32 max_len; int ntiles;
     i64 total_bytes;
+    // accounting / profiling
+    i64 launches[32]; i64 algbytes[32];
+    int prof_on; int prof_n; int prof_cat[8192]; cudaEvent_t* prof_ev;
+    i64 counters[8];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -206,6 +210,21 @@ __device__ __forceinline__ u64 block_scan_incl(u64 v, u64 identity, Op op, u64* 
     if (total) *total = tot;
     return op(pre, v);
 }
+
+// ------------------------------------------------------------------------------------------------
+// launch accounting + optional per-category CUDA-event timing (bench.py's roofline numbers)
+// ------------------------------------------------------------------------------------------------
+enum KernelCat { KC_TILES, KC_BOOT, KC_HIST, KC_SCAN, KC_SCATTER, KC_RERANK, KC_APPLY, KC_GATHER, KC_PLAN, KC_LYNDON, KC_EMIT,
+                 KC_MTF_PRE, KC_MTF_SCAN, KC_MTF_MAIN, KC_RICE_COST, KC_RICE_PLAN, KC_RICE_PACK, KC_ZERO, KC_INV, KC_MISC, KC_COUNT };
+#define KOLM_PROF_MAX 8192
+static inline void prof_begin(kolm_ctx* c, int cat, i64 bytes, cudaStream_t s) {
+    c->launches[cat]++; c->algbytes[cat] += bytes;
+    if (c->prof_on && c->prof_n < KOLM_PROF_MAX) { c->prof_cat[c->prof_n] = cat; cudaEventRecord(c->prof_ev[2 * c->prof_n], s); }
+}
+static inline void prof_end(kolm_ctx* c, cudaStream_t s) {
+    if (c->prof_on && c->prof_n < KOLM_PROF_MAX) { cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], s); c->prof_n++; }
+}
+#define KL(c, cat, bytes, s, ...) do { prof_begin((c), (cat), (i64)(bytes), (s)); __VA_ARGS__; prof_end((c), (s)); } while (0)
 
 // host-side helpers shared between translation units
 int kolm_set_batch(kolm_ctx* c, const i64* off_host, int nblocks, cudaStream_t s);

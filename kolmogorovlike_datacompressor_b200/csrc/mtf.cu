@@ -193,14 +193,16 @@ int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t 
     int sgrid = nb < 4 * c->sm_count ? nb : 4 * c->sm_count;
     int wgrid = (nt + MTF_WARPS - 1) / MTF_WARPS;
     if (!decode) {
-        k_mtf_last<<<nt, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_thist);
-        k_mtf_scan_max<<<sgrid, 256, 0, s>>>(c->d_thist, c->d_btile0, c->d_btilen, nb);
-        k_mtf_enc<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt);
+        const i64 N = c->total_bytes;
+        KL(c, KC_MTF_PRE, N + (i64)nt * 1024, s, k_mtf_last<<<nt, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_thist));
+        KL(c, KC_MTF_SCAN, (i64)nt * 2048, s, k_mtf_scan_max<<<sgrid, 256, 0, s>>>(c->d_thist, c->d_btile0, c->d_btilen, nb));
+        KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt));
     } else {
         u8* tperm = (u8*)c->d_thist;
-        k_mtf_dec_perm<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, c->d_tiles, c->d_binfo, tperm, nt);
-        k_mtf_dec_compose<<<sgrid, 256, 0, s>>>(tperm, c->d_btile0, c->d_btilen, nb);
-        k_mtf_dec<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt);
+        const i64 N = c->total_bytes;
+        KL(c, KC_MTF_PRE, N + (i64)nt * 256, s, k_mtf_dec_perm<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, c->d_tiles, c->d_binfo, tperm, nt));
+        KL(c, KC_MTF_SCAN, (i64)nt * 512, s, k_mtf_dec_compose<<<sgrid, 256, 0, s>>>(tperm, c->d_btile0, c->d_btilen, nb));
+        KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 256, s, k_mtf_dec<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt));
     }
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;

@@ -374,6 +374,7 @@ static int rice_finish(kolm_ctx* c, i64* out_off, int* params, i64* sizes, size_
     if (params) memcpy(params, c->h_params, (size_t)nb * 16);
     if (sizes) memcpy(sizes, c->h_sizes, (size_t)nb * 40);
     if ((size_t)out_off[nb] > out_cap) return KOLM_E_CAPACITY;
+    c->algbytes[KC_RICE_PACK] += out_off[nb];                 // payload bytes written
     return KOLM_OK;
 }
 
@@ -384,13 +385,13 @@ int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
     if (nt) {
         KOLM_TRY(kolm_lb_reset(c, nt, s));
-        k_rice_cost<true, false><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc);
+        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
     }
-    k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0);
-    k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4);
+    KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0));
+    KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
         KOLM_TRY(kolm_lb_reset(c, nt, s));
-        k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out);
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, params, nullptr, out_cap, s);
@@ -404,12 +405,12 @@ int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t
     if (slot < 0 || ((uintptr_t)out & 3) != 0) return KOLM_E_ARG;
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
-    if (nt) k_rice_cost<false, true><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc);
-    k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 2, slot);
-    k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4);
+    if (nt) KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<false, true><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
+    KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 2, slot));
+    KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
         KOLM_TRY(kolm_lb_reset(c, nt, s));
-        k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags);
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, nullptr, sizes, out_cap, s);

@@ -76,7 +76,7 @@ class Context:
     def counters(self):
         a = (C.c_int64 * 4)()
         _lib.lib().kolm_last_counters(self._h, a)
-        return dict(rounds_plain=a[0], rounds_cyclic=a[1], launches=a[2], factors=a[3])
+        return dict(rounds_plain=a[0], rounds_cyclic=a[1], launches=a[2], records_sorted=a[3])
 
     # ---- entropy coders -------------------------------------------------
     def rice_kf_encode(self, mtf, off, out: Optional[torch.Tensor] = None, want_params=False):

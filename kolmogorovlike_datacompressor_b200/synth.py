@@ -1,0 +1,151 @@
+"""Seeded synthetic corpora for the BASELINE.json configurations.
+
+S1  low-entropy text-like corpus (cfg 2): Zipfian words over a 4096-word vocabulary.
+S2  mixed gradient / sine / pattern / checker segments (cfg 3).
+S3  repeating 8-segment mix of S1, S2 and random bytes (cfg 4, 5).
+All generators are pure numpy and deterministic; `n` is the exact output size in bytes.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_LETTERS = np.frombuffer(b"etaoinshrdlcumwfgypbvkjxqz", dtype=np.uint8)
+MIB = 1 << 20
+
+
+def _vocab(rng):
+    lens = 2 + (np.arange(4096) % 9)
+    p = 1.0 / (np.arange(len(_LETTERS)) + 1.0)
+    p /= p.sum()
+    table = np.zeros((4096, 10), dtype=np.uint8)
+    for i in range(4096):
+        table[i, :lens[i]] = _LETTERS[rng.choice(len(_LETTERS), size=lens[i], p=p)]
+    return table, lens
+
+
+def s1_text(n: int, seed: int = 0xC0FFEE) -> np.ndarray:
+    """Words sampled with p(i) ~ 1/(i+1), joined by ' ', '\\n' after every 12th word, truncated to n bytes."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    table, lens = _vocab(rng)
+    ext = np.zeros((4096, 11), dtype=np.uint8)            # letters, then one separator slot
+    ext[:, :10] = table
+    flat = ext.reshape(-1)
+    pw = 1.0 / (np.arange(4096) + 1.0)
+    pw /= pw.sum()
+    cdf = np.cumsum(pw)
+    wl_tab = (lens + 1).astype(np.int64)
+    out = np.empty(n, dtype=np.uint8)
+    filled = 0
+    widx = 0
+    chunk = 1 << 21
+    while filled < n:
+        ids = np.searchsorted(cdf, rng.random(chunk), side="right").clip(0, 4095)
+        wl = wl_tab[ids]
+        ends = np.cumsum(wl)
+        tot = int(ends[-1])
+        word_of = np.repeat(np.arange(chunk, dtype=np.int64), wl)
+        within = np.arange(tot, dtype=np.int64) - np.repeat(ends - wl, wl)
+        buf = flat[ids[word_of] * 11 + within]
+        sep = np.full(chunk, 0x20, dtype=np.uint8)
+        sep[(np.arange(widx, widx + chunk) % 12) == 11] = 0x0A
+        buf[ends - 1] = sep
+        widx += chunk
+        take = min(tot, n - filled)
+        out[filled:filled + take] = buf[:take]
+        filled += take
+    return out
+
+
+def _seg_gradient(n):
+    i = np.arange(n, dtype=np.int64)
+    pix, ch = i // 3, i % 3
+    x, y = pix % 1024, pix // 1024
+    r = (255 - (x >> 2)) & 255
+    g = (255 - y // 3) & 255
+    b = ((x + y) >> 3) & 255
+    return np.where(ch == 0, r, np.where(ch == 1, g, b)).astype(np.uint8)
+
+
+def _seg_sine(n):
+    t = np.arange((n + 1) // 2, dtype=np.float64)
+    s = np.round(30000.0 * np.sin(2.0 * np.pi * 440.0 * t / 44100.0)).astype("<i2")
+    return s.view(np.uint8)[:n].copy()
+
+
+def _seg_pattern(n):
+    out = np.empty(n, dtype=np.uint8)
+    sub = 65536
+    for k in range(0, n, sub):
+        m = min(sub, n - k)
+        kind = (k // sub) % 6
+        if kind == 0:
+            out[k:k + m] = 0
+        elif kind == 1:
+            out[k:k + m] = 0xFF
+        elif kind == 2:
+            out[k:k + m] = np.arange(m) & 0xFF
+        elif kind == 3:
+            f = np.empty(m, dtype=np.uint8)
+            a, b = 1, 1
+            for i in range(m):
+                f[i] = a
+                a, b = b, (a + b) & 0xFF
+            out[k:k + m] = f
+        elif kind == 4:
+            x = np.empty(m, dtype=np.uint64)
+            v = 20251018
+            for i in range(m):
+                v = (1664525 * v + 1013904223) & 0xFFFFFFFF
+                x[i] = v >> 24
+            out[k:k + m] = x.astype(np.uint8)
+        else:
+            out[k:k + m] = ((np.arange(m) // 18) & 0xFF).astype(np.uint8)
+    return out
+
+
+def _seg_checker(n):
+    i = np.arange(n, dtype=np.int64)
+    pix = i // 3
+    x, y = pix % 640, pix // 640
+    return np.where(((x // 32) + (y // 32)) % 2 == 0, 40, 200).astype(np.uint8)
+
+
+_S2_CACHE = {}
+
+
+def s2_segment(kind: str, n: int = MIB) -> np.ndarray:
+    key = (kind, n)
+    if key not in _S2_CACHE:
+        _S2_CACHE[key] = {"g": _seg_gradient, "s": _seg_sine, "p": _seg_pattern, "c": _seg_checker}[kind](n)
+    return _S2_CACHE[key]
+
+
+def s2_mixed(n: int) -> np.ndarray:
+    """1 MiB segments cycling gradient, sine, pattern, checker."""
+    out = np.empty(n, dtype=np.uint8)
+    for k in range(0, n, MIB):
+        m = min(MIB, n - k)
+        out[k:k + m] = s2_segment("gspc"[(k // MIB) % 4], MIB)[:m]
+    return out
+
+
+def s3_mix(n: int, seed: int = 7) -> np.ndarray:
+    """1 MiB segments in the repeating pattern [S1, S1, S2g, S2s, S2p, S2c, S1, random]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nseg = (n + MIB - 1) // MIB
+    n_s1 = sum(1 for k in range(nseg) if k % 8 in (0, 1, 6))
+    text = s1_text(max(1, n_s1) * MIB)
+    out = np.empty(n, dtype=np.uint8)
+    ti = 0
+    for k in range(nseg):
+        a = k * MIB
+        m = min(MIB, n - a)
+        r = k % 8
+        if r in (0, 1, 6):
+            out[a:a + m] = text[ti * MIB:ti * MIB + m]
+            ti += 1
+        elif r == 7:
+            out[a:a + m] = rng.integers(0, 256, size=m, dtype=np.uint8)
+        else:
+            out[a:a + m] = s2_segment("gspc"[r - 2], MIB)[:m]
+    return out
