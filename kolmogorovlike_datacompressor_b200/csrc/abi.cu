@@ -64,7 +64,7 @@ int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** o
     CUDA_TRY(dalloc(&c->d_newcls, nb)); CUDA_TRY(dalloc(&c->d_done, nb)); CUDA_TRY(dalloc(&c->d_nfac, nb));
     CUDA_TRY(dalloc(&c->d_stats, 16)); CUDA_TRY(dalloc(&c->d_bacc, nb * 64));
     CUDA_TRY(dalloc(&c->d_tiles, nt)); CUDA_TRY(dalloc(&c->d_atiles, nt));
-    CUDA_TRY(dalloc(&c->d_lb, 16 + 2 * nt)); CUDA_TRY(dalloc(&c->d_thist, nt * 256));
+    CUDA_TRY(dalloc(&c->d_lb, 32 + 8 * nt)); CUDA_TRY(dalloc(&c->d_thist, nt * 256));
     CUDA_TRY(dalloc(&c->d_k0, e)); CUDA_TRY(dalloc(&c->d_v0, e)); CUDA_TRY(dalloc(&c->d_k1, e)); CUDA_TRY(dalloc(&c->d_v1, e));
     CUDA_TRY(dalloc(&c->d_sa, e)); CUDA_TRY(dalloc(&c->d_rank, e)); CUDA_TRY(dalloc(&c->d_nr, e));
     CUDA_TRY(dalloc(&c->d_single, e / 32 + 8)); CUDA_TRY(dalloc(&c->d_fstart, e));
@@ -73,6 +73,7 @@ int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** o
     CUDA_TRY(cudaMallocHost((void**)&c->h_u32, nb * 4 * sizeof(u32)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_stats, 16 * sizeof(u32)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_bacc, nb * 64 * sizeof(u64)));
+    CUDA_TRY(dalloc(&c->d_err, nb)); CUDA_TRY(cudaMallocHost((void**)&c->h_err, nb * sizeof(int)));
     CUDA_TRY(dalloc(&c->d_poff, nb + 1)); CUDA_TRY(dalloc(&c->d_params, nb * 4)); CUDA_TRY(dalloc(&c->d_sizes, nb * 5));
     CUDA_TRY(cudaMallocHost((void**)&c->h_poff, (nb + 1) * sizeof(i64)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_params, nb * 4 * sizeof(int)));
@@ -88,13 +89,14 @@ void kolm_destroy(kolm_ctx* c) {
     cudaSetDevice(c->device);
     void* dptrs[] = {c->d_binfo, c->d_btile0, c->d_btilen, c->d_atile0, c->d_atilen, c->d_active, c->d_newcls, c->d_done, c->d_nfac,
                      c->d_stats, c->d_bacc, c->d_tiles, c->d_atiles, c->d_lb, c->d_thist, c->d_k0, c->d_v0, c->d_k1, c->d_v1,
-                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes};
+                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes, c->d_jump, c->d_err};
     for (void* p : dptrs) if (p) cudaFree(p);
     if (c->prof_ev) { for (int i = 0; i < 2 * KOLM_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]); delete[] c->prof_ev; }
     if (c->h_binfo) cudaFreeHost(c->h_binfo);
     if (c->h_u32) cudaFreeHost(c->h_u32);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_bacc) cudaFreeHost(c->h_bacc);
+    if (c->h_err) cudaFreeHost(c->h_err);
     if (c->h_poff) cudaFreeHost(c->h_poff);
     if (c->h_params) cudaFreeHost(c->h_params);
     if (c->h_sizes) cudaFreeHost(c->h_sizes);
@@ -109,19 +111,20 @@ int kolm_set_batch(kolm_ctx* c, const i64* off, int nblocks, cudaStream_t s) {
     if (nblocks > c->max_blocks) return KOLM_E_CAPACITY;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(s));           // pinned staging below may still be in flight from the previous call
-    u64 p = 0; u32 t = 0, maxlen = 0;
+    u64 p = 0; u32 t = 0, maxlen = 0, rows = 0;
     u32* bt0 = c->h_u32; u32* btn = c->h_u32 + nblocks;
     for (int b = 0; b < nblocks; ++b) {
         i64 len = off[b + 1] - off[b];
         if (len < 0 || len >= (1ll << 30)) return KOLM_E_ARG;
         c->h_binfo[b].ioff = off[b]; c->h_binfo[b].pbase = (u32)p; c->h_binfo[b].len = (u32)len;
         bt0[b] = t; btn[b] = (u32)((len + KOLM_TILE - 1) / KOLM_TILE); t += btn[b];
+        if (btn[b] > rows) rows = btn[b];
         p += ((u64)len + KOLM_PAD - 1) / KOLM_PAD * KOLM_PAD;
         if ((u32)len > maxlen) maxlen = (u32)len;
         if (p + 2 * KOLM_PAD > c->max_elems) return KOLM_E_CAPACITY;
     }
     if ((int)t > c->max_tiles) return KOLM_E_CAPACITY;
-    c->nblocks = nblocks; c->total_elems = (u32)p; c->ntiles = (int)t; c->max_len = maxlen;
+    c->nblocks = nblocks; c->total_elems = (u32)p; c->ntiles = (int)t; c->max_len = maxlen; c->static_rows = rows; c->active_rows = 0;
     c->total_bytes = nblocks ? off[nblocks] - off[0] : 0;
     if (!nblocks) return KOLM_OK;
     CUDA_TRY(cudaMemcpyAsync(c->d_binfo, c->h_binfo, (size_t)nblocks * sizeof(BlockInfo), cudaMemcpyHostToDevice, s));

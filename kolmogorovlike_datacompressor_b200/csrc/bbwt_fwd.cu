@@ -19,6 +19,7 @@
 // tile of keys/values in shared memory with 1-D TMA (cp.async.bulk + mbarrier), ranks with
 // __match_any_sync into warp-private histograms, reorders inside shared memory and writes digit runs
 // back coalesced.
+#include <stdlib.h>
 #include "common.cuh"
 
 #define NWARPS (KOLM_THREADS / 32)
@@ -51,8 +52,8 @@ __global__ void k_build_tiles(const BlockInfo* __restrict__ binfo, const u32* __
 __global__ void k_plan_active(const u32* __restrict__ active, const u32* __restrict__ done, u32* __restrict__ atile0,
                               u32* __restrict__ atilen, u32* __restrict__ stats, int nblocks) {
     __shared__ u32 s_w[32];
-    __shared__ u32 s_carry, s_rec;
-    if (threadIdx.x == 0) { s_carry = 0; s_rec = 0; }
+    __shared__ u32 s_carry, s_rec, s_max;
+    if (threadIdx.x == 0) { s_carry = 0; s_rec = 0; s_max = 0; }
     __syncthreads();
     for (int base = 0; base < nblocks; base += blockDim.x) {
         int b = base + threadIdx.x;
@@ -70,10 +71,11 @@ __global__ void k_plan_active(const u32* __restrict__ active, const u32* __restr
         if (b < nblocks) { atile0[b] = carry + pre + v - nt; atilen[b] = nt; }
         __syncthreads();
         if (lane_id() == 0) atomicAdd(&s_rec, ra);
+        if (nt) atomicMax(&s_max, nt);
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + pre + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { stats[0] = s_carry; stats[1] = s_rec; }
+    if (threadIdx.x == 0) { stats[0] = s_carry; stats[1] = s_rec; stats[2] = s_max; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -266,27 +268,48 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
     __shared__ u32 s_cnt;
     const u32 tid = threadIdx.x;
     const u32 tile = lb_take_ticket(a.lb);
+    if (tile == LB_NO_TILE) return;
     const TileDesc td = a.tiles[tile];
     const BlockInfo bi = a.binfo[td.block];
     const u32 nrec = BOOT ? bi.len : a.active[td.block];
     const u32 t0 = td.start - bi.pbase;
     if (tid == 0) s_cnt = 0;
-    // stage (key, key2) of records t0-1 .. t0+count into smem slots 0 .. count+1
-    for (u32 x = tid; x < td.count + 2; x += KOLM_THREADS) {
-        i64 tl = (i64)t0 + x - 1;
-        u32 k = 0xffffffffu, k2 = 0xffffffffu;
-        if (tl >= 0 && tl < (i64)nrec) {
+    // stage (key, key2) of records t0-1 .. t0+count into smem slots 0 .. count+1.  Loads are issued in
+    // phases (all K/V, then all rank gathers) so that every thread keeps IPT+1 requests in flight.
+    {
+        constexpr int NS = KOLM_IPT + 1;                   // slot x = i*THREADS + tid, i < NS covers count+2 <= TILE+2
+        u32 kk[NS], vv[NS]; bool ok[NS];
+        const u32 nf = (!BOOT && CYCLIC) ? a.nfac[td.block] : 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            u32 x = i * KOLM_THREADS + tid;
+            i64 tl = (i64)t0 + x - 1;
+            ok[i] = x < td.count + 2 && tl >= 0 && tl < (i64)nrec;
             u32 g = bi.pbase + (u32)tl;
-            if (BOOT) { k = 0; k2 = a.K[g]; }
-            else {
-                k = a.K[g];
-                u32 lp = a.V[g] - bi.pbase, sp;
-                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, a.nfac[td.block], bi.len, lp, fs, fl); sp = fs + (u32)(((u64)(lp - fs) + a.h) % fl); }
-                else sp = lp + a.h;                    // active plain elements always have a successor (see boot keys)
-                k2 = a.rank[bi.pbase + sp];
+            kk[i] = ok[i] ? a.K[g] : 0xffffffffu;
+            vv[i] = (ok[i] && !BOOT) ? a.V[g] : 0;
+        }
+        u32 k2[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            k2[i] = 0xffffffffu;
+            if (BOOT) { if (ok[i]) { k2[i] = kk[i]; kk[i] = 0; } }
+            else if (ok[i]) {
+                u32 lp = vv[i] - bi.pbase, sp;
+                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); sp = fs + (u32)(((u64)(lp - fs) + a.h) % fl); }
+                else sp = lp + a.h;                        // active plain elements always have a successor (see boot keys)
+                vv[i] = bi.pbase + sp;
             }
         }
-        sk[SIDX(x)] = k; sk2[SIDX(x)] = k2;
+        if (!BOOT) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) if (ok[i]) k2[i] = a.rank[vv[i]];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            u32 x = i * KOLM_THREADS + tid;
+            if (x < td.count + 2) { sk[SIDX(x)] = kk[i]; sk2[SIDX(x)] = k2[i]; }
+        }
     }
     __syncthreads();
     // per-thread blocked scan: 1-based local record index of the last group-first / last head
@@ -351,10 +374,20 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
 __global__ void __launch_bounds__(KOLM_THREADS) k_apply(const u32* __restrict__ V, const u32* __restrict__ nr, const TileDesc* __restrict__ tiles,
                                                         u32* __restrict__ rank, u32* __restrict__ single) {
     TileDesc td = tiles[blockIdx.x];
-    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
-        u32 v = V[td.start + x], r = nr[td.start + x];
-        rank[v] = r & 0x7fffffffu;
-        if (r >> 31) atomicOr(single + (v >> 5), 1u << (v & 31));
+    u32 v[KOLM_IPT], r[KOLM_IPT];
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 x = i * KOLM_THREADS + threadIdx.x;
+        bool ok = x < td.count;
+        v[i] = ok ? V[td.start + x] : 0xffffffffu;
+        r[i] = ok ? nr[td.start + x] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        if (v[i] != 0xffffffffu) {
+            rank[v[i]] = r[i] & 0x7fffffffu;
+            if (r[i] >> 31) atomicOr(single + (v[i] >> 5), 1u << (v[i] & 31));
+        }
     }
 }
 
@@ -372,6 +405,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_gather(GatherArgs a) {
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
     const u32 tile = lb_take_ticket(a.lb);
+    if (tile == LB_NO_TILE) return;
     const TileDesc td = a.tiles[tile];
     const BlockInfo bi = a.binfo[td.block];
     const bool done = a.done[td.block] != 0;
@@ -380,20 +414,27 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_gather(GatherArgs a) {
     if (!done) {
         u32 nf = CYCLIC ? a.nfac[td.block] : 0;
         const u32* fst = a.fstart + bi.pbase;
+        u32 sv[KOLM_IPT], sw[KOLM_IPT];
 #pragma unroll
-        for (int i = 0; i < KOLM_IPT; ++i) {
+        for (int i = 0; i < KOLM_IPT; ++i) {               // phase 1: the order itself (coalesced)
             u32 r = tid * KOLM_IPT + i;
-            pk[i] = 0; pv[i] = 0;
-            if (r < td.count) {
-                u32 lp = a.sa[td.start + r] - bi.pbase, pp; bool ok = true;
-                if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); u32 hm = a.h % fl; u32 o = lp - fs; pp = fs + (o >= hm ? o - hm : o + fl - hm); }
-                else { ok = lp >= a.h; pp = lp - a.h; }
-                if (ok) {
-                    u32 pg = bi.pbase + pp;
-                    if (!((a.single[pg >> 5] >> (pg & 31)) & 1u)) { pk[i] = a.rank[pg]; pv[i] = pg; amask |= 1u << i; }
-                }
+            sv[i] = r < td.count ? a.sa[td.start + r] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) {               // phase 2: predecessor positions
+            pv[i] = 0xffffffffu;
+            if (sv[i] != 0xffffffffu) {
+                u32 lp = sv[i] - bi.pbase;
+                if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); u32 hm = a.h % fl; u32 o = lp - fs; pv[i] = bi.pbase + fs + (o >= hm ? o - hm : o + fl - hm); }
+                else if (lp >= a.h) pv[i] = bi.pbase + lp - a.h;
             }
         }
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) sw[i] = pv[i] != 0xffffffffu ? a.single[pv[i] >> 5] : 0xffffffffu;   // phase 3: settled bits
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) if (pv[i] != 0xffffffffu && !((sw[i] >> (pv[i] & 31)) & 1u)) amask |= 1u << i;
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) pk[i] = ((amask >> i) & 1u) ? a.rank[pv[i]] : 0;                     // phase 4: first keys
     }
     const u32 cnt = __popc(amask);
     u64 tot;
@@ -428,6 +469,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_lyndon(const u32* __restrict__
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
     const u32 tile = lb_take_ticket(lb);
+    if (tile == LB_NO_TILE) return;
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
     const u64 IDENT = 0x7fffffffull << 31;
@@ -523,8 +565,20 @@ static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, i64 nrec, 
     return KOLM_OK;
 }
 
-int kolm_lb_reset(kolm_ctx* c, int ntiles, cudaStream_t s) {
-    CUDA_TRY(cudaMemsetAsync(c->d_lb, 0, (size_t)(16 + 2 * (size_t)ntiles) * sizeof(u64), s));
+__global__ void k_lb_header(u64* lb, u64 rows, u64 nb, const u32* tile0, const u32* tilen, u64 group) {
+    lb[1] = rows; lb[2] = nb; lb[3] = (u64)tile0; lb[4] = (u64)tilen; lb[5] = group;
+}
+
+int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t s) {
+    static int G = -1;
+    if (G < 0) { const char* e = getenv("KOLM_LB_GROUP"); G = e ? atoi(e) : 0;   // measured on B200: block-major order wins (L2 locality of the rank gathers), see DESIGN.md }
+    u64 rows = active ? c->active_rows : c->static_rows;
+    u64 ngroups = G > 0 ? ((u64)c->nblocks + G - 1) / G : 0;
+    u64 g = rows * (u64)G * ngroups;
+    if (G < 2 || rows < 2 || c->nblocks < 2 || g > 4ull * (u64)ntiles) { rows = 0; g = (u64)ntiles; }   // ragged batch: keep block-major order
+    CUDA_TRY(cudaMemsetAsync(c->d_lb, 0, (size_t)(16 + 2 * g) * sizeof(u64), s));
+    if (rows) k_lb_header<<<1, 1, 0, s>>>(c->d_lb, rows, (u64)c->nblocks, active ? c->d_atile0 : c->d_btile0, active ? c->d_atilen : c->d_btilen, (u64)G);
+    *grid = (int)g;
     return KOLM_OK;
 }
 
@@ -544,12 +598,13 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     else KL(c, KC_BOOT, N * 9, s, k_boot_keys<false><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
     u32 *K, *V;
     KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, cyclic ? 32 : 27, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
-    KOLM_TRY(kolm_lb_reset(c, nt, s));
+    int lgrid = nt;
+    KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
     RerankArgs ra;
     ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
     ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = 0;
-    if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<true, true><<<nt, KOLM_THREADS, 0, s>>>(ra));
-    else KL(c, KC_RERANK, N * 16, s, k_rerank<true, false><<<nt, KOLM_THREADS, 0, s>>>(ra));
+    if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<true, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
+    else KL(c, KC_RERANK, N * 16, s, k_rerank<true, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
     CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
     CUDA_TRY(cudaGetLastError());
     const int kbits = ceil_log2_u32(c->max_len > 1 ? c->max_len : 2);
@@ -557,26 +612,27 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     for (u64 h = cyclic ? 4 : 3; rounds < 40; h <<= 1) {
         if (h > 0x7fffffffull) h = 0x7fffffffull;
         // ---- gather active predecessors
-        KOLM_TRY(kolm_lb_reset(c, nt, s));
+        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
         GatherArgs ga;
         ga.sa = c->d_sa; ga.rank = c->d_rank; ga.single = c->d_single; ga.tiles = c->d_tiles; ga.binfo = c->d_binfo; ga.fstart = c->d_fstart;
         ga.nfac = c->d_nfac; ga.done = c->d_done; ga.lb = c->d_lb; ga.K = c->d_k0; ga.V = c->d_v0; ga.active = c->d_active; ga.h = (u32)h;
-        if (cyclic) KL(c, KC_GATHER, N * 4, s, k_gather<true><<<nt, KOLM_THREADS, 0, s>>>(ga));
-        else KL(c, KC_GATHER, N * 4, s, k_gather<false><<<nt, KOLM_THREADS, 0, s>>>(ga));
+        if (cyclic) KL(c, KC_GATHER, N * 4, s, k_gather<true><<<lgrid, KOLM_THREADS, 0, s>>>(ga));
+        else KL(c, KC_GATHER, N * 4, s, k_gather<false><<<lgrid, KOLM_THREADS, 0, s>>>(ga));
         KL(c, KC_PLAN, (i64)nb * 16, s, k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb));
-        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 12, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         int ant = (int)c->h_stats[0];
         const i64 M = (i64)c->h_stats[1];
+        c->active_rows = c->h_stats[2];
         if (ant == 0) break;
         ++rounds;
         c->counters[4] += M;                                  // active records summed over rounds
         KL(c, KC_TILES, (i64)ant * 16, s, k_build_tiles<<<bgrid, 128, 0, s>>>(c->d_binfo, c->d_atile0, c->d_atilen, c->d_active, c->d_atiles, nb));
         KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
-        KOLM_TRY(kolm_lb_reset(c, ant, s));
+        KOLM_TRY(kolm_lb_reset(c, true, ant, &lgrid, s));
         ra.K = K; ra.V = V; ra.tiles = c->d_atiles; ra.h = (u32)h;
-        if (cyclic) KL(c, KC_RERANK, M * 20, s, k_rerank<false, true><<<ant, KOLM_THREADS, 0, s>>>(ra));
-        else KL(c, KC_RERANK, M * 20, s, k_rerank<false, false><<<ant, KOLM_THREADS, 0, s>>>(ra));
+        if (cyclic) KL(c, KC_RERANK, M * 20, s, k_rerank<false, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
+        else KL(c, KC_RERANK, M * 20, s, k_rerank<false, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
         KL(c, KC_APPLY, M * 12, s, k_apply<<<ant, KOLM_THREADS, 0, s>>>(V, c->d_nr, c->d_atiles, c->d_rank, c->d_single));
         KL(c, KC_PLAN, (i64)nb * 12, s, k_round_end<<<(nb + 255) / 256, 256, 0, s>>>(c->d_newcls, c->d_done, c->d_active, nb, cyclic ? 1 : 0));
         CUDA_TRY(cudaGetLastError());
@@ -590,8 +646,9 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
 int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, cudaStream_t s) {
     if (!c->ntiles) return KOLM_OK;
     KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
-    KOLM_TRY(kolm_lb_reset(c, c->ntiles, s));
-    KL(c, KC_LYNDON, c->total_bytes * 4, s, k_lyndon<<<c->ntiles, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out));
+    int lgrid = c->ntiles;
+    KOLM_TRY(kolm_lb_reset(c, false, c->ntiles, &lgrid, s));
+    KL(c, KC_LYNDON, c->total_bytes * 4, s, k_lyndon<<<lgrid, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out));
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;
 }

@@ -82,12 +82,15 @@ struct kolm_ctx {
     u32 *d_single;           // bitmap by position: rank is final and unique
     u32 *d_fstart;           // Lyndon factor starts, front-packed per block (block-local positions)
     u8  *d_tmp8a, *d_tmp8b;  // byte staging (bbwt out -> mtf -> rice)
+    void* d_jump;            // inverse BBWT pointer-jumping nodes (2 x 16 B / element), allocated on first decode
+    int* d_err; int* h_err;  // [max_blocks] per-block decode status
     // host mirrors
     BlockInfo* h_binfo;      // pinned
     u32* h_u32;              // pinned scratch [4*max_blocks]
     int nblocks; u32 total_elems; u32 max_len; int ntiles;
     i64 total_bytes;
     // accounting / profiling
+    u32 static_rows, active_rows;   // max tiles per block of the static / active tile map
     i64 launches[32]; i64 algbytes[32];
     int prof_on; int prof_n; int prof_cat[8192]; cudaEvent_t* prof_ev;
     i64 counters[8];
@@ -132,9 +135,27 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
 #define LB_PREFIX 2ull
 #define LB_PAYLOAD_MASK ((1ull << 62) - 1)
 
+// header words: [0] ticket counter, [1] rows (0: ticket == tile index), [2] nblocks, [3] tile0 ptr, [4] tilen ptr, [5] group size.
+// With rows > 0 tickets are handed out "row-major": ticket t -> tile k = t / nblocks of block b = t % nblocks, so the
+// co-resident CTAs cover a few tiles of EVERY block instead of many tiles of a few blocks; each block's look-back chain
+// then finds a published prefix within one 32-wide window.  A tile's predecessor always has a smaller ticket.
+#define LB_NO_TILE 0xffffffffu
 __device__ __forceinline__ u32 lb_take_ticket(u64* lb) {
     __shared__ u32 s_ticket;
-    if (threadIdx.x == 0) s_ticket = (u32)atomicAdd((unsigned long long*)lb, 1ull);
+    if (threadIdx.x == 0) {
+        u32 t = (u32)atomicAdd((unsigned long long*)lb, 1ull);
+        u32 tile = t;
+        u64 rows = lb[1];
+        if (rows) {
+            u32 nb = (u32)lb[2], G = (u32)lb[5];             // groups of G blocks: row-major inside a group, groups in sequence
+            u32 per = (u32)rows * G;
+            u32 g = t / per, tg = t - g * per;
+            u32 k = tg / G, b = g * G + (tg - k * G);
+            const u32* t0 = (const u32*)lb[3]; const u32* tn = (const u32*)lb[4];
+            tile = (b < nb && k < tn[b]) ? t0[b] + k : LB_NO_TILE;
+        }
+        s_ticket = tile;
+    }
     __syncthreads();
     return s_ticket;
 }
@@ -228,4 +249,5 @@ static inline void prof_end(kolm_ctx* c, cudaStream_t s) {
 
 // host-side helpers shared between translation units
 int kolm_set_batch(kolm_ctx* c, const i64* off_host, int nblocks, cudaStream_t s);
-int kolm_lb_reset(kolm_ctx* c, int ntiles, cudaStream_t s);
+// zero the look-back state for a launch over the static (active=false) or active tile map; returns the grid size
+int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t s);

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_cost(const u8* __restrict
     __shared__ unsigned long long s_acc[25];
     const u32 tid = threadIdx.x;
     const u32 tile = KF ? lb_take_ticket(lb) : blockIdx.x;
+    if (tile == LB_NO_TILE) return;
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
     const u32 t0 = td.start - bi.pbase;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_kf_pack(const u8* __restr
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
     const u32 tile = lb_take_ticket(lb);
+    if (tile == LB_NO_TILE) return;
     u64* lb2 = lb + gridDim.x;                              // second look-back (bit offsets)
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_k2_pack(const u8* __restr
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
     const u32 tile = lb_take_ticket(lb);
+    if (tile == LB_NO_TILE) return;
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
     const u64 bitbase = bacc[(size_t)td.block * RB_STRIDE + RB_OFF] * 8;
@@ -380,18 +383,19 @@ static int rice_finish(kolm_ctx* c, i64* out_off, int* params, i64* sizes, size_
 
 int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i64* out_off, int* params, cudaStream_t s) {
     const int nb = c->nblocks, nt = c->ntiles;
+    int lgrid = nt;
     if (((uintptr_t)out & 3) != 0) return KOLM_E_ARG;
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset(c, nt, s));
-        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
+        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
     }
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset(c, nt, s));
-        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out));
+        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, params, nullptr, out_cap, s);
@@ -409,12 +413,129 @@ int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 2, slot));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset(c, nt, s));
-        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags));
+        int lgrid = nt;
+        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, nullptr, sizes, out_cap, s);
 }
 
-int kolm_rice_kf_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u8* mtf_out, cudaStream_t s) { return KOLM_E_UNSUPPORTED; }
-int kolm_rice_k2_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, int flags, u8* mtf_out, cudaStream_t s) { return KOLM_E_UNSUPPORTED; }
+// ---------------------------------------------------------------------------------------------
+// decode (v0): one thread walks one block's bitstream; zero runs only advance the cursor because
+// the output is pre-zeroed.  Mirrors BitReader (KF.py:455-497) / rice_decode (V22.py:1423-1452).
+// ---------------------------------------------------------------------------------------------
+struct DBits {
+    const u8* p; u64 n; u64 pos; bool eof;
+    __device__ __forceinline__ u32 bit() {
+        if (pos >= n) { eof = true; return 0; }
+        u32 b = (p[pos >> 3] >> (7 - (pos & 7))) & 1u; ++pos; return b;
+    }
+    __device__ __forceinline__ u32 bits(int k) { u32 v = 0; for (int i = 0; i < k; ++i) v = (v << 1) | bit(); return v; }
+    __device__ __forceinline__ u64 run_of(u32 want) {            // consecutive `want` bits, terminator consumed
+        u64 q = 0;
+        const u8 full = want ? 0xFF : 0x00;
+        for (;;) {
+            if (pos >= n) { eof = true; return q; }
+            if ((pos & 7) == 0 && pos + 8 <= n && p[pos >> 3] == full) { q += 8; pos += 8; continue; }
+            if (bit() == want) ++q; else return q;
+        }
+    }
+};
+
+__global__ void k_rice_kf_dec(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo,
+                              u8* __restrict__ out, int* __restrict__ err, int nblocks) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    BlockInfo bi = binfo[b];
+    DBits br; br.p = pay + pay_off[b]; br.n = (u64)(pay_off[b + 1] - pay_off[b]) * 8; br.pos = 0; br.eof = false;
+    u8* dst = out + bi.ioff;
+    int e = KOLM_OK;
+    if (bi.len) {
+        u32 flags = br.bits(2), k0 = br.bits(4), k1 = br.bits(4);
+        bool urz = flags & 1u, urn = (flags >> 1) != 0;
+        u64 o = 0;
+        while (o < bi.len) {
+            u32 tag = br.bit();
+            if (br.eof) { e = KOLM_E_TRUNCATED; break; }
+            if (tag == 0) {
+                u64 run;
+                if (urz) { u64 q = br.run_of(1); u32 r = k0 ? br.bits(k0) : 0; run = (q << k0) | r; }
+                else { u64 z = br.run_of(0); run = z ? ((1ull << z) | br.bits((int)(z > 31 ? 31 : z))) : 1; if (z > 31) e = KOLM_E_CORRUPT; }
+                if (br.eof) { e = KOLM_E_TRUNCATED; break; }
+                o += run;
+            } else {
+                u64 v;
+                if (urn) { u64 q = br.run_of(1); u32 r = k1 ? br.bits(k1) : 0; v = (q << k1) | r; }
+                else { u64 z = br.run_of(0); v = (z ? ((1ull << z) | br.bits((int)(z > 31 ? 31 : z))) : 1) - 1; }
+                if (br.eof) { e = KOLM_E_TRUNCATED; break; }
+                if (v + 1 > 255) { e = KOLM_E_INDEX; break; }
+                dst[o++] = (u8)(v + 1);
+            }
+            if (e) break;
+        }
+    }
+    err[b] = e;
+}
+
+__global__ void k_rice_k2_dec(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo,
+                              u8* __restrict__ out, int* __restrict__ err, int nblocks, int flags) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    BlockInfo bi = binfo[b];
+    DBits br; br.p = pay + pay_off[b]; br.n = (u64)(pay_off[b + 1] - pay_off[b]) * 8; br.pos = 0; br.eof = false;
+    u8* dst = out + bi.ioff;
+    int e = KOLM_OK;
+    if ((flags & 1) && (bi.len % 8)) e = KOLM_E_INDEX;           // reference: bitplane_deinterleave IndexError
+    for (u32 o = 0; o < bi.len && !e; ++o) {
+        u64 q = br.run_of(1);
+        if (br.eof) { e = KOLM_E_TRUNCATED; break; }
+        if (br.pos + 2 > br.n) { e = KOLM_E_TRUNCATED; break; }
+        u32 r = br.bits(2);
+        u64 v = q * 4 + r;
+        if (v > 255) { e = KOLM_E_CORRUPT; break; }               // reference: bytes(seq) ValueError
+        u32 t = (u32)v;
+        if (flags & 16) { t ^= t >> 1; t ^= t >> 2; t ^= t >> 4; t &= 0xFF; }
+        if (flags & 8) t = dev_bitrev8(t);
+        if (flags & 4) t = ((t & 0x0F) << 4) | ((t & 0xF0) >> 4);
+        dst[o] = (u8)t;
+    }
+    if (!e && (flags & 1)) {                                       // inverse 8x8 transpose per group (self-inverse)
+        for (u32 g0 = 0; g0 < bi.len; g0 += 8) {
+            u64 g = 0;
+            for (int i = 0; i < 8; ++i) g |= (u64)dst[g0 + i] << (8 * i);
+            u64 t = bitplane8(g);
+            for (int i = 0; i < 8; ++i) dst[g0 + i] = (u8)(t >> (8 * i));
+        }
+    }
+    err[b] = e;
+}
+
+static int rice_dec_finish(kolm_ctx* c, cudaStream_t s) {
+    CUDA_TRY(cudaMemcpyAsync(c->h_err, c->d_err, (size_t)c->nblocks * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int b = 0; b < c->nblocks; ++b) if (c->h_err[b]) return c->h_err[b];
+    return KOLM_OK;
+}
+
+int kolm_rice_kf_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u8* mtf_out, cudaStream_t s) {
+    const int nb = c->nblocks;
+    if (!nb) return KOLM_OK;
+    memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (c->total_bytes) CUDA_TRY(cudaMemsetAsync(mtf_out + c->h_binfo[0].ioff, 0, (size_t)c->total_bytes, s));
+    KL(c, KC_RICE_PACK, c->total_bytes + pay_off[nb] - pay_off[0], s, k_rice_kf_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, mtf_out, c->d_err, nb));
+    CUDA_TRY(cudaGetLastError());
+    return rice_dec_finish(c, s);
+}
+
+int kolm_rice_k2_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, int flags, u8* mtf_out, cudaStream_t s) {
+    const int nb = c->nblocks;
+    if (k2_slot(flags) < 0) return KOLM_E_ARG;
+    if (!nb) return KOLM_OK;
+    memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
+    KL(c, KC_RICE_PACK, c->total_bytes + pay_off[nb] - pay_off[0], s, k_rice_k2_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, mtf_out, c->d_err, nb, flags));
+    CUDA_TRY(cudaGetLastError());
+    return rice_dec_finish(c, s);
+}

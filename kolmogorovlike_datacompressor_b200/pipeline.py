@@ -28,6 +28,8 @@ class BlockPipeline:
         self.cap = int(max_batch_bytes)
         self.max_blocks = int(max_blocks)
         self.profile_kf, self.profile_k2 = profile_kf, profile_k2
+        import os
+        self.wave_bytes = int(os.environ.get("KOLM_WAVE_MIB", "65536")) << 20
         with torch.cuda.device(self.device):
             self.d_in = torch.empty(self.cap + 64, dtype=torch.uint8, device=self.device)
             self.d_bbwt = torch.empty(self.cap + 64, dtype=torch.uint8, device=self.device)
@@ -43,7 +45,16 @@ class BlockPipeline:
         """x: uint8 CUDA tensor with the blocks back to back.  Returns a dict of device tensors + host offsets."""
         c = self.ctx
         r = {}
-        c.bbwt_forward(x, off, out=self.d_bbwt)
+        # optional waves of blocks (KOLM_WAVE_MIB); measured slower than one launch set over the whole batch, kept as a knob
+        off = np.asarray(off, dtype=np.int64)
+        nb = len(off) - 1
+        b0 = 0
+        while b0 < nb:
+            b1 = b0 + 1
+            while b1 < nb and off[b1 + 1] - off[b0] <= self.wave_bytes:
+                b1 += 1
+            c.bbwt_forward(x, off[b0:b1 + 1], out=self.d_bbwt)
+            b0 = b1
         c.mtf_encode(self.d_bbwt, off, out=self.d_mtf)
         if self.profile_kf:
             r["kf_payload"], r["kf_off"], r["kf_params"] = c.rice_kf_encode(self.d_mtf, off, out=self.d_kf, want_params=True)
