@@ -571,7 +571,8 @@ __global__ void k_lb_header(u64* lb, u64 rows, u64 nb, const u32* tile0, const u
 
 int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t s) {
     static int G = -1;
-    if (G < 0) { const char* e = getenv("KOLM_LB_GROUP"); G = e ? atoi(e) : 0;   // measured on B200: block-major order wins (L2 locality of the rank gathers), see DESIGN.md }
+    // default 0 = block-major tickets: measured on B200, interleaving blocks loses more L2 locality than it saves look-back steps
+    if (G < 0) { const char* e = getenv("KOLM_LB_GROUP"); G = e ? atoi(e) : 0; }
     u64 rows = active ? c->active_rows : c->static_rows;
     u64 ngroups = G > 0 ? ((u64)c->nblocks + G - 1) / G : 0;
     u64 g = rows * (u64)G * ngroups;
