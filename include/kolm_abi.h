@@ -87,6 +87,25 @@ int kolm_rice_k2_enc(kolm_ctx* ctx, const uint8_t* mtf, const int64_t* off, int 
 int kolm_rice_k2_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int flags,
                      uint8_t* mtf_out, kolm_stream_t stream);
 
+/* LZ77: exhaustive nearest-among-longest match (min 3, overlap allowed) + greedy parse, tokens [0,byte] / [1,ULEB len,ULEB dist].
+ *   KF  encode_model_lz77 (KF.py:567-617):  window 255,  max_len 127
+ *   V22 encode_lz77 (V22.py:1711-1763):     window 4096, max_len 0 (= unbounded)
+ * Any other (window, max_len) is a parameterisation of the same semantics (BASELINE cfg 3 uses 65536 / 0). */
+int kolm_lz77_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint32_t window, uint32_t max_len, uint8_t* out,
+                  size_t out_cap, int64_t* out_off, kolm_stream_t stream);
+/* decode_model_lz77 (KF.py:723-760; window_check 0) / decode_lz77 (V22.py:1765-1812; window_check 4096) */
+int kolm_lz77_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint32_t window_check,
+                  uint8_t* out, kolm_stream_t stream);
+
+/* byte-predictor residual coders, each residual one ULEB128 value.  kind 0 = XOR (KF.py:545-565, 702-721),
+ * 1 = delta (V22 "xor", V22.py:2105-2122), 2 = LFSR predictor (V22.py:1984-2019).
+ * kolm_residual_sizes: exact payload sizes of all three kinds (HOST int64[3*nblocks]) from one read. */
+int kolm_residual_sizes(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, int64_t* sizes3, kolm_stream_t stream);
+int kolm_residual_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, int kind, uint8_t* out, size_t out_cap,
+                      int64_t* out_off, kolm_stream_t stream);
+int kolm_residual_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int kind,
+                      uint8_t* out, kolm_stream_t stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
  * rounds, [2] kernels launched since the last profile reset, [3] records sorted (sum over rounds) */

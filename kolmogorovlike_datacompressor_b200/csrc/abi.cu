@@ -14,6 +14,8 @@ void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
 #include "bbwt_inv.cu"
 #include "mtf.cu"
 #include "rice.cu"
+#include "lz77.cu"
+#include "residual.cu"
 
 static size_t padded_capacity(size_t max_batch_bytes, int max_blocks) {
     return max_batch_bytes + (size_t)KOLM_PAD * (size_t)max_blocks + 4 * KOLM_PAD;
@@ -206,6 +208,40 @@ int kolm_rice_k2_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off
     cudaStream_t s = (cudaStream_t)stream;
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
     return kolm_rice_k2_dec_impl(c, payload, pay_off, flags, mtf_out, s);
+}
+
+int kolm_lz77_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint32_t window, uint32_t max_len, uint8_t* out,
+                  size_t out_cap, int64_t* out_off, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_lz77_enc_impl(c, in, window, max_len, out, out_cap, out_off, s);
+}
+
+int kolm_lz77_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint32_t window_check,
+                  uint8_t* out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_lz77_dec_impl(c, payload, pay_off, window_check, out, s);
+}
+
+int kolm_residual_sizes(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, int64_t* sizes3, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_residual_sizes_impl(c, in, sizes3, s);
+}
+
+int kolm_residual_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, int kind, uint8_t* out, size_t out_cap,
+                      int64_t* out_off, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_residual_enc_impl(c, in, kind, out, out_cap, out_off, s);
+}
+
+int kolm_residual_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int kind,
+                      uint8_t* out, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_residual_dec_impl(c, payload, pay_off, kind, out, s);
 }
 
 int kolm_last_counters(kolm_ctx* c, int64_t* out4) {

@@ -124,3 +124,46 @@ class Context:
         _lib.check(_lib.lib().kolm_rice_k2_dec(self._h, C.c_void_p(payload.data_ptr()), pp, op, nb, int(flags), C.c_void_p(out.data_ptr()),
                                                self._stream()), "kolm_rice_k2_dec")
         return out
+
+    # ---- LZ77 / residual coders -----------------------------------------
+    def _enc(self, fn, x, off, extra, cap_mul, out=None):
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        if out is None:
+            out = torch.empty(int(oa[-1] - oa[0]) * cap_mul + 16 * nb + 64, dtype=torch.uint8, device=x.device)
+        out_off = np.zeros(nb + 1, dtype=np.int64)
+        _lib.check(getattr(_lib.lib(), fn)(self._h, C.c_void_p(x.data_ptr()), op, nb, *extra, C.c_void_p(out.data_ptr()), out.numel(),
+                                           out_off.ctypes.data_as(C.POINTER(C.c_int64)), self._stream()), fn)
+        return out, out_off
+
+    def _dec(self, fn, payload, pay_off, off, extra, out=None):
+        pa, pp = _offsets(pay_off)
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        if out is None:
+            out = torch.empty(max(1, int(oa[-1])), dtype=torch.uint8, device=payload.device)
+        _lib.check(getattr(_lib.lib(), fn)(self._h, C.c_void_p(payload.data_ptr()), pp, op, nb, *extra, C.c_void_p(out.data_ptr()),
+                                           self._stream()), fn)
+        return out
+
+    def lz77_encode(self, x, off, window: int, max_len: int, out=None):
+        """encode_model_lz77 (window 255, max_len 127) / encode_lz77 (window 4096, max_len 0 = unbounded)."""
+        return self._enc("kolm_lz77_enc", x, off, (C.c_uint32(window), C.c_uint32(max_len)), 2, out)
+
+    def lz77_decode(self, payload, pay_off, off, window_check: int = 0, out=None):
+        return self._dec("kolm_lz77_dec", payload, pay_off, off, (C.c_uint32(window_check),), out)
+
+    def residual_sizes(self, x, off):
+        """Exact payload sizes [nb, 3] of the XOR / delta / LFSR-predictor candidates."""
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        sizes = np.zeros(3 * max(1, nb), dtype=np.int64)
+        _lib.check(_lib.lib().kolm_residual_sizes(self._h, C.c_void_p(x.data_ptr()), op, nb, sizes.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                  self._stream()), "kolm_residual_sizes")
+        return sizes.reshape(-1, 3)[:nb]
+
+    def residual_encode(self, x, off, kind: int, out=None):
+        return self._enc("kolm_residual_enc", x, off, (C.c_int(kind),), 2, out)
+
+    def residual_decode(self, payload, pay_off, off, kind: int, out=None):
+        return self._dec("kolm_residual_dec", payload, pay_off, off, (C.c_int(kind),), out)

@@ -1,0 +1,84 @@
+"""GPU parity: LZ77 (both reference parameter sets + the 64 KiB-window parameterisation) and the
+XOR / delta / LFSR residual coders vs the CPU oracle (bit-exact), encode and decode."""
+import random
+
+import numpy as np
+import pytest
+
+import datasets
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    c = {**datasets.small_cases(), **datasets.medium_cases()}
+    rnd = random.Random(21)
+    for i in range(16):
+        n = rnd.choice([1, 2, 3, 4, 5, 255, 256, 257, 300, 4095, 4096, 4097, 6000, 10000])
+        alpha = rnd.choice([1, 2, 3, 8, 256])
+        c["rnd%d" % i] = bytes(rnd.randrange(alpha) for _ in range(n))
+    c["zeros_20k"] = bytes(20000)
+    c["run_then_noise"] = bytes(9000) + bytes(rnd.randrange(256) for _ in range(3000)) + b"\x07" * 5000
+    c["period_1920"] = (bytes(rnd.randrange(256) for _ in range(1920)) * 9)[:16000]
+    c["abc_x"] = b"".join(b"abc" + bytes([rnd.randrange(256)]) for _ in range(3000))
+    for name in datasets.FIXTURES:
+        c["fx_" + name] = datasets.fixture(name)[5000:5000 + 40000]
+    return c
+
+
+@pytest.mark.parametrize("window,maxlen", [(255, 127), (4096, 0), (65536, 0)])
+def test_lz77_encode_decode(window, maxlen):
+    import gpu_util as G
+    cases = _cases()
+    names = sorted(cases)
+    blocks = [cases[k] for k in names]
+    t, off = G.batch(blocks)
+    out, out_off = G.ctx().lz77_encode(t, off, window, maxlen)
+    got = out.cpu().numpy().tobytes()
+    for i, k in enumerate(names):
+        want = O.lz77_encode(blocks[i], window, maxlen)
+        assert got[out_off[i]:out_off[i + 1]] == want, (k, window, maxlen)
+    dec = G.unbatch(G.ctx().lz77_decode(out, out_off, off, 4096 if window == 4096 else 0), off)
+    for k, b, d in zip(names, blocks, dec):
+        assert d == b, k
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_residual_coders(kind):
+    import gpu_util as G
+    cases = _cases()
+    names = sorted(cases)
+    blocks = [cases[k] for k in names]
+    t, off = G.batch(blocks)
+    sizes = G.ctx().residual_sizes(t, off)
+    out, out_off = G.ctx().residual_encode(t, off, kind)
+    got = out.cpu().numpy().tobytes()
+    for i, k in enumerate(names):
+        want = O.residual_encode(blocks[i], kind)
+        assert got[out_off[i]:out_off[i + 1]] == want, (k, kind)
+        assert sizes[i][kind] == len(want), (k, kind)
+    dec = G.unbatch(G.ctx().residual_decode(out, out_off, off, kind), off)
+    for k, b, d in zip(names, blocks, dec):
+        assert d == b, (k, kind)
+
+
+def test_lz77_1mib_blocks_roundtrip():
+    import gpu_util as G
+    import torch
+    from kolmogorovlike_datacompressor_b200 import synth
+    data = np.concatenate([synth.s2_mixed(4 << 20), synth.s1_text(1 << 20)])
+    n = data.size
+    off = np.arange(0, n + 1, 1 << 20, dtype=np.int64)
+    t = torch.from_numpy(data).cuda()
+    for window, maxlen, wc in ((255, 127, 0), (4096, 0, 4096)):
+        out, out_off = G.ctx().lz77_encode(t, off, window, maxlen)
+        back = G.ctx().lz77_decode(out, out_off, off, wc)
+        assert torch.equal(back[:n], t[:n])
+        # oracle parity on the text block (cheap for the exhaustive CPU scan) and the pattern block
+        for b in (4, 2):
+            blk = data[b << 20:(b + 1) << 20].tobytes()
+            if window == 4096 and b == 2:
+                continue   # exhaustive oracle on 1 MiB of pattern data takes minutes with the 4 KiB window
+            want = O.lz77_encode(blk, window, maxlen)
+            assert out[out_off[b]:out_off[b + 1]].cpu().numpy().tobytes() == want, (window, b)
