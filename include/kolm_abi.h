@@ -106,6 +106,14 @@ int kolm_residual_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int 
 int kolm_residual_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int kind,
                       uint8_t* out, kolm_stream_t stream);
 
+/* Re-Pair grammar candidate: repair_compress / repair_decompress (V22.py:1841-1911, 1916-1978).
+ * Blocks longer than kolm_repair_max_block() bytes return KOLM_E_UNSUPPORTED (one CTA keeps the sequence in shared memory). */
+int kolm_repair_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
+                    kolm_stream_t stream);
+int kolm_repair_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,
+                    kolm_stream_t stream);
+int kolm_repair_max_block(void);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
  * rounds, [2] kernels launched since the last profile reset, [3] records sorted (sum over rounds) */

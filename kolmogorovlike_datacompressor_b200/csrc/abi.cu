@@ -16,6 +16,7 @@ void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
 #include "rice.cu"
 #include "lz77.cu"
 #include "residual.cu"
+#include "repair.cu"
 
 static size_t padded_capacity(size_t max_batch_bytes, int max_blocks) {
     return max_batch_bytes + (size_t)KOLM_PAD * (size_t)max_blocks + 4 * KOLM_PAD;
@@ -121,7 +122,7 @@ int kolm_set_batch(kolm_ctx* c, const i64* off, int nblocks, cudaStream_t s) {
         c->h_binfo[b].ioff = off[b]; c->h_binfo[b].pbase = (u32)p; c->h_binfo[b].len = (u32)len;
         bt0[b] = t; btn[b] = (u32)((len + KOLM_TILE - 1) / KOLM_TILE); t += btn[b];
         if (btn[b] > rows) rows = btn[b];
-        p += ((u64)len + KOLM_PAD - 1) / KOLM_PAD * KOLM_PAD;
+        p += len ? ((u64)len + KOLM_PAD - 1) / KOLM_PAD * KOLM_PAD : KOLM_PAD;   // empty blocks still own a scratch slot
         if ((u32)len > maxlen) maxlen = (u32)len;
         if (p + 2 * KOLM_PAD > c->max_elems) return KOLM_E_CAPACITY;
     }
@@ -243,6 +244,22 @@ int kolm_residual_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_of
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
     return kolm_residual_dec_impl(c, payload, pay_off, kind, out, s);
 }
+
+int kolm_repair_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
+                    kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_repair_enc_impl(c, in, out, out_cap, out_off, s);
+}
+
+int kolm_repair_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,
+                    kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_repair_dec_impl(c, payload, pay_off, out, s);
+}
+
+int kolm_repair_max_block(void) { return REPAIR_MAX; }
 
 int kolm_last_counters(kolm_ctx* c, int64_t* out4) {
     i64 total = 0;

@@ -1,0 +1,257 @@
+// repair.cu — Re-Pair grammar candidate, exact reference semantics.
+//
+//   repair_compress   kolm_final_researched_v2-2.py:1841-1911  (_count_pairs :1817, _replace_non_overlapping :1824)
+//   repair_decompress kolm_final_researched_v2-2.py:1916-1978
+//
+// Per round: count ALL adjacent (overlapping) pairs, take the most frequent (count >= 2, ties -> the
+// lexicographically smallest pair), replace its occurrences left to right without overlap by a new
+// symbol 256+r; stop when fewer than 2 replacements happened (that rule is not recorded).
+//
+// One CTA per block, the whole symbol sequence in shared memory (blocks of up to REPAIR_MAX symbols):
+//   pair histogram  = open-addressing hash table in shared memory (atomicCAS insert, atomicAdd count)
+//   argmax          = 64-bit atomicMax of (count << 32 | ~pair)   -> max count, smallest pair
+//   replacement     = inside a maximal run of overlapping matches (only when a == b) every other one
+//                     from the run start is taken; then a block-wide compaction.
+// Larger blocks return KOLM_E_UNSUPPORTED (the reference's own algorithm is O(rounds * n) there).
+#include "common.cuh"
+
+#define REPAIR_MAX 8192
+#define REPAIR_THREADS 1024
+#define REPAIR_HASH 16384          // slots; load factor <= 0.5
+#define REPAIR_EMPTY 0xffffffffu
+
+struct RepairSmem {
+    u16 seq[2][REPAIR_MAX];
+    u32 hkey[REPAIR_HASH];
+    u32 hcnt[REPAIR_HASH];
+    u32 scan[REPAIR_THREADS / 32];
+    unsigned long long best;
+    u32 replaced, m;
+};
+
+__device__ __forceinline__ u32 rp_hash(u32 k) { k *= 2654435761u; return (k >> 15) & (REPAIR_HASH - 1); }
+
+// block-wide inclusive scan (sum or max) of one u32 per thread
+template <bool MAXOP>
+__device__ __forceinline__ u32 rp_scan(u32 v, u32* s_w, u32* total) {
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v = MAXOP ? max(v, n) : v + n; }
+    if (lane == 31) s_w[w] = v;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (int i = 0; i < REPAIR_THREADS / 32; ++i) { u32 x = s_w[i]; if ((u32)i < w) pre = MAXOP ? max(pre, x) : pre + x; tot = MAXOP ? max(tot, x) : tot + x; }
+    __syncthreads();
+    if (total) *total = tot;
+    return MAXOP ? max(pre, v) : pre + v;
+}
+
+__device__ __forceinline__ u32 rp_uleb_size(u32 v) { return v < 128u ? 1u : v < 16384u ? 2u : 3u; }
+__device__ __forceinline__ u8* rp_put_uleb(u8* p, u32 v) { while (v >= 128) { *p++ = (u8)(v | 0x80); v >>= 7; } *p++ = (u8)v; return p; }
+
+// out_tmp: per block a staging region of 4*len+64 bytes at tmp + 4*pbase; sizes[b] = payload bytes
+__global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
+                                                                  u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    RepairSmem& S = *reinterpret_cast<RepairSmem*>(smem_raw);
+    const u32 tid = threadIdx.x, b = blockIdx.x;
+    const BlockInfo bi = binfo[b];
+    if (bi.len > REPAIR_MAX) { if (tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }
+    const u8* src = in + bi.ioff;
+    u32* rules = rules_scratch + bi.pbase;                  // up to len/2 rules, (a<<16|b)
+    for (u32 i = tid; i < bi.len; i += REPAIR_THREADS) S.seq[0][i] = src[i];
+    if (tid == 0) S.m = bi.len;
+    __syncthreads();
+    u32 cur = 0, nrules = 0;
+    constexpr u32 IPT = REPAIR_MAX / REPAIR_THREADS;        // 8 consecutive positions per thread
+    for (;;) {
+        const u32 m = S.m;
+        if (m < 2) break;
+        // ---- pair histogram
+        for (u32 i = tid; i < REPAIR_HASH; i += REPAIR_THREADS) { S.hkey[i] = REPAIR_EMPTY; S.hcnt[i] = 0; }
+        if (tid == 0) { S.best = 0; S.replaced = 0; }
+        __syncthreads();
+        const u16* q = S.seq[cur];
+        for (u32 i = tid; i + 1 < m; i += REPAIR_THREADS) {
+            u32 key = ((u32)q[i] << 16) | q[i + 1];
+            u32 h = rp_hash(key);
+            for (;;) {
+                u32 old = atomicCAS(&S.hkey[h], REPAIR_EMPTY, key);
+                if (old == REPAIR_EMPTY || old == key) { atomicAdd(&S.hcnt[h], 1u); break; }
+                h = (h + 1) & (REPAIR_HASH - 1);
+            }
+        }
+        __syncthreads();
+        for (u32 i = tid; i < REPAIR_HASH; i += REPAIR_THREADS) {
+            u32 k = S.hkey[i];
+            if (k != REPAIR_EMPTY && S.hcnt[i] >= 2) atomicMax(&S.best, ((unsigned long long)S.hcnt[i] << 32) | (unsigned long long)(~k));
+        }
+        __syncthreads();
+        const unsigned long long best = S.best;
+        if ((u32)(best >> 32) < 2) break;                    // V22.py:1875-1876
+        const u32 bkey = ~(u32)best;
+        const u32 newsym = 256 + nrules;
+        // ---- which occurrences are replaced: position i is "flagged" if pair(i) == best
+        //      taken(i) = flagged(i) and (i - start of its maximal flagged run) is even
+        u32 flags = 0, lastun = 0;                           // lastun: 1 + index of the last unflagged position among mine
+#pragma unroll
+        for (u32 k = 0; k < IPT; ++k) {
+            u32 i = tid * IPT + k;
+            bool f = (i + 1 < m) && ((((u32)q[i] << 16) | q[i + 1]) == bkey);
+            if (f) flags |= 1u << k; else lastun = i + 1;
+        }
+        u32 incl = rp_scan<true>(lastun, S.scan, nullptr);
+        u32 prevun = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive: last unflagged before my first item
+        if ((tid & 31) == 0) prevun = 0;
+        // cross-warp exclusive: recompute from the scan array is gone; do it with a second tiny scan on warp leaders
+        __shared__ u32 s_wlast[REPAIR_THREADS / 32];
+        if ((tid & 31) == 31) s_wlast[tid >> 5] = incl;
+        __syncthreads();
+        if ((tid & 31) == 0 && tid) prevun = s_wlast[(tid >> 5) - 1];
+        __syncthreads();
+        u32 taken = 0, run0 = prevun;                        // run0 = first index of the current flagged run
+        u32 ntaken = 0;
+#pragma unroll
+        for (u32 k = 0; k < IPT; ++k) {
+            u32 i = tid * IPT + k;
+            if ((flags >> k) & 1u) { if (((i - run0) & 1u) == 0) { taken |= 1u << k; ++ntaken; } }
+            else run0 = i + 1;
+        }
+        // removed(i) = taken(i-1): the second symbol of a replaced pair disappears
+        u32 tprev = __shfl_up_sync(0xffffffffu, taken >> (IPT - 1), 1) & 1u;
+        __shared__ u32 s_wt[REPAIR_THREADS / 32];
+        if ((tid & 31) == 31) s_wt[tid >> 5] = (taken >> (IPT - 1)) & 1u;
+        __syncthreads();
+        if ((tid & 31) == 0) tprev = tid ? s_wt[(tid >> 5) - 1] : 0;
+        u32 removed = ((taken << 1) | tprev) & ((1u << IPT) - 1);
+        u32 keep = 0;
+#pragma unroll
+        for (u32 k = 0; k < IPT; ++k) { u32 i = tid * IPT + k; if (i < m && !((removed >> k) & 1u)) ++keep; }
+        u32 tot_taken;
+        u32 tincl = rp_scan<false>(ntaken, S.scan, &tot_taken);
+        (void)tincl;
+        if (tot_taken < 2) break;                            // V22.py:1880-1882: rule not recorded, sequence unchanged
+        u32 newm;
+        u32 kincl = rp_scan<false>(keep, S.scan, &newm);
+        u32 o = kincl - keep;
+        u16* nq = S.seq[cur ^ 1];
+#pragma unroll
+        for (u32 k = 0; k < IPT; ++k) {
+            u32 i = tid * IPT + k;
+            if (i < m && !((removed >> k) & 1u)) nq[o++] = ((taken >> k) & 1u) ? (u16)newsym : q[i];
+        }
+        if (tid == 0) { rules[nrules] = bkey; S.m = newm; }
+        ++nrules; cur ^= 1;
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- serialise: 'R','P', ULEB 256, ULEB nrules, rules, ULEB len, symbols   (V22.py:1889-1903)
+    const u32 m = S.m;
+    const u16* q = S.seq[cur];
+    u8* dst = tmp + (size_t)bi.pbase * 4;
+    __shared__ u32 s_hdr;
+    u32 rbytes = 0;
+    for (u32 r = tid; r < nrules; r += REPAIR_THREADS) { u32 k = rules[r]; rbytes += rp_uleb_size(k >> 16) + rp_uleb_size(k & 0xffff); }
+    u32 rtot;
+    rp_scan<false>(rbytes, S.scan, &rtot);
+    // rules are few thousand at most: thread 0 writes header + rules sequentially, everyone writes symbols
+    if (tid == 0) {
+        u8* p = dst; *p++ = 'R'; *p++ = 'P'; p = rp_put_uleb(p, 256); p = rp_put_uleb(p, nrules);
+        for (u32 r = 0; r < nrules; ++r) { u32 k = rules[r]; p = rp_put_uleb(p, k >> 16); p = rp_put_uleb(p, k & 0xffff); }
+        p = rp_put_uleb(p, m);
+        s_hdr = (u32)(p - dst);
+    }
+    u32 sb = 0;
+#pragma unroll
+    for (u32 k = 0; k < IPT; ++k) { u32 i = tid * IPT + k; if (i < m) sb += rp_uleb_size(q[i]); }
+    u32 stot;
+    u32 sincl = rp_scan<false>(sb, S.scan, &stot);
+    __syncthreads();
+    u8* p = dst + s_hdr + (sincl - sb);
+#pragma unroll
+    for (u32 k = 0; k < IPT; ++k) { u32 i = tid * IPT + k; if (i < m) p = rp_put_uleb(p, q[i]); }
+    if (tid == 0) { bacc[(size_t)b * 64 + 32] = (u64)s_hdr + stot; err[b] = KOLM_OK; }
+}
+
+__global__ void k_repair_gather(const u8* __restrict__ tmp, const BlockInfo* __restrict__ binfo, const u64* __restrict__ bacc, u8* __restrict__ out) {
+    const u32 b = blockIdx.x;
+    const u8* src = tmp + (size_t)binfo[b].pbase * 4;
+    u8* dst = out + bacc[(size_t)b * 64 + 33];
+    u64 n = bacc[(size_t)b * 64 + 32];
+    for (u64 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// decode (v0): one thread per block; iterative expansion with an explicit stack in global scratch
+__global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo, u8* __restrict__ out,
+                             u32* __restrict__ scratch_rules, u32* __restrict__ scratch_stack, int* __restrict__ err, int nblocks) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    BlockInfo bi = binfo[b];
+    const u8* d = pay + pay_off[b];
+    i64 n = pay_off[b + 1] - pay_off[b], p = 2;
+    u32* rules = scratch_rules + bi.pbase;       // capacity len (+pad) entries of (a<<16|b): enough for encoder output (<= len/2 rules)
+    u32* stack = scratch_stack + bi.pbase;
+    u32 cap = ((bi.len + KOLM_PAD - 1) / KOLM_PAD) * KOLM_PAD;
+    if (cap < KOLM_PAD) cap = KOLM_PAD;
+    u8* dst = out + bi.ioff;
+    int e = KOLM_OK;
+    auto get = [&](u64& v) -> bool { v = 0; int sh = 0; for (;;) { if (p >= n) return false; u8 x = d[p++]; if (sh < 64) v |= (u64)(x & 0x7F) << sh; if (!(x & 0x80)) return true; sh += 7; } };
+    u64 term = 0, nr = 0, sl = 0;
+    if (n < 2 || d[0] != 'R' || d[1] != 'P') e = KOLM_E_CORRUPT;
+    if (!e && !get(term)) e = KOLM_E_TRUNCATED;
+    if (!e && term != 256) e = KOLM_E_CORRUPT;
+    if (!e && !get(nr)) e = KOLM_E_TRUNCATED;
+    if (!e && nr > cap) e = KOLM_E_UNSUPPORTED;
+    for (u64 r = 0; r < nr && !e; ++r) {
+        u64 x, y;
+        if (!get(x) || !get(y)) { e = KOLM_E_TRUNCATED; break; }
+        if (x >= 256 + r || y >= 256 + r || x > 0xffff || y > 0xffff) { e = KOLM_E_CORRUPT; break; }
+        rules[r] = ((u32)x << 16) | (u32)y;
+    }
+    if (!e && !get(sl)) e = KOLM_E_TRUNCATED;
+    u32 o = 0;
+    for (u64 t = 0; t < sl && !e; ++t) {
+        u64 s;
+        if (!get(s)) { e = KOLM_E_TRUNCATED; break; }
+        if (s >= 256 + nr) { e = KOLM_E_CORRUPT; break; }
+        u32 sp = 0; stack[sp++] = (u32)s;
+        while (sp) {
+            u32 x = stack[--sp];
+            if (x < 256) { if (o >= bi.len) { e = KOLM_E_CORRUPT; break; } dst[o++] = (u8)x; }
+            else { if (sp + 2 > cap) { e = KOLM_E_UNSUPPORTED; break; } u32 k = rules[x - 256]; stack[sp++] = k & 0xffff; stack[sp++] = k >> 16; }
+        }
+    }
+    if (!e && o != bi.len) e = KOLM_E_CORRUPT;
+    err[b] = e;
+}
+
+int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
+    const int nb = c->nblocks;
+    if (!nb) { out_off[0] = 0; return KOLM_OK; }
+    if (c->max_len > REPAIR_MAX) return KOLM_E_UNSUPPORTED;
+    static bool attr_set[64];
+    if (c->device < 64 && !attr_set[c->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
+        attr_set[c->device] = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * 64 * 8, s));
+    u8* tmp = (u8*)c->d_k0;                                   // 4 bytes per padded element
+    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+    KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
+    KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_poff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(out_off, c->h_poff, (size_t)(nb + 1) * 8);
+    if ((size_t)out_off[nb] > out_cap) return KOLM_E_CAPACITY;
+    return KOLM_OK;
+}
+
+int kolm_repair_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u8* out, cudaStream_t s) {
+    const int nb = c->nblocks;
+    if (!nb) return KOLM_OK;
+    memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
+    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_k0, c->d_v0, c->d_err, nb));
+    CUDA_TRY(cudaGetLastError());
+    return rice_dec_finish(c, s);
+}

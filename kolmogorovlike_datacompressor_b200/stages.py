@@ -167,3 +167,10 @@ class Context:
 
     def residual_decode(self, payload, pay_off, off, kind: int, out=None):
         return self._dec("kolm_residual_dec", payload, pay_off, off, (C.c_int(kind),), out)
+
+    def repair_encode(self, x, off, out=None):
+        """repair_compress per block (blocks <= kolm_repair_max_block() bytes)."""
+        return self._enc("kolm_repair_enc", x, off, (), 4, out)
+
+    def repair_decode(self, payload, pay_off, off, out=None):
+        return self._dec("kolm_repair_dec", payload, pay_off, off, (), out)
