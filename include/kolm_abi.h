@@ -114,6 +114,13 @@ int kolm_repair_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_of
                     kolm_stream_t stream);
 int kolm_repair_max_block(void);
 
+/* Content-defined chunking, HOST buffers (adjacent to the hot path; bit-identical boundaries are a precondition of
+ * byte-identical containers).  ends[i] = exclusive end of chunk i; returns the chunk count or a negative error.
+ *   kolm_cdc_kf : cdc_fast_boundaries (KF.py:161-194), gear table of KF.py:148-159
+ *   kolm_cdc_v22: cdc_fast_boundaries_strict (V22.py:210-309, merge_orphan_tail=True), gear table of V22.py:152-167 */
+int64_t kolm_cdc_kf(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap);
+int64_t kolm_cdc_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
  * rounds, [2] kernels launched since the last profile reset, [3] records sorted (sum over rounds) */

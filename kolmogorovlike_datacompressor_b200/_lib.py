@@ -17,7 +17,7 @@ EXPORTS = [
     "kolm_lyndon", "kolm_bbwt_fwd", "kolm_bbwt_inv", "kolm_mtf_enc", "kolm_mtf_dec",
     "kolm_rice_kf_enc", "kolm_rice_kf_dec", "kolm_rice_k2_enc", "kolm_rice_k2_dec", "kolm_last_counters",
     "kolm_lz77_enc", "kolm_lz77_dec", "kolm_residual_sizes", "kolm_residual_enc", "kolm_residual_dec",
-    "kolm_repair_enc", "kolm_repair_dec", "kolm_repair_max_block",
+    "kolm_repair_enc", "kolm_repair_dec", "kolm_repair_max_block", "kolm_cdc_kf", "kolm_cdc_v22",
     "kolm_profile_categories", "kolm_profile_name", "kolm_profile_enable", "kolm_profile_reset", "kolm_profile_read",
 ]
 
@@ -65,6 +65,9 @@ def lib():
     L.kolm_last_counters.argtypes = [p, i64p]
     L.kolm_lz77_enc.argtypes = [p, p, i64p, C.c_int, C.c_uint32, C.c_uint32, p, C.c_size_t, i64p, p]
     L.kolm_lz77_dec.argtypes = [p, p, i64p, i64p, C.c_int, C.c_uint32, p, p]
+    for f in ("kolm_cdc_kf", "kolm_cdc_v22"):
+        getattr(L, f).restype = C.c_int64
+        getattr(L, f).argtypes = [p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, C.c_int64]
     L.kolm_repair_enc.argtypes = [p, p, i64p, C.c_int, p, C.c_size_t, i64p, p]
     L.kolm_repair_dec.argtypes = [p, p, i64p, i64p, C.c_int, p, p]
     L.kolm_residual_sizes.argtypes = [p, p, i64p, C.c_int, i64p, p]

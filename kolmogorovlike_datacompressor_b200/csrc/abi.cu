@@ -288,3 +288,77 @@ int kolm_profile_read(kolm_ctx* c, double* ms, int64_t* launches, int64_t* algby
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// content-defined chunking (host side; SURVEY §8f row 1 — adjacent to the hot path, must be bit-identical
+// to the reference or every later byte of the container differs)
+//   KF  cdc_fast_boundaries        kolm_final.py:161-194, gear = random.Random(2025).getrandbits(32) x 256 (:148-159)
+//   V22 cdc_fast_boundaries_strict kolm_final_researched_v2-2.py:210-309, gear = xorshift32(0x243F6A88) | 1 (:152-167)
+// ------------------------------------------------------------------------------------------------
+static void kf_gear_table(u32* g) {
+    // MT19937 seeded the way CPython seeds random.Random(int): init_by_array([seed])
+    const int N = 624, M = 397; static u32 mt[624];
+    mt[0] = 19650218u; for (int i = 1; i < N; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (u32)i;
+    { u32 key = 2025u; int i = 1;
+      for (int k = N; k; --k) { mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key; if (++i >= N) { mt[0] = mt[N - 1]; i = 1; } }
+      for (int k = N - 1; k; --k) { mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (u32)i; if (++i >= N) { mt[0] = mt[N - 1]; i = 1; } }
+      mt[0] = 0x80000000u; }
+    int idx = N;
+    for (int t = 0; t < 256; ++t) {
+        if (idx >= N) {
+            for (int k = 0; k < N; ++k) { u32 y = (mt[k] & 0x80000000u) | (mt[(k + 1) % N] & 0x7fffffffu); mt[k] = mt[(k + M) % N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+            idx = 0;
+        }
+        u32 y = mt[idx++]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18; g[t] = y;
+    }
+}
+
+extern "C" {
+
+// ends[i] = exclusive end of chunk i; returns the number of chunks, or <0
+int64_t kolm_cdc_kf(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap) {
+    static u32 G[256]; static bool init = false;
+    if (!init) { kf_gear_table(G); init = true; }
+    if (n <= 0) return 0;
+    int bl = 0; for (i64 a = avg_size; a > 0; a >>= 1) ++bl;
+    int k = bl - 1; if (k > 20) k = 20; if (k < 6) k = 6;
+    const u32 mask = (1u << k) - 1u;
+    i64 i = 0, cnt = 0;
+    while (i < n) {
+        i64 start = i; u32 h = 0;
+        i64 emin = start + min_size < n ? start + min_size : n, emax = start + max_size < n ? start + max_size : n;
+        i = emin;
+        while (i < emax) { h = (h << 1) + G[data[i]]; ++i; if ((h & mask) == 0) break; }
+        if (cnt >= cap) return KOLM_E_CAPACITY;
+        ends[cnt++] = i;
+        if (i == start) return KOLM_E_ARG;            // min_size = max_size = 0 would never advance
+    }
+    return cnt;
+}
+
+int64_t kolm_cdc_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap) {
+    static u32 G[256]; static bool init = false;
+    if (!init) { u32 x = 0x243F6A88u; for (int i = 0; i < 256; ++i) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; G[i] = x | 1u; } init = true; }
+    if (n <= 0) return 0;
+    if (!(min_size > 0 && min_size <= avg_size && avg_size <= max_size) || avg_size < 64) return KOLM_E_ARG;
+    int bl = 0; for (i64 a = avg_size; a > 0; a >>= 1) ++bl;
+    int k = bl - 1; if (k < 6) k = 6; if (k > 20) k = 20;
+    const int ks = (k + 2 <= 20) ? k + 2 : 20, kl = (k > 2) ? k - 2 : 1;
+    const u32 ms = (1u << ks) - 1u, ml = (1u << kl) - 1u;
+    i64 i = 0, cnt = 0, last_start = 0;
+    while (i < n) {
+        i64 start = i, rem = n - start; last_start = start;
+        if (cnt >= cap) return KOLM_E_CAPACITY;
+        if (rem <= min_size) { ends[cnt++] = n; break; }
+        i64 lmax = rem < max_size ? rem : max_size, normal = avg_size < lmax ? avg_size : lmax;
+        i64 pos = start + min_size, en = start + normal, el = start + lmax; u32 fp = 0; bool found = false;
+        while (pos < en && pos < el) { fp = (fp << 1) + G[data[pos]]; ++pos; if ((fp & ms) == 0) { found = true; break; } }
+        if (!found) while (pos < el) { fp = (fp << 1) + G[data[pos]]; ++pos; if ((fp & ml) == 0) { found = true; break; } }
+        if (!found) pos = el;
+        ends[cnt++] = pos; i = pos;
+    }
+    if (cnt >= 2 && ends[cnt - 1] - last_start < min_size) { ends[cnt - 2] = ends[cnt - 1]; --cnt; }   // orphan tail merged (V22.py:301-306)
+    return cnt;
+}
+
+}  // extern "C"

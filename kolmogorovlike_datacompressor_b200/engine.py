@@ -1,0 +1,327 @@
+"""Host-side engine shared by the two drop-in modules: batching of blocks, per-block candidate evaluation on
+the GPU (through the C-ABI stage operators), exact model selection, payload collection.
+
+Mirrors the reference's per-block loops:
+    KOLM  _encode_block            kolm_final.py:821-864            (ids 0..3, smallest payload, lowest id on ties)
+    KOLR  selection loops          kolm_final_researched_v2-2.py:2233-2252 / 2350-2369  (ids = list index, strict '<')
+There is no CPU fallback: everything below needs the CUDA library and a device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .stages import Context
+
+KOLR_NAMES = ["raw", "xor", "bbwt", "bbwt_bp", "bbwt_nib", "bbwt_br", "bbwt_gray", "lz77", "lfsr_pred", "repair", "v2_new"]
+K2_FLAG_OF = {"bbwt": 0, "bbwt_bp": 1, "bbwt_nib": 4, "bbwt_br": 8, "bbwt_gray": 16}
+K2_SLOT = {0: 0, 1: 1, 4: 2, 8: 3, 16: 4}
+_BIG = np.iinfo(np.int64).max
+
+
+def raise_like_reference(e: _lib.KolmError):
+    """Map C-ABI error codes onto the exception types the reference raises."""
+    if e.code == -4:
+        raise EOFError(str(e)) from e
+    if e.code == -7:
+        raise IndexError(str(e)) from e
+    if e.code in (-5, -2):
+        raise ValueError(str(e)) from e
+    raise e
+
+
+def cdc_boundaries(which: str, data: bytes, mn: int, avg: int, mx: int) -> List[Tuple[int, int]]:
+    n = len(data)
+    if n == 0:
+        return []
+    L = _lib.lib()
+    cap = n // max(1, mn) + 4
+    ends = np.zeros(cap, dtype=np.int64)
+    buf = (C.c_uint8 * n).from_buffer_copy(data)
+    k = getattr(L, "kolm_cdc_" + which)(buf, n, mn, avg, mx, ends.ctypes.data_as(C.POINTER(C.c_int64)), cap)
+    if k < 0:
+        if k == -2:
+            raise ValueError("Require 0 < min_size <= avg_size <= max_size and avg_size >= 64")
+        raise _lib.KolmError(int(k))
+    out, a = [], 0
+    for e in ends[:k]:
+        out.append((a, int(e)))
+        a = int(e)
+    return out
+
+
+class Engine:
+    """One GPU, one context that grows on demand."""
+
+    _shared: Dict[int, "Engine"] = {}
+
+    def __init__(self, device: Optional[int] = None, batch_bytes: int = 128 << 20):
+        if not torch.cuda.is_available():
+            raise RuntimeError("kolmogorovlike_datacompressor_b200: no CUDA device — the GPU path has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.batch_bytes = int(batch_bytes)
+        self.ctx: Optional[Context] = None
+        self.cap_bytes = 0
+        self.cap_blocks = 0
+        self.repair_max = int(_lib.lib().kolm_repair_max_block())
+
+    @classmethod
+    def shared(cls, device: Optional[int] = None) -> "Engine":
+        d = torch.cuda.current_device() if device is None else int(device)
+        if d not in cls._shared:
+            cls._shared[d] = Engine(d)
+        return cls._shared[d]
+
+    # ------------------------------------------------------------------
+    def _ensure(self, nbytes: int, nblocks: int):
+        if self.ctx is None or nbytes > self.cap_bytes or nblocks > self.cap_blocks:
+            if self.ctx is not None:
+                self.ctx.close()
+                self.ctx = None
+                torch.cuda.empty_cache()
+            self.cap_bytes = max(nbytes, min(self.batch_bytes, 1 << 22), self.cap_bytes)
+            self.cap_blocks = max(nblocks, 1024, self.cap_blocks)
+            with torch.cuda.device(self.device):
+                self.ctx = Context(self.cap_bytes, self.cap_blocks, self.device)
+
+    def _batches(self, bounds: Sequence[Tuple[int, int]]):
+        """Consecutive blocks grouped so that a batch holds <= batch_bytes (a single larger block forms its own batch)."""
+        i, n = 0, len(bounds)
+        while i < n:
+            j, tot = i, 0
+            while j < n and (j == i or tot + (bounds[j][1] - bounds[j][0]) <= self.batch_bytes) and j - i < (1 << 20):
+                tot += bounds[j][1] - bounds[j][0]
+                j += 1
+            yield i, j
+            i = j
+
+    def _upload(self, data, a: int, b: int) -> torch.Tensor:
+        arr = np.frombuffer(data, dtype=np.uint8, count=b - a, offset=a) if b > a else np.zeros(0, dtype=np.uint8)
+        t = torch.empty(max(4, b - a + 4), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        if b > a:
+            t[:b - a].copy_(torch.from_numpy(arr.copy()))
+        return t
+
+    @staticmethod
+    def _host(t: torch.Tensor, n: int) -> bytes:
+        return t[:n].cpu().numpy().tobytes() if n else b""
+
+    # ------------------------------------------------------------------
+    # KOLM profile
+    def encode_kolm(self, data: bytes, bounds: Sequence[Tuple[int, int]]) -> List[Tuple[int, bytes]]:
+        res: List[Tuple[int, bytes]] = []
+        for i, j in self._batches(bounds):
+            a, b = bounds[i][0], bounds[j - 1][1]
+            nb = j - i
+            off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
+            lens = np.diff(off)
+            self._ensure(b - a, nb)
+            with torch.cuda.device(self.device):
+                c = self.ctx
+                x = self._upload(data, a, b)
+                sx = c.residual_sizes(x, off)[:, 0]
+                L = c.bbwt_forward(x, off)
+                m = c.mtf_encode(L, off)
+                kfp, kfo = c.rice_kf_encode(m, off)
+                lzp, lzo = c.lz77_encode(x, off, 255, 127)
+                sizes = np.stack([lens, sx, np.diff(kfo), np.diff(lzo)], axis=1)
+                mids = np.argmin(sizes, axis=1)                      # first minimum == lowest id on ties (KF.py:857)
+                hx = None
+                if (mids == 1).any():
+                    xp, xo = c.residual_encode(x, off, 0)
+                    hx = self._host(xp, int(xo[-1]))
+                hk = self._host(kfp, int(kfo[-1])) if (mids == 2).any() else b""
+                hl = self._host(lzp, int(lzo[-1])) if (mids == 3).any() else b""
+            for k in range(nb):
+                mid = int(mids[k])
+                if mid == 0:
+                    p = bytes(data[bounds[i + k][0]:bounds[i + k][1]])
+                elif mid == 1:
+                    p = hx[xo[k]:xo[k + 1]]
+                elif mid == 2:
+                    p = hk[kfo[k]:kfo[k + 1]]
+                else:
+                    p = hl[lzo[k]:lzo[k + 1]]
+                res.append((mid, p))
+        return res
+
+    def kolm_model_payloads(self, block: bytes, mid: int) -> bytes:
+        """One model on one block (the reference's _ENCODERS[mid])."""
+        off = np.array([0, len(block)], dtype=np.int64)
+        self._ensure(len(block), 1)
+        with torch.cuda.device(self.device):
+            c = self.ctx
+            x = self._upload(block, 0, len(block))
+            if mid == 0:
+                return bytes(block)
+            if mid == 1:
+                p, o = c.residual_encode(x, off, 0)
+            elif mid == 2:
+                p, o = c.rice_kf_encode(c.mtf_encode(c.bbwt_forward(x, off), off), off)
+            elif mid == 3:
+                p, o = c.lz77_encode(x, off, 255, 127)
+            else:
+                raise KeyError(mid)
+            return self._host(p, int(o[-1]))
+
+    # ------------------------------------------------------------------
+    # KOLR profile.  `names` = candidate names in id order (the reference's _select_encoders() list).
+    def encode_kolr(self, data: bytes, bounds: Sequence[Tuple[int, int]], names: Sequence[str]) -> List[Tuple[int, bytes]]:
+        res: List[Tuple[int, bytes]] = []
+        for i, j in self._batches(bounds):
+            a, b = bounds[i][0], bounds[j - 1][1]
+            nb = j - i
+            off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
+            lens = np.diff(off)
+            self._ensure(b - a, nb)
+            with torch.cuda.device(self.device):
+                c = self.ctx
+                x = self._upload(data, a, b)
+                cols = []
+                need_res = any(n in ("xor", "lfsr_pred") for n in names)
+                rs = c.residual_sizes(x, off) if need_res else None
+                need_bbwt = any(n in K2_FLAG_OF for n in names)
+                m = k2p = k2o = k2s = None
+                if need_bbwt:
+                    m = c.mtf_encode(c.bbwt_forward(x, off), off)
+                    k2p, k2o, k2s = c.rice_k2_encode(m, off, 0)
+                lzp = lzo = None
+                if "lz77" in names:
+                    lzp, lzo = c.lz77_encode(x, off, 4096, 0)
+                rpp = rpo = None
+                if "repair" in names:
+                    if int(lens.max(initial=0)) <= self.repair_max:
+                        rpp, rpo = c.repair_encode(x, off)
+                    else:
+                        warnings.warn("Re-Pair candidate skipped: block longer than %d bytes (GPU kernel limit; the reference's own "
+                                      "algorithm is O(rounds*n) there)" % self.repair_max, RuntimeWarning, stacklevel=3)
+                for nme in names:
+                    if nme == "raw":
+                        cols.append(lens)
+                    elif nme == "xor":
+                        cols.append(rs[:, 1])
+                    elif nme == "lfsr_pred":
+                        cols.append(rs[:, 2])
+                    elif nme in K2_FLAG_OF:
+                        cols.append(k2s[:, K2_SLOT[K2_FLAG_OF[nme]]])
+                    elif nme == "lz77":
+                        cols.append(np.diff(lzo))
+                    elif nme == "repair" and rpo is not None:
+                        cols.append(np.diff(rpo))
+                    else:                                            # v2_new raises NameError in the shipped reference; skipped repair
+                        cols.append(np.full(nb, _BIG, dtype=np.int64))
+                sizes = np.stack(cols, axis=1)
+                mids = np.argmin(sizes, axis=1)                      # strict '<' in the reference == first minimum
+                host: Dict[str, Tuple[bytes, np.ndarray]] = {}
+                for mid in sorted(set(int(v) for v in mids)):
+                    nme = names[mid]
+                    if nme == "raw":
+                        continue
+                    if nme == "xor":
+                        p, o = c.residual_encode(x, off, 1)
+                    elif nme == "lfsr_pred":
+                        p, o = c.residual_encode(x, off, 2)
+                    elif nme == "bbwt":
+                        p, o = k2p, k2o
+                    elif nme in K2_FLAG_OF:
+                        p, o, _ = c.rice_k2_encode(m, off, K2_FLAG_OF[nme])
+                    elif nme == "lz77":
+                        p, o = lzp, lzo
+                    elif nme == "repair":
+                        p, o = rpp, rpo
+                    else:
+                        raise RuntimeError("unreachable candidate " + nme)
+                    host[nme] = (self._host(p, int(o[-1])), o)
+            for k in range(nb):
+                mid = int(mids[k])
+                nme = names[mid]
+                if nme == "raw":
+                    p = bytes(data[bounds[i + k][0]:bounds[i + k][1]])
+                else:
+                    hb, o = host[nme]
+                    p = hb[o[k]:o[k + 1]]
+                res.append((mid, p))
+        return res
+
+    def kolr_model_payload(self, block: bytes, name: str) -> bytes:
+        off = np.array([0, len(block)], dtype=np.int64)
+        self._ensure(len(block), 1)
+        with torch.cuda.device(self.device):
+            c = self.ctx
+            x = self._upload(block, 0, len(block))
+            if name == "raw":
+                return bytes(block)
+            if name == "xor":
+                p, o = c.residual_encode(x, off, 1)
+            elif name == "lfsr_pred":
+                p, o = c.residual_encode(x, off, 2)
+            elif name in K2_FLAG_OF:
+                p, o, _ = c.rice_k2_encode(c.mtf_encode(c.bbwt_forward(x, off), off), off, K2_FLAG_OF[name])
+            elif name == "lz77":
+                p, o = c.lz77_encode(x, off, 4096, 0)
+            elif name == "repair":
+                p, o = c.repair_encode(x, off)
+            else:
+                raise NameError("name 'os' is not defined")          # v2_new: what the shipped reference raises
+            return self._host(p, int(o[-1]))
+
+    # ------------------------------------------------------------------
+    # decode: blocks = [(method name, payload, orig_len)], returns the decoded blocks in order
+    def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:
+        out: List[Optional[bytes]] = [None] * len(blocks)
+        groups: Dict[str, List[int]] = {}
+        for idx, (nme, _, _) in enumerate(blocks):
+            groups.setdefault(nme, []).append(idx)
+        for nme, idxs in groups.items():
+            if nme == "raw":
+                for t in idxs:
+                    _, p, ol = blocks[t]
+                    assert len(p) == ol, "Payload length mismatch for RAW"
+                    out[t] = bytes(p)
+                continue
+            # sub-batches bounded by decoded size
+            s = 0
+            while s < len(idxs):
+                e, tot = s, 0
+                while e < len(idxs) and (e == s or tot + blocks[idxs[e]][2] <= self.batch_bytes):
+                    tot += blocks[idxs[e]][2]
+                    e += 1
+                sub = idxs[s:e]
+                pays = [blocks[t][1] for t in sub]
+                ols = [blocks[t][2] for t in sub]
+                poff = np.zeros(len(sub) + 1, dtype=np.int64)
+                poff[1:] = np.cumsum([len(p) for p in pays])
+                off = np.zeros(len(sub) + 1, dtype=np.int64)
+                off[1:] = np.cumsum(ols)
+                self._ensure(max(int(off[-1]), 1), len(sub))
+                with torch.cuda.device(self.device):
+                    c = self.ctx
+                    blob = b"".join(pays)
+                    pt = self._upload(blob, 0, len(blob))
+                    try:
+                        if nme in ("kf_xor", "xor", "lfsr_pred"):
+                            y = c.residual_decode(pt, poff, off, {"kf_xor": 0, "xor": 1, "lfsr_pred": 2}[nme])
+                        elif nme == "kf_bbwt":
+                            y = c.bbwt_inverse(c.mtf_decode(c.rice_kf_decode(pt, poff, off), off), off)
+                        elif nme in K2_FLAG_OF:
+                            y = c.bbwt_inverse(c.mtf_decode(c.rice_k2_decode(pt, poff, off, K2_FLAG_OF[nme]), off), off)
+                        elif nme == "kf_lz77":
+                            y = c.lz77_decode(pt, poff, off, 0)
+                        elif nme == "lz77":
+                            y = c.lz77_decode(pt, poff, off, 4096)
+                        elif nme == "repair":
+                            y = c.repair_decode(pt, poff, off)
+                        else:
+                            raise NotImplementedError("decoder for method '%s' is outside the GPU hot path (SURVEY §8 row a17)" % nme)
+                    except _lib.KolmError as err:
+                        raise_like_reference(err)
+                    hb = self._host(y, int(off[-1]))
+                for q, t in enumerate(sub):
+                    out[t] = hb[off[q]:off[q + 1]]
+                s = e
+        return out  # type: ignore[return-value]

@@ -1,0 +1,201 @@
+"""Drop-in for the reference's final/kolm_final.py ('KOLM' container) with the per-block hot path on the GPU.
+
+Same entry points, signatures, container bytes and error behaviour:
+    compress(data, target_block=8192) -> bytes            kolm_final.py:866-902
+    decompress(blob) -> bytes                             kolm_final.py:904-957
+    _ENCODERS / _DECODERS                                 kolm_final.py:808-819
+    cdc_fast_boundaries, duval_lyndon, bbwt_forward, bbwt_inverse, mtf_encode, mtf_decode,
+    uleb128_encode, uleb128_decode_stream, encode_model_* / decode_model_*  (the names benchmark_compare.py imports)
+
+Model ids: 0 RAW, 1 XOR+ULEB128, 2 BBWT->MTF->Rice/gamma token stream, 3 LZ77(255/127).  Every block's four candidates
+are evaluated on the device; the smallest payload wins, ties go to the lowest id (kolm_final.py:857).  The entropy guard
+of the reference (kolm_final.py:834-840) can never trigger (at most 127 samples => H < 7.8) and is therefore omitted.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Callable, Dict, List, Tuple
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine, cdc_boundaries, raise_like_reference
+
+_NAMES = {0: "raw", 1: "kf_xor", 2: "kf_bbwt", 3: "kf_lz77"}
+
+
+def _engine() -> Engine:
+    return Engine.shared()
+
+
+# ---- utilities with the reference's names -------------------------------------------------------
+def uleb128_encode(n: int) -> bytes:
+    out = bytearray()
+    while True:
+        b = n & 0x7F
+        n >>= 7
+        if n:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def uleb128_decode_stream(data: bytes, pos: int = 0) -> Tuple[int, int]:
+    result = shift = 0
+    while True:
+        if pos >= len(data):
+            raise EOFError("Truncated ULEB128")
+        b = data[pos]
+        pos += 1
+        result |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return result, pos
+        shift += 7
+
+
+def cdc_fast_boundaries(data: bytes, min_size: int = 4096, avg_size: int = 8192, max_size: int = 16384) -> List[Tuple[int, int]]:
+    return cdc_boundaries("kf", bytes(data), min_size, avg_size, max_size)
+
+
+def _one(fn: str, data: bytes) -> bytes:
+    import torch
+    e = _engine()
+    n = len(data)
+    if n == 0:
+        return b""
+    off = np.array([0, n], dtype=np.int64)
+    e._ensure(n, 1)
+    with torch.cuda.device(e.device):
+        x = e._upload(bytes(data), 0, n)
+        try:
+            y = getattr(e.ctx, fn)(x, off)
+        except _lib.KolmError as err:
+            raise_like_reference(err)
+        return e._host(y, n)
+
+
+def duval_lyndon(s: bytes) -> List[Tuple[int, int]]:
+    flags = _one("duval_lyndon_flags", s)
+    starts = [i for i, f in enumerate(flags) if f]
+    return [(a, b) for a, b in zip(starts, starts[1:] + [len(s)])]
+
+
+def bbwt_forward(s: bytes) -> bytes:
+    return _one("bbwt_forward", s)
+
+
+def bbwt_inverse(L: bytes) -> bytes:
+    return _one("bbwt_inverse", L)
+
+
+def mtf_encode(data: bytes) -> List[int]:
+    return list(_one("mtf_encode", data))
+
+
+def mtf_decode(seq) -> bytes:
+    return _one("mtf_decode", bytes(seq))
+
+
+# ---- per-model operators --------------------------------------------------------------------------
+def _enc(mid: int):
+    def f(block: bytes):
+        return _engine().kolm_model_payloads(bytes(block), mid), {}
+    return f
+
+
+def _dec(mid: int):
+    def f(payload: bytes, orig_len: int) -> bytes:
+        return _engine().decode_blocks([(_NAMES[mid], bytes(payload), orig_len)])[0]
+    return f
+
+
+encode_model_raw, encode_model_xor, encode_model_bbwt_mtf, encode_model_lz77 = _enc(0), _enc(1), _enc(2), _enc(3)
+decode_model_raw, decode_model_xor, decode_model_bbwt_mtf, decode_model_lz77 = _dec(0), _dec(1), _dec(2), _dec(3)
+
+_ENCODERS: Dict[int, Callable] = {0: encode_model_raw, 1: encode_model_xor, 2: encode_model_bbwt_mtf, 3: encode_model_lz77}
+_DECODERS: Dict[int, Callable] = {0: decode_model_raw, 1: decode_model_xor, 2: decode_model_bbwt_mtf, 3: decode_model_lz77}
+
+
+def _encode_block(block: bytes) -> Tuple[int, bytes, int]:
+    (mid, payload), = _engine().encode_kolm(bytes(block), [(0, len(block))])
+    return mid, payload, len(payload)
+
+
+# ---- container ------------------------------------------------------------------------------------
+def compress(data: bytes, target_block: int = 8192) -> bytes:
+    data = bytes(data)
+    cuts = cdc_fast_boundaries(data, min_size=target_block // 2, avg_size=target_block, max_size=target_block * 2)
+    out = bytearray()
+    out += b"KOLM"
+    out += struct.pack("<I", target_block & 0xFFFFFFFF)
+    out += struct.pack("<Q", len(data))
+    out += struct.pack("<H", len(cuts) & 0xFFFF)          # wraps silently like the reference (kolm_final.py:889-890)
+    if cuts:
+        for (a, b), (mid, payload) in zip(cuts, _engine().encode_kolm(data, cuts)):
+            out.append(mid & 0xFF)
+            out += struct.pack("<I", (b - a) & 0xFFFFFFFF)
+            out += struct.pack("<I", len(payload) & 0xFFFFFFFF)
+            out += payload
+    return bytes(out)
+
+
+def decompress(blob: bytes) -> bytes:
+    blob = bytes(blob)
+    p = 0
+    if blob[p:p + 4] != b"KOLM":
+        raise ValueError("Bad magic header")
+    p += 4
+    struct.unpack_from("<I", blob, p)
+    p += 4
+    total_len = struct.unpack_from("<Q", blob, p)[0]
+    p += 8
+    nblocks = struct.unpack_from("<H", blob, p)[0]
+    p += 2
+    todo = []
+    for _ in range(nblocks):
+        if p >= len(blob):
+            raise EOFError("Truncated block header")
+        method_id = blob[p]
+        p += 1
+        if method_id not in _DECODERS:
+            raise ValueError(f"Unknown method id {method_id}")
+        if p + 8 > len(blob):
+            raise EOFError("Truncated block lengths")
+        orig_len, payload_len = struct.unpack_from("<II", blob, p)
+        p += 8
+        if p + payload_len > len(blob):
+            raise EOFError("Truncated payload")
+        todo.append((_NAMES[method_id], blob[p:p + payload_len], orig_len))
+        p += payload_len
+    blocks = _engine().decode_blocks(todo) if todo else []
+    out = bytearray()
+    for (nme, _, orig_len), block in zip(todo, blocks):
+        if len(block) != orig_len:
+            raise ValueError(f"Decoded length mismatch: expected {orig_len}, got {len(block)}")
+        out += block
+    if len(out) != total_len:
+        raise ValueError(f"Total decoded length mismatch: expected {total_len}, got {len(out)}")
+    return bytes(out)
+
+
+if __name__ == "__main__":
+    import argparse
+    import os
+    ap = argparse.ArgumentParser(description="KOLM compressor (GPU hot path)")
+    ap.add_argument("input")
+    ap.add_argument("-d", "--decompress", action="store_true")
+    ap.add_argument("-o", "--output")
+    ap.add_argument("-b", "--block", type=int, default=8192)
+    a = ap.parse_args()
+    src = open(a.input, "rb").read()
+    if a.decompress:
+        dst = decompress(src)
+        name = a.output or (os.path.splitext(a.input)[0] + ".out")
+        open(name, "wb").write(dst)
+        print(f"Decompressed {len(src)} bytes to {len(dst)} bytes → {name}")
+    else:
+        dst = compress(src, target_block=a.block)
+        name = a.output or (a.input + ".kolm")
+        open(name, "wb").write(dst)
+        print(f"Compressed {len(src)} bytes to {len(dst)} bytes (ratio {len(dst) / len(src) if src else 1.0:.3f}) → {name}")

@@ -1,0 +1,436 @@
+"""Drop-in for the reference's final_researched/kolm_final_researched_v2-2.py ('KOLR' container + TOC) with the
+per-block hot path on the GPU.
+
+Same entry points, signatures, container bytes and error behaviour:
+    compress_blocks_fixed(data, block_size=8192)                       v2-2.py:2332-2445
+    compress_blocks_cdc(data, min_size=4096, avg_size=8192, max_size=16384)   v2-2.py:2213-2326
+    decompress(container)                                              v2-2.py:2451-2550
+    _select_encoders() / _select_decoders(), G_NO_LZ77 / G_ONLY_METHOD / G_PROGRESS   v2-2.py:92-96, 2152-2207
+    fixed_boundaries, cdc_fast_boundaries_strict                       v2-2.py:210-320
+
+Candidate ids = index in the (possibly filtered) list {raw, xor(delta), bbwt, bbwt_bp, bbwt_nib, bbwt_br, bbwt_gray, lz77,
+lfsr_pred, repair, v2_new}; the smallest payload wins, first wins ties.  v2_new raises NameError in the shipped reference
+and is therefore never selected; the same holds here.  The TOC (RLE + canonical Huffman of method ids, Rice
+run lengths, ZigZag/Rice block lengths in CDC mode, Elias-Fano payload ends) is built on the host with the same heapq
+tie behaviour as the reference.
+"""
+from __future__ import annotations
+
+import heapq
+import struct
+from collections import Counter
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+from .engine import KOLR_NAMES, Engine, cdc_boundaries
+
+G_NO_LZ77: bool = False
+G_ONLY_METHOD: Optional[str] = None
+G_PROGRESS: bool = False
+
+MODE_FIXED = 0
+MODE_CDC = 1
+
+
+def _engine() -> Engine:
+    return Engine.shared()
+
+
+def _print_progress(label: str, i: int, n: int, final: bool = False) -> None:
+    if not G_PROGRESS:
+        return
+    if not final:
+        print(f"[{label}] block {i}/{n} ...", end="\r", flush=True)
+    else:
+        print(f"[{label}] block {n}/{n} done.", flush=True)
+
+
+# ---- ULEB128 / chunking ----------------------------------------------------------------------------
+def uleb128_encode(n: int) -> bytes:
+    if n < 0:
+        raise ValueError("ULEB128 only supports unsigned integers")
+    out = bytearray()
+    while True:
+        b = n & 0x7F
+        n >>= 7
+        if n:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def uleb128_decode_stream(data: bytes, pos: int = 0) -> Tuple[int, int]:
+    shift = result = 0
+    while True:
+        if pos >= len(data):
+            raise ValueError("Truncated ULEB128")
+        b = data[pos]
+        pos += 1
+        result |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return result, pos
+        shift += 7
+
+
+def fixed_boundaries(data: bytes, block_size: int = 8192) -> List[Tuple[int, int]]:
+    n = len(data)
+    if n == 0:
+        return []
+    if block_size <= 0:
+        raise ValueError("block_size must be positive")
+    return [(i, min(n, i + block_size)) for i in range(0, n, block_size)]
+
+
+def cdc_fast_boundaries_strict(data: bytes, min_size: int = 4096, avg_size: int = 8192, max_size: int = 16384,
+                               merge_orphan_tail: bool = True) -> List[Tuple[int, int]]:
+    if len(data) == 0:
+        return []
+    if not (min_size > 0 and min_size <= avg_size <= max_size):
+        raise ValueError("Require 0 < min_size <= avg_size <= max_size")
+    if avg_size < 64:
+        raise ValueError("avg_size too small; use >= 64")
+    if not merge_orphan_tail:
+        raise NotImplementedError("merge_orphan_tail=False is not used by the reference's compressors")
+    return cdc_boundaries("v22", bytes(data), min_size, avg_size, max_size)
+
+
+# ---- candidate registry ------------------------------------------------------------------------------
+def _candidate_names() -> List[str]:
+    names = list(KOLR_NAMES)
+    if G_NO_LZ77:
+        names = [n for n in names if n != "lz77"]
+    if G_ONLY_METHOD is not None:
+        only = G_ONLY_METHOD.lower()
+        names = [n for n in names if n.lower() == only]
+        if not names:
+            raise ValueError(f"--only={G_ONLY_METHOD} not found in candidates")
+    return names
+
+
+def _select_encoders() -> List[Tuple[Callable[[bytes], Tuple[bytes, Dict[str, Any]]], str]]:
+    def mk(name):
+        return lambda block: (_engine().kolr_model_payload(bytes(block), name), {})
+    return [(mk(n), n) for n in _candidate_names()]
+
+
+def _select_decoders() -> List[Callable[[bytes, int, Dict[str, Any]], bytes]]:
+    def mk(name):
+        return lambda payload, byte_length, meta=None: _engine().decode_blocks([(name, bytes(payload), byte_length)])[0]
+    return [mk(n) for n in KOLR_NAMES]
+
+
+# ---- TOC coders (host; O(nblocks)) ---------------------------------------------------------------------
+class _Bits:
+    """MSB-first bit accumulator (== _BitWriter.getvalue_bits)."""
+
+    def __init__(self):
+        self.acc = 0
+        self.n = 0
+
+    def put(self, val: int, k: int):
+        if k:
+            self.acc = (self.acc << k) | (val & ((1 << k) - 1))
+            self.n += k
+
+    def unary(self, q: int):
+        self.acc = (self.acc << (q + 1)) | (((1 << q) - 1) << 1)
+        self.n += q + 1
+
+    def rice(self, seq, k: int):
+        for v in seq:
+            self.unary(v >> k)
+            self.put(v, k)
+
+    def value(self) -> Tuple[bytes, int]:
+        nbytes = (self.n + 7) // 8
+        return (self.acc << (nbytes * 8 - self.n)).to_bytes(nbytes, "big"), self.n
+
+
+class _BitsIn:
+    def __init__(self, buf: bytes):
+        self.v = int.from_bytes(buf, "big")
+        self.total = len(buf) * 8
+        self.pos = 0
+
+    def bit(self) -> int:
+        if self.pos >= self.total:
+            raise ValueError("BitReader: out of data")
+        b = (self.v >> (self.total - 1 - self.pos)) & 1
+        self.pos += 1
+        return b
+
+    def bits(self, k: int) -> int:
+        v = 0
+        for _ in range(k):
+            v = (v << 1) | self.bit()
+        return v
+
+    def rice(self, k: int) -> int:
+        q = 0
+        while self.bit() == 1:
+            q += 1
+        return (q << k) | self.bits(k)
+
+
+def _zz_enc(x: int) -> int:
+    return (x << 1) if x >= 0 else ((-x) << 1) - 1
+
+
+def _zz_dec(n: int) -> int:
+    return (n >> 1) if (n & 1) == 0 else -((n + 1) >> 1)
+
+
+class _HuffNode:
+    __slots__ = ("w", "sym", "left", "right")
+
+    def __init__(self, w, sym=None, left=None, right=None):
+        self.w, self.sym, self.left, self.right = w, sym, left, right
+
+    def __lt__(self, other):                       # same ordering as the reference node (v2-2.py:1271-1276)
+        if self.w != other.w:
+            return self.w < other.w
+        return (self.sym if self.sym is not None else -1) < (other.sym if other.sym is not None else -1)
+
+
+def _huff_lengths(freq: Dict[int, int]) -> Dict[int, int]:
+    heap = [_HuffNode(max(1, f), sym=s) for s, f in freq.items()]
+    if not heap:
+        return {}
+    if len(heap) == 1:
+        return {heap[0].sym: 1}
+    heapq.heapify(heap)
+    while len(heap) > 1:
+        a = heapq.heappop(heap)
+        b = heapq.heappop(heap)
+        heapq.heappush(heap, _HuffNode(a.w + b.w, left=a, right=b))
+    lengths: Dict[int, int] = {}
+    stack = [(heap[0], 0)]
+    while stack:
+        nd, d = stack.pop()
+        if nd.sym is not None:
+            lengths[nd.sym] = max(1, d)
+        else:
+            stack.append((nd.left, d + 1))
+            stack.append((nd.right, d + 1))
+    return lengths
+
+
+def _huff_canonical(lengths: Dict[int, int]):
+    enc, dec = {}, {}
+    code = prev = maxlen = 0
+    for sym, L in sorted(lengths.items(), key=lambda kv: (kv[1], kv[0])):
+        if L != prev:
+            code <<= (L - prev)
+            prev = L
+        enc[sym] = (code, L)
+        dec[(L, code)] = sym
+        maxlen = max(maxlen, L)
+        code += 1
+    return enc, dec, maxlen
+
+
+def _best_rice_k(seq) -> int:
+    best_k, best_bits = 0, 1 << 60
+    for k in range(8):
+        bits = sum((v >> k) + 1 + k for v in seq)
+        if bits < best_bits:
+            best_bits, best_k = bits, k
+    return best_k
+
+
+def _ef_choose_l(U: int, n: int) -> int:
+    if n <= 0 or U <= 1:
+        return 0
+    avg = U // n
+    if avg <= 1:
+        return 0
+    return max(0, avg.bit_length() - 1)
+
+
+def _pack_mode_and_size(mode: int, size: int) -> int:
+    if mode not in (MODE_FIXED, MODE_CDC):
+        raise ValueError("invalid mode")
+    if size < 0 or size > 0x7FFFFFFF:
+        raise ValueError("size out of range (must fit in 31 bits)")
+    return ((mode & 1) << 31) | (size & 0x7FFFFFFF)
+
+
+def _assemble(data: bytes, boundaries, mode: int, size_field: int) -> bytes:
+    out = bytearray(b"KOLR")
+    out += struct.pack("<I", _pack_mode_and_size(mode, size_field))
+    out += struct.pack("<I", len(data))                 # struct.error beyond 4 GiB-1 / 65535 blocks, like the reference
+    out += struct.pack("<H", len(boundaries))
+    names = _candidate_names()
+    nblocks = len(boundaries)
+    label = "FIXED" if mode == MODE_FIXED else "Fast CDC"
+    _print_progress(label, 0, nblocks)
+    chosen = _engine().encode_kolr(data, boundaries, names) if nblocks else []
+    _print_progress(label + " COMPRESS", nblocks, nblocks, final=True)
+    method_ids = [m for m, _ in chosen]
+    payloads = [p for _, p in chosen]
+    orig_lens = [b - a for a, b in boundaries]
+    payload_lens = [len(p) for p in payloads]
+    total_payload = sum(payload_lens)
+    # ---- TOC header
+    run_syms: List[int] = []
+    run_lens: List[int] = []
+    for x in method_ids:
+        if run_syms and x == run_syms[-1]:
+            run_lens[-1] += 1
+        else:
+            run_syms.append(x)
+            run_lens.append(1)
+    lengths = _huff_lengths(Counter(run_syms))
+    enc_tbl, _, _ = _huff_canonical(lengths)
+    best_k = _best_rice_k(run_lens)
+    toc_header = bytearray()
+    toc_header += uleb128_encode(len(run_syms))
+    toc_header += uleb128_encode(len(enc_tbl))
+    for sym, L in sorted(lengths.items(), key=lambda kv: (kv[1], kv[0])):
+        toc_header += uleb128_encode(sym)
+        toc_header += uleb128_encode(L)
+    toc_header += uleb128_encode(best_k)
+    deltas: List[int] = []
+    best_k2 = 0
+    if mode == MODE_FIXED:
+        toc_header += uleb128_encode(orig_lens[-1] if nblocks > 0 else 0)
+    else:
+        deltas = [_zz_enc(ol - size_field) for ol in orig_lens]
+        best_k2 = _best_rice_k(deltas)
+        toc_header += uleb128_encode(best_k2)
+    # ---- TOC bitstream
+    bw = _Bits()
+    for s in run_syms:
+        c, L = enc_tbl[s]
+        bw.put(c, L)
+    bw.rice(run_lens, best_k)
+    if mode == MODE_CDC:
+        bw.rice(deltas, best_k2)
+    n = len(payload_lens)
+    l = _ef_choose_l(total_payload, n)
+    P, s = [], 0
+    for L in payload_lens:
+        s += L
+        P.append(s)
+    for x in P:
+        bw.put(x, l)
+    m = (total_payload + ((1 << l) - 1)) >> l
+    total = m + n
+    if total:
+        bitmap = 0
+        for i, x in enumerate(P):
+            bitmap |= 1 << (total - 1 - ((x >> l) + i))
+        bw.put(bitmap, total)
+    toc_bits, toc_bitlen = bw.value()
+    out += uleb128_encode(len(toc_header))
+    out += uleb128_encode(toc_bitlen)
+    out += uleb128_encode(total_payload)
+    out += toc_header
+    out += toc_bits
+    for p in payloads:
+        out += p
+    return bytes(out)
+
+
+def compress_blocks_fixed(data: bytes, block_size: int = 8192) -> bytes:
+    data = bytes(data)
+    return _assemble(data, fixed_boundaries(data, block_size), MODE_FIXED, block_size)
+
+
+def compress_blocks_cdc(data: bytes, min_size: int = 4096, avg_size: int = 8192, max_size: int = 16384) -> bytes:
+    data = bytes(data)
+    return _assemble(data, cdc_fast_boundaries_strict(data, min_size, avg_size, max_size), MODE_CDC, avg_size)
+
+
+def decompress(container: bytes) -> bytes:
+    container = bytes(container)
+    if len(container) < 4 or container[:4] != b"KOLR":
+        raise ValueError("Invalid magic")
+    pos = 4
+    packed = struct.unpack_from("<I", container, pos)[0]
+    pos += 4
+    mode, size_field = (packed >> 31) & 1, packed & 0x7FFFFFFF
+    total_len = struct.unpack_from("<I", container, pos)[0]
+    pos += 4
+    nblocks = struct.unpack_from("<H", container, pos)[0]
+    pos += 2
+    toc_hdr_len, pos = uleb128_decode_stream(container, pos)
+    toc_bitlen, pos = uleb128_decode_stream(container, pos)
+    total_payload, pos = uleb128_decode_stream(container, pos)
+    if pos + toc_hdr_len > len(container):
+        raise ValueError("Truncated TOC header")
+    toc_header = container[pos:pos + toc_hdr_len]
+    pos += toc_hdr_len
+    toc_bit_bytes = (toc_bitlen + 7) // 8
+    if pos + toc_bit_bytes > len(container):
+        raise ValueError("Truncated TOC bits")
+    toc_bits = container[pos:pos + toc_bit_bytes]
+    pos += toc_bit_bytes
+    p = 0
+    n_runs, p = uleb128_decode_stream(toc_header, p)
+    K, p = uleb128_decode_stream(toc_header, p)
+    lengths = {}
+    for _ in range(K):
+        sym, p = uleb128_decode_stream(toc_header, p)
+        L, p = uleb128_decode_stream(toc_header, p)
+        lengths[sym] = L
+    k_runs, p = uleb128_decode_stream(toc_header, p)
+    if mode == MODE_FIXED:
+        last_orig_len, p = uleb128_decode_stream(toc_header, p)
+    else:
+        k_orig, p = uleb128_decode_stream(toc_header, p)
+    _, dec_tbl, maxlen = _huff_canonical(lengths)
+    br = _BitsIn(toc_bits)
+    run_syms = []
+    for _ in range(n_runs):
+        c = 0
+        for L in range(1, maxlen + 1):
+            c = (c << 1) | br.bit()
+            if (L, c) in dec_tbl:
+                run_syms.append(dec_tbl[(L, c)])
+                break
+        else:
+            raise ValueError("Huffman decode failed")
+    run_lens = [br.rice(k_runs) for _ in range(n_runs)]
+    method_ids: List[int] = []
+    for s, r in zip(run_syms, run_lens):
+        method_ids.extend([s] * r)
+    if len(method_ids) != nblocks:
+        raise ValueError("Method id RLE expands to wrong size")
+    if mode == MODE_FIXED:
+        orig_lens = [size_field] * (nblocks - 1) + ([last_orig_len] if nblocks > 0 else [])
+    else:
+        orig_lens = [size_field + _zz_dec(br.rice(k_orig)) for _ in range(nblocks)]
+    l = _ef_choose_l(total_payload, nblocks)
+    lows = [br.bits(l) for _ in range(nblocks)]
+    m = (total_payload + ((1 << l) - 1)) >> l
+    ones = []
+    for idx in range(m + nblocks):
+        if br.bit():
+            ones.append(idx)
+            if len(ones) == nblocks:
+                break
+    P = [((ones[i] - i) << l) | lows[i] for i in range(nblocks)]
+    if P and P[-1] != total_payload:
+        raise ValueError("Payload EF sum mismatch")
+    if pos + total_payload > len(container):
+        raise ValueError("Truncated payload area")
+    area = container[pos:pos + total_payload]
+    pos += total_payload
+    todo = []
+    start = 0
+    for i in range(nblocks):
+        mid = method_ids[i]
+        if mid < 0 or mid >= len(KOLR_NAMES):
+            raise ValueError(f"Unknown method_id {mid}")
+        todo.append((KOLR_NAMES[mid], area[start:P[i]], orig_lens[i]))
+        start = P[i]
+    _print_progress("DECOMPRESS", 0, nblocks)
+    blocks = _engine().decode_blocks(todo) if todo else []
+    _print_progress("DECOMPRESS", nblocks, nblocks, final=True)
+    out = b"".join(blocks)
+    if len(out) != total_len:
+        raise ValueError(f"Length mismatch: got {len(out)}, expect {total_len}")
+    if pos != len(container):
+        raise ValueError(f"Extra trailing {len(container) - pos} bytes after container end")
+    return out
