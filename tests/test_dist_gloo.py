@@ -1,0 +1,73 @@
+"""World-size-2 gloo test (CPU) of the block-sharding host logic: partitioning, table all_gather, payload send/recv,
+ordering.  The per-block encoder is injected (the CPU oracle) because this container has no GPU."""
+import os
+import socket
+
+import pytest
+import torch.multiprocessing as mp
+
+import datasets
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from kolmogorovlike_datacompressor_b200 import dist as kd
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = datasets.medium_cases()["text_big"] + datasets.fixture("pattern")[:30000]
+    bounds = O.kf_cdc(data, 1024, 2048, 4096)
+
+    def enc(d, bs):
+        out = []
+        for a, b in bs:
+            mid, payload, _ = O.encode_block(O.PROFILE_KOLM, d[a:b])
+            out.append((mid, payload))
+        return out
+
+    got = kd.sharded_encode(data, bounds, enc)
+    if rank == 0:
+        want = enc(data, bounds)
+        q.put(("ok", got == want, len(bounds), kd.partition_blocks(bounds, world)))
+    else:
+        q.put(("none", got is None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_encode_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ok = [r for r in res if r[0] == "ok"][0]
+    assert ok[1] is True
+    parts = ok[3]
+    assert parts[0][0] == 0 and parts[-1][1] == ok[2] and parts[0][1] == parts[1][0]
+    assert [r for r in res if r[0] == "none"][0][1] is True
+
+
+def test_partition_balanced_and_total():
+    from kolmogorovlike_datacompressor_b200 import dist as kd
+    bounds = [(i * 1000, (i + 1) * 1000) for i in range(37)]
+    for world in (1, 2, 3, 4, 8, 64):
+        parts = kd.partition_blocks(bounds, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 37
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        sizes = [e - s for s, e in parts]
+        assert max(sizes) - min(sizes) <= 1 or world > 37
+    assert kd.partition_blocks([], 4) == [(0, 0)] * 4
