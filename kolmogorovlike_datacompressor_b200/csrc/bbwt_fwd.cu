@@ -525,6 +525,137 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_lyndon(const u32* __restrict__
     if (tid == 0 && (td.flags & 2u)) nfac[td.block] = (u32)(s_excl + ctot);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Lyndon fast path.  Factor starts are the strict prefix minima of the suffix order, so a position can
+// only start a factor if its 6-byte prefix (+ length code) is <= every earlier one.  k_lyn_cand finds
+// those candidates with one look-back min-scan over 51-bit keys; k_lyn_resolve (one warp per block) walks
+// them in order and settles ties against the current champion by direct suffix comparison.  Text-like data
+// has a handful of candidates per block; degenerate data (long runs / periods) exceeds the work budget and
+// the whole batch takes the robust ISA path (plain suffix sort + k_lyndon) instead.  Both paths are exact.
+// ------------------------------------------------------------------------------------------------
+#define LYN_MAX_CAND 4096u
+#define LYN_MAX_ITERS 8192u
+#define LYN_KEY_INF ((1ull << 52) - 1)
+
+__device__ __forceinline__ u64 lyn_key(const u8* __restrict__ src, u32 lp, u32 len) {
+    u32 rem = len - lp;
+    u64 k = 0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) k = (k << 8) | (u64)((u32)t < rem ? src[lp + t] : 0);
+    return (k << 3) | (u64)(rem < 7 ? rem : 7);
+}
+
+__global__ void __launch_bounds__(KOLM_THREADS) k_lyn_cand(const u8* __restrict__ in, const TileDesc* __restrict__ tiles,
+                                                           const BlockInfo* __restrict__ binfo, u64* lb, u32* __restrict__ cand,
+                                                           u32* __restrict__ ncand) {
+    __shared__ u64 s_warp[NWARPS];
+    __shared__ u64 s_last[NWARPS];
+    __shared__ u64 s_excl;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(lb);
+    if (tile == LB_NO_TILE) return;
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u8* src = in + bi.ioff;
+    const u32 t0 = td.start - bi.pbase;
+    u64 key[KOLM_IPT];
+    u64 mn = LYN_KEY_INF;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        key[i] = r < td.count ? lyn_key(src, t0 + r, bi.len) : LYN_KEY_INF;
+        mn = key[i] < mn ? key[i] : mn;
+    }
+    struct OpMin { __device__ __forceinline__ u64 operator()(u64 a, u64 b) const { return a < b ? a : b; } };
+    u64 tot;
+    u64 incl = block_scan_incl(mn, LYN_KEY_INF, OpMin(), s_warp, &tot);
+    u64 prev = __shfl_up_sync(FULL, incl, 1);
+    if ((tid & 31) == 31) s_last[tid >> 5] = incl;
+    __syncthreads();
+    if ((tid & 31) == 0) prev = (tid >> 5) ? s_last[(tid >> 5) - 1] : LYN_KEY_INF;
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb, tile, (td.flags & 1u) != 0, tot, LYN_KEY_INF, OpMin());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u64 run = s_excl < prev ? s_excl : prev;
+    u32 cmask = 0, smask = 0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        if (key[i] != LYN_KEY_INF || tid * KOLM_IPT + i < td.count) {
+            if (tid * KOLM_IPT + i < td.count) {
+                if (key[i] < run) { cmask |= 1u << i; smask |= 1u << i; run = key[i]; }
+                else if (key[i] == run) cmask |= 1u << i;
+            }
+        }
+    }
+    __syncthreads();
+    u64* lb2 = lb + gridDim.x;
+    const u32 cnt = __popc(cmask);
+    u64 ctot;
+    u64 cincl = block_scan_incl((u64)cnt, 0ull, OpAdd(), s_warp, &ctot);
+    if (tid < 32) {
+        u64 e = lb_exclusive(lb2, tile, (td.flags & 1u) != 0, ctot, 0ull, OpAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 o = (u32)s_excl + (u32)(cincl - cnt);
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        if ((cmask >> i) & 1u) {
+            if (o < LYN_MAX_CAND + 1) cand[bi.pbase + o] = (t0 + tid * KOLM_IPT + i) | (((smask >> i) & 1u) << 31);
+            ++o;
+        }
+    }
+    if (tid == 0 && (td.flags & 2u)) ncand[td.block] = (u32)(s_excl + ctot);
+}
+
+// one warp per block
+__global__ void __launch_bounds__(128) k_lyn_resolve(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, const u32* __restrict__ cand,
+                                                     const u32* __restrict__ ncand, u32* __restrict__ fstart, u32* __restrict__ nfac,
+                                                     u8* __restrict__ flags_out, u32* __restrict__ fallback, int nblocks) {
+    const u32 lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const BlockInfo bi = binfo[b];
+    if (bi.len == 0) { if (lane == 0) nfac[b] = 0; return; }
+    const u32 nc = ncand[b];
+    if (nc > LYN_MAX_CAND || bi.len > LYN_MAX_CAND && nc > bi.len / 8) { if (lane == 0) atomicExch(fallback, 1u); return; }
+    const u8* src = in + bi.ioff;
+    u32 champ = 0, nf = 0, iters = 0;
+    for (u32 k = 0; k < nc; ++k) {
+        u32 cv = cand[bi.pbase + k];
+        u32 pos = cv & 0x7fffffffu;
+        bool win = (cv >> 31) != 0;
+        if (!win) {
+            // tie on the 6-byte key (both suffixes have >= 7 bytes): compare from offset 6, 32 bytes per step
+            u32 o = 6;
+            for (;;) {
+                if (++iters > LYN_MAX_ITERS) { if (lane == 0) atomicExch(fallback, 1u); return; }
+                u32 x = o + lane;
+                bool inb = pos + x < bi.len;                 // pos > champ, so pos's suffix ends first
+                u32 a = inb ? src[pos + x] : 0, c = inb ? src[champ + x] : 0;
+                u32 ne = __ballot_sync(FULL, !inb || a != c);
+                if (ne) {
+                    u32 l = __ffs(ne) - 1;
+                    u32 aa = __shfl_sync(FULL, a, l), cc = __shfl_sync(FULL, c, l);
+                    bool ended = !__shfl_sync(FULL, (u32)inb, l);
+                    win = ended || aa < cc;                  // a proper prefix is the smaller suffix
+                    break;
+                }
+                o += 32;
+            }
+        }
+        if (win) {
+            champ = pos;
+            if (lane == 0) { fstart[bi.pbase + nf] = pos; if (flags_out) flags_out[bi.ioff + pos] = 1; }
+            ++nf;
+        }
+    }
+    if (lane == 0) nfac[b] = nf;
+}
+
 // out[j] = byte preceding rotation sa[j] inside its factor  (kolm_final.py:321)
 __global__ void __launch_bounds__(KOLM_THREADS) k_bbwt_emit(const u8* __restrict__ in, u8* __restrict__ out, const u32* __restrict__ sa,
                                                             const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
@@ -646,8 +777,25 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
 // a1: Lyndon factorisation of every block.  Leaves factor lists in the context for the cyclic sort.
 int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, cudaStream_t s) {
     if (!c->ntiles) return KOLM_OK;
-    KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
+    static int fast = -1;
+    if (fast < 0) { const char* e = getenv("KOLM_LYNDON_FAST"); fast = e ? atoi(e) : 1; }
     int lgrid = c->ntiles;
+    if (fast) {
+        // fast path: candidate scan + per-block tie resolution; falls back to the ISA path if any block is degenerate
+        u32* cand = c->d_nr;                                  // free until the first sort round
+        u32* ncand = c->d_active;
+        CUDA_TRY(cudaMemsetAsync(c->d_stats + 8, 0, 4, s));
+        if (flags_out && c->total_bytes) CUDA_TRY(cudaMemsetAsync(flags_out + c->h_binfo[0].ioff, 0, (size_t)c->total_bytes, s));
+        KOLM_TRY(kolm_lb_reset(c, false, c->ntiles, &lgrid, s));
+        KL(c, KC_LYNDON, c->total_bytes * 2, s, k_lyn_cand<<<lgrid, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_lb, cand, ncand));
+        KL(c, KC_LYNDON, c->total_bytes / 64, s, k_lyn_resolve<<<(c->nblocks + 3) / 4, 128, 0, s>>>(in, c->d_binfo, cand, ncand, c->d_fstart, c->d_nfac,
+                                                                                                  flags_out, c->d_stats + 8, c->nblocks));
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats + 8, c->d_stats + 8, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaGetLastError());
+        if (c->h_stats[8] == 0) { if (rounds_out) *rounds_out = 0; return KOLM_OK; }
+    }
+    KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
     KOLM_TRY(kolm_lb_reset(c, false, c->ntiles, &lgrid, s));
     KL(c, KC_LYNDON, c->total_bytes * 4, s, k_lyndon<<<lgrid, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out));
     CUDA_TRY(cudaGetLastError());
