@@ -700,10 +700,16 @@ __global__ void k_lb_header(u64* lb, u64 rows, u64 nb, const u32* tile0, const u
     lb[1] = rows; lb[2] = nb; lb[3] = (u64)tile0; lb[4] = (u64)tilen; lb[5] = group;
 }
 
-int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t s) {
-    static int G = -1;
-    // default 0 = block-major tickets: measured on B200, interleaving blocks loses more L2 locality than it saves look-back steps
-    if (G < 0) { const char* e = getenv("KOLM_LB_GROUP"); G = e ? atoi(e) : 0; }
+// mode 0: sort kernels (rerank / gather) — block-major tickets by default: measured on B200, interleaving blocks there loses
+//         more L2 locality of the rank gathers than it saves look-back steps (KOLM_LB_GROUP overrides).
+// mode 1: cheap streaming scans (Rice cost/pack, residual/LZ emit, Lyndon, inverse offsets) — row-major over all blocks, so
+//         that each block's look-back chain is one window deep instead of tiles_per_block/32 dependent steps.
+int kolm_lb_reset_mode(kolm_ctx* c, bool active, int ntiles, int* grid, int mode, cudaStream_t s) {
+    static int G0 = -1, G1 = -1;
+    if (G0 < 0) { const char* e = getenv("KOLM_LB_GROUP"); G0 = e ? atoi(e) : 0; }
+    if (G1 < 0) { const char* e = getenv("KOLM_LB_GROUP_STREAM"); G1 = e ? atoi(e) : (1 << 30); }
+    int G = mode ? G1 : G0;
+    if (G > c->nblocks) G = c->nblocks;
     u64 rows = active ? c->active_rows : c->static_rows;
     u64 ngroups = G > 0 ? ((u64)c->nblocks + G - 1) / G : 0;
     u64 g = rows * (u64)G * ngroups;
@@ -713,6 +719,7 @@ int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t 
     *grid = (int)g;
     return KOLM_OK;
 }
+int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t s) { return kolm_lb_reset_mode(c, active, ntiles, grid, 0, s); }
 
 // Sort all suffixes (plain) or all rotations (cyclic) of every block of the current batch.
 // On return c->d_sa holds the order and c->d_rank the (group-start) ranks.  *rounds_out = doubling rounds run.
@@ -786,7 +793,7 @@ int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, 
         u32* ncand = c->d_active;
         CUDA_TRY(cudaMemsetAsync(c->d_stats + 8, 0, 4, s));
         if (flags_out && c->total_bytes) CUDA_TRY(cudaMemsetAsync(flags_out + c->h_binfo[0].ioff, 0, (size_t)c->total_bytes, s));
-        KOLM_TRY(kolm_lb_reset(c, false, c->ntiles, &lgrid, s));
+        KOLM_TRY(kolm_lb_reset_mode(c, false, c->ntiles, &lgrid, 1, s));
         KL(c, KC_LYNDON, c->total_bytes * 2, s, k_lyn_cand<<<lgrid, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_lb, cand, ncand));
         KL(c, KC_LYNDON, c->total_bytes / 64, s, k_lyn_resolve<<<(c->nblocks + 3) / 4, 128, 0, s>>>(in, c->d_binfo, cand, ncand, c->d_fstart, c->d_nfac,
                                                                                                   flags_out, c->d_stats + 8, c->nblocks));
@@ -796,7 +803,7 @@ int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, 
         if (c->h_stats[8] == 0) { if (rounds_out) *rounds_out = 0; return KOLM_OK; }
     }
     KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
-    KOLM_TRY(kolm_lb_reset(c, false, c->ntiles, &lgrid, s));
+    KOLM_TRY(kolm_lb_reset_mode(c, false, c->ntiles, &lgrid, 1, s));
     KL(c, KC_LYNDON, c->total_bytes * 4, s, k_lyndon<<<lgrid, KOLM_THREADS, 0, s>>>(c->d_rank, c->d_tiles, c->d_binfo, c->d_lb, c->d_fstart, c->d_nfac, flags_out));
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;

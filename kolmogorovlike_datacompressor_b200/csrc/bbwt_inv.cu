@@ -128,7 +128,7 @@ int kolm_bbwt_inv_impl(kolm_ctx* c, const u8* in, u8* out, cudaStream_t s) {
         span <<= 1;
     }
     int lgrid = nt;
-    KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+    KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
     KL(c, KC_INV, N * 24, s, k_inv_offsets<<<lgrid, KOLM_THREADS, 0, s>>>(A, V, c->d_tiles, c->d_binfo, c->d_lb, c->d_sa, c->d_rank));
     KL(c, KC_INV, N * 26, s, k_inv_emit<<<nt, KOLM_THREADS, 0, s>>>(in, out, A, c->d_tiles, c->d_binfo, c->d_sa, c->d_rank));
     CUDA_TRY(cudaGetLastError());

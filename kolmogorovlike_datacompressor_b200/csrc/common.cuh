@@ -251,3 +251,4 @@ static inline void prof_end(kolm_ctx* c, cudaStream_t s) {
 int kolm_set_batch(kolm_ctx* c, const i64* off_host, int nblocks, cudaStream_t s);
 // zero the look-back state for a launch over the static (active=false) or active tile map; returns the grid size
 int kolm_lb_reset(kolm_ctx* c, bool active, int ntiles, int* grid, cudaStream_t s);
+int kolm_lb_reset_mode(kolm_ctx* c, bool active, int ntiles, int* grid, int mode, cudaStream_t s);

@@ -319,7 +319,7 @@ int kolm_lz77_enc_impl(kolm_ctx* c, const u8* in, u32 window, u32 maxlen, u8* ou
         KL(c, KC_MISC, N, s, k_lz_emit<false><<<nt, KOLM_THREADS, 0, s>>>(a, c->d_lb, c->d_bacc, out));
         KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
         int lgrid = nt;
-        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
         KL(c, KC_MISC, N * 10, s, k_lz_emit<true><<<lgrid, KOLM_THREADS, 0, s>>>(a, c->d_lb, c->d_bacc, out));
     } else {
         KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));

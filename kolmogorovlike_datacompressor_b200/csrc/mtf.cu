@@ -96,6 +96,107 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_enc(const u8* __restrict
     }
 }
 
+
+// pass C (encode), v2: one THREAD per tile, 128 tiles per CTA.
+//   step 1 (warp-cooperative): turn each tile's entry timestamps into its entry list — seen symbols by last occurrence
+//           (rank by counting among the seen ones only), then the never-seen ones in identity order;
+//   step 2 (thread-serial): the classic list walk, but on a packed list (4 symbols per 32-bit word, word 0 in a register,
+//           words 1..63 in shared memory laid out [word][thread] = conflict free): zero-byte test finds the symbol inside a
+//           word, funnel shift + byte permute moves it to the front.  BWT output is dominated by small indices, so most
+//           symbols never leave the register word.
+#define MTF2_THREADS 128
+__device__ __forceinline__ u32 mtf_zero_byte(u32 x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
+
+__global__ void __launch_bounds__(MTF2_THREADS) k_mtf_enc2(const u8* __restrict__ in, u8* __restrict__ out, const TileDesc* __restrict__ tiles,
+                                                           const BlockInfo* __restrict__ binfo, const u32* __restrict__ tlast, int ntiles) {
+    __shared__ u32 lst[64][MTF2_THREADS];                  // packed entry lists, word k of thread t at lst[k][t]
+    __shared__ u32 s_ts[MTF2_THREADS / 32][256];           // per warp: timestamps of the tile being converted
+    __shared__ u8 s_sym[MTF2_THREADS / 32][256];
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    u8* lb = reinterpret_cast<u8*>(&lst[0][0]);
+    // ---- step 1: warp w builds the lists of tiles (blockIdx*128 + w*32 + q), q = 0..31
+    for (u32 q = 0; q < 32; ++q) {
+        const u32 T = w * 32 + q;                          // thread column that will own this tile
+        const int tile = blockIdx.x * MTF2_THREADS + T;
+        if (tile >= ntiles) break;
+        u32 ts[8]; u32 seenmask = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ts[k] = tlast[(size_t)tile * 256 + k * 32 + lane]; if (ts[k]) seenmask |= 1u << k; }   // symbol c = k*32+lane
+        // compact the seen symbols (any order) into smem
+        u32 nseen = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            u32 bal = __ballot_sync(0xffffffffu, ts[k] != 0);
+            if (ts[k]) { u32 o = nseen + __popc(bal & lanemask_lt()); s_ts[w][o] = ts[k]; s_sym[w][o] = (u8)(k * 32 + lane); }
+            nseen += __popc(bal);
+        }
+        __syncwarp();
+        // rank by counting: position of a seen symbol = #seen symbols with a larger timestamp (timestamps are distinct)
+        for (u32 e = lane; e < nseen; e += 32) {
+            u32 my = s_ts[w][e], r = 0;
+            for (u32 f = 0; f < nseen; ++f) r += (s_ts[w][f] > my);
+            u32 p = r;
+            lb[(((p >> 2) * MTF2_THREADS + T) << 2) + (p & 3)] = s_sym[w][e];
+        }
+        // never-seen symbols keep identity order behind the seen ones: position = nseen + #unseen symbols smaller than c
+        u32 below = 0;                                      // unseen symbols in rows k' < k (all lanes) handled incrementally
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            u32 bal = __ballot_sync(0xffffffffu, ts[k] == 0);
+            if (!ts[k]) { u32 p = nseen + below + __popc(bal & lanemask_lt()); lb[(((p >> 2) * MTF2_THREADS + T) << 2) + (p & 3)] = (u8)(k * 32 + lane); }
+            below += __popc(bal);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- step 2
+    const int tile = blockIdx.x * MTF2_THREADS + tid;
+    if (tile >= ntiles) return;
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u32 t0 = td.start - bi.pbase;
+    const u8* src = in + bi.ioff + t0;
+    u8* dst = out + bi.ioff + t0;
+    u32 w0 = lst[0][tid];
+    const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    for (u32 x0 = 0; x0 < td.count; x0 += 16) {
+        u32 inw[4], outw[4] = {0, 0, 0, 0};
+        const u32 nb = min(16u, td.count - x0);
+        if (aligned && nb == 16) { uint4 v = *reinterpret_cast<const uint4*>(src + x0); inw[0] = v.x; inw[1] = v.y; inw[2] = v.z; inw[3] = v.w; }
+        else { inw[0] = inw[1] = inw[2] = inw[3] = 0; for (u32 i = 0; i < nb; ++i) inw[i >> 2] |= (u32)src[x0 + i] << (8 * (i & 3)); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((u32)i < nb) {
+                const u32 b = (inw[i >> 2] >> (8 * (i & 3))) & 0xFF;
+                u32 idx = 0;
+                if (b != (w0 & 0xFF)) {
+                    const u32 bbbb = b * 0x01010101u;
+                    u32 z = mtf_zero_byte(w0 ^ bbbb);
+                    if (z) {                                // inside the register word: positions 1..3
+                        idx = (__ffs(z) - 1) >> 3;
+                        w0 = __byte_perm(w0, b, idx == 1 ? 0x3204 : idx == 2 ? 0x3104 : 0x2104);
+                    } else {
+                        u32 carry = w0 >> 24;
+                        w0 = (w0 << 8) | b;
+                        for (u32 k = 1;; ++k) {
+                            u32 wk = lst[k][tid];
+                            z = mtf_zero_byte(wk ^ bbbb);
+                            if (!z) { lst[k][tid] = (wk << 8) | carry; carry = wk >> 24; continue; }
+                            u32 j = (__ffs(z) - 1) >> 3;
+                            idx = 4 * k + j;
+                            lst[k][tid] = __byte_perm(wk, carry, j == 0 ? 0x3214 : j == 1 ? 0x3204 : j == 2 ? 0x3104 : 0x2104);
+                            break;
+                        }
+                    }
+                }
+                outw[i >> 2] |= idx << (8 * (i & 3));
+            }
+        }
+        if (aligned && nb == 16) *reinterpret_cast<uint4*>(dst + x0) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+        else for (u32 i = 0; i < nb; ++i) dst[x0 + i] = (u8)(outw[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // decode
 // ---------------------------------------------------------------------------------------------
@@ -196,7 +297,10 @@ int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t 
         const i64 N = c->total_bytes;
         KL(c, KC_MTF_PRE, N + (i64)nt * 1024, s, k_mtf_last<<<nt, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_thist));
         KL(c, KC_MTF_SCAN, (i64)nt * 2048, s, k_mtf_scan_max<<<sgrid, 256, 0, s>>>(c->d_thist, c->d_btile0, c->d_btilen, nb));
-        KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt));
+        static int v2 = -1;
+        if (v2 < 0) { const char* e = getenv("KOLM_MTF_V2"); v2 = e ? atoi(e) : 1; }
+        if (v2) KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc2<<<(nt + MTF2_THREADS - 1) / MTF2_THREADS, MTF2_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt));
+        else KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt));
     } else {
         u8* tperm = (u8*)c->d_thist;
         const i64 N = c->total_bytes;

@@ -137,7 +137,7 @@ int kolm_residual_enc_impl(kolm_ctx* c, const u8* in, int kind, u8* out, size_t 
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     if (nt) {
         int lgrid = nt;
-        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
         KL(c, KC_MISC, c->total_bytes * 2, s, k_res_emit<<<lgrid, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, out, kind));
     }
     CUDA_TRY(cudaGetLastError());

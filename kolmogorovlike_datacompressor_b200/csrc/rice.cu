@@ -388,13 +388,13 @@ int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
         KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
     }
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
         KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out));
     }
     CUDA_TRY(cudaGetLastError());
@@ -414,7 +414,7 @@ int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
         int lgrid = nt;
-        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
         KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags));
     }
     CUDA_TRY(cudaGetLastError());
