@@ -74,13 +74,69 @@ __device__ __forceinline__ void put_gamma(u32* base, u64 bitpos, u32 x) {       
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory staging of one tile's bit range: codes are OR-ed into shared words, the tile's interior words are then
+// stored coalesced and only the two boundary words (shared with the neighbouring tiles) use a global atomic.
+// A tile whose bit range does not fit (long unary runs) scatters straight to global memory.
+// ---------------------------------------------------------------------------------------------
+#define STAGE_WORDS 8704
+struct BitStage {
+    u32* sm; u32* out; u64 first_word; u32 nwords; bool use;
+    __device__ __forceinline__ void begin(u32* smem, u32* out_, u64 bit0, u64 nbits) {
+        sm = smem; out = out_;
+        first_word = bit0 >> 5;
+        u64 nw = nbits ? ((bit0 + nbits - 1) >> 5) - first_word + 1 : 0;
+        use = nw <= STAGE_WORDS; nwords = use ? (u32)nw : 0;
+        for (u32 i = threadIdx.x; i < nwords; i += KOLM_THREADS) sm[i] = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void word(u64 w, u32 be_bits) const {
+        if (!be_bits) return;
+        if (use) atomicOr(sm + (u32)(w - first_word), be_bits);
+        else atomicOr(out + w, __byte_perm(be_bits, 0, 0x0123));
+    }
+    __device__ __forceinline__ void bits(u64 bitpos, u32 value, u32 n) const {      // n in 1..32, value < 2^n
+        u64 w = bitpos >> 5; u32 o = (u32)bitpos & 31;
+        u64 v = (u64)value << (64 - n - o);
+        word(w, (u32)(v >> 32)); word(w + 1, (u32)v);
+    }
+    __device__ __forceinline__ void ones(u64 bitpos, u64 q) const {
+        while (q >= 32) { bits(bitpos, 0xffffffffu, 32); bitpos += 32; q -= 32; }
+        if (q) bits(bitpos, (1u << q) - 1u, (u32)q);
+    }
+    __device__ __forceinline__ void rice(u64 bitpos, u64 x, u32 k) const {
+        u64 q = x >> k; ones(bitpos, q);
+        if (k) bits(bitpos + q + 1, (u32)(x & ((1u << k) - 1u)), k);
+    }
+    __device__ __forceinline__ void gamma(u64 bitpos, u32 x) const { u32 b = bitlen32(x); bits(bitpos + (b - 1), x, b); }
+    __device__ __forceinline__ void flush() const {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < nwords; i += KOLM_THREADS) {
+            u32 v = sm[i];
+            if (!v) continue;
+            v = __byte_perm(v, 0, 0x0123);
+            if (i == 0 || i == nwords - 1) atomicOr(out + first_word + i, v); else out[first_word + i] = v;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // shared tile prologue: symbols of my IPT items plus the one after (run-end detection)
 // ---------------------------------------------------------------------------------------------
 #define V_END 0x100u      // beyond the end of the block
 __device__ __forceinline__ void load_items(const u8* __restrict__ src, u32 t0, u32 count, u32 blen, u32 (&v)[KOLM_IPT + 1]) {
+    const u32 r0 = threadIdx.x * KOLM_IPT;
+    if (r0 + KOLM_IPT <= count && ((uintptr_t)(src + r0) & 15) == 0) {      // full, 16-byte aligned: one 128-bit load
+        uint4 q = *reinterpret_cast<const uint4*>(src + r0);
+        u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) v[i] = (w[i >> 2] >> (8 * (i & 3))) & 0xFF;
+        u32 r = r0 + KOLM_IPT;
+        v[KOLM_IPT] = (r < count || (r == count && t0 + r < blen)) ? (u32)src[r] : V_END;
+        return;
+    }
 #pragma unroll
     for (int i = 0; i <= KOLM_IPT; ++i) {
-        u32 r = threadIdx.x * KOLM_IPT + i;
+        u32 r = r0 + i;
         v[i] = (r < count || (r == count && t0 + r < blen)) ? (u32)src[r] : V_END;
     }
 }
@@ -108,7 +164,7 @@ __device__ __forceinline__ u32 scan_last_nonzero(u32 mine, u64* lb, u32 tile, bo
 // ---------------------------------------------------------------------------------------------
 template <bool KF, bool K2>
 __global__ void __launch_bounds__(KOLM_THREADS) k_rice_cost(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
-                                                            const BlockInfo* __restrict__ binfo, u64* lb, u64* __restrict__ bacc) {
+                                                            const BlockInfo* __restrict__ binfo, u64* lb, u64* __restrict__ tacc) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_last[KOLM_THREADS / 32];
     __shared__ u64 s_excl;
@@ -192,7 +248,25 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_cost(const u8* __restrict
         for (int k = 0; k < 5; ++k) red(k2[k], 20 + k);
     }
     __syncthreads();
-    if (tid < 25 && s_acc[tid]) atomicAdd((unsigned long long*)(bacc + (size_t)td.block * RB_STRIDE + tid), s_acc[tid]);
+    // per-tile partial sums; k_tile_reduce adds them per block (same-address global atomics from 256 tiles serialise in L2)
+    if (tid < 32) tacc[(size_t)tile * 32 + tid] = tid < 25 ? s_acc[tid] : 0ull;
+}
+
+// bacc[b*64 + slot] (+)= sum over the tiles of block b of tacc[tile*32 + slot], slot < 32
+__global__ void __launch_bounds__(256) k_tile_reduce(const u64* __restrict__ tacc, const u32* __restrict__ tile0, const u32* __restrict__ tilen,
+                                                     u64* __restrict__ bacc, int slot0, int nslots) {
+    __shared__ u64 s[8][32];
+    const u32 b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 t0 = tile0[b], nt = tilen[b];
+    u64 acc = 0;
+    for (u32 t = w; t < nt; t += 8) acc += tacc[(size_t)(t0 + t) * 32 + lane];
+    s[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && (int)lane >= slot0 && (int)lane < slot0 + nslots) {
+        u64 tot = 0;
+        for (int i = 0; i < 8; ++i) tot += s[i][lane];
+        bacc[(size_t)b * RB_STRIDE + lane] = tot;
+    }
 }
 
 // single CTA: per-block parameter choice, payload size, exclusive offsets.  mode 1 = KF, 2 = K2 (slot)
@@ -289,7 +363,14 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_kf_pack(const u8* __restr
     }
     __syncthreads();
     u64 bp = bitbase + 10 + s_excl + (bincl - mybits);
-    if ((td.flags & 1u) && tid == 0) put_bits(out, bitbase, (((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1, 10);   // KF.py:664-668
+    __shared__ u32 s_stage[STAGE_WORDS];
+    BitStage st;
+    {   // this tile's bit range (the first tile of a block also owns the 10 header bits)
+        u64 tb0 = bitbase + 10 + s_excl, tbn = btot;
+        if (td.flags & 1u) { tb0 = bitbase; tbn += 10; }
+        st.begin(s_stage, out, tb0, tbn);
+    }
+    if ((td.flags & 1u) && tid == 0) st.bits(bitbase, (((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1, 10);   // KF.py:664-668
     ln = ln0;
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
@@ -299,16 +380,17 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_kf_pack(const u8* __restr
             if (v[i]) {
                 ln = pos1;
                 u32 x = v[i] - 1;
-                put_bits(out, bp, 1, 1);
-                if (urn) { put_rice(out, bp + 1, x, k1); bp += 1 + (u64)(x >> k1) + 1 + k1; }
-                else { put_gamma(out, bp + 1, v[i]); bp += 1 + 2 * bitlen32(v[i]) - 1; }
+                st.bits(bp, 1, 1);
+                if (urn) { st.rice(bp + 1, x, k1); bp += 1 + (u64)(x >> k1) + 1 + k1; }
+                else { st.gamma(bp + 1, v[i]); bp += 1 + 2 * bitlen32(v[i]) - 1; }
             } else if (v[i + 1] != 0) {
                 u32 run = pos1 - ln;                         // tag bit 0: nothing to write
-                if (urz) { put_rice(out, bp + 1, run, k0); bp += 1 + (u64)(run >> k0) + 1 + k0; }
-                else { put_gamma(out, bp + 1, run); bp += 1 + 2 * bitlen32(run) - 1; }
+                if (urz) { st.rice(bp + 1, run, k0); bp += 1 + (u64)(run >> k0) + 1 + k0; }
+                else { st.gamma(bp + 1, run); bp += 1 + 2 * bitlen32(run) - 1; }
             }
         }
     }
+    st.flush();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -353,15 +435,19 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_k2_pack(const u8* __restr
     }
     __syncthreads();
     u64 bp = bitbase + s_excl + (bincl - mybits);
+    __shared__ u32 s_stage[STAGE_WORDS];
+    BitStage st;
+    st.begin(s_stage, out, bitbase + s_excl, btot);
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
         if ((nsym_mask >> i) & 1u) {
             u32 t = sym[i], q = t >> 2;
-            put_ones(out, bp, q);
-            put_bits(out, bp + q, t & 3u, 3);               // the terminating 0 and the 2 remainder bits
+            st.ones(bp, q);
+            st.bits(bp + q, t & 3u, 3);                     // the terminating 0 and the 2 remainder bits
             bp += q + 3;
         }
     }
+    st.flush();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,7 +475,8 @@ int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
     if (nt) {
         KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
-        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
+        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, (u64*)c->d_thist));
+        KL(c, KC_RICE_COST, (i64)nt * 256, s, k_tile_reduce<<<nb, 256, 0, s>>>((const u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 0, 20));
     }
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
@@ -409,7 +496,10 @@ int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t
     if (slot < 0 || ((uintptr_t)out & 3) != 0) return KOLM_E_ARG;
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
-    if (nt) KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<false, true><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc));
+    if (nt) {
+        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<false, true><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, (u64*)c->d_thist));
+        KL(c, KC_RICE_COST, (i64)nt * 256, s, k_tile_reduce<<<nb, 256, 0, s>>>((const u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 20, 5));
+    }
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 2, slot));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
