@@ -257,6 +257,7 @@ struct RerankArgs {
     const u32* K; const u32* V; const TileDesc* tiles; const BlockInfo* binfo; const u32* active;
     const u32* fstart; const u32* nfac; u64* lb;
     u32* sa; u32* rank; u32* nr; u32* single; u32* newcls; u32 h;
+    u32* survivors;                     // [1] records that remain unsettled after this round (non-BOOT only)
 };
 
 template <bool BOOT, bool CYCLIC>
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
     __shared__ u32 sk2[SPAD];
     __shared__ u64 s_warp[NWARPS];
     __shared__ u64 s_excl;
-    __shared__ u32 s_cnt;
+    __shared__ u32 s_cnt, s_surv;
     const u32 tid = threadIdx.x;
     const u32 tile = lb_take_ticket(a.lb);
     if (tile == LB_NO_TILE) return;
@@ -273,7 +274,8 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
     const BlockInfo bi = a.binfo[td.block];
     const u32 nrec = BOOT ? bi.len : a.active[td.block];
     const u32 t0 = td.start - bi.pbase;
-    if (tid == 0) s_cnt = 0;
+    if (tid == 0) { s_cnt = 0; s_surv = 0; }
+    u32 nsurv = 0;
     // stage (key, key2) of records t0-1 .. t0+count into smem slots 0 .. count+1.  Loads are issued in
     // phases (all K/V, then all rank gathers) so that every thread keeps IPT+1 requests in flight.
     {
@@ -361,14 +363,16 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
             if (BOOT) {
                 a.rank[val] = nrk;
                 if (single) atomicOr(a.single + (val >> 5), 1u << (val & 31));
-            } else a.nr[td.start + r] = nrk | (single ? 0x80000000u : 0u);
+            } else { a.nr[td.start + r] = nrk | (single ? 0x80000000u : 0u); nsurv += single ? 0u : 1u; }
         }
     }
-    // classes created in this tile
-    for (int o = 16; o > 0; o >>= 1) nh += __shfl_xor_sync(FULL, nh, o);
+    // classes created in this tile (+ records left unsettled, packed in the high half)
+    for (int o = 16; o > 0; o >>= 1) { nh += __shfl_xor_sync(FULL, nh, o); nsurv += __shfl_xor_sync(FULL, nsurv, o); }
     if ((tid & 31) == 0 && nh) atomicAdd(&s_cnt, nh);
+    if ((tid & 31) == 0 && nsurv) atomicAdd(&s_surv, nsurv);
     __syncthreads();
     if (tid == 0 && s_cnt) atomicAdd(a.newcls + td.block, s_cnt);
+    if (!BOOT && tid == 0 && s_surv) atomicAdd(a.survivors, s_surv);
 }
 
 __global__ void __launch_bounds__(KOLM_THREADS) k_apply(const u32* __restrict__ V, const u32* __restrict__ nr, const TileDesc* __restrict__ tiles,
@@ -448,6 +452,75 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_gather(GatherArgs a) {
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) if ((amask >> i) & 1u) { u32 d = o + __popc(amask & ((1u << i) - 1u)); a.K[d] = pk[i]; a.V[d] = pv[i]; }
     if (tid == 0 && (td.flags & 2u)) a.active[td.block] = (u32)(s_excl + tot);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Larsson–Sadakane rounds for small active sets.  The Manber–Myers gather streams the whole order every round; once few
+// records are left (< 1/8 of the batch) it is cheaper to start from the survivors of the previous round:
+//   k_ls_build: survivors (v) -> (second key rank[succ_h(v)], v), compacted per block; sort by the second key;
+//   k_ls_key1 : replace the key by the first key rank[v]; stable sort by it -> same record order the gather path produces.
+// ------------------------------------------------------------------------------------------------
+struct LsArgs {
+    const u32* V; const u32* nr; const TileDesc* tiles; const BlockInfo* binfo; const u32* rank; const u32* fstart; const u32* nfac;
+    const u32* done; u64* lb; u32* K2; u32* V2; u32* active; u32 h;
+};
+
+template <bool CYCLIC>
+__global__ void __launch_bounds__(KOLM_THREADS) k_ls_build(LsArgs a) {
+    __shared__ u64 s_warp[NWARPS];
+    __shared__ u64 s_excl;
+    const u32 tid = threadIdx.x;
+    const u32 tile = lb_take_ticket(a.lb);
+    if (tile == LB_NO_TILE) return;
+    const TileDesc td = a.tiles[tile];
+    const BlockInfo bi = a.binfo[td.block];
+    const bool done = a.done[td.block] != 0;
+    u32 pv[KOLM_IPT], pk[KOLM_IPT];
+    u32 amask = 0;
+    if (!done) {
+        const u32 nf = CYCLIC ? a.nfac[td.block] : 0;
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) {
+            u32 r = tid * KOLM_IPT + i;
+            pv[i] = 0;
+            if (r < td.count && !(a.nr[td.start + r] >> 31)) { pv[i] = a.V[td.start + r]; amask |= 1u << i; }
+        }
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) {
+            pk[i] = 0;
+            if ((amask >> i) & 1u) {
+                u32 lp = pv[i] - bi.pbase, sp;
+                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); sp = fs + (u32)(((u64)(lp - fs) + a.h) % fl); }
+                else sp = lp + a.h;
+                pk[i] = bi.pbase + sp;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) if ((amask >> i) & 1u) pk[i] = a.rank[pk[i]];
+    }
+    const u32 cnt = __popc(amask);
+    u64 tot;
+    u64 incl = block_scan_incl((u64)cnt, 0ull, OpAdd(), s_warp, &tot);
+    if (tid < 32) {
+        u64 e = lb_exclusive(a.lb, tile, (td.flags & 1u) != 0, tot, 0ull, OpAdd());
+        if (tid == 0) s_excl = e;
+    }
+    __syncthreads();
+    u32 o = bi.pbase + (u32)s_excl + (u32)(incl - cnt);
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) if ((amask >> i) & 1u) { u32 d = o + __popc(amask & ((1u << i) - 1u)); a.K2[d] = pk[i]; a.V2[d] = pv[i]; }
+    if (tid == 0 && (td.flags & 2u)) a.active[td.block] = (u32)(s_excl + tot);
+}
+
+__global__ void __launch_bounds__(KOLM_THREADS) k_ls_key1(u32* __restrict__ K, const u32* __restrict__ V, const TileDesc* __restrict__ tiles,
+                                                          const u32* __restrict__ rank) {
+    TileDesc td = tiles[blockIdx.x];
+    u32 v[KOLM_IPT];
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) { u32 x = i * KOLM_THREADS + threadIdx.x; v[i] = x < td.count ? V[td.start + x] : 0xffffffffu; }
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) { u32 x = i * KOLM_THREADS + threadIdx.x; if (v[i] != 0xffffffffu) K[td.start + x] = rank[v[i]]; }
 }
 
 __global__ void k_round_end(u32* __restrict__ newcls, u32* __restrict__ done, const u32* __restrict__ active, int nblocks, int cyclic) {
@@ -748,15 +821,34 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     CUDA_TRY(cudaGetLastError());
     const int kbits = ceil_log2_u32(c->max_len > 1 ? c->max_len : 2);
     int rounds = 0;
+    static int ls_div = -1;
+    if (ls_div < 0) { const char* e = getenv("KOLM_LS_DIV"); ls_div = e ? atoi(e) : 8; }     // LS rounds once survivors < N / ls_div (0: never)
+    ra.survivors = c->d_stats + 4;
+    bool use_ls = false;
+    u32 *Kprev = nullptr, *Vprev = nullptr;                  // sorted records of the previous round (aligned with d_nr)
     for (u64 h = cyclic ? 4 : 3; rounds < 40; h <<= 1) {
         if (h > 0x7fffffffull) h = 0x7fffffffull;
-        // ---- gather active predecessors
-        KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
-        GatherArgs ga;
-        ga.sa = c->d_sa; ga.rank = c->d_rank; ga.single = c->d_single; ga.tiles = c->d_tiles; ga.binfo = c->d_binfo; ga.fstart = c->d_fstart;
-        ga.nfac = c->d_nfac; ga.done = c->d_done; ga.lb = c->d_lb; ga.K = c->d_k0; ga.V = c->d_v0; ga.active = c->d_active; ga.h = (u32)h;
-        if (cyclic) KL(c, KC_GATHER, N * 4, s, k_gather<true><<<lgrid, KOLM_THREADS, 0, s>>>(ga));
-        else KL(c, KC_GATHER, N * 4, s, k_gather<false><<<lgrid, KOLM_THREADS, 0, s>>>(ga));
+        if (!use_ls) {
+            // ---- Manber–Myers gather: stream the order, emit unsettled predecessors
+            KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+            GatherArgs ga;
+            ga.sa = c->d_sa; ga.rank = c->d_rank; ga.single = c->d_single; ga.tiles = c->d_tiles; ga.binfo = c->d_binfo; ga.fstart = c->d_fstart;
+            ga.nfac = c->d_nfac; ga.done = c->d_done; ga.lb = c->d_lb; ga.K = c->d_k0; ga.V = c->d_v0; ga.active = c->d_active; ga.h = (u32)h;
+            if (cyclic) KL(c, KC_GATHER, N * 4, s, k_gather<true><<<lgrid, KOLM_THREADS, 0, s>>>(ga));
+            else KL(c, KC_GATHER, N * 4, s, k_gather<false><<<lgrid, KOLM_THREADS, 0, s>>>(ga));
+        } else {
+            // ---- Larsson–Sadakane build from the survivors of the previous round (old active tile map)
+            const int pant = (int)c->h_stats[0];
+            u32* Ko = (Kprev == c->d_k0) ? c->d_k1 : c->d_k0;
+            u32* Vo = (Vprev == c->d_v0) ? c->d_v1 : c->d_v0;
+            KOLM_TRY(kolm_lb_reset(c, true, pant, &lgrid, s));
+            CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
+            LsArgs la;
+            la.V = Vprev; la.nr = c->d_nr; la.tiles = c->d_atiles; la.binfo = c->d_binfo; la.rank = c->d_rank; la.fstart = c->d_fstart;
+            la.nfac = c->d_nfac; la.done = c->d_done; la.lb = c->d_lb; la.K2 = Ko; la.V2 = Vo; la.active = c->d_active; la.h = (u32)h;
+            if (cyclic) KL(c, KC_GATHER, (i64)c->h_stats[1] * 12, s, k_ls_build<true><<<lgrid, KOLM_THREADS, 0, s>>>(la));
+            else KL(c, KC_GATHER, (i64)c->h_stats[1] * 12, s, k_ls_build<false><<<lgrid, KOLM_THREADS, 0, s>>>(la));
+        }
         KL(c, KC_PLAN, (i64)nb * 16, s, k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb));
         CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 12, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -767,8 +859,20 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         ++rounds;
         c->counters[4] += M;                                  // active records summed over rounds
         KL(c, KC_TILES, (i64)ant * 16, s, k_build_tiles<<<bgrid, 128, 0, s>>>(c->d_binfo, c->d_atile0, c->d_atilen, c->d_active, c->d_atiles, nb));
-        KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
+        if (!use_ls) {
+            KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
+        } else {
+            u32* Ko = (Kprev == c->d_k0) ? c->d_k1 : c->d_k0;
+            u32* Vo = (Vprev == c->d_v0) ? c->d_v1 : c->d_v0;
+            u32 *K1, *V1;
+            KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, Ko, Vo, Kprev, Vprev, &K1, &V1, s));
+            KL(c, KC_GATHER, M * 12, s, k_ls_key1<<<ant, KOLM_THREADS, 0, s>>>(K1, V1, c->d_atiles, c->d_rank));
+            u32* K1o = (K1 == c->d_k0) ? c->d_k1 : c->d_k0;
+            u32* V1o = (V1 == c->d_v0) ? c->d_v1 : c->d_v0;
+            KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, K1, V1, K1o, V1o, &K, &V, s));
+        }
         KOLM_TRY(kolm_lb_reset(c, true, ant, &lgrid, s));
+        CUDA_TRY(cudaMemsetAsync(c->d_stats + 4, 0, 4, s));
         ra.K = K; ra.V = V; ra.tiles = c->d_atiles; ra.h = (u32)h;
         if (cyclic) KL(c, KC_RERANK, M * 20, s, k_rerank<false, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
         else KL(c, KC_RERANK, M * 20, s, k_rerank<false, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
@@ -776,6 +880,13 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         KL(c, KC_PLAN, (i64)nb * 12, s, k_round_end<<<(nb + 255) / 256, 256, 0, s>>>(c->d_newcls, c->d_done, c->d_active, nb, cyclic ? 1 : 0));
         CUDA_TRY(cudaGetLastError());
         if (h >= 0x7fffffffull) break;
+        // survivors decide how the next round starts (and whether there is one)
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats + 4, c->d_stats + 4, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        const u64 surv = c->h_stats[4];
+        if (surv == 0) break;
+        Kprev = K; Vprev = V;
+        use_ls = ls_div > 0 && surv * (u64)ls_div < (u64)N;
     }
     if (rounds_out) *rounds_out = rounds;
     return KOLM_OK;
