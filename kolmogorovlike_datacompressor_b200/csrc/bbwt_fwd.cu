@@ -124,19 +124,25 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_boot_keys(const u8* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KOLM_THREADS) k_radix_hist(const u32* __restrict__ K, const TileDesc* __restrict__ tiles,
                                                              u32* __restrict__ thist, int shift, u32 mask) {
-    __shared__ u32 h[256];
+    __shared__ u32 wh[NWARPS][256];                        // warp-private histograms: conflicts only inside a warp
     TileDesc td = tiles[blockIdx.x];
-    h[threadIdx.x] = 0;
+    const u32 tid = threadIdx.x, w = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NWARPS; ++i) wh[i][tid] = 0;
     __syncthreads();
-    const u32* k = K + td.start;
-    for (u32 x0 = 0; x0 < td.count; x0 += KOLM_THREADS) {
-        u32 x = x0 + threadIdx.x;
-        u32 d = x < td.count ? ((k[x] >> shift) & mask) : 0xffffffffu;
-        u32 peers = __match_any_sync(FULL, d);
-        if (x < td.count && (peers & lanemask_lt()) == 0) atomicAdd(&h[d], __popc(peers));
+    const u32* k = K + td.start;                            // 128-byte aligned (padded index space)
+    const u32 full4 = td.count >> 2;
+    for (u32 x = tid; x < full4; x += KOLM_THREADS) {
+        uint4 q = reinterpret_cast<const uint4*>(k)[x];
+        atomicAdd(&wh[w][(q.x >> shift) & mask], 1u); atomicAdd(&wh[w][(q.y >> shift) & mask], 1u);
+        atomicAdd(&wh[w][(q.z >> shift) & mask], 1u); atomicAdd(&wh[w][(q.w >> shift) & mask], 1u);
     }
+    for (u32 x = (full4 << 2) + tid; x < td.count; x += KOLM_THREADS) atomicAdd(&wh[w][(k[x] >> shift) & mask], 1u);
     __syncthreads();
-    thist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+    u32 tot = 0;
+#pragma unroll
+    for (int i = 0; i < NWARPS; ++i) tot += wh[i][tid];
+    thist[(size_t)blockIdx.x * 256 + tid] = tot;
 }
 
 // radix pass 2/3: per block, turn tile histograms into block-relative scatter bases (digit-major, tile-minor)
