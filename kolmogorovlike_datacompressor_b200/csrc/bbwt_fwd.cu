@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
             if (BOOT) { if (ok[i]) { k2[i] = kk[i]; kk[i] = 0; } }
             else if (ok[i]) {
                 u32 lp = vv[i] - bi.pbase, sp;
-                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); sp = fs + (u32)(((u64)(lp - fs) + a.h) % fl); }
+                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
                 else sp = lp + a.h;                        // active plain elements always have a successor (see boot keys)
                 vv[i] = bi.pbase + sp;
             }
@@ -336,6 +336,16 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
             if (nxt) nextbits |= 1u << i;
         }
     }
+    // records of my items: issued before the scans so the loads overlap the block scan and the look-back
+    const u32* Vt = a.V + td.start;
+    const u32* Kt = a.K + td.start;
+    u32 val2[KOLM_IPT], key2r[KOLM_IPT];
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 r = tid * KOLM_IPT + i;
+        val2[i] = r < td.count ? Vt[r] : 0u;
+        key2r[i] = (!BOOT && r < td.count) ? Kt[r] : 0u;
+    }
     u64 agg = ((u64)lf << 31) | lh, tot;
     u64 incl = block_scan_incl(agg, 0ull, OpMax2(), s_warp, &tot);
     // exclusive for this thread = scan of preceding threads
@@ -351,25 +361,26 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
     __syncthreads();
     u64 ex = OpMax2()(s_excl, prev);
     u32 cf = (u32)(ex >> 31), ch = (u32)(ex & 0x7fffffffu);
-    const u32* Vt = a.V + td.start;
-    const u32* Kt = a.K + td.start;
+    u32 pos_[KOLM_IPT], nrk_[KOLM_IPT]; u32 singles = 0;
+#pragma unroll
+    for (int i = 0; i < KOLM_IPT; ++i) {
+        u32 tl1 = t0 + tid * KOLM_IPT + i + 1;
+        if ((firstbits >> i) & 1u) cf = tl1;
+        if ((headbits >> i) & 1u) ch = tl1;
+        pos_[i] = key2r[i] + (tl1 - cf);
+        nrk_[i] = key2r[i] + (ch - cf);
+        if (((headbits >> i) & 1u) && ((nextbits >> i) & 1u)) singles |= 1u << i;
+    }
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
         u32 r = tid * KOLM_IPT + i;
         if (r < td.count) {
-            u32 tl1 = t0 + r + 1;
-            if ((firstbits >> i) & 1u) cf = tl1;
-            if ((headbits >> i) & 1u) ch = tl1;
-            u32 key = BOOT ? 0u : Kt[r];
-            u32 val = Vt[r];
-            u32 pos = key + (tl1 - cf);
-            u32 nrk = key + (ch - cf);
-            bool single = ((headbits >> i) & 1u) && ((nextbits >> i) & 1u);
-            a.sa[bi.pbase + pos] = val;
+            const bool single = (singles >> i) & 1u;
+            a.sa[bi.pbase + pos_[i]] = val2[i];
             if (BOOT) {
-                a.rank[val] = nrk;
-                if (single) atomicOr(a.single + (val >> 5), 1u << (val & 31));
-            } else { a.nr[td.start + r] = nrk | (single ? 0x80000000u : 0u); nsurv += single ? 0u : 1u; }
+                a.rank[val2[i]] = nrk_[i];
+                if (single) atomicOr(a.single + (val2[i] >> 5), 1u << (val2[i] & 31));
+            } else { a.nr[td.start + r] = nrk_[i] | (single ? 0x80000000u : 0u); nsurv += single ? 0u : 1u; }
         }
     }
     // classes created in this tile (+ records left unsettled, packed in the high half)
@@ -497,7 +508,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_ls_build(LsArgs a) {
             pk[i] = 0;
             if ((amask >> i) & 1u) {
                 u32 lp = pv[i] - bi.pbase, sp;
-                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); sp = fs + (u32)(((u64)(lp - fs) + a.h) % fl); }
+                if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
                 else sp = lp + a.h;
                 pk[i] = bi.pbase + sp;
             }

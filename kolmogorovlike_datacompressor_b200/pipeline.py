@@ -38,7 +38,9 @@ class BlockPipeline:
             self.d_kf = torch.empty(3 * self.cap + 16 * self.max_blocks + 64, dtype=torch.uint8, device=self.device) if profile_kf else None
             self.d_k2 = torch.empty(9 * self.cap + 16 * self.max_blocks + 64, dtype=torch.uint8, device=self.device) if profile_k2 else None
         self.h_in = torch.empty(self.cap, dtype=torch.uint8).pin_memory()
-        self.h_out = None
+        self.h_kf = self.h_k2 = None
+        with torch.cuda.device(self.device):
+            self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     # ------------------------------------------------------------------
     def encode_device(self, x: torch.Tensor, off: Sequence[int], k2_flags: int = 0):
@@ -63,44 +65,96 @@ class BlockPipeline:
         r["bbwt"], r["mtf"] = self.d_bbwt, self.d_mtf
         return r
 
-    def encode_host(self, data, off: Sequence[int], k2_flags: int = 0):
-        """data: bytes / numpy uint8 / CPU uint8 tensor.  H2D, encode, D2H of the payloads (all inside this call)."""
-        n = int(off[-1])
+    def encode_host(self, data, off: Sequence[int], k2_flags: int = 0, chunks: Optional[int] = None):
+        """data: bytes / numpy uint8 / CPU uint8 tensor (pinned tensors are used in place).  Host in, host out: the batch is
+        cut into `chunks` consecutive groups of blocks; the H2D copy of group i+1 and the D2H copy of group i-1's payloads run
+        on their own streams while group i is being encoded."""
+        off = np.asarray(off, dtype=np.int64)
+        n, nb = int(off[-1]), len(off) - 1
         if isinstance(data, torch.Tensor):
             src = data
         else:
-            src = torch.from_numpy(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+            arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+            src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
         if not src.is_pinned():
             self.h_in[:n].copy_(src[:n])
             src = self.h_in
+        if chunks is None:
+            chunks = 1          # measured on B200: splitting the batch costs as much as the overlap hides (tools/e2e_chunks.py)
+        chunks = max(1, min(chunks, nb))
+        cuts = [int(round(i * nb / chunks)) for i in range(chunks + 1)]
+        if self.h_kf is None and self.profile_kf:
+            self.h_kf = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+        if self.h_k2 is None and self.profile_k2:
+            self.h_k2 = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+        kf_off = np.zeros(nb + 1, dtype=np.int64)
+        k2_off = np.zeros(nb + 1, dtype=np.int64)
+        kf_params, k2_sizes = [], []
         with torch.cuda.device(self.device):
-            self.d_in[:n].copy_(src[:n], non_blocking=True)
-            r = self.encode_device(self.d_in, off, k2_flags)
-            out = {}
-            total = 0
-            for key in ("kf", "k2"):
-                if key + "_payload" in r:
-                    m = int(r[key + "_off"][-1])
-                    total += m
-            if self.h_out is None or self.h_out.numel() < total:
-                self.h_out = torch.empty(max(total, 1) + (total >> 2), dtype=torch.uint8).pin_memory()
-            p = 0
-            for key in ("kf", "k2"):
-                if key + "_payload" in r:
-                    m = int(r[key + "_off"][-1])
-                    self.h_out[p:p + m].copy_(r[key + "_payload"][:m], non_blocking=True)
-                    out[key] = (p, m)
-                    p += m
-            torch.cuda.current_stream().synchronize()
-        res = {"h2d_bytes": n, "d2h_bytes": total}
-        for key, (p0, m) in out.items():
-            res[key + "_payload"] = self.h_out[p0:p0 + m]
-            res[key + "_off"] = r[key + "_off"]
-        if "kf_params" in r:
-            res["kf_params"] = r["kf_params"]
-        if "k2_sizes" in r:
-            res["k2_sizes"] = r["k2_sizes"]
+            main = torch.cuda.current_stream()
+            ev_in = []
+            with torch.cuda.stream(self.s_in):
+                self.s_in.wait_stream(main)
+                for ci in range(chunks):
+                    a, b = int(off[cuts[ci]]), int(off[cuts[ci + 1]])
+                    self.d_in[a:b].copy_(src[a:b], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(self.s_in)
+                    ev_in.append(e)
+            kpos = k2pos = 0
+            for ci in range(chunks):
+                b0, b1 = cuts[ci], cuts[ci + 1]
+                sub = off[b0:b1 + 1]
+                main.wait_event(ev_in[ci])
+                c = self.ctx
+                c.bbwt_forward(self.d_in, sub, out=self.d_bbwt)
+                c.mtf_encode(self.d_bbwt, sub, out=self.d_mtf)
+                done = []
+
+                def ship():
+                    # payloads go home on the output stream while the next kernels run
+                    with torch.cuda.stream(self.s_out):
+                        self.s_out.wait_stream(main)
+                        for hbuf, hpos, p_, m_ in done:
+                            hbuf[hpos:hpos + m_].copy_(p_[:m_], non_blocking=True)
+                    done.clear()
+                if self.profile_kf:
+                    base = (3 * int(sub[0]) + 16 * b0 + 15) & ~15
+                    p, o, prm = c.rice_kf_encode(self.d_mtf, sub, out=self.d_kf[base:], want_params=True)
+                    m = int(o[-1])
+                    kf_off[b0:b1 + 1] = kpos + o
+                    kf_params.append(prm)
+                    self.h_kf = self._grow(self.h_kf, kpos, m)
+                    done.append((self.h_kf, kpos, p, m))
+                    kpos += m
+                    ship()
+                if self.profile_k2:
+                    base = (9 * int(sub[0]) + 16 * b0 + 15) & ~15
+                    p, o, sz = c.rice_k2_encode(self.d_mtf, sub, k2_flags, out=self.d_k2[base:])
+                    m = int(o[-1])
+                    k2_off[b0:b1 + 1] = k2pos + o
+                    k2_sizes.append(sz)
+                    self.h_k2 = self._grow(self.h_k2, k2pos, m)
+                    done.append((self.h_k2, k2pos, p, m))
+                    k2pos += m
+                ship()
+            self.s_out.synchronize()
+            main.synchronize()
+        res = {"h2d_bytes": n, "d2h_bytes": kpos + k2pos, "chunks": chunks}
+        if self.profile_kf:
+            res["kf_payload"], res["kf_off"], res["kf_params"] = self.h_kf[:kpos], kf_off, np.concatenate(kf_params)
+        if self.profile_k2:
+            res["k2_payload"], res["k2_off"], res["k2_sizes"] = self.h_k2[:k2pos], k2_off, np.concatenate(k2_sizes)
         return res
+
+    def _grow(self, hbuf: torch.Tensor, used: int, more: int) -> torch.Tensor:
+        """Pinned host buffer with room for used+more bytes (payloads usually shrink; incompressible data can expand)."""
+        if used + more <= hbuf.numel():
+            return hbuf
+        self.s_out.synchronize()
+        nb = torch.empty(max(used + more, 2 * hbuf.numel()), dtype=torch.uint8).pin_memory()
+        nb[:used].copy_(hbuf[:used])
+        return nb
 
     # ------------------------------------------------------------------
     def profile(self, enable: bool):
