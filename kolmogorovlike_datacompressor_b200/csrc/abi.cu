@@ -14,6 +14,7 @@ void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
 #include "bbwt_inv.cu"
 #include "mtf.cu"
 #include "rice.cu"
+#include "rice_dec.cu"
 #include "lz77.cu"
 #include "residual.cu"
 #include "repair.cu"

@@ -421,7 +421,7 @@ struct GatherArgs {
 };
 
 template <bool CYCLIC>
-__global__ void __launch_bounds__(KOLM_THREADS) k_gather(GatherArgs a) {
+__global__ void __launch_bounds__(KOLM_THREADS, 5) k_gather(GatherArgs a) {
     __shared__ u64 s_warp[NWARPS];
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;

@@ -288,6 +288,63 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_dec(const u8* __restrict
     mtf_replay_tile(in + bi.ioff + t0, out + bi.ioff + t0, td.count, list[w], res[w]);
 }
 
+
+// decode, v2: thread-serial replay on the packed list (same layout as k_mtf_enc2).  PERM: start from the identity list and
+// store the final list (= the permutation the tile applies); otherwise start from the tile's entry list and write symbols.
+template <bool PERM>
+__global__ void __launch_bounds__(MTF2_THREADS) k_mtf_dec2(const u8* __restrict__ in, u8* __restrict__ out, const TileDesc* __restrict__ tiles,
+                                                           const BlockInfo* __restrict__ binfo, u8* __restrict__ tperm, int ntiles) {
+    __shared__ u32 lst[64][MTF2_THREADS];
+    const u32 tid = threadIdx.x;
+    const int tile = blockIdx.x * MTF2_THREADS + tid;
+    if (tile >= ntiles) return;
+    const u32* row = reinterpret_cast<const u32*>(tperm + (size_t)tile * 256);
+#pragma unroll 8
+    for (u32 k = 0; k < 64; ++k) lst[k][tid] = PERM ? (0x03020100u + 0x04040404u * k) : row[k];
+    const TileDesc td = tiles[tile];
+    const BlockInfo bi = binfo[td.block];
+    const u32 t0 = td.start - bi.pbase;
+    const u8* src = in + bi.ioff + t0;
+    u8* dst = PERM ? nullptr : out + bi.ioff + t0;
+    u32 w0 = lst[0][tid];
+    const bool aligned = ((uintptr_t)src & 15) == 0 && (PERM || ((uintptr_t)dst & 15) == 0);
+    for (u32 x0 = 0; x0 < td.count; x0 += 16) {
+        u32 inw[4], outw[4] = {0, 0, 0, 0};
+        const u32 nb = min(16u, td.count - x0);
+        if (aligned && nb == 16) { uint4 v = *reinterpret_cast<const uint4*>(src + x0); inw[0] = v.x; inw[1] = v.y; inw[2] = v.z; inw[3] = v.w; }
+        else { inw[0] = inw[1] = inw[2] = inw[3] = 0; for (u32 i = 0; i < nb; ++i) inw[i >> 2] |= (u32)src[x0 + i] << (8 * (i & 3)); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((u32)i < nb) {
+                const u32 idx = (inw[i >> 2] >> (8 * (i & 3))) & 0xFF;
+                u32 sym;
+                if (idx < 4) {
+                    sym = (w0 >> (8 * idx)) & 0xFF;
+                    if (idx) w0 = __byte_perm(w0, sym, idx == 1 ? 0x3204 : idx == 2 ? 0x3104 : 0x2104);
+                } else {
+                    const u32 k = idx >> 2, j = idx & 3;
+                    const u32 wk = lst[k][tid];
+                    sym = (wk >> (8 * j)) & 0xFF;
+                    u32 carry = w0 >> 24;
+                    w0 = (w0 << 8) | sym;
+                    for (u32 q = 1; q < k; ++q) { u32 w = lst[q][tid]; lst[q][tid] = (w << 8) | carry; carry = w >> 24; }
+                    lst[k][tid] = __byte_perm(wk, carry, j == 0 ? 0x3214 : j == 1 ? 0x3204 : j == 2 ? 0x3104 : 0x2104);
+                }
+                outw[i >> 2] |= sym << (8 * (i & 3));
+            }
+        }
+        if (!PERM) {
+            if (aligned && nb == 16) *reinterpret_cast<uint4*>(dst + x0) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+            else for (u32 i = 0; i < nb; ++i) dst[x0 + i] = (u8)(outw[i >> 2] >> (8 * (i & 3)));
+        }
+    }
+    if (PERM) {
+        u32* orow = reinterpret_cast<u32*>(tperm + (size_t)tile * 256);
+        orow[0] = w0;
+        for (u32 k = 1; k < 64; ++k) orow[k] = lst[k][tid];
+    }
+}
+
 int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t s) {
     const int nt = c->ntiles, nb = c->nblocks;
     if (!nt) return KOLM_OK;
@@ -304,9 +361,14 @@ int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t 
     } else {
         u8* tperm = (u8*)c->d_thist;
         const i64 N = c->total_bytes;
-        KL(c, KC_MTF_PRE, N + (i64)nt * 256, s, k_mtf_dec_perm<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, c->d_tiles, c->d_binfo, tperm, nt));
+        static int v2 = -1;
+        if (v2 < 0) { const char* e = getenv("KOLM_MTF_V2"); v2 = e ? atoi(e) : 1; }
+        const int g2 = (nt + MTF2_THREADS - 1) / MTF2_THREADS;
+        if (v2) KL(c, KC_MTF_PRE, N + (i64)nt * 256, s, k_mtf_dec2<true><<<g2, MTF2_THREADS, 0, s>>>(in, nullptr, c->d_tiles, c->d_binfo, tperm, nt));
+        else KL(c, KC_MTF_PRE, N + (i64)nt * 256, s, k_mtf_dec_perm<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, c->d_tiles, c->d_binfo, tperm, nt));
         KL(c, KC_MTF_SCAN, (i64)nt * 512, s, k_mtf_dec_compose<<<sgrid, 256, 0, s>>>(tperm, c->d_btile0, c->d_btilen, nb));
-        KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 256, s, k_mtf_dec<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt));
+        if (v2) KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 256, s, k_mtf_dec2<false><<<g2, MTF2_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt));
+        else KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 256, s, k_mtf_dec<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt));
     }
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;

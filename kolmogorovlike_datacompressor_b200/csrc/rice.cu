@@ -608,24 +608,3 @@ static int rice_dec_finish(kolm_ctx* c, cudaStream_t s) {
     return KOLM_OK;
 }
 
-int kolm_rice_kf_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u8* mtf_out, cudaStream_t s) {
-    const int nb = c->nblocks;
-    if (!nb) return KOLM_OK;
-    memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
-    CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
-    if (c->total_bytes) CUDA_TRY(cudaMemsetAsync(mtf_out + c->h_binfo[0].ioff, 0, (size_t)c->total_bytes, s));
-    KL(c, KC_RICE_PACK, c->total_bytes + pay_off[nb] - pay_off[0], s, k_rice_kf_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, mtf_out, c->d_err, nb));
-    CUDA_TRY(cudaGetLastError());
-    return rice_dec_finish(c, s);
-}
-
-int kolm_rice_k2_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, int flags, u8* mtf_out, cudaStream_t s) {
-    const int nb = c->nblocks;
-    if (k2_slot(flags) < 0) return KOLM_E_ARG;
-    if (!nb) return KOLM_OK;
-    memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
-    CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
-    KL(c, KC_RICE_PACK, c->total_bytes + pay_off[nb] - pay_off[0], s, k_rice_k2_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, mtf_out, c->d_err, nb, flags));
-    CUDA_TRY(cudaGetLastError());
-    return rice_dec_finish(c, s);
-}

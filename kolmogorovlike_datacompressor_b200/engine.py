@@ -319,6 +319,8 @@ class Engine:
                         else:
                             raise NotImplementedError("decoder for method '%s' is outside the GPU hot path (SURVEY §8 row a17)" % nme)
                     except _lib.KolmError as err:
+                        if err.code == -4 and not nme.startswith("kf_"):
+                            raise ValueError(str(err)) from err     # V22's readers raise ValueError on truncation (v2-2.py:131-132, 1437-1447)
                         raise_like_reference(err)
                     hb = self._host(y, int(off[-1]))
                 for q, t in enumerate(sub):

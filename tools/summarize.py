@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """Print a compact summary of bench.py's JSON line (stdin).  usage: python bench.py ... | python tools/summarize.py [label]"""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 
 label = sys.argv[1] if len(sys.argv) > 1 else ""
 line = [l for l in sys.stdin.read().splitlines() if l.startswith("{")][-1]
