@@ -242,6 +242,27 @@ def run_ours(args):
     e2e = {"value": round(world * nbytes * e2e_steps / e2e_s / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": res["h2d_bytes"] * world,
            "d2h_bytes_per_step": res["d2h_bytes"] * world, "steps": e2e_steps}
 
+    # ---- decode chain (device resident): KF payload -> Rice/gamma parse -> inverse MTF -> inverse BBWT --------------
+    c = pipe.ctx
+    kf_dev, kf_off = r["kf_payload"], r["kf_off"]
+    def decode_once():
+        m_ = c.rice_kf_decode(kf_dev, kf_off, off)
+        return c.bbwt_inverse(c.mtf_decode(m_, off), off)
+    x = decode_once()
+    roundtrip_ok = bool(torch.equal(x[:nbytes], d_in[:nbytes]))
+    barrier()
+    dsteps = max(1, min(args.steps, 3))
+    dv0, dv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dv0.record()
+    for _ in range(dsteps):
+        decode_once()
+    dv1.record()
+    barrier()
+    dms = gmax(dv0.elapsed_time(dv1))
+    decode = {"metric": "decompress_throughput_rice_mtf_bbwt", "value": round(world * nbytes * dsteps / (dms / 1e3) / 1e6, 2), "unit": UNIT,
+              "ms_per_step": round(dms / dsteps, 3), "steps": dsteps, "roundtrip_bit_exact": roundtrip_ok}
+    del x
+
     # ---- per-kernel event timing (one extra, untimed-for-value step) -----------------------------
     pipe.profile_reset()
     pipe.profile(True)
@@ -283,7 +304,7 @@ def run_ours(args):
                            "corpus_mib_per_gpu": args.mib, "block_bytes": block, "blocks_per_gpu": int(nblocks),
                            "l2": "inputs (256 MiB) and scratch (GBs) are larger than L2, no flush needed",
                            "outputs": {"kf_payload_bytes": kf_bytes, "k2_payload_bytes": k2_bytes}},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "decode": decode}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
