@@ -14,7 +14,7 @@
 #include "common.cuh"
 
 #define RD_CHUNK 1024u            // bits per chunk
-#define RD_MAX_ITERS 24
+#define RD_MAX_ITERS 64
 
 struct RdecArgs {
     const u8* pay; const i64* pay_off; const BlockInfo* binfo;
@@ -96,26 +96,38 @@ __device__ __forceinline__ KfHdr kf_header(const BitWin& bw) {
 
 template <bool KF>
 __global__ void __launch_bounds__(128) k_rdec_iter(RdecArgs a, int first_iter) {
-    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.nchunks) return;
     const u32 b = a.cblock[c];
-    const u32 lc = c - a.cfirst[b];
+    const u32 c0 = a.cfirst[b];
     BitWin bw; bw.p = a.pay + a.pay_off[b]; bw.nbits = (u64)(a.pay_off[b + 1] - a.pay_off[b]) * 8;
-    const u64 cend = (u64)(lc + 1) * RD_CHUNK;
+    const u32 nc = (u32)((bw.nbits + RD_CHUNK - 1) / RD_CHUNK);
+    u32 lc = c - c0;
     u64 e;
     if (lc == 0) e = KF ? 10 : 0;
     else e = first_iter ? (u64)lc * RD_CHUNK : a.exitp[c - 1];
     if (!first_iter && a.entry[c] == (u32)e) return;
     KfHdr h; if (KF) h = kf_header(bw);
-    u64 pos = e, cnt = 0; bool bad = false;
-    while (pos < cend) {
-        u64 np, ns = 1; u32 val;
-        bool ok = KF ? kf_token(bw, pos, h.k0, h.k1, h.urz, h.urn, np, ns, val, bad) : k2_token(bw, pos, np, val, bad);
-        if (!ok) { pos = bw.nbits > cend ? bw.nbits : cend; break; }      // truncated token: nothing more starts in this block
-        cnt += ns; pos = np;
+    // Decode my chunk from the new entry; if that moves my exit, keep walking into the following chunks until the parse
+    // meets an entry that is already recorded there (re-synchronised) — periodic streams can otherwise hold a shifted,
+    // self-consistent parse for many chunks and would need one sweep per chunk.
+    for (u32 walked = 0;; ++walked) {
+        const u64 cend = (u64)(lc + 1) * RD_CHUNK;
+        u64 pos = e, cnt = 0; bool bad = false;
+        while (pos < cend) {
+            u64 np, ns = 1; u32 val;
+            bool ok = KF ? kf_token(bw, pos, h.k0, h.k1, h.urz, h.urn, np, ns, val, bad) : k2_token(bw, pos, np, val, bad);
+            if (!ok) { pos = bw.nbits > cend ? bw.nbits : cend; break; }      // truncated token: nothing more starts in this block
+            cnt += ns; pos = np;
+        }
+        if (cnt > 0xffffffffull) cnt = 0xffffffffull;
+        a.entry[c0 + lc] = (u32)e; a.exitp[c0 + lc] = (u32)pos; a.count[c0 + lc] = (u32)cnt;
+        if (first_iter) break;
+        ++lc;
+        if (lc >= nc || walked >= 4096u) break;
+        if (a.entry[c0 + lc] == (u32)pos) break;                               // the next chunk already starts there
+        e = pos;
     }
-    if (cnt > 0xffffffffull) cnt = 0xffffffffull;
-    a.entry[c] = (u32)e; a.exitp[c] = (u32)pos; a.count[c] = (u32)cnt;
     *a.changed = 1;
 }
 
