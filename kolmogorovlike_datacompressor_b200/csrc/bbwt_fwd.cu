@@ -23,6 +23,9 @@
 #include "common.cuh"
 
 #define NWARPS (KOLM_THREADS / 32)
+#ifndef KOLM_BALLOT_MATCH
+#define KOLM_BALLOT_MATCH 0     // measured: 8 ballots per item are slower than MATCH.ANY on sm_100a (scatter 13.9 vs 11.9 ms)
+#endif
 #define FULL 0xffffffffu
 #define SIDX(x) ((x) + ((x) >> 4))                    // smem padding: 1 word per 16 (IPT) -> conflict-free blocked access
 #define SPAD (KOLM_TILE + 2 + ((KOLM_TILE + 2) >> 4) + 1)
@@ -206,7 +209,14 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __res
         bool valid = idx < td.count;
         key[k] = valid ? sk[idx] : 0; val[k] = valid ? sv[idx] : 0;
         u32 d = valid ? ((key[k] >> shift) & mask) : 0xffffffffu;
+#if KOLM_BALLOT_MATCH
+        u32 peers = __ballot_sync(FULL, valid);
+        if (!valid) peers = ~peers;
+#pragma unroll
+        for (int bb = 0; bb < 8; ++bb) { u32 m = __ballot_sync(FULL, (d >> bb) & 1u); peers &= ((d >> bb) & 1u) ? m : ~m; }
+#else
         u32 peers = __match_any_sync(FULL, d);
+#endif
         u32 lt = __popc(peers & lanemask_lt());
         u32 old = 0;
         if (valid && lt == 0) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
@@ -267,7 +277,7 @@ struct RerankArgs {
 };
 
 template <bool BOOT, bool CYCLIC>
-__global__ void __launch_bounds__(KOLM_THREADS) k_rerank(RerankArgs a) {
+__global__ void __launch_bounds__(KOLM_THREADS, 4) k_rerank(RerankArgs a) {
     __shared__ u32 sk[SPAD];
     __shared__ u32 sk2[SPAD];
     __shared__ u64 s_warp[NWARPS];
