@@ -122,6 +122,70 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_boot_keys(const u8* __restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Alphabet compression for the cyclic bootstrap: a block that uses sigma distinct byte values needs ceil(log2 sigma)
+// bits per symbol, so a 32-bit key holds h0 = floor(32 / bits) >= 4 symbols of the rotation instead of 4 bytes (text:
+// sigma ~ 28 -> 5 bits -> h0 = 6).  Dense ranks preserve byte order, so the keys stay order preserving; h0 is the minimum
+// over the batch because every round uses one h for all blocks.
+//   per block in bacc: u32 mask[8] at u64 slot 0..3, u8 rmap[256] at u64 slot 8..39, u32 bits at u64 slot 40
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KOLM_THREADS) k_alpha_mask(const u8* __restrict__ in, const TileDesc* __restrict__ tiles,
+                                                             const BlockInfo* __restrict__ binfo, u64* __restrict__ bacc) {
+    __shared__ u32 m[8];
+    TileDesc td = tiles[blockIdx.x];
+    BlockInfo bi = binfo[td.block];
+    if (threadIdx.x < 8) m[threadIdx.x] = 0;
+    __syncthreads();
+    const u8* src = in + bi.ioff + (td.start - bi.pbase);
+    u32 loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) { u32 b = src[x]; 
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if ((b >> 5) == (u32)k) loc[k] |= 1u << (b & 31); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { u32 v = __reduce_or_sync(FULL, loc[k]); if ((threadIdx.x & 31) == 0 && v) atomicOr(&m[k], v); }
+    __syncthreads();
+    if (threadIdx.x < 8 && m[threadIdx.x]) atomicOr(reinterpret_cast<u32*>(bacc + (size_t)td.block * 64) + threadIdx.x, m[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_alpha_map(u64* __restrict__ bacc, const BlockInfo* __restrict__ binfo, u32* __restrict__ min_syms, int nblocks) {
+    const int b = blockIdx.x;
+    if (b >= nblocks) return;
+    u32* mask = reinterpret_cast<u32*>(bacc + (size_t)b * 64);
+    u8* rmap = reinterpret_cast<u8*>(bacc + (size_t)b * 64 + 8);
+    const u32 c = threadIdx.x;
+    u32 below = 0;
+    for (u32 k = 0; k < (c >> 5); ++k) below += __popc(mask[k]);
+    below += __popc(mask[c >> 5] & ((1u << (c & 31)) - 1u));
+    rmap[c] = (u8)below;
+    if (c == 255) {
+        u32 sigma = below + ((mask[7] >> 31) & 1u);
+        u32 bits = 1; while ((1u << bits) < sigma) ++bits;
+        reinterpret_cast<u32*>(bacc + (size_t)b * 64 + 40)[0] = bits;
+        if (binfo[b].len) atomicMin(min_syms, 32u / bits);
+    }
+}
+
+__global__ void __launch_bounds__(KOLM_THREADS) k_boot_keys_alpha(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo,
+                                                                  const TileDesc* __restrict__ tiles, const u32* __restrict__ fstart,
+                                                                  const u32* __restrict__ nfac, const u64* __restrict__ bacc, u32 h0,
+                                                                  u32* __restrict__ K, u32* __restrict__ V) {
+    __shared__ u8 rmap[256];
+    TileDesc td = tiles[blockIdx.x];
+    BlockInfo bi = binfo[td.block];
+    rmap[threadIdx.x] = reinterpret_cast<const u8*>(bacc + (size_t)td.block * 64 + 8)[threadIdx.x];
+    const u32 bits = reinterpret_cast<const u32*>(bacc + (size_t)td.block * 64 + 40)[0];
+    __syncthreads();
+    const u8* src = in + bi.ioff;
+    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
+        u32 pg = td.start + x, lp = pg - bi.pbase, key = 0;
+        u32 fs, fl; find_factor(fstart + bi.pbase, nfac[td.block], bi.len, lp, fs, fl);
+        u32 o = lp - fs;
+        for (u32 t = 0; t < h0; ++t) { key = (key << bits) | rmap[src[fs + o]]; if (++o == fl) o = 0; }
+        K[pg] = key; V[pg] = pg;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // radix pass 1/3: per-tile digit histogram
 // ------------------------------------------------------------------------------------------------
@@ -833,7 +897,22 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     int bgrid = nb < 1024 ? nb : 1024;
     // ---- bootstrap
     const i64 N = c->total_bytes;
-    if (cyclic) KL(c, KC_BOOT, N * 9, s, k_boot_keys<true><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
+    u32 h0 = cyclic ? 4 : 3;
+    static int alpha = -1;
+    if (alpha < 0) { const char* e = getenv("KOLM_ALPHA_BOOT"); alpha = e ? atoi(e) : 1; }
+    if (cyclic && alpha) {
+        // dense symbol ranks: more than 4 symbols per 32-bit bootstrap key when the batch's alphabets are small
+        CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * 64 * 8, s));
+        CUDA_TRY(cudaMemsetAsync(c->d_stats + 9, 0xff, 4, s));
+        KL(c, KC_BOOT, N, s, k_alpha_mask<<<nt, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_bacc));
+        KL(c, KC_BOOT, (i64)nb * 512, s, k_alpha_map<<<nb, 256, 0, s>>>(c->d_bacc, c->d_binfo, c->d_stats + 9, nb));
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats + 9, c->d_stats + 9, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        u32 syms = c->h_stats[9];
+        if (syms != 0xffffffffu && syms > 4) h0 = syms > 32 ? 32 : syms;
+    }
+    if (cyclic && h0 > 4) KL(c, KC_BOOT, N * 9, s, k_boot_keys_alpha<<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_bacc, h0, c->d_k0, c->d_v0));
+    else if (cyclic) KL(c, KC_BOOT, N * 9, s, k_boot_keys<true><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
     else KL(c, KC_BOOT, N * 9, s, k_boot_keys<false><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
     u32 *K, *V;
     KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, cyclic ? 32 : 27, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
@@ -853,7 +932,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     ra.survivors = c->d_stats + 4;
     bool use_ls = false;
     u32 *Kprev = nullptr, *Vprev = nullptr;                  // sorted records of the previous round (aligned with d_nr)
-    for (u64 h = cyclic ? 4 : 3; rounds < 40; h <<= 1) {
+    for (u64 h = h0; rounds < 40; h <<= 1) {
         if (h > 0x7fffffffull) h = 0x7fffffffull;
         if (!use_ls) {
             // ---- Manber–Myers gather: stream the order, emit unsettled predecessors
