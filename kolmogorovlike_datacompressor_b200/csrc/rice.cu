@@ -163,7 +163,7 @@ __device__ __forceinline__ u32 scan_last_nonzero(u32 mine, u64* lb, u32 tile, bo
 // cost pass: every candidate parameterisation in one read of the MTF bytes
 // ---------------------------------------------------------------------------------------------
 template <bool KF, bool K2>
-__global__ void __launch_bounds__(KOLM_THREADS) k_rice_cost(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+__global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                             const BlockInfo* __restrict__ binfo, u64* lb, u64* __restrict__ tacc) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_last[KOLM_THREADS / 32];
@@ -321,7 +321,7 @@ __global__ void k_zero_words(u32* __restrict__ out, const i64* __restrict__ tota
 // ---------------------------------------------------------------------------------------------
 // KF pack (KF.py:662-684)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KOLM_THREADS) k_rice_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+__global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                                const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
                                                                u32* __restrict__ out) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_rice_kf_pack(const u8* __restr
 // ---------------------------------------------------------------------------------------------
 // V22 Rice(k=2) pack of T_flags(mtf)  (V22.py:1413-1421)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KOLM_THREADS) k_rice_k2_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+__global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_k2_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                                const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
                                                                u32* __restrict__ out, int flags) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
