@@ -96,8 +96,22 @@ struct BitStage {
     }
     __device__ __forceinline__ void bits(u64 bitpos, u32 value, u32 n) const {      // n in 1..32, value < 2^n
         u64 w = bitpos >> 5; u32 o = (u32)bitpos & 31;
+        if (o + n <= 32) { word(w, value << (32 - n - o)); return; }                  // inside one word: one OR
         u64 v = (u64)value << (64 - n - o);
         word(w, (u32)(v >> 32)); word(w + 1, (u32)v);
+    }
+    // whole tokens in one OR when they fit 32 bits: [tag] q ones, 0, k bits   /   [tag] (b-1) zeros, b bits
+    __device__ __forceinline__ void rice_tok(u64 bitpos, u32 tagbits, u32 tag, u64 x, u32 k) const {
+        u64 q = x >> k; u64 total = tagbits + q + 1 + k;
+        if (total <= 32) {
+            u32 code = (tag << (total - tagbits)) | ((((u32)1 << q) - 1u) << (k + 1)) | (u32)(x & ((1u << k) - 1u));
+            bits(bitpos, code, (u32)total);
+        } else { if (tagbits && tag) bits(bitpos, 1, 1); rice(bitpos + tagbits, x, k); }
+    }
+    __device__ __forceinline__ void gamma_tok(u64 bitpos, u32 tag, u32 x) const {      // 1 tag bit + gamma(x)
+        u32 b = bitlen32(x);
+        if (2 * b <= 32) bits(bitpos, (tag << (2 * b - 1)) | x, 2 * b);
+        else { if (tag) bits(bitpos, 1, 1); gamma(bitpos + 1, x); }
     }
     __device__ __forceinline__ void ones(u64 bitpos, u64 q) const {
         while (q >= 32) { bits(bitpos, 0xffffffffu, 32); bitpos += 32; q -= 32; }
@@ -380,13 +394,12 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
             if (v[i]) {
                 ln = pos1;
                 u32 x = v[i] - 1;
-                st.bits(bp, 1, 1);
-                if (urn) { st.rice(bp + 1, x, k1); bp += 1 + (u64)(x >> k1) + 1 + k1; }
-                else { st.gamma(bp + 1, v[i]); bp += 1 + 2 * bitlen32(v[i]) - 1; }
+                if (urn) { st.rice_tok(bp, 1, 1, x, k1); bp += 1 + (u64)(x >> k1) + 1 + k1; }
+                else { st.gamma_tok(bp, 1, v[i]); bp += 2 * bitlen32(v[i]); }
             } else if (v[i + 1] != 0) {
-                u32 run = pos1 - ln;                         // tag bit 0: nothing to write
-                if (urz) { st.rice(bp + 1, run, k0); bp += 1 + (u64)(run >> k0) + 1 + k0; }
-                else { st.gamma(bp + 1, run); bp += 1 + 2 * bitlen32(run) - 1; }
+                u32 run = pos1 - ln;
+                if (urz) { st.rice_tok(bp, 1, 0, run, k0); bp += 1 + (u64)(run >> k0) + 1 + k0; }
+                else { st.gamma_tok(bp, 0, run); bp += 2 * bitlen32(run); }
             }
         }
     }
@@ -442,8 +455,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_k2_pack(const u8* __re
     for (int i = 0; i < KOLM_IPT; ++i) {
         if ((nsym_mask >> i) & 1u) {
             u32 t = sym[i], q = t >> 2;
-            st.ones(bp, q);
-            st.bits(bp + q, t & 3u, 3);                     // the terminating 0 and the 2 remainder bits
+            st.rice_tok(bp, 0, 0, t, 2);                    // q ones, the terminating 0 and the 2 remainder bits
             bp += q + 3;
         }
     }
