@@ -121,6 +121,17 @@ int kolm_repair_max_block(void);
 int64_t kolm_cdc_kf(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap);
 int64_t kolm_cdc_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap);
 
+/* Payload gather after model selection: block b's winning payload is len[b] bytes at DEVICE address src_addr[b] (any of
+ * the per-model payload buffers, or the input itself for RAW); they are laid out back to back at `out` in block order —
+ * the payload area of a container (KF.py:896-901; V22.py:2443-2444).  src_addr/len: HOST arrays; out_off (HOST, nblocks+1)
+ * receives the exclusive prefix sums. */
+int kolm_gather_payloads(kolm_ctx* ctx, const uint64_t* src_addr, const int64_t* len, int nblocks, uint8_t* out, int64_t* out_off,
+                         kolm_stream_t stream);
+
+/* Batched device-to-device copy: len[b] bytes from src_addr[b] to dst_addr[b] (absolute DEVICE addresses in HOST arrays).
+ * Used on the decode side to put each method group's decoded blocks at their final offsets. */
+int kolm_copy_blocks(kolm_ctx* ctx, const uint64_t* src_addr, const uint64_t* dst_addr, const int64_t* len, int nblocks, kolm_stream_t stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
  * rounds, [2] kernels launched since the last profile reset, [3] records sorted (sum over rounds) */

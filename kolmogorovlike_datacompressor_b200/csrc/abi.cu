@@ -363,3 +363,78 @@ int64_t kolm_cdc_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t a
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// payload gather (device part): after model selection the winners' payloads live in different
+// per-model buffers; one kernel lays them out back to back in block order (= the container's payload area).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_payloads(const u64* __restrict__ src, const i64* __restrict__ len, const i64* __restrict__ dst_off,
+                                                         u8* __restrict__ out, int nblocks) {
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const u8* s = reinterpret_cast<const u8*>(src[b]);
+        u8* d = out + dst_off[b];
+        const i64 n = len[b];
+        // 16-byte body when source and destination are mutually aligned, bytes otherwise
+        if ((((uintptr_t)s ^ (uintptr_t)d) & 15) == 0) {
+            i64 head = (16 - ((uintptr_t)s & 15)) & 15; if (head > n) head = n;
+            for (i64 i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+            const i64 body = (n - head) >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(s + head); uint4* d4 = reinterpret_cast<uint4*>(d + head);
+            for (i64 i = threadIdx.x; i < body; i += blockDim.x) d4[i] = s4[i];
+            for (i64 i = head + (body << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        } else for (i64 i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+}
+
+extern "C" int kolm_gather_payloads(kolm_ctx* c, const uint64_t* src_addr, const int64_t* len, int nblocks, uint8_t* out, int64_t* out_off,
+                                    kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || nblocks < 0 || nblocks > c->max_blocks) return KOLM_E_ARG;
+    if (!nblocks) { out_off[0] = 0; return KOLM_OK; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(s));                    // pinned staging reuse
+    // staging in the pinned accumulator mirror: [src | len | off], each nblocks (+1) 8-byte words
+    u64* hs = c->h_bacc; i64* hl = (i64*)(c->h_bacc + nblocks); i64* ho = (i64*)(c->h_bacc + 2 * (size_t)nblocks);
+    i64 run = 0;
+    for (int b = 0; b < nblocks; ++b) { hs[b] = src_addr[b]; hl[b] = len[b]; ho[b] = run; out_off[b] = run; run += len[b]; }
+    out_off[nblocks] = run;
+    u64* ds = c->d_bacc; i64* dl = (i64*)(c->d_bacc + nblocks); i64* dofs = (i64*)(c->d_bacc + 2 * (size_t)nblocks);
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, (size_t)nblocks * 24, cudaMemcpyHostToDevice, s));
+    int grid = nblocks < 8 * c->sm_count ? nblocks : 8 * c->sm_count;
+    KL(c, KC_MISC, run * 2, s, k_gather_payloads<<<grid, 256, 0, s>>>(ds, dl, dofs, out, nblocks));
+    CUDA_TRY(cudaGetLastError());
+    return KOLM_OK;
+}
+
+// general batched device-to-device copy: block b = len[b] bytes from src_addr[b] to dst_addr[b] (absolute device addresses, HOST arrays)
+__global__ void __launch_bounds__(256) k_copy_blocks(const u64* __restrict__ src, const u64* __restrict__ dst, const i64* __restrict__ len, int nblocks) {
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const u8* s = reinterpret_cast<const u8*>(src[b]);
+        u8* d = reinterpret_cast<u8*>(dst[b]);
+        const i64 n = len[b];
+        if ((((uintptr_t)s ^ (uintptr_t)d) & 15) == 0) {
+            i64 head = (16 - ((uintptr_t)s & 15)) & 15; if (head > n) head = n;
+            for (i64 i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+            const i64 body = (n - head) >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(s + head); uint4* d4 = reinterpret_cast<uint4*>(d + head);
+            for (i64 i = threadIdx.x; i < body; i += blockDim.x) d4[i] = s4[i];
+            for (i64 i = head + (body << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        } else for (i64 i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+}
+
+extern "C" int kolm_copy_blocks(kolm_ctx* c, const uint64_t* src_addr, const uint64_t* dst_addr, const int64_t* len, int nblocks, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || nblocks < 0 || nblocks > c->max_blocks) return KOLM_E_ARG;
+    if (!nblocks) return KOLM_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    u64* hs = c->h_bacc; u64* hd = c->h_bacc + nblocks; i64* hl = (i64*)(c->h_bacc + 2 * (size_t)nblocks);
+    i64 total = 0;
+    for (int b = 0; b < nblocks; ++b) { hs[b] = src_addr[b]; hd[b] = dst_addr[b]; hl[b] = len[b]; total += len[b]; }
+    CUDA_TRY(cudaMemcpyAsync(c->d_bacc, c->h_bacc, (size_t)nblocks * 24, cudaMemcpyHostToDevice, s));
+    int grid = nblocks < 8 * c->sm_count ? nblocks : 8 * c->sm_count;
+    KL(c, KC_MISC, total * 2, s, k_copy_blocks<<<grid, 256, 0, s>>>(c->d_bacc, c->d_bacc + nblocks, (const i64*)(c->d_bacc + 2 * (size_t)nblocks), nblocks));
+    CUDA_TRY(cudaGetLastError());
+    return KOLM_OK;
+}

@@ -284,6 +284,54 @@ __global__ void k_lz_dec(const u8* __restrict__ pay, const i64* __restrict__ pay
     err[b] = e;
 }
 
+
+// decode: one warp per block.  Tokens are parsed in order, but a match is copied by all 32 lanes at once: the copied region is
+// periodic with period `dist`, so byte k of the match equals out[o - dist + (k mod dist)] — every lane reads only bytes that
+// were complete before the token started, overlapping matches included.
+__global__ void __launch_bounds__(128) k_lz_dec_warp(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo,
+                                                     u8* __restrict__ out, int* __restrict__ err, int nblocks, u32 window_check) {
+    const u32 lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const BlockInfo bi = binfo[b];
+    const u8* d = pay + pay_off[b];
+    const i64 n = pay_off[b + 1] - pay_off[b];
+    u8* dst = out + bi.ioff;
+    i64 i = 0; u32 o = 0; int e = KOLM_OK;
+    while (i < n && o < bi.len) {
+        // every lane parses the (short) token header redundantly from the same addresses (broadcast loads)
+        u8 flag = d[i++];
+        if (flag == 0) {
+            if (i >= n) { e = KOLM_E_TRUNCATED; break; }
+            if (lane == 0) dst[o] = d[i];
+            ++i; ++o;
+        } else if (flag == 1) {
+            u64 v[2];
+            for (int q = 0; q < 2 && !e; ++q) {
+                u64 r = 0; int sh = 0;
+                for (;;) { if (i >= n) { e = KOLM_E_TRUNCATED; break; } u8 x = d[i++]; if (sh < 64) r |= (u64)(x & 0x7F) << sh; if (!(x & 0x80)) break; sh += 7; }
+                v[q] = r;
+            }
+            if (e) break;
+            u64 len = v[0], dist = v[1];
+            if (dist == 0) { e = KOLM_E_CORRUPT; break; }
+            u32 avail = window_check ? min(o, window_check) : o;
+            u64 room = (u64)(bi.len - o);
+            u32 cnt = (u32)(len < room ? len : room);
+            if (cnt && dist > avail) { e = KOLM_E_CORRUPT; break; }       // reference: "distance beyond window" / "Invalid LZ77 distance"
+            __syncwarp();                                                  // earlier literal / match stores are visible to all lanes
+            const u32 dd = (u32)dist;
+            const u8* srcp = dst + o - dd;
+            if (dd >= 32) { for (u32 k = lane; k < cnt; k += 32) dst[o + k] = srcp[k % dd]; }
+            else { for (u32 k = lane; k < cnt; k += 32) dst[o + k] = srcp[k % dd]; }
+            o += cnt;
+            __syncwarp();
+        } else { e = KOLM_E_CORRUPT; break; }
+    }
+    if (!e && o != bi.len) e = KOLM_E_CORRUPT;
+    if (lane == 0) err[b] = e;
+}
+
 int kolm_lz77_enc_impl(kolm_ctx* c, const u8* in, u32 window, u32 maxlen, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
     const int nb = c->nblocks, nt = c->ntiles;
     if (!nb) { out_off[0] = 0; return KOLM_OK; }
@@ -337,7 +385,10 @@ int kolm_lz77_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u32 windo
     if (!nb) return KOLM_OK;
     memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
     CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
-    KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
+    static int warpdec = -1;
+    if (warpdec < 0) { const char* e = getenv("KOLM_LZ_DEC_WARP"); warpdec = e ? atoi(e) : 1; }
+    if (warpdec) KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec_warp<<<(nb + 3) / 4, 128, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
+    else KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
     CUDA_TRY(cudaGetLastError());
     return rice_dec_finish(c, s);
 }

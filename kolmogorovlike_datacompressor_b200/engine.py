@@ -42,7 +42,7 @@ def cdc_boundaries(which: str, data: bytes, mn: int, avg: int, mx: int) -> List[
     L = _lib.lib()
     cap = n // max(1, mn) + 4
     ends = np.zeros(cap, dtype=np.int64)
-    buf = (C.c_uint8 * n).from_buffer_copy(data)
+    buf = C.cast(C.c_char_p(data), C.c_void_p)              # bytes are immutable and contiguous: no copy
     k = getattr(L, "kolm_cdc_" + which)(buf, n, mn, avg, mx, ends.ctypes.data_as(C.POINTER(C.c_int64)), cap)
     if k < 0:
         if k == -2:
@@ -101,10 +101,13 @@ class Engine:
             i = j
 
     def _upload(self, data, a: int, b: int) -> torch.Tensor:
-        arr = np.frombuffer(data, dtype=np.uint8, count=b - a, offset=a) if b > a else np.zeros(0, dtype=np.uint8)
         t = torch.empty(max(4, b - a + 4), dtype=torch.uint8, device=torch.device("cuda", self.device))
         if b > a:
-            t[:b - a].copy_(torch.from_numpy(arr.copy()))
+            import warnings as _w
+            with _w.catch_warnings():
+                _w.simplefilter("ignore")                   # read-only buffer: we only read it
+                src = torch.frombuffer(data, dtype=torch.uint8, count=b - a, offset=a)
+            t[:b - a].copy_(src)
         return t
 
     @staticmethod
@@ -113,8 +116,16 @@ class Engine:
 
     # ------------------------------------------------------------------
     # KOLM profile
-    def encode_kolm(self, data: bytes, bounds: Sequence[Tuple[int, int]]) -> List[Tuple[int, bytes]]:
-        res: List[Tuple[int, bytes]] = []
+    def _gather_home(self, c: Context, addr: np.ndarray, lens: np.ndarray):
+        """Winners' payloads -> one device buffer in block order -> host memory.  Returns a uint8 numpy array."""
+        total = int(lens.sum())
+        dev = torch.empty(max(total, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        c.gather_payloads(addr, lens, dev)
+        return dev[:total].cpu().numpy()
+
+    def encode_kolm_area(self, data: bytes, bounds: Sequence[Tuple[int, int]]):
+        """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLM candidates."""
+        mids_all, lens_all, areas = [], [], []
         for i, j in self._batches(bounds):
             a, b = bounds[i][0], bounds[j - 1][1]
             nb = j - i
@@ -131,24 +142,25 @@ class Engine:
                 lzp, lzo = c.lz77_encode(x, off, 255, 127)
                 sizes = np.stack([lens, sx, np.diff(kfo), np.diff(lzo)], axis=1)
                 mids = np.argmin(sizes, axis=1)                      # first minimum == lowest id on ties (KF.py:857)
-                hx = None
+                base = np.zeros((nb, 4), dtype=np.uint64)
+                base[:, 0] = np.uint64(x.data_ptr()) + off[:-1].astype(np.uint64)
                 if (mids == 1).any():
                     xp, xo = c.residual_encode(x, off, 0)
-                    hx = self._host(xp, int(xo[-1]))
-                hk = self._host(kfp, int(kfo[-1])) if (mids == 2).any() else b""
-                hl = self._host(lzp, int(lzo[-1])) if (mids == 3).any() else b""
-            for k in range(nb):
-                mid = int(mids[k])
-                if mid == 0:
-                    p = bytes(data[bounds[i + k][0]:bounds[i + k][1]])
-                elif mid == 1:
-                    p = hx[xo[k]:xo[k + 1]]
-                elif mid == 2:
-                    p = hk[kfo[k]:kfo[k + 1]]
-                else:
-                    p = hl[lzo[k]:lzo[k + 1]]
-                res.append((mid, p))
-        return res
+                    base[:, 1] = np.uint64(xp.data_ptr()) + xo[:-1].astype(np.uint64)
+                base[:, 2] = np.uint64(kfp.data_ptr()) + kfo[:-1].astype(np.uint64)
+                base[:, 3] = np.uint64(lzp.data_ptr()) + lzo[:-1].astype(np.uint64)
+                plen = sizes[np.arange(nb), mids].astype(np.int64)
+                areas.append(self._gather_home(c, base[np.arange(nb), mids], plen))
+            mids_all.append(mids.astype(np.int64))
+            lens_all.append(plen)
+        if not areas:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
+        return np.concatenate(mids_all), np.concatenate(lens_all), (areas[0] if len(areas) == 1 else np.concatenate(areas))
+
+    def encode_kolm(self, data: bytes, bounds: Sequence[Tuple[int, int]]) -> List[Tuple[int, bytes]]:
+        mids, lens, area = self.encode_kolm_area(data, bounds)
+        ends = np.cumsum(lens)
+        return [(int(mids[k]), area[ends[k] - lens[k]:ends[k]].tobytes()) for k in range(len(mids))]
 
     def kolm_model_payloads(self, block: bytes, mid: int) -> bytes:
         """One model on one block (the reference's _ENCODERS[mid])."""
@@ -171,8 +183,9 @@ class Engine:
 
     # ------------------------------------------------------------------
     # KOLR profile.  `names` = candidate names in id order (the reference's _select_encoders() list).
-    def encode_kolr(self, data: bytes, bounds: Sequence[Tuple[int, int]], names: Sequence[str]) -> List[Tuple[int, bytes]]:
-        res: List[Tuple[int, bytes]] = []
+    def encode_kolr_area(self, data: bytes, bounds: Sequence[Tuple[int, int]], names: Sequence[str]):
+        """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLR candidate list `names`."""
+        mids_all, lens_all, areas = [], [], []
         for i, j in self._batches(bounds):
             a, b = bounds[i][0], bounds[j - 1][1]
             nb = j - i
@@ -217,10 +230,12 @@ class Engine:
                         cols.append(np.full(nb, _BIG, dtype=np.int64))
                 sizes = np.stack(cols, axis=1)
                 mids = np.argmin(sizes, axis=1)                      # strict '<' in the reference == first minimum
-                host: Dict[str, Tuple[bytes, np.ndarray]] = {}
+                base = np.zeros((nb, len(names)), dtype=np.uint64)
+                keep = [x]                                           # keep every payload tensor alive until the gather ran
                 for mid in sorted(set(int(v) for v in mids)):
                     nme = names[mid]
                     if nme == "raw":
+                        base[:, mid] = np.uint64(x.data_ptr()) + off[:-1].astype(np.uint64)
                         continue
                     if nme == "xor":
                         p, o = c.residual_encode(x, off, 1)
@@ -236,17 +251,20 @@ class Engine:
                         p, o = rpp, rpo
                     else:
                         raise RuntimeError("unreachable candidate " + nme)
-                    host[nme] = (self._host(p, int(o[-1])), o)
-            for k in range(nb):
-                mid = int(mids[k])
-                nme = names[mid]
-                if nme == "raw":
-                    p = bytes(data[bounds[i + k][0]:bounds[i + k][1]])
-                else:
-                    hb, o = host[nme]
-                    p = hb[o[k]:o[k + 1]]
-                res.append((mid, p))
-        return res
+                    keep.append(p)
+                    base[:, mid] = np.uint64(p.data_ptr()) + o[:-1].astype(np.uint64)
+                plen = sizes[np.arange(nb), mids].astype(np.int64)
+                areas.append(self._gather_home(c, base[np.arange(nb), mids], plen))
+            mids_all.append(mids.astype(np.int64))
+            lens_all.append(plen)
+        if not areas:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
+        return np.concatenate(mids_all), np.concatenate(lens_all), (areas[0] if len(areas) == 1 else np.concatenate(areas))
+
+    def encode_kolr(self, data: bytes, bounds: Sequence[Tuple[int, int]], names: Sequence[str]) -> List[Tuple[int, bytes]]:
+        mids, lens, area = self.encode_kolr_area(data, bounds, names)
+        ends = np.cumsum(lens)
+        return [(int(mids[k]), area[ends[k] - lens[k]:ends[k]].tobytes()) for k in range(len(mids))]
 
     def kolr_model_payload(self, block: bytes, name: str) -> bytes:
         off = np.array([0, len(block)], dtype=np.int64)
@@ -271,59 +289,76 @@ class Engine:
             return self._host(p, int(o[-1]))
 
     # ------------------------------------------------------------------
-    # decode: blocks = [(method name, payload, orig_len)], returns the decoded blocks in order
-    def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:
-        out: List[Optional[bytes]] = [None] * len(blocks)
-        groups: Dict[str, List[int]] = {}
-        for idx, (nme, _, _) in enumerate(blocks):
-            groups.setdefault(nme, []).append(idx)
-        for nme, idxs in groups.items():
-            if nme == "raw":
-                for t in idxs:
-                    _, p, ol = blocks[t]
-                    assert len(p) == ol, "Payload length mismatch for RAW"
-                    out[t] = bytes(p)
-                continue
-            # sub-batches bounded by decoded size
-            s = 0
-            while s < len(idxs):
-                e, tot = s, 0
-                while e < len(idxs) and (e == s or tot + blocks[idxs[e]][2] <= self.batch_bytes):
-                    tot += blocks[idxs[e]][2]
-                    e += 1
-                sub = idxs[s:e]
-                pays = [blocks[t][1] for t in sub]
-                ols = [blocks[t][2] for t in sub]
-                poff = np.zeros(len(sub) + 1, dtype=np.int64)
-                poff[1:] = np.cumsum([len(p) for p in pays])
-                off = np.zeros(len(sub) + 1, dtype=np.int64)
-                off[1:] = np.cumsum(ols)
-                self._ensure(max(int(off[-1]), 1), len(sub))
-                with torch.cuda.device(self.device):
-                    c = self.ctx
+    # decode: blocks = [(method name, payload, orig_len)]
+    def decode_area(self, blocks: Sequence[Tuple[str, bytes, int]]) -> np.ndarray:
+        """All blocks decoded back to back (uint8 array of sum(orig_len) bytes).  Each method group is decoded as one batch
+        into a temporary device buffer and copied to its blocks' final offsets on the device; one D2H per output batch."""
+        nb = len(blocks)
+        ols = np.array([b[2] for b in blocks], dtype=np.int64)
+        ends = np.cumsum(ols)
+        total = int(ends[-1]) if nb else 0
+        out = np.empty(total, dtype=np.uint8)
+        # output batches of <= batch_bytes
+        i = 0
+        while i < nb:
+            j, tot = i, 0
+            while j < nb and (j == i or tot + blocks[j][2] <= self.batch_bytes):
+                tot += blocks[j][2]
+                j += 1
+            base_off = int(ends[i] - ols[i])
+            with torch.cuda.device(self.device):
+                dev_out = torch.empty(max(tot, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
+                groups: Dict[str, List[int]] = {}
+                for idx in range(i, j):
+                    groups.setdefault(blocks[idx][0], []).append(idx)
+                for nme, sub in groups.items():
+                    pays = [blocks[t][1] for t in sub]
+                    sol = ols[sub]
+                    poff = np.zeros(len(sub) + 1, dtype=np.int64)
+                    poff[1:] = np.cumsum([len(p) for p in pays])
+                    off = np.zeros(len(sub) + 1, dtype=np.int64)
+                    off[1:] = np.cumsum(sol)
+                    dst = np.uint64(dev_out.data_ptr()) + (ends[sub] - sol - base_off).astype(np.uint64)
                     blob = b"".join(pays)
+                    self._ensure(max(int(off[-1]), len(blob), 1), len(sub))
+                    c = self.ctx
                     pt = self._upload(blob, 0, len(blob))
-                    try:
-                        if nme in ("kf_xor", "xor", "lfsr_pred"):
-                            y = c.residual_decode(pt, poff, off, {"kf_xor": 0, "xor": 1, "lfsr_pred": 2}[nme])
-                        elif nme == "kf_bbwt":
-                            y = c.bbwt_inverse(c.mtf_decode(c.rice_kf_decode(pt, poff, off), off), off)
-                        elif nme in K2_FLAG_OF:
-                            y = c.bbwt_inverse(c.mtf_decode(c.rice_k2_decode(pt, poff, off, K2_FLAG_OF[nme]), off), off)
-                        elif nme == "kf_lz77":
-                            y = c.lz77_decode(pt, poff, off, 0)
-                        elif nme == "lz77":
-                            y = c.lz77_decode(pt, poff, off, 4096)
-                        elif nme == "repair":
-                            y = c.repair_decode(pt, poff, off)
-                        else:
-                            raise NotImplementedError("decoder for method '%s' is outside the GPU hot path (SURVEY §8 row a17)" % nme)
-                    except _lib.KolmError as err:
-                        if err.code == -4 and not nme.startswith("kf_"):
-                            raise ValueError(str(err)) from err     # V22's readers raise ValueError on truncation (v2-2.py:131-132, 1437-1447)
-                        raise_like_reference(err)
-                    hb = self._host(y, int(off[-1]))
-                for q, t in enumerate(sub):
-                    out[t] = hb[off[q]:off[q + 1]]
-                s = e
-        return out  # type: ignore[return-value]
+                    if nme == "raw":
+                        for t in sub:
+                            assert len(blocks[t][1]) == blocks[t][2], "Payload length mismatch for RAW"
+                        y = pt
+                    else:
+                        try:
+                            if nme in ("kf_xor", "xor", "lfsr_pred"):
+                                y = c.residual_decode(pt, poff, off, {"kf_xor": 0, "xor": 1, "lfsr_pred": 2}[nme])
+                            elif nme == "kf_bbwt":
+                                y = c.bbwt_inverse(c.mtf_decode(c.rice_kf_decode(pt, poff, off), off), off)
+                            elif nme in K2_FLAG_OF:
+                                y = c.bbwt_inverse(c.mtf_decode(c.rice_k2_decode(pt, poff, off, K2_FLAG_OF[nme]), off), off)
+                            elif nme == "kf_lz77":
+                                y = c.lz77_decode(pt, poff, off, 0)
+                            elif nme == "lz77":
+                                y = c.lz77_decode(pt, poff, off, 4096)
+                            elif nme == "repair":
+                                y = c.repair_decode(pt, poff, off)
+                            else:
+                                raise NotImplementedError("decoder for method '%s' is outside the GPU hot path (SURVEY §8 row a17)" % nme)
+                        except _lib.KolmError as err:
+                            if err.code == -4 and not nme.startswith("kf_"):
+                                raise ValueError(str(err)) from err     # V22's readers raise ValueError on truncation (v2-2.py:131-132, 1437-1447)
+                            raise_like_reference(err)
+                    src = np.uint64(y.data_ptr()) + off[:-1].astype(np.uint64)
+                    self.ctx.copy_blocks(src, dst, sol)
+                    torch.cuda.current_stream().synchronize()        # y / pt may be freed when the loop moves on
+                if tot:
+                    out[base_off:base_off + tot] = dev_out[:tot].cpu().numpy()
+            i = j
+        return out
+
+    def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:
+        area = self.decode_area(blocks)
+        res, p = [], 0
+        for _, _, ol in blocks:
+            res.append(area[p:p + ol].tobytes())
+            p += ol
+        return res

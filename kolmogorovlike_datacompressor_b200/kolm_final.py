@@ -126,17 +126,20 @@ def _encode_block(block: bytes) -> Tuple[int, bytes, int]:
 def compress(data: bytes, target_block: int = 8192) -> bytes:
     data = bytes(data)
     cuts = cdc_fast_boundaries(data, min_size=target_block // 2, avg_size=target_block, max_size=target_block * 2)
-    out = bytearray()
-    out += b"KOLM"
-    out += struct.pack("<I", target_block & 0xFFFFFFFF)
-    out += struct.pack("<Q", len(data))
-    out += struct.pack("<H", len(cuts) & 0xFFFF)          # wraps silently like the reference (kolm_final.py:889-890)
-    if cuts:
-        for (a, b), (mid, payload) in zip(cuts, _engine().encode_kolm(data, cuts)):
-            out.append(mid & 0xFF)
-            out += struct.pack("<I", (b - a) & 0xFFFFFFFF)
-            out += struct.pack("<I", len(payload) & 0xFFFFFFFF)
-            out += payload
+    head = b"KOLM" + struct.pack("<I", target_block & 0xFFFFFFFF) + struct.pack("<Q", len(data)) + struct.pack("<H", len(cuts) & 0xFFFF)
+    if not cuts:                                          # nblocks wraps silently like the reference (kolm_final.py:889-890)
+        return head
+    mids, lens, area = _engine().encode_kolm_area(data, cuts)
+    out = bytearray(18 + 9 * len(cuts) + int(lens.sum()))
+    out[:18] = head
+    view, src = memoryview(out), memoryview(area)
+    p = 18
+    q = 0
+    for (a, b), mid, ln in zip(cuts, mids.tolist(), lens.tolist()):
+        struct.pack_into("<BII", out, p, mid & 0xFF, (b - a) & 0xFFFFFFFF, ln & 0xFFFFFFFF)
+        view[p + 9:p + 9 + ln] = src[q:q + ln]
+        p += 9 + ln
+        q += ln
     return bytes(out)
 
 
@@ -168,15 +171,10 @@ def decompress(blob: bytes) -> bytes:
             raise EOFError("Truncated payload")
         todo.append((_NAMES[method_id], blob[p:p + payload_len], orig_len))
         p += payload_len
-    blocks = _engine().decode_blocks(todo) if todo else []
-    out = bytearray()
-    for (nme, _, orig_len), block in zip(todo, blocks):
-        if len(block) != orig_len:
-            raise ValueError(f"Decoded length mismatch: expected {orig_len}, got {len(block)}")
-        out += block
+    out = _engine().decode_area(todo).tobytes() if todo else b""      # every decoder yields exactly orig_len bytes or raises
     if len(out) != total_len:
         raise ValueError(f"Total decoded length mismatch: expected {total_len}, got {len(out)}")
-    return bytes(out)
+    return out
 
 
 if __name__ == "__main__":

@@ -264,12 +264,13 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int) -> bytes:
     nblocks = len(boundaries)
     label = "FIXED" if mode == MODE_FIXED else "Fast CDC"
     _print_progress(label, 0, nblocks)
-    chosen = _engine().encode_kolr(data, boundaries, names) if nblocks else []
+    if nblocks:
+        mids_np, lens_np, area = _engine().encode_kolr_area(data, boundaries, names)
+        method_ids, payload_lens = mids_np.tolist(), lens_np.tolist()
+    else:
+        method_ids, payload_lens, area = [], [], b""
     _print_progress(label + " COMPRESS", nblocks, nblocks, final=True)
-    method_ids = [m for m, _ in chosen]
-    payloads = [p for _, p in chosen]
     orig_lens = [b - a for a, b in boundaries]
-    payload_lens = [len(p) for p in payloads]
     total_payload = sum(payload_lens)
     # ---- TOC header
     run_syms: List[int] = []
@@ -327,8 +328,7 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int) -> bytes:
     out += uleb128_encode(total_payload)
     out += toc_header
     out += toc_bits
-    for p in payloads:
-        out += p
+    out += memoryview(area)
     return bytes(out)
 
 
@@ -426,9 +426,8 @@ def decompress(container: bytes) -> bytes:
         todo.append((KOLR_NAMES[mid], area[start:P[i]], orig_lens[i]))
         start = P[i]
     _print_progress("DECOMPRESS", 0, nblocks)
-    blocks = _engine().decode_blocks(todo) if todo else []
+    out = _engine().decode_area(todo).tobytes() if todo else b""
     _print_progress("DECOMPRESS", nblocks, nblocks, final=True)
-    out = b"".join(blocks)
     if len(out) != total_len:
         raise ValueError(f"Length mismatch: got {len(out)}, expect {total_len}")
     if pos != len(container):

@@ -174,3 +174,21 @@ class Context:
 
     def repair_decode(self, payload, pay_off, off, out=None):
         return self._dec("kolm_repair_dec", payload, pay_off, off, (), out)
+
+    def gather_payloads(self, src_addr: np.ndarray, lens: np.ndarray, out: torch.Tensor):
+        """Winning payloads (device addresses + lengths per block) -> back to back in `out`; returns out_off."""
+        nb = len(lens)
+        src_addr = np.ascontiguousarray(src_addr, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        out_off = np.zeros(nb + 1, dtype=np.int64)
+        _lib.check(_lib.lib().kolm_gather_payloads(self._h, src_addr.ctypes.data_as(C.POINTER(C.c_uint64)), lens.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                   nb, C.c_void_p(out.data_ptr()), out_off.ctypes.data_as(C.POINTER(C.c_int64)), self._stream()),
+                   "kolm_gather_payloads")
+        return out_off
+
+    def copy_blocks(self, src_addr: np.ndarray, dst_addr: np.ndarray, lens: np.ndarray):
+        src_addr = np.ascontiguousarray(src_addr, dtype=np.uint64)
+        dst_addr = np.ascontiguousarray(dst_addr, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        _lib.check(_lib.lib().kolm_copy_blocks(self._h, src_addr.ctypes.data_as(C.POINTER(C.c_uint64)), dst_addr.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               lens.ctypes.data_as(C.POINTER(C.c_int64)), len(lens), self._stream()), "kolm_copy_blocks")
