@@ -69,6 +69,17 @@ class Engine:
         self.cap_bytes = 0
         self.cap_blocks = 0
         self.repair_max = int(_lib.lib().kolm_repair_max_block())
+        self._pin: Optional[torch.Tensor] = None
+
+    def _home(self, dev: torch.Tensor, n: int) -> np.ndarray:
+        """Device bytes -> host through a persistent pinned staging buffer (pageable D2H runs at ~2 GB/s, pinned at PCIe speed)."""
+        if n == 0:
+            return np.zeros(0, dtype=np.uint8)
+        if self._pin is None or self._pin.numel() < n:
+            self._pin = torch.empty(max(n, 1 << 20) + (n >> 3), dtype=torch.uint8).pin_memory()
+        self._pin[:n].copy_(dev[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin[:n].numpy()
 
     @classmethod
     def shared(cls, device: Optional[int] = None) -> "Engine":
@@ -121,7 +132,7 @@ class Engine:
         total = int(lens.sum())
         dev = torch.empty(max(total, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
         c.gather_payloads(addr, lens, dev)
-        return dev[:total].cpu().numpy()
+        return self._home(dev, total).copy()
 
     def encode_kolm_area(self, data: bytes, bounds: Sequence[Tuple[int, int]]):
         """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLM candidates."""
@@ -351,7 +362,7 @@ class Engine:
                     self.ctx.copy_blocks(src, dst, sol)
                     torch.cuda.current_stream().synchronize()        # y / pt may be freed when the loop moves on
                 if tot:
-                    out[base_off:base_off + tot] = dev_out[:tot].cpu().numpy()
+                    out[base_off:base_off + tot] = self._home(dev_out, tot)
             i = j
         return out
 

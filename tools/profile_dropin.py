@@ -12,3 +12,8 @@ for name, fn in (("KOLR", lambda: V.compress_blocks_fixed(data, 1 << 20)), ("KOL
     t = time.perf_counter(); pr = cProfile.Profile(); pr.enable(); blob = fn(); pr.disable(); dt = time.perf_counter() - t
     print(name, "compress", round(n / dt / 1e6, 1), "MB/s", len(blob))
     pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+for name, fn, dec in (("KOLR", lambda: V.compress_blocks_fixed(data, 1 << 20), V.decompress), ("KOLM", lambda: KF.compress(data, 1 << 20), KF.decompress)):
+    blob = fn(); dec(blob)
+    t = time.perf_counter(); pr = cProfile.Profile(); pr.enable(); back = dec(blob); pr.disable(); dt = time.perf_counter() - t
+    print(name, "decompress", round(n / dt / 1e6, 1), "MB/s", back == data)
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(16)
