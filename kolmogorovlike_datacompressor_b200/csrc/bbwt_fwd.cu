@@ -778,14 +778,15 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_lyn_cand(const u8* __restrict_
 // one warp per block
 __global__ void __launch_bounds__(128) k_lyn_resolve(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, const u32* __restrict__ cand,
                                                      const u32* __restrict__ ncand, u32* __restrict__ fstart, u32* __restrict__ nfac,
-                                                     u8* __restrict__ flags_out, u32* __restrict__ fallback, int nblocks) {
+                                                     u8* __restrict__ flags_out, u32* __restrict__ fallback, u32* __restrict__ blockfail, int nblocks) {
     const u32 lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nblocks) return;
     const BlockInfo bi = binfo[b];
+    if (lane == 0) blockfail[b] = 0;
     if (bi.len == 0) { if (lane == 0) nfac[b] = 0; return; }
     const u32 nc = ncand[b];
-    if (nc > LYN_MAX_CAND || bi.len > LYN_MAX_CAND && nc > bi.len / 8) { if (lane == 0) atomicExch(fallback, 1u); return; }
+    if (nc > LYN_MAX_CAND || (bi.len > LYN_MAX_CAND && nc > bi.len / 8)) { if (lane == 0) { blockfail[b] = 1; atomicExch(fallback, 1u); } return; }
     const u8* src = in + bi.ioff;
     u32 champ = 0, nf = 0, iters = 0;
     for (u32 k = 0; k < nc; ++k) {
@@ -796,7 +797,7 @@ __global__ void __launch_bounds__(128) k_lyn_resolve(const u8* __restrict__ in, 
             // tie on the 6-byte key (both suffixes have >= 7 bytes): compare from offset 6, 32 bytes per step
             u32 o = 6;
             for (;;) {
-                if (++iters > LYN_MAX_ITERS) { if (lane == 0) atomicExch(fallback, 1u); return; }
+                if (++iters > LYN_MAX_ITERS) { if (lane == 0) { blockfail[b] = 1; atomicExch(fallback, 1u); } return; }
                 u32 x = o + lane;
                 bool inb = pos + x < bi.len;                 // pos > champ, so pos's suffix ends first
                 u32 a = inb ? src[pos + x] : 0, c = inb ? src[champ + x] : 0;
@@ -813,9 +814,66 @@ __global__ void __launch_bounds__(128) k_lyn_resolve(const u8* __restrict__ in, 
         }
         if (win) {
             champ = pos;
-            if (lane == 0) { fstart[bi.pbase + nf] = pos; if (flags_out) flags_out[bi.ioff + pos] = 1; }
+            if (lane == 0) fstart[bi.pbase + nf] = pos;
             ++nf;
         }
+    }
+    if (lane == 0) nfac[b] = nf;
+    if (flags_out) for (u32 t = lane; t < nf; t += 32) flags_out[bi.ioff + fstart[bi.pbase + t]] = 1;   // only once the block succeeded
+}
+
+// Blocks the candidate path gave up on (long runs / periods): Duval's walk (kolm_final.py:200-225) by one warp, with the
+// run of equal comparisons s[k]==s[j] taken 128 bytes at a time.  Degenerate data is exactly where those runs are long, so
+// the walk needs few steps there; an iteration cap sends pathological blocks to the ISA path.
+#define DUVAL_MAX_ITERS (1u << 18)
+#define DUVAL_MAX_BLOCK (2u << 20)
+__global__ void __launch_bounds__(128) k_lyn_duval(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, const u32* __restrict__ blockfail,
+                                                   u32* __restrict__ fstart, u32* __restrict__ nfac, u8* __restrict__ flags_out,
+                                                   u32* __restrict__ fallback, int nblocks) {
+    const u32 lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks || !blockfail[b]) return;
+    const BlockInfo bi = binfo[b];
+    const u8* s = in + bi.ioff;
+    const u32 n = bi.len;
+    // one warp walks the block serially: only worth it for blocks it can finish in a few ms; larger ones go to the ISA path
+    if (n > DUVAL_MAX_BLOCK) { if (lane == 0) atomicExch(fallback, 2u); return; }
+    u32 i = 0, nf = 0, iters = 0, siters = 0;
+    while (i < n) {
+        u32 j = i + 1, k = i;
+        const u32 si = s[i];
+        u32 run = 0;                                         // consecutive equal comparisons
+        u32 jw = 0, jwbase = 0xffffffffu;                    // 4-byte window of s around j (one load per 4 scalar steps)
+        for (;;) {
+            if (j >= n) break;
+            if (run >= 16) {
+                // long common prefix of s[k..] and s[j..]: skip it 128 bytes per step with the whole warp
+                for (;;) {
+                    if (++iters > DUVAL_MAX_ITERS) { if (lane == 0) atomicExch(fallback, 2u); return; }
+                    u32 x = lane * 4, m = 4;
+#pragma unroll
+                    for (int t = 3; t >= 0; --t) { u32 jj = j + x + t; if (jj >= n || s[k + x + t] != s[jj]) m = t; }
+                    u32 bal = __ballot_sync(FULL, m < 4);
+                    if (bal) { u32 l = __ffs(bal) - 1; u32 adv = l * 4 + __shfl_sync(FULL, m, l); k += adv; j += adv; break; }
+                    k += 128; j += 128;
+                }
+                run = 0;
+                if (j >= n) break;
+            }
+            // scalar step (all lanes redundantly: uniform control flow, broadcast loads)
+            if (++siters > 3u * DUVAL_MAX_BLOCK) { if (lane == 0) atomicExch(fallback, 2u); return; }
+            if ((j & ~3u) != jwbase) { jwbase = j & ~3u; jw = 0; for (u32 t = 0; t < 4 && jwbase + t < n; ++t) jw |= (u32)s[jwbase + t] << (8 * t); }
+            const u32 cj = (jw >> (8 * (j & 3))) & 0xFF;
+            const u32 ck = (k == i) ? si : (u32)s[k];
+            if (ck == cj) { ++k; ++j; ++run; continue; }
+            run = 0;
+            if (ck < cj) { k = i; ++j; } else break;
+        }
+        const u32 p = j - k;
+        const u32 cnt = (k - i) / p + 1;                     // while i <= k: emit i; i += p
+        for (u32 t = lane; t < cnt; t += 32) { u32 st = i + t * p; fstart[bi.pbase + nf + t] = st; if (flags_out) flags_out[bi.ioff + st] = 1; }
+        iters += cnt >> 5;
+        nf += cnt; i += cnt * p;
     }
     if (lane == 0) nfac[b] = nf;
 }
@@ -1012,12 +1070,25 @@ int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, 
         if (flags_out && c->total_bytes) CUDA_TRY(cudaMemsetAsync(flags_out + c->h_binfo[0].ioff, 0, (size_t)c->total_bytes, s));
         KOLM_TRY(kolm_lb_reset_mode(c, false, c->ntiles, &lgrid, 1, s));
         KL(c, KC_LYNDON, c->total_bytes * 2, s, k_lyn_cand<<<lgrid, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_lb, cand, ncand));
+        u32* blockfail = c->d_atilen;                          // free until the first sort round
         KL(c, KC_LYNDON, c->total_bytes / 64, s, k_lyn_resolve<<<(c->nblocks + 3) / 4, 128, 0, s>>>(in, c->d_binfo, cand, ncand, c->d_fstart, c->d_nfac,
-                                                                                                  flags_out, c->d_stats + 8, c->nblocks));
+                                                                                                  flags_out, c->d_stats + 8, blockfail, c->nblocks));
         CUDA_TRY(cudaMemcpyAsync(c->h_stats + 8, c->d_stats + 8, 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         CUDA_TRY(cudaGetLastError());
         if (c->h_stats[8] == 0) { if (rounds_out) *rounds_out = 0; return KOLM_OK; }
+        static int duval = -1;
+        if (duval < 0) { const char* e = getenv("KOLM_LYNDON_DUVAL"); duval = e ? atoi(e) : 1; }
+        if (duval) {
+            // second chance for the blocks that failed: vectorised Duval walk, one warp per block
+            CUDA_TRY(cudaMemsetAsync(c->d_stats + 8, 0, 4, s));
+            KL(c, KC_LYNDON, c->total_bytes / 8, s, k_lyn_duval<<<(c->nblocks + 3) / 4, 128, 0, s>>>(in, c->d_binfo, blockfail, c->d_fstart, c->d_nfac, flags_out,
+                                                                                                   c->d_stats + 8, c->nblocks));
+            CUDA_TRY(cudaMemcpyAsync(c->h_stats + 8, c->d_stats + 8, 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            CUDA_TRY(cudaGetLastError());
+            if (c->h_stats[8] == 0) { if (rounds_out) *rounds_out = 0; return KOLM_OK; }
+        }
     }
     KOLM_TRY(sort_batch(c, in, false, rounds_out, s));
     KOLM_TRY(kolm_lb_reset_mode(c, false, c->ntiles, &lgrid, 1, s));
