@@ -291,8 +291,10 @@ def run_ours(args):
     stages["mtf"] = {"ms": round(mtf_ms, 3), "alg_bytes_per_input_byte": 2, "frac_of_peak": frac(2 * nbytes, mtf_ms)}
     c_ratio = (kf_bytes + k2_bytes) / nbytes
     stages["rice"] = {"ms": round(rice_ms, 3), "alg_bytes_per_input_byte": round(4 + c_ratio, 3), "frac_of_peak": frac((4 + c_ratio) * nbytes, rice_ms)}
+    traffic, traffic_note = ncu_traffic(dom_name, args)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "peak_source": peak_src, "launches": dom_v["launches"], "share_of_step": round(dom_v["ms"] / step_ms_prof, 3),
+                "traffic": traffic, "traffic_note": traffic_note, "alg_bytes_per_launch": int(dom_v["alg_bytes"] / max(1, dom_v["launches"])),
+                "peak_source": peak_src, "launches": dom_v["launches"], "share_of_step": round(dom_v["ms"] / step_ms_prof, 3),
                 "per_category_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}, "stages": stages}
 
     if rank == 0:
@@ -311,6 +313,23 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic(category, args):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/r1_final_traffic.json, written by tools/make_profile_summary.py).
+    ncu captured only the largest launches of the category, so the figure is their mean; it is not measured by this run."""
+    kname = {"rerank": "k_rerank", "radix_scatter": "k_radix_scatter", "gather": "k_gather"}.get(category)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_final_traffic.json")
+    if kname is None or not os.path.isfile(path) or args.mib != 256 or args.block_kib != 1024:
+        return None, "no ncu capture for this kernel/workload"
+    doc = json.load(open(path))
+    rows = [r for k, v in doc["kernels"].items() if k.startswith(kname) for r in v]
+    if not rows:
+        return None, "kernel not in the ncu capture"
+    mean = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows) / len(rows)
+    return int(mean), "mean of the %d largest launches in %s (%s); those launches cover %s tiles of <= 4096 records" % (
+        len(rows), "profiles/r1_final_traffic.json", doc["source"], "/".join(str(r["grid"]) for r in rows))
 
 
 def main():

@@ -166,23 +166,78 @@ __global__ void __launch_bounds__(256) k_alpha_map(u64* __restrict__ bacc, const
     }
 }
 
+// The tile's symbol codes are staged once in shared memory; a thread owns 16 consecutive positions and slides a window over
+// them (one code in, one out per key).  Only positions whose h0-symbol window crosses the end of their Lyndon factor (the
+// rotation wraps) take the per-position path.
 __global__ void __launch_bounds__(KOLM_THREADS) k_boot_keys_alpha(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo,
                                                                   const TileDesc* __restrict__ tiles, const u32* __restrict__ fstart,
                                                                   const u32* __restrict__ nfac, const u64* __restrict__ bacc, u32 h0,
                                                                   u32* __restrict__ K, u32* __restrict__ V) {
     __shared__ u8 rmap[256];
-    TileDesc td = tiles[blockIdx.x];
-    BlockInfo bi = binfo[td.block];
-    rmap[threadIdx.x] = reinterpret_cast<const u8*>(bacc + (size_t)td.block * 64 + 8)[threadIdx.x];
+    __shared__ __align__(16) u8 sc[KOLM_TILE + 32];
+    const u32 tid = threadIdx.x;
+    const TileDesc td = tiles[blockIdx.x];
+    const BlockInfo bi = binfo[td.block];
+    rmap[tid] = reinterpret_cast<const u8*>(bacc + (size_t)td.block * 64 + 8)[tid];
     const u32 bits = reinterpret_cast<const u32*>(bacc + (size_t)td.block * 64 + 40)[0];
     __syncthreads();
     const u8* src = in + bi.ioff;
-    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
-        u32 pg = td.start + x, lp = pg - bi.pbase, key = 0;
-        u32 fs, fl; find_factor(fstart + bi.pbase, nfac[td.block], bi.len, lp, fs, fl);
-        u32 o = lp - fs;
-        for (u32 t = 0; t < h0; ++t) { key = (key << bits) | rmap[src[fs + o]]; if (++o == fl) o = 0; }
-        K[pg] = key; V[pg] = pg;
+    const u32 t0 = td.start - bi.pbase;
+    {   // stage codes of block positions [t0, t0 + count + 32) (zero beyond the block)
+        const u32 want = min(td.count + 32u, bi.len - t0);
+        const u8* g = src + t0;
+        if (((uintptr_t)g & 15) == 0) {
+            for (u32 x = tid * 16; x < KOLM_TILE + 32; x += KOLM_THREADS * 16) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (x + 16 <= want) v = *reinterpret_cast<const uint4*>(g + x);
+                else if (x < want) { u32 w[4] = {0, 0, 0, 0}; for (u32 i = 0; x + i < want; ++i) w[i >> 2] |= (u32)g[x + i] << (8 * (i & 3)); v = make_uint4(w[0], w[1], w[2], w[3]); }
+                u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    w[i] = (u32)rmap[w[i] & 0xFF] | ((u32)rmap[(w[i] >> 8) & 0xFF] << 8) | ((u32)rmap[(w[i] >> 16) & 0xFF] << 16) | ((u32)rmap[w[i] >> 24] << 24);
+                *reinterpret_cast<uint4*>(sc + x) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            for (u32 x = tid; x < KOLM_TILE + 32; x += KOLM_THREADS) sc[x] = x < want ? rmap[g[x]] : 0;
+        }
+    }
+    __syncthreads();
+    const u32 r0 = tid * KOLM_IPT;
+    if (r0 >= td.count) return;
+    const u32 nmine = min((u32)KOLM_IPT, td.count - r0);
+    const u32* fst = fstart + bi.pbase;
+    const u32 nf = nfac[td.block];
+    u32 fs, fl; find_factor(fst, nf, bi.len, t0 + r0, fs, fl);
+    const u32 kmask = bits * h0 >= 32 ? 0xffffffffu : ((1u << (bits * h0)) - 1u);
+    u32 keys[KOLM_IPT];
+    if (t0 + r0 + nmine - 1 + h0 <= fs + fl) {               // every window of mine stays inside one factor: slide
+        u32 key = 0;
+        for (u32 t = 0; t + 1 < h0; ++t) key = (key << bits) | sc[r0 + t];
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) { key = ((key << bits) | sc[r0 + i + h0 - 1]) & kmask; keys[i] = key; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) {
+            keys[i] = 0;
+            if ((u32)i < nmine) {
+                const u32 lp = t0 + r0 + i;
+                if (lp >= fs + fl) find_factor(fst, nf, bi.len, lp, fs, fl);
+                u32 o = lp - fs, key = 0;
+                for (u32 t = 0; t < h0; ++t) { key = (key << bits) | rmap[src[fs + o]]; if (++o == fl) o = 0; }
+                keys[i] = key;
+            }
+        }
+    }
+    const u32 pg = td.start + r0;
+    if (nmine == KOLM_IPT) {                                 // td.start is a multiple of 32 elements: 16-byte aligned stores
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; i += 4) {
+            *reinterpret_cast<uint4*>(K + pg + i) = make_uint4(keys[i], keys[i + 1], keys[i + 2], keys[i + 3]);
+            *reinterpret_cast<uint4*>(V + pg + i) = make_uint4(pg + i, pg + i + 1, pg + i + 2, pg + i + 3);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; ++i) if ((u32)i < nmine) { K[pg + i] = keys[i]; V[pg + i] = pg + i; }
     }
 }
 

@@ -133,6 +133,33 @@ struct BitStage {
     }
 };
 
+// Per-thread bit accumulator over a staged tile: a thread's tokens are contiguous in the stream, so they are shifted into a
+// 64-bit register and leave as whole words.  Words that lie completely inside the thread's bit range are stored plainly; only
+// the first word it touches and the trailing partial word can be shared with a neighbouring thread and use an atomic OR.
+struct BitAcc {
+    u64 acc; u32 fill, w; bool first;
+    __device__ __forceinline__ void init(const BitStage& st, u64 bp) {
+        w = (u32)((bp >> 5) - st.first_word); fill = (u32)bp & 31u; acc = 0; first = true;
+    }
+    __device__ __forceinline__ u64 bitpos(const BitStage& st) const { return ((st.first_word + w) << 5) + fill; }
+    __device__ __forceinline__ void push(const BitStage& st, u32 code, u32 n) {      // n in 1..32, code < 2^n
+        acc |= (u64)code << (64u - fill - n); fill += n;
+        if (fill >= 32u) {
+            u32 word = (u32)(acc >> 32);
+            if (first) { if (word) atomicOr(st.sm + w, word); first = false; } else st.sm[w] = word;
+            ++w; acc <<= 32; fill -= 32u;
+        }
+    }
+    __device__ __forceinline__ void finish(const BitStage& st) {
+        u32 word = (u32)(acc >> 32);
+        if (word) atomicOr(st.sm + w, word);
+        acc = 0;
+    }
+};
+// tokens longer than 32 bits (long unary parts, gamma of runs >= 2^16): rare, kept out of line
+__device__ __noinline__ void long_rice_tok(const BitStage* st, u64 bp, u32 tagbits, u32 tag, u32 x, u32 k) { st->rice_tok(bp, tagbits, tag, x, k); }
+__device__ __noinline__ void long_gamma_tok(const BitStage* st, u64 bp, u32 tag, u32 x) { st->gamma_tok(bp, tag, x); }
+
 // ---------------------------------------------------------------------------------------------
 // shared tile prologue: symbols of my IPT items plus the one after (run-end detection)
 // ---------------------------------------------------------------------------------------------
@@ -191,9 +218,17 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
     const u32 t0 = td.start - bi.pbase;
     const u8* src = mtf + bi.ioff + t0;
     if (tid < 25) s_acc[tid] = 0;
+    // s_ptab[x] = (x>>0) | (x>>1)<<12 | (x>>2)<<23 | (x>>3)<<33 | (x>>4)<<42 | (x>>5)<<50 | (x>>6)<<57 : field k is wide enough for
+    // the sum of a thread's 16 items (x <= 254), so one 64-bit add per non-zero symbol replaces seven shift/add pairs
+    __shared__ u64 s_ptab[256];
+    if (KF) {
+        u64 x = tid;
+        s_ptab[tid] = x | ((x >> 1) << 12) | ((x >> 2) << 23) | ((x >> 3) << 33) | ((x >> 4) << 42) | ((x >> 5) << 50) | ((x >> 6) << 57);
+    }
+    u64 packn = 0;
     u32 v[KOLM_IPT + 1];
     load_items(src, t0, td.count, bi.len, v);
-    u64 accz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 accz[8] = {0, 0, 0, 0, 0, 0, 0, 0};                  // zero runs are disjoint ranges of one block (< 2^30 bytes): warp sums fit 32 bits
     u32 accn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     u32 nzt = 0, nnt = 0;
     u32 k2[5] = {0, 0, 0, 0, 0};
@@ -207,22 +242,25 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
             u32 r = tid * KOLM_IPT + i;
             if (r < td.count) {
                 u32 pos1 = t0 + r + 1;
-                if (v[i]) {
+                if (v[i]) {                                 // all seven Rice quotients of x = v-1 in one table word
                     ln = pos1;
-                    u32 x = v[i] - 1;
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) accn[k] += (x >> k) + 1 + k;
+                    packn += s_ptab[v[i] - 1];
                     accn[7] += 2 * bitlen32(v[i]) - 1;
                     ++nnt;
                 } else if (v[i + 1] != 0) {                 // zero run ends here (next is non-zero or end of block)
                     u32 run = pos1 - ln;
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) accz[k] += (u64)(run >> k) + 1 + k;
+                    for (int k = 0; k < 7; ++k) accz[k] += (run >> k) + 1 + k;
                     accz[7] += 2 * bitlen32(run) - 1;
                     ++nzt;
                 }
             }
         }
+    }
+    if (KF) {                                                // unpack the quotient sums, add the per-token constants 1 + k
+        const int off[7] = {0, 12, 23, 33, 42, 50, 57}, wid[7] = {12, 11, 10, 9, 8, 7, 6};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) accn[k] = (u32)((packn >> off[k]) & ((1u << wid[k]) - 1u)) + nnt * (1 + k);
     }
     if (K2) {
 #pragma unroll
@@ -248,8 +286,8 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
         }
     }
     __syncthreads();
-    auto red = [&](u64 x, int slot) {
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    auto red = [&](u32 x, int slot) {                        // REDUX.ADD: one instruction per warp sum
+        x = __reduce_add_sync(0xffffffffu, x);
         if ((tid & 31) == 0 && x) atomicAdd(&s_acc[slot], (unsigned long long)x);
     };
     if (KF) {
@@ -358,15 +396,25 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
     const u32 ln0 = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
-    // token bit lengths of my items
+    // token of item i (KF.py:670-684): tag bit, then Rice(k) of x or gamma of x.  non-zero v -> tag 1, x = v-1 (Rice) / v (gamma);
+    // a zero that ends a run -> tag 0, x = run length.  The parameters are uniform over the block, so these branches do not diverge.
     u64 mybits = 0; u32 ln = ln0;
+    u32 tokmask = 0;
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
         u32 r = tid * KOLM_IPT + i;
         if (r < td.count) {
             u32 pos1 = t0 + r + 1;
-            if (v[i]) { ln = pos1; u32 x = v[i] - 1; mybits += 1 + (urn ? (u64)(x >> k1) + 1 + k1 : (u64)(2 * bitlen32(v[i]) - 1)); }
-            else if (v[i + 1] != 0) { u32 run = pos1 - ln; mybits += 1 + (urz ? (u64)(run >> k0) + 1 + k0 : (u64)(2 * bitlen32(run) - 1)); }
+            bool nz = v[i] != 0, tok = nz || v[i + 1] != 0;
+            u32 x = nz ? v[i] - (urn ? 1u : 0u) : pos1 - ln;
+            if (nz) ln = pos1;
+            if (tok) {
+                const bool rice = nz ? urn : urz; const u32 k = nz ? k1 : k0;
+                mybits += rice ? (x >> k) + 2 + k : 2 * bitlen32(x);
+                tokmask |= 1u << i;
+                v[i] = x;                                    // keep the coded value; v[i+1] was already consumed
+            }
+            v[i] |= nz ? 0x80000000u : 0u;
         }
     }
     u64 btot;
@@ -376,7 +424,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
         if (tid == 0) s_excl = e;
     }
     __syncthreads();
-    u64 bp = bitbase + 10 + s_excl + (bincl - mybits);
+    const u64 bp0 = bitbase + 10 + s_excl + (bincl - mybits);
     __shared__ u32 s_stage[STAGE_WORDS];
     BitStage st;
     {   // this tile's bit range (the first tile of a block also owns the 10 header bits)
@@ -385,23 +433,26 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
         st.begin(s_stage, out, tb0, tbn);
     }
     if ((td.flags & 1u) && tid == 0) st.bits(bitbase, (((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1, 10);   // KF.py:664-668
-    ln = ln0;
+    {   // a tile whose bit range is too long for the stage (st.use false) sends every token down the out-of-line path
+        BitAcc ba; ba.init(st, bp0);
 #pragma unroll
-    for (int i = 0; i < KOLM_IPT; ++i) {
-        u32 r = tid * KOLM_IPT + i;
-        if (r < td.count) {
-            u32 pos1 = t0 + r + 1;
-            if (v[i]) {
-                ln = pos1;
-                u32 x = v[i] - 1;
-                if (urn) { st.rice_tok(bp, 1, 1, x, k1); bp += 1 + (u64)(x >> k1) + 1 + k1; }
-                else { st.gamma_tok(bp, 1, v[i]); bp += 2 * bitlen32(v[i]); }
-            } else if (v[i + 1] != 0) {
-                u32 run = pos1 - ln;
-                if (urz) { st.rice_tok(bp, 1, 0, run, k0); bp += 1 + (u64)(run >> k0) + 1 + k0; }
-                else { st.gamma_tok(bp, 0, run); bp += 2 * bitlen32(run); }
+        for (int i = 0; i < KOLM_IPT; ++i) {
+            if ((tokmask >> i) & 1u) {
+                const bool nz = v[i] >> 31; const u32 x = v[i] & 0x7fffffffu, tag = nz ? 1u : 0u;
+                const bool rice = nz ? urn : urz; const u32 k = nz ? k1 : k0;
+                u32 n, code;
+                if (rice) { u32 q = x >> k; n = q + 2 + k; code = (tag << ((n - 1) & 31)) | ((((u32)1 << (q & 31)) - 1u) << (k + 1)) | (x & ((1u << k) - 1u)); }
+                else { n = 2 * bitlen32(x); code = (tag << ((n - 1) & 31)) | x; }
+                if (n <= 32 && st.use) ba.push(st, code, n);
+                else {
+                    ba.finish(st);
+                    u64 bp = ba.bitpos(st);
+                    if (rice) long_rice_tok(&st, bp, 1, tag, x, k); else long_gamma_tok(&st, bp, tag, x);
+                    ba.init(st, bp + n);
+                }
             }
         }
+        ba.finish(st);
     }
     st.flush();
 }
@@ -447,18 +498,25 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_k2_pack(const u8* __re
         if (tid == 0) s_excl = e;
     }
     __syncthreads();
-    u64 bp = bitbase + s_excl + (bincl - mybits);
+    const u64 bp0 = bitbase + s_excl + (bincl - mybits);
     __shared__ u32 s_stage[STAGE_WORDS];
     BitStage st;
     st.begin(s_stage, out, bitbase + s_excl, btot);
+    BitAcc ba; ba.init(st, bp0);
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
         if ((nsym_mask >> i) & 1u) {
-            u32 t = sym[i], q = t >> 2;
-            st.rice_tok(bp, 0, 0, t, 2);                    // q ones, the terminating 0 and the 2 remainder bits
-            bp += q + 3;
+            const u32 t = sym[i], q = t >> 2, n = q + 3;     // q ones, the terminating 0 and the 2 remainder bits
+            if (n <= 32 && st.use) ba.push(st, ((((u32)1 << q) - 1u) << 3) | (t & 3u), n);
+            else {
+                ba.finish(st);
+                u64 bp = ba.bitpos(st);
+                long_rice_tok(&st, bp, 0, 0, t, 2);
+                ba.init(st, bp + n);
+            }
         }
     }
+    ba.finish(st);
     st.flush();
 }
 

@@ -42,5 +42,13 @@ for r in rows[2:]:
         scaled(r, "dram__bytes_read.sum", 1e6), scaled(r, "dram__bytes_write.sum", 1e6),
         float(g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")), float(g(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed")),
         float(g(r, "sm__warps_active.avg.pct_of_peak_sustained_active")), g(r, "launch__registers_per_thread"), int(float(g(r, "smsp__inst_executed.sum")))))
+# machine-readable DRAM traffic per captured launch (bench.py reads it for roofline.traffic)
+import json
+traffic = collections.defaultdict(list)
+for r in rows[2:]:
+    name = g(r, "Kernel Name").split("(")[0].replace("void ", "")
+    traffic[name].append({"grid": int(g(r, "launch__grid_size")), "time_us": round(scaled(r, "gpu__time_duration.sum", 1), 1),
+                          "dram_read_bytes": int(scaled(r, "dram__bytes_read.sum", 1)), "dram_write_bytes": int(scaled(r, "dram__bytes_write.sum", 1))})
+json.dump({"command": cmd, "source": f"ncu --set full, {rep.split('/')[-1]}", "kernels": traffic}, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
 open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out))
