@@ -147,6 +147,90 @@ class BlockPipeline:
             res["k2_payload"], res["k2_off"], res["k2_sizes"] = self.h_k2[:k2pos], k2_off, np.concatenate(k2_sizes)
         return res
 
+    # ------------------------------------------------------------------
+    def encode_host_many(self, batches, k2_flags: int = 0):
+        """Streaming form of `encode_host` for corpora larger than one batch: `batches` yields (data, off) pairs, the results
+        come back in order (same dict as `encode_host`).  Two device input buffers and two pinned payload buffers alternate, so
+        the H2D copy of batch i+1 and the D2H copy of batch i's payloads run on their own streams underneath the kernels of the
+        neighbouring batch; every batch is still copied in and its payloads copied out.  A result (its tensors alias the pinned
+        buffers) must be consumed before the generator is advanced."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        if not hasattr(self, "_slots"):
+            with torch.cuda.device(self.device):
+                self._slots = [dict(d_in=self.d_in, h_in=self.h_in, h_kf=None, h_k2=None),
+                               dict(d_in=torch.empty(self.cap + 64, dtype=torch.uint8, device=self.device), h_in=None, h_kf=None, h_k2=None)]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+
+            def h2d(batch, slot):
+                data, off = batch
+                off = np.asarray(off, dtype=np.int64)
+                n = int(off[-1])
+                if isinstance(data, torch.Tensor):
+                    src = data
+                else:
+                    arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+                    src = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
+                sl = self._slots[slot]
+                if not src.is_pinned():
+                    if sl["h_in"] is None:
+                        sl["h_in"] = torch.empty(self.cap, dtype=torch.uint8).pin_memory()
+                    sl["h_in"][:n].copy_(src[:n])
+                    src = sl["h_in"]
+                with torch.cuda.stream(self.s_in):
+                    self.s_in.wait_stream(main)             # the previous user of this input buffer has finished
+                    sl["d_in"][:n].copy_(src[:n], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.s_in)
+                return off, n, ev
+
+            def run(slot, off, n, ev):
+                sl, c = self._slots[slot], self.ctx
+                nb = len(off) - 1
+                main.wait_event(ev)
+                c.bbwt_forward(sl["d_in"], off, out=self.d_bbwt)
+                c.mtf_encode(self.d_bbwt, off, out=self.d_mtf)
+                main.wait_stream(self.s_out)                # the previous batch's payloads have left d_kf / d_k2
+                res = {"h2d_bytes": n, "d2h_bytes": 0, "chunks": 1}
+                for on, key, enc in ((self.profile_kf, "kf", lambda: c.rice_kf_encode(self.d_mtf, off, out=self.d_kf, want_params=True)),
+                                     (self.profile_k2, "k2", lambda: c.rice_k2_encode(self.d_mtf, off, k2_flags, out=self.d_k2))):
+                    if not on:
+                        continue
+                    pay, o, extra = enc()
+                    m = int(o[-1])
+                    hk = "h_" + key
+                    if sl[hk] is None or sl[hk].numel() < m:
+                        sl[hk] = torch.empty(max(m + (m >> 3), n, 1 << 16), dtype=torch.uint8).pin_memory()
+                    with torch.cuda.stream(self.s_out):
+                        self.s_out.wait_stream(main)
+                        sl[hk][:m].copy_(pay[:m], non_blocking=True)
+                    res[key + "_payload"], res[key + "_off"] = sl[hk][:m], o
+                    res["kf_params" if key == "kf" else "k2_sizes"] = extra
+                    res["d2h_bytes"] += m
+                done = torch.cuda.Event()
+                done.record(self.s_out)
+                return res, done
+
+            slot = 0
+            off, n, ev = h2d(cur, slot)
+            pending = None
+            while cur is not None:
+                nxt = next(it, None)
+                if nxt is not None:
+                    nxt_args = h2d(nxt, slot ^ 1)           # travels while this batch is being encoded
+                out = run(slot, off, n, ev)
+                if pending is not None:
+                    pending[1].synchronize()
+                    yield pending[0]
+                pending, cur, slot = out, nxt, slot ^ 1
+                if nxt is not None:
+                    off, n, ev = nxt_args
+            pending[1].synchronize()
+            yield pending[0]
+
     def _grow(self, hbuf: torch.Tensor, used: int, more: int) -> torch.Tensor:
         """Pinned host buffer with room for used+more bytes (payloads usually shrink; incompressible data can expand)."""
         if used + more <= hbuf.numel():

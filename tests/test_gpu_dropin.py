@@ -128,3 +128,4 @@ def test_error_behaviour():
     assert KF.compress(b"") == bytes.fromhex("4b4f4c4d" "00200000" "0000000000000000" "0000")
     assert V.compress_blocks_fixed(b"", 2048) == bytes.fromhex("4b4f4c520008000000000000000004000000000000")
     assert V.decompress(V.compress_blocks_fixed(b"", 2048)) == b""
+
