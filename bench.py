@@ -339,12 +339,15 @@ def ncu_traffic(category, args):
     if kname is None or not os.path.isfile(path) or args.mib != 256 or args.block_kib != 1024:
         return None, "no ncu capture for this kernel/workload"
     doc = json.load(open(path))
-    rows = [r for k, v in doc["kernels"].items() if k.startswith(kname) for r in v]
+    rows = [(k, r) for k, v in doc["kernels"].items() if k.startswith(kname) for r in v]
     if not rows:
         return None, "kernel not in the ncu capture"
-    mean = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows) / len(rows)
-    return int(mean), "mean of the %d largest launches in %s (%s); those launches cover %s tiles of <= 4096 records" % (
-        len(rows), "profiles/r1_final_traffic.json", doc["source"], "/".join(str(r["grid"]) for r in rows))
+    mean = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for _, r in rows) / len(rows)
+    # algorithmic bytes of the SAME launches (grid = tiles of 4096 records; bytes per record as in the KL() launch macros)
+    per_rec = {"k_rerank": lambda k: 16 if k.startswith("k_rerank<1") else 20, "k_radix_scatter": lambda k: 16, "k_gather": lambda k: 4}[kname]
+    alg = sum(r["grid"] * 4096 * per_rec(k) for k, r in rows) / len(rows)
+    return int(mean), "mean of the %d largest launches in %s (%s): DRAM %.2f GB vs %.2f GB algorithmic for those launches (ratio %.2f)" % (
+        len(rows), "profiles/r1_final_traffic.json", doc["source"], mean / 1e9, alg / 1e9, mean / alg)
 
 
 def main():
