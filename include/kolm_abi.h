@@ -121,6 +121,25 @@ int kolm_repair_max_block(void);
 int64_t kolm_cdc_kf(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap);
 int64_t kolm_cdc_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, int64_t* ends, int64_t cap);
 
+/* GPU-assisted chunking: the per-byte scan of the two functions above runs on the device, the chain over
+ * chunks on the host.  Both reference loops roll h = (h << 1) + GEAR[byte] from h = 0 at start+min_size (KF.py:176-190,
+ * V22.py:262-296); once k bytes are in the hash its low k bits depend on the last k bytes only, i.e. on the position alone.
+ *   kolm_cdc_candidates : evaluates that window test at every position lo <= p < hi of d_data (device pointer; bytes
+ *                         d_data[max(0, lo-32) .. lo) are read as history) and writes d_out[0] = number found,
+ *                         d_out[1 + i] = ((base + p) << 1) | strict  in arbitrary order.  variant 0 = KF gear, one mask of
+ *                         k bits (strict == loose); variant 1 = V22 gear, loose mask k-2 bits, strict mask k+2 bits
+ *                         (V22.py:233-240).  d_out must hold 1 + cap words; *count (host) receives the number found;
+ *                         KOLM_E_CAPACITY if it exceeds cap (the list is then incomplete: enlarge cap or use kolm_cdc_*).
+ *   kolm_cdc_walk_kf / _v22 : host.  data = the same bytes in host memory (only the <= 19 bytes after each start+min_size are
+ *                         read: the truncated hash), cand/ncand = the list (sorted in place).  Return value, ends[] and error
+ *                         codes exactly as kolm_cdc_kf / kolm_cdc_v22. */
+int kolm_cdc_candidates(kolm_ctx* ctx, const uint8_t* d_data, int64_t lo, int64_t hi, int64_t base, int variant, int64_t avg_size,
+                        uint64_t* d_out, int64_t cap, int64_t* count, cudaStream_t stream);
+int64_t kolm_cdc_walk_kf(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, uint64_t* cand, int64_t ncand,
+                         int64_t* ends, int64_t cap);
+int64_t kolm_cdc_walk_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, uint64_t* cand, int64_t ncand,
+                          int64_t* ends, int64_t cap);
+
 /* Payload gather after model selection: block b's winning payload is len[b] bytes at DEVICE address src_addr[b] (any of
  * the per-model payload buffers, or the input itself for RAW); they are laid out back to back at `out` in block order —
  * the payload area of a container (KF.py:896-901; V22.py:2443-2444).  src_addr/len: HOST arrays; out_off (HOST, nblocks+1)

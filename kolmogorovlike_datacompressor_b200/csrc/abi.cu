@@ -1,6 +1,7 @@
 // abi.cu — extern "C" surface of libkolm_b200.so (include/kolm_abi.h), context and batch setup.
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -363,6 +364,9 @@ int64_t kolm_cdc_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t a
 }
 
 }  // extern "C"
+
+#include "cdc.cu"
+
 
 // ------------------------------------------------------------------------------------------------
 // payload gather (device part): after model selection the winners' payloads live in different

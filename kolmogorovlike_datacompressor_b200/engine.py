@@ -89,6 +89,57 @@ class Engine:
         return cls._shared[d]
 
     # ------------------------------------------------------------------
+    def cdc_boundaries(self, which: str, data: bytes, mn: int, avg: int, mx: int, piece: int = 64 << 20) -> List[Tuple[int, int]]:
+        """Content-defined chunk boundaries with the per-byte scan on the GPU: the data goes up in pieces
+        (32 bytes of history each), `kolm_cdc_candidates` returns the positions whose window hash passes the mask test and
+        `kolm_cdc_walk_*` (host C++) follows the chain over them.  Bit-identical to the host functions; degenerate inputs whose
+        candidate list would not be sparse (e.g. constant data where every position passes) use the host scan."""
+        n = len(data)
+        if n == 0:
+            return []
+        if which == "v22" and (not (0 < mn <= avg <= mx) or avg < 64):
+            raise ValueError("Require 0 < min_size <= avg_size <= max_size and avg_size >= 64")
+        L = _lib.lib()
+        self._ensure(1 << 20, 16)
+        variant = 0 if which == "kf" else 1
+        k = max(6, min(20, int(avg).bit_length() - 1))
+        kl = k if variant == 0 else (k - 2 if k > 2 else 1)
+        arr = np.frombuffer(data, dtype=np.uint8)
+        lists = []
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            sp = C.c_void_p(stream.cuda_stream)
+            pin = torch.empty(min(n, piece) + 32, dtype=torch.uint8).pin_memory()
+            dbuf = torch.empty(min(n, piece) + 32, dtype=torch.uint8, device="cuda")
+            cap = max(4096, 4 * ((min(n, piece) >> kl) + 1))
+            dout = torch.empty(cap + 1, dtype=torch.int64, device="cuda")
+            for a in range(0, n, piece):
+                b = min(n, a + piece)
+                hist = min(a, 32)
+                m = b - a + hist
+                pin[:m].numpy()[:] = arr[a - hist:b]
+                dbuf[:m].copy_(pin[:m], non_blocking=True)
+                cnt = C.c_int64(0)
+                rc = L.kolm_cdc_candidates(self.ctx._h, C.c_void_p(dbuf.data_ptr()), hist, m, a - hist, variant, avg,
+                                           C.c_void_p(dout.data_ptr()), cap, C.byref(cnt), sp)
+                if rc == -3:                                 # not sparse: the host scan is the right tool
+                    return cdc_boundaries(which, data, mn, avg, mx)
+                _lib.check(rc)
+                if cnt.value:
+                    lists.append(dout[1:1 + cnt.value].cpu().numpy().view(np.uint64))
+        cand = np.ascontiguousarray(np.concatenate(lists)) if lists else np.zeros(0, dtype=np.uint64)
+        capn = n // max(1, mn) + 4
+        ends = np.zeros(capn, dtype=np.int64)
+        buf = C.cast(C.c_char_p(data), C.c_void_p)
+        r = getattr(L, "kolm_cdc_walk_" + which)(buf, n, mn, avg, mx, C.c_void_p(cand.ctypes.data), cand.size,
+                                                 ends.ctypes.data_as(C.POINTER(C.c_int64)), capn)
+        if r < 0:
+            if r == -2:
+                raise ValueError("Require 0 < min_size <= avg_size <= max_size and avg_size >= 64")
+            raise _lib.KolmError(int(r))
+        e = ends[:r]
+        return list(zip([0] + e[:-1].tolist(), e.tolist()))
+
     def _ensure(self, nbytes: int, nblocks: int):
         if self.ctx is None or nbytes > self.cap_bytes or nblocks > self.cap_blocks:
             if self.ctx is not None:

@@ -24,6 +24,9 @@ from .engine import Engine, cdc_boundaries, raise_like_reference
 _NAMES = {0: "raw", 1: "kf_xor", 2: "kf_bbwt", 3: "kf_lz77"}
 
 
+GPU_CDC_MIN_BYTES = 8 << 20   # below this the host scan (~1 GB/s) beats a copy + launch + list read-back
+
+
 def _engine() -> Engine:
     return Engine.shared()
 
@@ -55,7 +58,10 @@ def uleb128_decode_stream(data: bytes, pos: int = 0) -> Tuple[int, int]:
 
 
 def cdc_fast_boundaries(data: bytes, min_size: int = 4096, avg_size: int = 8192, max_size: int = 16384) -> List[Tuple[int, int]]:
-    return cdc_boundaries("kf", bytes(data), min_size, avg_size, max_size)
+    data = bytes(data)
+    if len(data) >= GPU_CDC_MIN_BYTES:                       # the per-byte scan runs on the GPU, the chain over chunks on the host
+        return _engine().cdc_boundaries("kf", data, min_size, avg_size, max_size)
+    return cdc_boundaries("kf", data, min_size, avg_size, max_size)
 
 
 def _one(fn: str, data: bytes) -> bytes:
@@ -177,15 +183,16 @@ def decompress(blob: bytes) -> bytes:
     return out
 
 
-if __name__ == "__main__":
+def main(argv=None) -> int:
+    """Command line of the reference (kolm_final.py:963-984): same arguments, defaults and messages."""
     import argparse
     import os
     ap = argparse.ArgumentParser(description="KOLM compressor (GPU hot path)")
-    ap.add_argument("input")
-    ap.add_argument("-d", "--decompress", action="store_true")
-    ap.add_argument("-o", "--output")
-    ap.add_argument("-b", "--block", type=int, default=8192)
-    a = ap.parse_args()
+    ap.add_argument("input", help="Input file to compress or decompress")
+    ap.add_argument("-d", "--decompress", action="store_true", help="Decompress instead of compress")
+    ap.add_argument("-o", "--output", help="Output file")
+    ap.add_argument("-b", "--block", type=int, default=8192, help="Target block size for compression (default 8192)")
+    a = ap.parse_args(argv)
     src = open(a.input, "rb").read()
     if a.decompress:
         dst = decompress(src)
@@ -197,3 +204,8 @@ if __name__ == "__main__":
         name = a.output or (a.input + ".kolm")
         open(name, "wb").write(dst)
         print(f"Compressed {len(src)} bytes to {len(dst)} bytes (ratio {len(dst) / len(src) if src else 1.0:.3f}) → {name}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -31,6 +31,9 @@ MODE_FIXED = 0
 MODE_CDC = 1
 
 
+GPU_CDC_MIN_BYTES = 8 << 20   # below this the host scan (~1 GB/s) beats a copy + launch + list read-back
+
+
 def _engine() -> Engine:
     return Engine.shared()
 
@@ -91,7 +94,10 @@ def cdc_fast_boundaries_strict(data: bytes, min_size: int = 4096, avg_size: int 
         raise ValueError("avg_size too small; use >= 64")
     if not merge_orphan_tail:
         raise NotImplementedError("merge_orphan_tail=False is not used by the reference's compressors")
-    return cdc_boundaries("v22", bytes(data), min_size, avg_size, max_size)
+    data = bytes(data)
+    if len(data) >= GPU_CDC_MIN_BYTES:                       # the per-byte scan runs on the GPU, the chain over chunks on the host
+        return _engine().cdc_boundaries("v22", data, min_size, avg_size, max_size)
+    return cdc_boundaries("v22", data, min_size, avg_size, max_size)
 
 
 # ---- candidate registry ------------------------------------------------------------------------------
@@ -433,3 +439,51 @@ def decompress(container: bytes) -> bytes:
     if pos != len(container):
         raise ValueError(f"Extra trailing {len(container) - pos} bytes after container end")
     return out
+
+
+def main(argv=None) -> int:
+    """Command line of the reference (v2-2.py:2624-2692): same flags, defaults, derived FastCDC sizes and messages.  `--experiment`
+    (matplotlib plot over random.Random data) is not part of the hot path and is not offered."""
+    import argparse
+    import os
+    global G_NO_LZ77, G_ONLY_METHOD, G_PROGRESS
+    ap = argparse.ArgumentParser(description="Kolmogorov researched compressor (GPU hot path)")
+    ap.add_argument("-i", "--input", nargs="?", help="Input file to compress or decompress")
+    ap.add_argument("-d", "--decompress", action="store_true", help="Decompress")
+    ap.add_argument("-o", "--output", help="Output file")
+    ap.add_argument("-b", "--block", type=int, default=2048, help="Target block size (FIXED) or avg_size (FastCDC)")
+    ap.add_argument("--FastCDC", "--fastcdc", dest="fastcdc", action="store_true",
+                    help="Use Fast Content-Defined Chunking (avg_size = --block). When off, use fixed-size chunking.")
+    ap.add_argument("--no-lz77", action="store_true", help="Disable LZ77 candidate")
+    ap.add_argument("--only", type=str, default=None, help="Only use a single model by name (e.g. lz77, raw)")
+    ap.add_argument("--progress", action="store_true", help="Show per-block progress")
+    a = ap.parse_args(argv)
+    G_NO_LZ77, G_ONLY_METHOD, G_PROGRESS = bool(a.no_lz77), a.only, bool(a.progress)
+    if not a.input:
+        ap.print_help()
+        return 0
+    data = open(a.input, "rb").read()
+    if a.decompress:
+        out = decompress(data)
+        name = a.output or (os.path.splitext(a.input)[0] + ".out")
+        open(name, "wb").write(out)
+        print(f"Decompressed {len(data)} bytes to {len(out)} bytes → {name}")
+        return 0
+    if a.fastcdc:
+        avg = max(64, a.block)                               # v2-2.py:2672-2675
+        mn = max(64, min(avg, avg // 2 if avg >= 2 else 64))
+        mx = max(avg, avg * 2)
+        blob = compress_blocks_cdc(data, min_size=mn, avg_size=avg, max_size=mx)
+        mode = f"FastCDC(min={mn}, avg={avg}, max={mx})"
+    else:
+        blob = compress_blocks_fixed(data, block_size=a.block)
+        mode = f"FIXED(block={a.block})"
+    name = a.output or (a.input + ".kolr")
+    open(name, "wb").write(blob)
+    ratio = len(blob) / len(data) if len(data) else 1.0
+    print(f"[{mode}] Compressed {len(data)} bytes to {len(blob)} bytes (ratio {ratio:.3f}) → {name}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -129,3 +129,33 @@ def test_error_behaviour():
     assert V.compress_blocks_fixed(b"", 2048) == bytes.fromhex("4b4f4c520008000000000000000004000000000000")
     assert V.decompress(V.compress_blocks_fixed(b"", 2048)) == b""
 
+
+
+def test_command_lines(tmp_path, capsys):
+    """The reference's two command lines (kolm_final.py:963-984, kolm_final_researched_v2-2.py:2624-2692): same flags, same
+    default output names and messages, byte-identical containers (cfg 1: checker.bmp -> 1843 bytes)."""
+    from kolmogorovlike_datacompressor_b200 import kolm_final as KF, kolm_final_researched_v2_2 as V
+    name = sorted(datasets.FIXTURES)[0]
+    d = datasets.fixture(name)
+    src = tmp_path / "in.bin"
+    src.write_bytes(d)
+    assert KF.main([str(src)]) == 0
+    blob = (tmp_path / "in.bin.kolm").read_bytes()
+    g = json.load(open(os.path.join(GOLD, "fixture_%s_kf.json" % name)))
+    assert same(blob, g["container"])
+    assert f"Compressed {len(d)} bytes to {len(blob)} bytes" in capsys.readouterr().out
+    assert KF.main(["-d", str(tmp_path / "in.bin.kolm"), "-o", str(tmp_path / "back")]) == 0
+    assert (tmp_path / "back").read_bytes() == d
+    assert V.main(["-i", str(src), "-b", "2048"]) == 0
+    blob = (tmp_path / "in.bin.kolr").read_bytes()
+    g = json.load(open(os.path.join(GOLD, "fixture_%s_v22.json" % name)))
+    assert same(blob, g["container"])
+    assert "[FIXED(block=2048)] Compressed" in capsys.readouterr().out
+    # --only filters the candidate list and method ids index the FILTERED list (v2-2.py:2170-2176), so, as in the reference,
+    # only a filter that keeps id 0 = raw in place decodes again with the full decoder table
+    assert V.main(["-i", str(src), "--fastcdc", "-b", "4096", "--only", "raw", "-o", str(tmp_path / "c.kolr")]) == 0
+    assert "[FastCDC(min=2048, avg=4096, max=8192)]" in capsys.readouterr().out
+    assert V.main(["-d", "-i", str(tmp_path / "c.kolr")]) == 0
+    assert (tmp_path / "c.out").read_bytes() == d
+    assert V.main(["-i", str(src), "--fastcdc", "-b", "4096"]) == 0 and V.G_ONLY_METHOD is None
+    assert V.decompress((tmp_path / "in.bin.kolr").read_bytes()) == d
