@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(256) k_radix_scan(u32* __restrict__ thist, con
 }
 
 // radix pass 3/3: stable scatter of one tile.  Keys/values staged with 1-D TMA into shared memory.
+// The kernel is bound by shared-memory wavefronts (ncu: ~1 per element), so the reorder step keeps them low: the per-warp
+// digit offsets are folded with the digit starts (one table lookup per element instead of two) and the global base is
+// pre-reduced by the digit start.  (Moving key and value as one 64-bit word costs 30 more registers and a CTA per SM.)
 __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __restrict__ Kin, const u32* __restrict__ Vin,
                                                                 u32* __restrict__ Kout, u32* __restrict__ Vout,
                                                                 const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __res
     __shared__ __align__(128) u32 sv[KOLM_TILE];
     __shared__ u32 whist[NWARPS][256];
     __shared__ u32 dstart[256];
-    __shared__ u32 gbase[256];
+    __shared__ u32 gofs[256];
     __shared__ __align__(8) u64 bar;
     const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     TileDesc td = tiles[blockIdx.x];
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __res
         tma_load_1d(sk, Kin + td.start, bytes, &bar);
         tma_load_1d(sv, Vin + td.start, bytes, &bar);
     }
-    gbase[tid] = thist[(size_t)blockIdx.x * 256 + tid] + binfo[td.block].pbase;
+    const u32 gb = thist[(size_t)blockIdx.x * 256 + tid] + binfo[td.block].pbase;
     mbar_wait(&bar, 0);
     // ---- rank: warp w owns elements [w*IPT*32, (w+1)*IPT*32), iteration k covers 32 consecutive ones
     u32 key[KOLM_IPT], val[KOLM_IPT]; u16 off[KOLM_IPT];
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __res
         off[k] = (u16)(old + lt);
         __syncwarp();
     }
-    __syncthreads();
+    __syncthreads();                                        // every thread holds its records in registers: the staging area is free
     // ---- per digit: exclusive scan over warps, then over digits
     {
         u32 run = 0;
@@ -364,22 +367,28 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __res
         for (int i = 0; i < 8; ++i) dstart[tid * 8 + i] = pre + loc[i];
     }
     __syncthreads();
+    {   // whist[i][d] = slot of warp i's first element of digit d inside the tile; gofs[d] = global base - digit start
+        const u32 ds = dstart[tid];
+#pragma unroll
+        for (int i = 0; i < NWARPS; ++i) whist[i][tid] += ds;
+        gofs[tid] = gb - ds;
+    }
+    __syncthreads();
     // ---- reorder inside shared memory (everything is in registers now)
 #pragma unroll
     for (int k = 0; k < KOLM_IPT; ++k) {
         u32 idx = w * (KOLM_IPT * 32) + k * 32 + lane;
         if (idx < td.count) {
             u32 d = (key[k] >> shift) & mask;
-            u32 pos = dstart[d] + whist[w][d] + off[k];
+            const u32 pos = whist[w][d] + off[k];
             sk[pos] = key[k]; sv[pos] = val[k];
         }
     }
     __syncthreads();
     // ---- coalesced digit runs to global
     for (u32 s = tid; s < td.count; s += KOLM_THREADS) {
-        u32 kk = sk[s];
-        u32 d = (kk >> shift) & mask;
-        u32 g = gbase[d] + (s - dstart[d]);
+        const u32 kk = sk[s];
+        const u32 g = gofs[(kk >> shift) & mask] + s;
         Kout[g] = kk; Vout[g] = sv[s];
     }
 }
@@ -880,11 +889,10 @@ __global__ void __launch_bounds__(128) k_lyn_resolve(const u8* __restrict__ in, 
 // Blocks the candidate path gave up on (long runs / periods): Duval's walk (kolm_final.py:200-225) by one warp, with the
 // run of equal comparisons s[k]==s[j] taken 128 bytes at a time.  Degenerate data is exactly where those runs are long, so
 // the walk needs few steps there; an iteration cap sends pathological blocks to the ISA path.
-#define DUVAL_MAX_ITERS (1u << 18)
-#define DUVAL_MAX_BLOCK (2u << 20)
+#define DUVAL_MAX_BLOCK_DEFAULT (64u << 20)   // KOLM_DUVAL_MAX_MIB: larger failed blocks send the batch to the ISA path
 __global__ void __launch_bounds__(128) k_lyn_duval(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, const u32* __restrict__ blockfail,
                                                    u32* __restrict__ fstart, u32* __restrict__ nfac, u8* __restrict__ flags_out,
-                                                   u32* __restrict__ fallback, int nblocks) {
+                                                   u32* __restrict__ fallback, int nblocks, u32 max_block) {
     const u32 lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nblocks || !blockfail[b]) return;
@@ -892,19 +900,20 @@ __global__ void __launch_bounds__(128) k_lyn_duval(const u8* __restrict__ in, co
     const u8* s = in + bi.ioff;
     const u32 n = bi.len;
     // one warp walks the block serially: only worth it for blocks it can finish in a few ms; larger ones go to the ISA path
-    if (n > DUVAL_MAX_BLOCK) { if (lane == 0) atomicExch(fallback, 2u); return; }
+    if (n > max_block) { if (lane == 0) atomicExch(fallback, 2u); return; }
+    const u32 max_iters = (1u << 18) + n / 16, max_siters = (1u << 20) + n / 8;   // work caps (about 0.1-0.3 s worst case): beyond them the ISA path decides
     u32 i = 0, nf = 0, iters = 0, siters = 0;
     while (i < n) {
         u32 j = i + 1, k = i;
         const u32 si = s[i];
-        u32 run = 0;                                         // consecutive equal comparisons
+        u32 run = 0, adv = 0;                                // consecutive equal comparisons / consecutive plain advances
         u32 jw = 0, jwbase = 0xffffffffu;                    // 4-byte window of s around j (one load per 4 scalar steps)
         for (;;) {
             if (j >= n) break;
             if (run >= 16) {
                 // long common prefix of s[k..] and s[j..]: skip it 128 bytes per step with the whole warp
                 for (;;) {
-                    if (++iters > DUVAL_MAX_ITERS) { if (lane == 0) atomicExch(fallback, 2u); return; }
+                    if (++iters > max_iters) { if (lane == 0) atomicExch(fallback, 2u); return; }
                     u32 x = lane * 4, m = 4;
 #pragma unroll
                     for (int t = 3; t >= 0; --t) { u32 jj = j + x + t; if (jj >= n || s[k + x + t] != s[jj]) m = t; }
@@ -915,14 +924,45 @@ __global__ void __launch_bounds__(128) k_lyn_duval(const u8* __restrict__ in, co
                 run = 0;
                 if (j >= n) break;
             }
+            if (k == i && adv >= 8) {                       // only after a streak of plain advances: dense stops would cost a step each
+                // fresh comparison against the factor's first byte: every byte > s[i] only advances j, so the warp skips to the
+                // first byte <= s[i], 512 bytes (32 aligned 16-byte loads) per step
+                const u8* sa16 = reinterpret_cast<const u8*>(reinterpret_cast<uintptr_t>(s + j) & ~(uintptr_t)15);
+                const i64 rel0 = (i64)(sa16 - s);                      // block offset of the aligned base (may be negative by < 16)
+                const u32 pat = si * 0x01010101u;
+                bool found = false;
+                for (i64 base = rel0;; base += 512) {
+                    if (++iters > max_iters) { if (lane == 0) atomicExch(fallback, 2u); return; }
+                    const i64 o = base + lane * 16;
+                    u32 first = 16;
+                    if (o < (i64)n && o + 16 > (i64)j) {
+                        // the aligned 16 bytes may start before the block or end after it: stay inside [0, n) of the batch buffer's
+                        // allocation by reading bytes when the vector would cross either end
+                        u32 w[4];
+                        if (o >= 0 && o + 16 <= (i64)n) { const uint4 q = *reinterpret_cast<const uint4*>(s + o); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+                        else { w[0] = w[1] = w[2] = w[3] = 0xffffffffu; for (int t = 0; t < 16; ++t) { i64 x = o + t; if (x >= 0 && x < (i64)n) { w[t >> 2] = (w[t >> 2] & ~(0xFFu << (8 * (t & 3)))) | ((u32)s[x] << (8 * (t & 3))); } } }
+#pragma unroll
+                        for (int q4 = 3; q4 >= 0; --q4) {
+                            u32 le = __vcmpleu4(w[q4], pat);                       // 0xFF in every byte <= s[i]
+#pragma unroll
+                            for (int t = 3; t >= 0; --t) { const i64 x = o + q4 * 4 + t; if (((le >> (8 * t)) & 1u) && x >= (i64)j && x < (i64)n) first = q4 * 4 + t; }
+                        }
+                    }
+                    const u32 bal = __ballot_sync(FULL, first < 16);
+                    if (bal) { const u32 l = __ffs(bal) - 1; j = (u32)(base + l * 16 + __shfl_sync(FULL, first, l)); found = true; break; }
+                    if (base + 512 >= (i64)n) break;
+                }
+                if (!found) { j = n; break; }
+                adv = 0;
+            }
             // scalar step (all lanes redundantly: uniform control flow, broadcast loads)
-            if (++siters > 3u * DUVAL_MAX_BLOCK) { if (lane == 0) atomicExch(fallback, 2u); return; }
+            if (++siters > max_siters) { if (lane == 0) atomicExch(fallback, 2u); return; }
             if ((j & ~3u) != jwbase) { jwbase = j & ~3u; jw = 0; for (u32 t = 0; t < 4 && jwbase + t < n; ++t) jw |= (u32)s[jwbase + t] << (8 * t); }
             const u32 cj = (jw >> (8 * (j & 3))) & 0xFF;
             const u32 ck = (k == i) ? si : (u32)s[k];
-            if (ck == cj) { ++k; ++j; ++run; continue; }
+            if (ck == cj) { ++k; ++j; ++run; adv = 0; continue; }
             run = 0;
-            if (ck < cj) { k = i; ++j; } else break;
+            if (ck < cj) { k = i; ++j; ++adv; } else break;
         }
         const u32 p = j - k;
         const u32 cnt = (k - i) / p + 1;                     // while i <= k: emit i; i += p
@@ -1134,11 +1174,13 @@ int kolm_lyndon_impl(kolm_ctx* c, const u8* in, u8* flags_out, int* rounds_out, 
         if (c->h_stats[8] == 0) { if (rounds_out) *rounds_out = 0; return KOLM_OK; }
         static int duval = -1;
         if (duval < 0) { const char* e = getenv("KOLM_LYNDON_DUVAL"); duval = e ? atoi(e) : 1; }
+        static u32 duval_max = 0;
+        if (!duval_max) { const char* e = getenv("KOLM_DUVAL_MAX_MIB"); duval_max = e ? (u32)atoi(e) << 20 : DUVAL_MAX_BLOCK_DEFAULT; }
         if (duval) {
             // second chance for the blocks that failed: vectorised Duval walk, one warp per block
             CUDA_TRY(cudaMemsetAsync(c->d_stats + 8, 0, 4, s));
             KL(c, KC_LYNDON, c->total_bytes / 8, s, k_lyn_duval<<<(c->nblocks + 3) / 4, 128, 0, s>>>(in, c->d_binfo, blockfail, c->d_fstart, c->d_nfac, flags_out,
-                                                                                                   c->d_stats + 8, c->nblocks));
+                                                                                                   c->d_stats + 8, c->nblocks, duval_max));
             CUDA_TRY(cudaMemcpyAsync(c->h_stats + 8, c->d_stats + 8, 4, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
             CUDA_TRY(cudaGetLastError());
