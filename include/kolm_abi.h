@@ -114,6 +114,13 @@ int kolm_repair_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_of
                     kolm_stream_t stream);
 int kolm_repair_max_block(void);
 
+/* decode_new_pipeline  V22.py:1578-1648 (method 10, "v2_new": header, eight bit planes RAW or Rice(k)-coded run lengths of the
+ * plane's BBWT, inverse of the circuit_map_automaton model V22.py:1054-1092).  The shipped reference never emits this method
+ *  but decodes it.  The context must have been created for >= 8x the batch bytes and 8x the blocks (the planes
+ * are inverse-transformed as one batch of 8*nblocks blocks); otherwise KOLM_E_CAPACITY.  ValueError cases -> KOLM_E_CORRUPT. */
+int kolm_v2new_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,
+                   kolm_stream_t stream);
+
 /* Content-defined chunking, HOST buffers (adjacent to the hot path; bit-identical boundaries are a precondition of
  * byte-identical containers).  ends[i] = exclusive end of chunk i; returns the chunk count or a negative error.
  *   kolm_cdc_kf : cdc_fast_boundaries (KF.py:161-194), gear table of KF.py:148-159

@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,6 +20,7 @@ void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
 #include "lz77.cu"
 #include "residual.cu"
 #include "repair.cu"
+#include "v2new.cu"
 
 static size_t padded_capacity(size_t max_batch_bytes, int max_blocks) {
     return max_batch_bytes + (size_t)KOLM_PAD * (size_t)max_blocks + 4 * KOLM_PAD;
@@ -262,6 +264,12 @@ int kolm_repair_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off,
 }
 
 int kolm_repair_max_block(void) { return REPAIR_MAX; }
+
+int kolm_v2new_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,
+                   kolm_stream_t stream) {
+    if (!c || !pay_off || !off || nblocks < 0) return KOLM_E_ARG;
+    return kolm_v2new_dec_impl(c, payload, pay_off, off, nblocks, out, (cudaStream_t)stream);
+}
 
 int kolm_last_counters(kolm_ctx* c, int64_t* out4) {
     i64 total = 0;

@@ -15,31 +15,63 @@
 
 #define MTF_WARPS 4
 
-// pass A (encode): tlast[tile][c] = 1 + block-local position of the last c in the tile, 0 if absent
-__global__ void __launch_bounds__(KOLM_THREADS) k_mtf_last(const u8* __restrict__ in, const TileDesc* __restrict__ tiles,
-                                                           const BlockInfo* __restrict__ binfo, u32* __restrict__ tlast) {
-    __shared__ u32 last[256];
-    TileDesc td = tiles[blockIdx.x];
-    BlockInfo bi = binfo[td.block];
-    last[threadIdx.x] = 0;
-    __syncthreads();
-    u32 t0 = td.start - bi.pbase;
-    const u8* src = in + bi.ioff + t0;
-    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
-        u8 s = src[x];
-        if (x + 1 == td.count || src[x + 1] != s) atomicMax(&last[s], t0 + x + 1);
-    }
-    __syncthreads();
-    tlast[(size_t)blockIdx.x * 256 + threadIdx.x] = last[threadIdx.x];
+// Sub-tiles: the encode passes can cut every tile into 2^ss pieces of (KOLM_TILE >> ss) bytes (piece x = tile (x >> ss), part
+// (x & mask); parts beyond the tile's count are empty).  More pieces = more independent list walks in k_mtf_enc2, which is
+// bound by the latency of its serial walk and not by traffic (r1 ncu: 10-20 % of the warp slots occupied at 4096 bytes/thread).
+__device__ __forceinline__ void mtf_piece(const TileDesc& td, u32 x, u32 ss, u32& start, u32& count) {
+    const u32 part = x & ((1u << ss) - 1u), plen = KOLM_TILE >> ss, o = part * plen;
+    start = td.start + o;
+    count = td.count > o ? min(plen, td.count - o) : 0u;
 }
 
-// pass B (encode): exclusive running max over the tiles of each block
-__global__ void __launch_bounds__(256) k_mtf_scan_max(u32* __restrict__ tlast, const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks) {
-    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        u32 nt = tilen[b];
-        u32* base = tlast + (size_t)tile0[b] * 256 + threadIdx.x;
+// pass A (encode): tlast[piece][c] = 1 + block-local position of the last c in the piece, 0 if absent.
+// With G > 1 the pieces of a block form G consecutive groups whose column maxima are collected in gt[block][group][c]
+// (pass B then scans the groups independently).
+__global__ void __launch_bounds__(KOLM_THREADS) k_mtf_last(const u8* __restrict__ in, const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
+                                                           const u32* __restrict__ tile0, const u32* __restrict__ tilen, u32* __restrict__ tlast,
+                                                           u32* __restrict__ gt, u32 ss, u32 G) {
+    __shared__ u32 last[256];
+    TileDesc td = tiles[blockIdx.x >> ss];
+    BlockInfo bi = binfo[td.block];
+    u32 start, count;
+    mtf_piece(td, blockIdx.x, ss, start, count);
+    last[threadIdx.x] = 0;
+    __syncthreads();
+    u32 t0 = start - bi.pbase;
+    const u8* src = in + bi.ioff + t0;
+    for (u32 x = threadIdx.x; x < count; x += KOLM_THREADS) {
+        u8 s = src[x];
+        if (x + 1 == count || src[x + 1] != s) atomicMax(&last[s], t0 + x + 1);
+    }
+    __syncthreads();
+    const u32 v = last[threadIdx.x];
+    tlast[(size_t)blockIdx.x * 256 + threadIdx.x] = v;
+    if (G > 1 && v) {
+        const u32 np = tilen[td.block] << ss, Q = (np + G - 1) / G;
+        const u32 g = (blockIdx.x - (tile0[td.block] << ss)) / Q;
+        atomicMax(gt + ((size_t)td.block * G + g) * 256 + threadIdx.x, v);
+    }
+}
+
+// pass B (encode): exclusive running max over the pieces of each block; CTA (block, group) starts from the maxima of the
+// groups before it and walks its own rows, eight in flight per step
+__global__ void __launch_bounds__(256) k_mtf_scan_max(u32* __restrict__ tlast, const u32* __restrict__ tile0, const u32* __restrict__ tilen,
+                                                      const u32* __restrict__ gt, int nblocks, u32 ss, u32 G) {
+    for (u32 x = blockIdx.x; x < (u32)nblocks * G; x += gridDim.x) {
+        const u32 b = x / G, g = x - b * G;
+        const u32 np = tilen[b] << ss, Q = (np + G - 1) / G;
+        const u32 r0 = g * Q, r1 = min(np, r0 + Q);
+        if (r0 >= r1) continue;
         u32 run = 0;
-        for (u32 t = 0; t < nt; ++t) { u32 v = base[(size_t)t * 256]; base[(size_t)t * 256] = run; run = max(run, v); }
+        for (u32 k = 0; k < g; ++k) run = max(run, gt[((size_t)b * G + k) * 256 + threadIdx.x]);
+        u32* base = tlast + ((size_t)tile0[b] << ss) * 256 + threadIdx.x;
+        for (u32 t = r0; t < r1; t += 8) {
+            u32 v[8];
+#pragma unroll
+            for (u32 k = 0; k < 8; ++k) v[k] = t + k < r1 ? base[(size_t)(t + k) * 256] : 0u;
+#pragma unroll
+            for (u32 k = 0; k < 8; ++k) if (t + k < r1) { base[(size_t)(t + k) * 256] = run; run = max(run, v[k]); }
+        }
     }
 }
 
@@ -108,7 +140,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_enc(const u8* __restrict
 __device__ __forceinline__ u32 mtf_zero_byte(u32 x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
 
 __global__ void __launch_bounds__(MTF2_THREADS) k_mtf_enc2(const u8* __restrict__ in, u8* __restrict__ out, const TileDesc* __restrict__ tiles,
-                                                           const BlockInfo* __restrict__ binfo, const u32* __restrict__ tlast, int ntiles) {
+                                                           const BlockInfo* __restrict__ binfo, const u32* __restrict__ tlast, int ntiles, u32 ss) {
     __shared__ u32 lst[64][MTF2_THREADS];                  // packed entry lists, word k of thread t at lst[k][t]
     __shared__ u32 s_ts[MTF2_THREADS / 32][256];           // per warp: timestamps of the tile being converted
     __shared__ u8 s_sym[MTF2_THREADS / 32][256];
@@ -150,18 +182,20 @@ __global__ void __launch_bounds__(MTF2_THREADS) k_mtf_enc2(const u8* __restrict_
     }
     __syncthreads();
     // ---- step 2
-    const int tile = blockIdx.x * MTF2_THREADS + tid;
+    const int tile = blockIdx.x * MTF2_THREADS + tid;          // piece index (ntiles = number of pieces)
     if (tile >= ntiles) return;
-    const TileDesc td = tiles[tile];
+    const TileDesc td = tiles[(u32)tile >> ss];
     const BlockInfo bi = binfo[td.block];
-    const u32 t0 = td.start - bi.pbase;
+    u32 pstart, pcount;
+    mtf_piece(td, (u32)tile, ss, pstart, pcount);
+    const u32 t0 = pstart - bi.pbase;
     const u8* src = in + bi.ioff + t0;
     u8* dst = out + bi.ioff + t0;
     u32 w0 = lst[0][tid];
     const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
-    for (u32 x0 = 0; x0 < td.count; x0 += 16) {
+    for (u32 x0 = 0; x0 < pcount; x0 += 16) {
         u32 inw[4], outw[4] = {0, 0, 0, 0};
-        const u32 nb = min(16u, td.count - x0);
+        const u32 nb = min(16u, pcount - x0);
         if (aligned && nb == 16) { uint4 v = *reinterpret_cast<const uint4*>(src + x0); inw[0] = v.x; inw[1] = v.y; inw[2] = v.z; inw[3] = v.w; }
         else { inw[0] = inw[1] = inw[2] = inw[3] = 0; for (u32 i = 0; i < nb; ++i) inw[i >> 2] |= (u32)src[x0 + i] << (8 * (i & 3)); }
 #pragma unroll
@@ -352,12 +386,25 @@ int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t 
     int wgrid = (nt + MTF_WARPS - 1) / MTF_WARPS;
     if (!decode) {
         const i64 N = c->total_bytes;
-        KL(c, KC_MTF_PRE, N + (i64)nt * 1024, s, k_mtf_last<<<nt, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_thist));
-        KL(c, KC_MTF_SCAN, (i64)nt * 2048, s, k_mtf_scan_max<<<sgrid, 256, 0, s>>>(c->d_thist, c->d_btile0, c->d_btilen, nb));
-        static int v2 = -1;
+        static int v2 = -1, sub = -1;
         if (v2 < 0) { const char* e = getenv("KOLM_MTF_V2"); v2 = e ? atoi(e) : 1; }
-        if (v2) KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc2<<<(nt + MTF2_THREADS - 1) / MTF2_THREADS, MTF2_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt));
-        else KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, c->d_thist, nt));
+        if (sub < 0) { const char* e = getenv("KOLM_MTF_SUB"); sub = e ? atoi(e) : 2; if (sub < 0 || sub > 3) sub = 2; }
+        // pieces of 4096 >> ss bytes; their last-occurrence tables (1 KB each) live in the idle sort buffer d_k0 when they
+        // outgrow d_thist (batches of many tiny blocks keep whole tiles)
+        u32 ss = v2 ? (u32)sub : 0u;
+        if (((size_t)nt << ss) * 256 > c->max_elems) ss = 0;
+        u32* tl = ss ? c->d_k0 : c->d_thist;
+        const int np = nt << ss;
+        // groups per block for the scan: their maxima sit in d_thist, which is free once the tables moved to d_k0
+        u32 G = ss ? (u32)std::min<i64>(8, (i64)c->max_tiles / nb) : 1u;
+        if (G < 1) G = 1;
+        u32* gt = c->d_thist;
+        if (G > 1) CUDA_TRY(cudaMemsetAsync(gt, 0, (size_t)nb * G * 1024, s));
+        const int sg = (int)std::min<i64>((i64)nb * G, 16 * (i64)c->sm_count);
+        KL(c, KC_MTF_PRE, N + (i64)np * 1024, s, k_mtf_last<<<np, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_btile0, c->d_btilen, tl, gt, ss, G));
+        KL(c, KC_MTF_SCAN, (i64)np * 2048, s, k_mtf_scan_max<<<sg, 256, 0, s>>>(tl, c->d_btile0, c->d_btilen, gt, nb, ss, G));
+        if (v2) KL(c, KC_MTF_MAIN, 2 * N + (i64)np * 1024, s, k_mtf_enc2<<<(np + MTF2_THREADS - 1) / MTF2_THREADS, MTF2_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tl, np, ss));
+        else KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 1024, s, k_mtf_enc<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tl, nt));
     } else {
         u8* tperm = (u8*)c->d_thist;
         const i64 N = c->total_bytes;

@@ -403,6 +403,10 @@ class Engine:
                                 y = c.lz77_decode(pt, poff, off, 4096)
                             elif nme == "repair":
                                 y = c.repair_decode(pt, poff, off)
+                            elif nme == "v2_new":
+                                self._ensure(8 * int(off[-1]) + 64, 8 * len(sub))   # the eight bit planes of every block form one batch
+                                c = self.ctx
+                                y = c.v2new_decode(pt, poff, off)
                             else:
                                 raise NotImplementedError("decoder for method '%s' is outside the GPU hot path (SURVEY §8 row a17)" % nme)
                         except _lib.KolmError as err:

@@ -175,6 +175,10 @@ class Context:
     def repair_decode(self, payload, pay_off, off, out=None):
         return self._dec("kolm_repair_dec", payload, pay_off, off, (), out)
 
+    def v2new_decode(self, payload, pay_off, off, out=None):
+        """decode_new_pipeline per block (method 10).  The context must hold 8x the batch (the bit planes are one batch)."""
+        return self._dec("kolm_v2new_dec", payload, pay_off, off, (), out)
+
     def gather_payloads(self, src_addr: np.ndarray, lens: np.ndarray, out: torch.Tensor):
         """Winning payloads (device addresses + lengths per block) -> back to back in `out`; returns out_off."""
         nb = len(lens)

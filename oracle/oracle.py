@@ -46,7 +46,7 @@ def dir_exports():
     return ["ko_duval", "ko_bbwt_forward_literal", "ko_bbwt_forward", "ko_bbwt_inverse", "ko_mtf_encode", "ko_mtf_decode",
             "ko_kf_rice_pack", "ko_kf_rice_unpack", "ko_v22_rice_pack", "ko_v22_rice_unpack", "ko_lz77_encode", "ko_lz77_decode",
             "ko_residual_encode", "ko_residual_decode", "ko_repair_compress", "ko_repair_decompress", "ko_kf_cdc", "ko_v22_cdc",
-            "ko_encode_model", "ko_decode_model", "ko_encode_block", "ko_kf_compress", "ko_kf_decompress"]
+            "ko_v2new_encode", "ko_v2new_decode", "ko_v2new_encode_forced", "ko_encode_model", "ko_decode_model", "ko_encode_block", "ko_kf_compress", "ko_kf_decompress"]
 
 
 def _buf(n):
@@ -160,6 +160,27 @@ def repair_decompress(payload, orig_len):
     p, n = _in(payload)
     out = _buf(orig_len)
     _chk(lib().ko_repair_decompress(p, C.c_int64(n), C.c_int64(orig_len), out))
+    return bytes(out[:orig_len])
+
+
+def v2new_encode(data, force=None):
+    """encode_new_pipeline with circuit_map_automaton_forward(parallel=False) (V22.py:1498-1576).
+    force=(mode, param): skip the model search and use that model (test hook, mirrors make_golden_v2new.py)."""
+    p, n = _in(data)
+    cap = 2 * n + 64
+    out = _buf(cap)
+    if force is None:
+        r = _chk(lib().ko_v2new_encode(p, C.c_int64(n), out, C.c_int64(cap)))
+    else:
+        r = _chk(lib().ko_v2new_encode_forced(p, C.c_int64(n), C.c_int(force[0]), C.c_uint32(force[1]), out, C.c_int64(cap)))
+    return bytes(out[:r])
+
+
+def v2new_decode(payload, orig_len):
+    """decode_new_pipeline (V22.py:1578-1648)."""
+    p, n = _in(payload)
+    out = _buf(orig_len)
+    _chk(lib().ko_v2new_decode(p, C.c_int64(n), C.c_int64(orig_len), out))
     return bytes(out[:orig_len])
 
 
