@@ -224,8 +224,14 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
     if (KF) {
         u64 x = tid;
         s_ptab[tid] = x | ((x >> 1) << 12) | ((x >> 2) << 23) | ((x >> 3) << 33) | ((x >> 4) << 42) | ((x >> 5) << 50) | ((x >> 6) << 57);
+    } else {
+        // K2: Rice(k=2) length (t >> 2) + 3 <= 66 of the plain / nibble-swapped / bit-reversed / Gray byte in 11-bit fields (16 items/thread)
+        const u32 b = tid;
+        s_ptab[tid] = (u64)((b >> 2) + 3) | ((u64)((v22_xform(b, 4) >> 2) + 3) << 11) | ((u64)((v22_xform(b, 8) >> 2) + 3) << 22) |
+                      ((u64)((v22_xform(b, 16) >> 2) + 3) << 33);
+        __syncthreads();
     }
-    u64 packn = 0;
+    u64 packn = 0, packz = 0, packk = 0;
     u32 v[KOLM_IPT + 1];
     load_items(src, t0, td.count, bi.len, v);
     u32 accz[8] = {0, 0, 0, 0, 0, 0, 0, 0};                  // zero runs are disjoint ranges of one block (< 2^30 bytes): warp sums fit 32 bits
@@ -249,8 +255,11 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
                     ++nnt;
                 } else if (v[i + 1] != 0) {                 // zero run ends here (next is non-zero or end of block)
                     u32 run = pos1 - ln;
+                    if (run < 256u) packz += s_ptab[run];   // same packed quotient sums as the non-zeros
+                    else {
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) accz[k] += (run >> k) + 1 + k;
+                        for (int k = 0; k < 7; ++k) accz[k] += run >> k;
+                    }
                     accz[7] += 2 * bitlen32(run) - 1;
                     ++nzt;
                 }
@@ -260,7 +269,10 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
     if (KF) {                                                // unpack the quotient sums, add the per-token constants 1 + k
         const int off[7] = {0, 12, 23, 33, 42, 50, 57}, wid[7] = {12, 11, 10, 9, 8, 7, 6};
 #pragma unroll
-        for (int k = 0; k < 7; ++k) accn[k] = (u32)((packn >> off[k]) & ((1u << wid[k]) - 1u)) + nnt * (1 + k);
+        for (int k = 0; k < 7; ++k) {
+            accn[k] = (u32)((packn >> off[k]) & ((1u << wid[k]) - 1u)) + nnt * (1 + k);
+            accz[k] += (u32)((packz >> off[k]) & ((1u << wid[k]) - 1u)) + nzt * (1 + k);
+        }
     }
     if (K2) {
 #pragma unroll
@@ -274,17 +286,13 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     u32 b = (u32)(g >> (8 * i)) & 0xFF, t = (u32)(tp >> (8 * i)) & 0xFF;
-                    if (r0 + i < td.count) {
-                        k2[0] += (b >> 2) + 3;
-                        k2[2] += (v22_xform(b, 4) >> 2) + 3;
-                        k2[3] += (v22_xform(b, 8) >> 2) + 3;
-                        k2[4] += (v22_xform(b, 16) >> 2) + 3;
-                    }
+                    if (r0 + i < td.count) packk += s_ptab[b];       // four variants' code lengths in one packed add
                     k2[1] += (t >> 2) + 3;                  // bit-plane variant codes the zero-padded group (V22.py:1112-1113)
                 }
             }
         }
     }
+    if (K2) { k2[0] = (u32)(packk & 0x7FF); k2[2] = (u32)((packk >> 11) & 0x7FF); k2[3] = (u32)((packk >> 22) & 0x7FF); k2[4] = (u32)((packk >> 33) & 0x7FF); }
     __syncthreads();
     auto red = [&](u32 x, int slot) {                        // REDUX.ADD: one instruction per warp sum
         x = __reduce_add_sync(0xffffffffu, x);
@@ -397,7 +405,31 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
     for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
     const u32 ln0 = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
     // token of item i (KF.py:670-684): tag bit, then Rice(k) of x or gamma of x.  non-zero v -> tag 1, x = v-1 (Rice) / v (gamma);
-    // a zero that ends a run -> tag 0, x = run length.  The parameters are uniform over the block, so these branches do not diverge.
+    // a zero that ends a run -> tag 0, x = run length.  The parameters are uniform over the block, so every token with a
+    // value below 256 (all non-zeros, almost all runs) comes from one of two 256-entry tables built per CTA:
+    // s_tok[class][value] = code | length << 32; length 0 = "does not fit 32 bits" -> the out-of-line path.
+    __shared__ u64 s_tok[2][256];
+    {
+        const u32 t = tid;
+#pragma unroll
+        for (int cls = 0; cls < 2; ++cls) {
+            const bool rice = cls ? urn : urz; const u32 k = cls ? k1 : k0, tag = (u32)cls;
+            const u32 x = cls ? t - (urn ? 1u : 0u) : t;       // class 1 is indexed by the symbol v, class 0 by the run length
+            u32 n = 0, code = 0;
+            if (t) {
+                if (rice) { const u32 q = x >> k; n = q + 2 + k; if (n <= 32) code = (tag << (n - 1)) | ((((u32)1 << q) - 1u) << (k + 1)) | (x & ((1u << k) - 1u)); }
+                else { n = 2 * bitlen32(x); code = (tag << ((n - 1) & 31)) | x; }
+                if (n > 32) n = 0;
+            }
+            s_tok[cls][t] = (u64)code | ((u64)n << 32);
+        }
+    }
+    __syncthreads();
+    auto exact_len = [&](bool nz, u32 idx) -> u32 {            // tokens outside the tables
+        const bool rice = nz ? urn : urz; const u32 k = nz ? k1 : k0;
+        const u32 x = nz ? idx - (urn ? 1u : 0u) : idx;
+        return rice ? (x >> k) + 2 + k : 2 * bitlen32(x);
+    };
     u64 mybits = 0; u32 ln = ln0;
     u32 tokmask = 0;
 #pragma unroll
@@ -405,16 +437,16 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
         u32 r = tid * KOLM_IPT + i;
         if (r < td.count) {
             u32 pos1 = t0 + r + 1;
-            bool nz = v[i] != 0, tok = nz || v[i + 1] != 0;
-            u32 x = nz ? v[i] - (urn ? 1u : 0u) : pos1 - ln;
+            const bool nz = v[i] != 0, tok = nz || v[i + 1] != 0;
+            const u32 idx = nz ? v[i] : pos1 - ln;             // the symbol, or the length of the zero run ending here
             if (nz) ln = pos1;
             if (tok) {
-                const bool rice = nz ? urn : urz; const u32 k = nz ? k1 : k0;
-                mybits += rice ? (x >> k) + 2 + k : 2 * bitlen32(x);
+                u32 n = idx < 256u ? (u32)(s_tok[nz ? 1 : 0][idx] >> 32) : 0u;
+                if (n == 0) n = exact_len(nz, idx);
+                mybits += n;
                 tokmask |= 1u << i;
-                v[i] = x;                                    // keep the coded value; v[i+1] was already consumed
+                v[i] = idx | (nz ? 0x80000000u : 0u);
             }
-            v[i] |= nz ? 0x80000000u : 0u;
         }
     }
     u64 btot;
@@ -438,17 +470,17 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
 #pragma unroll
         for (int i = 0; i < KOLM_IPT; ++i) {
             if ((tokmask >> i) & 1u) {
-                const bool nz = v[i] >> 31; const u32 x = v[i] & 0x7fffffffu, tag = nz ? 1u : 0u;
-                const bool rice = nz ? urn : urz; const u32 k = nz ? k1 : k0;
-                u32 n, code;
-                if (rice) { u32 q = x >> k; n = q + 2 + k; code = (tag << ((n - 1) & 31)) | ((((u32)1 << (q & 31)) - 1u) << (k + 1)) | (x & ((1u << k) - 1u)); }
-                else { n = 2 * bitlen32(x); code = (tag << ((n - 1) & 31)) | x; }
-                if (n <= 32 && st.use) ba.push(st, code, n);
+                const bool nz = v[i] >> 31; const u32 idx = v[i] & 0x7fffffffu;
+                const u64 e = idx < 256u ? s_tok[nz ? 1 : 0][idx] : 0ull;
+                const u32 n = (u32)(e >> 32);
+                if (n && st.use) ba.push(st, (u32)e, n);
                 else {
+                    const bool rice = nz ? urn : urz; const u32 k = nz ? k1 : k0, tag = nz ? 1u : 0u;
+                    const u32 x = nz ? idx - (urn ? 1u : 0u) : idx;
                     ba.finish(st);
                     u64 bp = ba.bitpos(st);
                     if (rice) long_rice_tok(&st, bp, 1, tag, x, k); else long_gamma_tok(&st, bp, tag, x);
-                    ba.init(st, bp + n);
+                    ba.init(st, bp + exact_len(nz, idx));
                 }
             }
         }
