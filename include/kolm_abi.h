@@ -118,6 +118,13 @@ int kolm_repair_max_block(void);
  * plane's BBWT, inverse of the circuit_map_automaton model V22.py:1054-1092).  The shipped reference never emits this method
  *  but decodes it.  The context must have been created for >= 8x the batch bytes and 8x the blocks (the planes
  * are inverse-transformed as one batch of 8*nblocks blocks); otherwise KOLM_E_CAPACITY.  ValueError cases -> KOLM_E_CORRUPT. */
+/* encode_new_pipeline  V22.py:1498-1576 with circuit_map_automaton_forward(parallel=False) (V22.py:1013-1052: 13 candidate
+ * models scored by fp64 zero-order entropy, _pick_better tie rules :936-946), then per plane RAW vs BBWT -> RLE -> Rice(best k of
+ * 0..15).  The shipped reference raises NameError before reaching this code, so the KOLR drop-in offers the
+ * candidate only as an opt-in; the bytes equal the reference function's output once that path is taken.  Same context
+ * requirement as kolm_v2new_dec.  The entropy scores are computed on the host in fp64 (glibc log2) from device histograms. */
+int kolm_v2new_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
+                   kolm_stream_t stream);
 int kolm_v2new_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,
                    kolm_stream_t stream);
 

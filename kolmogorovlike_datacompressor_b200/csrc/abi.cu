@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -264,6 +265,12 @@ int kolm_repair_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off,
 }
 
 int kolm_repair_max_block(void) { return REPAIR_MAX; }
+
+int kolm_v2new_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
+                   kolm_stream_t stream) {
+    if (!c || !off || !out_off || nblocks < 0) return KOLM_E_ARG;
+    return kolm_v2new_enc_impl(c, in, off, nblocks, out, out_cap, out_off, (cudaStream_t)stream);
+}
 
 int kolm_v2new_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,
                    kolm_stream_t stream) {

@@ -1146,7 +1146,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     RerankArgs ra;
     ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
     ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0;
-    if (deep) { KL(c, KC_RERANK, N * 20, s, k_rerank<2, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra)); h0 *= 2; }
+    if (deep) { KL(c, KC_RERANK, N * 20, s, k_rerank<2, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra)); h0 *= 2; c->counters[4] += N; }   // second full sort
     else if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<1, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
     else KL(c, KC_RERANK, N * 16, s, k_rerank<1, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
     CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
@@ -1224,7 +1224,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         Kprev = K; Vprev = V;
         use_ls = ls_div > 0 && surv * (u64)ls_div < (u64)N;
     }
-    if (rounds_out) *rounds_out = rounds;
+    if (rounds_out) *rounds_out = rounds + (deep ? 1 : 0);    // doublings of the sorted depth: the deep bootstrap is one (h0 -> 2*h0)
     return KOLM_OK;
 }
 

@@ -69,6 +69,7 @@ class Engine:
         self.cap_bytes = 0
         self.cap_blocks = 0
         self.repair_max = int(_lib.lib().kolm_repair_max_block())
+        self.enable_v2_new = False     # method 10 as an encode candidate (dead in the shipped reference; see kolm_final_researched_v2_2.G_ENABLE_V2_NEW)
         self._pin: Optional[torch.Tensor] = None
 
     def _home(self, dev: torch.Tensor, n: int) -> np.ndarray:
@@ -253,11 +254,18 @@ class Engine:
             nb = j - i
             off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
             lens = np.diff(off)
-            self._ensure(b - a, nb)
+            v2 = self.enable_v2_new and "v2_new" in names
+            if v2:                                                   # the eight bit planes of every block are sorted as one batch
+                self._ensure(max(8 * (b - a) + 64, 1024 * nb), 8 * nb)
+            else:
+                self._ensure(b - a, nb)
             with torch.cuda.device(self.device):
                 c = self.ctx
                 x = self._upload(data, a, b)
                 cols = []
+                v2p = v2o = None
+                if v2:
+                    v2p, v2o = c.v2new_encode(x, off)
                 need_res = any(n in ("xor", "lfsr_pred") for n in names)
                 rs = c.residual_sizes(x, off) if need_res else None
                 need_bbwt = any(n in K2_FLAG_OF for n in names)
@@ -288,6 +296,8 @@ class Engine:
                         cols.append(np.diff(lzo))
                     elif nme == "repair" and rpo is not None:
                         cols.append(np.diff(rpo))
+                    elif nme == "v2_new" and v2o is not None:
+                        cols.append(np.diff(v2o))
                     else:                                            # v2_new raises NameError in the shipped reference; skipped repair
                         cols.append(np.full(nb, _BIG, dtype=np.int64))
                 sizes = np.stack(cols, axis=1)
@@ -311,6 +321,8 @@ class Engine:
                         p, o = lzp, lzo
                     elif nme == "repair":
                         p, o = rpp, rpo
+                    elif nme == "v2_new":
+                        p, o = v2p, v2o
                     else:
                         raise RuntimeError("unreachable candidate " + nme)
                     keep.append(p)
@@ -346,6 +358,9 @@ class Engine:
                 p, o = c.lz77_encode(x, off, 4096, 0)
             elif name == "repair":
                 p, o = c.repair_encode(x, off)
+            elif name == "v2_new" and self.enable_v2_new:
+                self._ensure(max(8 * len(block) + 64, 1024), 8)
+                p, o = self.ctx.v2new_encode(x, off)
             else:
                 raise NameError("name 'os' is not defined")          # v2_new: what the shipped reference raises
             return self._host(p, int(o[-1]))

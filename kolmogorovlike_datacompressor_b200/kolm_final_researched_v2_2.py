@@ -26,6 +26,11 @@ from .engine import KOLR_NAMES, Engine, cdc_boundaries
 G_NO_LZ77: bool = False
 G_ONLY_METHOD: Optional[str] = None
 G_PROGRESS: bool = False
+# Not a reference global.  The shipped reference can never select method 10: its encode_new_pipeline raises NameError (missing
+# imports on the default parallel=True path, v2-2.py:1037-1042) and the selection loops swallow it.  False reproduces that —
+# containers are byte-identical to the reference's.  True evaluates the candidate the way the reference's own function does
+# with parallel=False (v2-2.py:1030-1032), i.e. what the file produces once its imports are repaired.
+G_ENABLE_V2_NEW: bool = False
 
 MODE_FIXED = 0
 MODE_CDC = 1
@@ -35,7 +40,9 @@ GPU_CDC_MIN_BYTES = 8 << 20   # below this the host scan (~1 GB/s) beats a copy 
 
 
 def _engine() -> Engine:
-    return Engine.shared()
+    e = Engine.shared()
+    e.enable_v2_new = bool(G_ENABLE_V2_NEW)
+    return e
 
 
 def _print_progress(label: str, i: int, n: int, final: bool = False) -> None:

@@ -175,6 +175,10 @@ class Context:
     def repair_decode(self, payload, pay_off, off, out=None):
         return self._dec("kolm_repair_dec", payload, pay_off, off, (), out)
 
+    def v2new_encode(self, x, off, out=None):
+        """encode_new_pipeline per block with parallel=False semantics (method 10).  Context of 8x the batch, like the decoder."""
+        return self._enc("kolm_v2new_enc", x, off, (), 2, out)
+
     def v2new_decode(self, payload, pay_off, off, out=None):
         """decode_new_pipeline per block (method 10).  The context must hold 8x the batch (the bit planes are one batch)."""
         return self._dec("kolm_v2new_dec", payload, pay_off, off, (), out)

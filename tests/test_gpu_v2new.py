@@ -89,3 +89,54 @@ def test_v2new_dropin_decoder_and_container():
     finally:
         eng.encode_kolr_area = real
     assert V.decompress(blob) == data
+
+
+def test_v2new_encode_golden_and_large():
+    """kolm_v2new_enc == the reference's encode_new_pipeline (parallel=False) on the golden inputs, == the oracle on large blocks."""
+    import gpu_util as G
+    names = sorted(k for k, v in GOLD.items() if not v["forced"])
+    blocks = [bytes.fromhex(GOLD[k]["input_hex"]) for k in names]
+    t, off = G.batch(blocks)
+    out, out_off = G.ctx().v2new_encode(t, off)
+    got = out.cpu().numpy().tobytes()
+    for i, k in enumerate(names):
+        assert got[out_off[i]:out_off[i + 1]] == bytes.fromhex(GOLD[k]["payload_hex"]), k
+    rnd = random.Random(9)
+    text = datasets.medium_cases()["text_big"]
+    blocks = [(text * 8)[:65536], datasets.fixture("sine")[:50001], datasets.fixture("gradient")[3000:3000 + 40000],
+              bytes(rnd.randrange(256) for _ in range(4097)), b"", b"x", datasets.fixture("pattern")[60000:60000 + 70000],
+              bytes(20000), datasets.fixture("checker")[:30000], bytes(rnd.randrange(4) for _ in range(12345)), b"ab" * 4097]
+    t, off = G.batch(blocks)
+    out, out_off = G.ctx().v2new_encode(t, off)
+    got = out.cpu().numpy().tobytes()
+    for i, b in enumerate(blocks):
+        assert got[out_off[i]:out_off[i + 1]] == O.v2new_encode(b), i
+    dec = G.unbatch(G.ctx().v2new_decode(out, out_off, off), off)
+    assert dec == blocks
+
+
+def test_v2new_dropin_opt_in():
+    """G_ENABLE_V2_NEW: off = the shipped reference (NameError swallowed, never method 10); on = candidate 10 competes."""
+    from kolmogorovlike_datacompressor_b200 import kolm_final_researched_v2_2 as V
+    data = bytes.fromhex(GOLD["sine_1000"]["input_hex"])
+    enc = dict((n, f) for f, n in V._select_encoders())["v2_new"]
+    with pytest.raises(NameError):
+        enc(data)
+    ref_blob = V.compress_blocks_fixed(data, 2048)
+    V.G_ENABLE_V2_NEW = True
+    try:
+        payload, _ = enc(data)
+        assert payload == bytes.fromhex(GOLD["sine_1000"]["payload_hex"])
+        # full selection with candidate 10 in play: winners == first minimum over the oracle's eleven sizes; container round-trips
+        big = datasets.fixture("sine")[2000:2000 + 6 * 2048] + datasets.fixture("gradient")[5000:5000 + 3 * 2048] + bytes(range(256)) * 16
+        bounds = V.fixed_boundaries(big, 2048)
+        mids, lens, _ = V._engine().encode_kolr_area(big, bounds, V._candidate_names())
+        for (a, b), mid, ln in zip(bounds, mids, lens):
+            sizes = [len(O.encode_model(2, m, big[a:b])) for m in range(10)] + [len(O.v2new_encode(big[a:b]))]
+            assert (int(mid), int(ln)) == (sizes.index(min(sizes)), min(sizes)), (a, sizes)
+        assert 10 in set(int(m) for m in mids)
+        blob = V.compress_blocks_fixed(big, 2048)
+        assert V.decompress(blob) == big
+    finally:
+        V.G_ENABLE_V2_NEW = False
+    assert V.compress_blocks_fixed(data, 2048) == ref_blob
