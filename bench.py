@@ -344,7 +344,8 @@ def ncu_traffic(category, args):
         return None, "kernel not in the ncu capture"
     mean = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for _, r in rows) / len(rows)
     # algorithmic bytes of the SAME launches (grid = tiles of 4096 records; bytes per record as in the KL() launch macros)
-    per_rec = {"k_rerank": lambda k: 16 if k.startswith("k_rerank<1") else 20,     # <1>: key32 bootstrap; <2> deep bootstrap and <0> rounds also gather a second key "k_radix_scatter": lambda k: 16, "k_gather": lambda k: 4}[kname]
+    # k_rerank<1>: key32 bootstrap; <2> (deep bootstrap) and <0> (rounds) also gather a second key
+    per_rec = {"k_rerank": lambda k: 16 if k.startswith("k_rerank<1") else 20, "k_radix_scatter": lambda k: 16, "k_gather": lambda k: 4}[kname]
     alg = sum(r["grid"] * 4096 * per_rec(k) for k, r in rows) / len(rows)
     return int(mean), "mean of the %d largest launches in %s (%s): DRAM %.2f GB vs %.2f GB algorithmic for those launches (ratio %.2f)" % (
         len(rows), "profiles/r1b_traffic.json", doc["source"], mean / 1e9, alg / 1e9, mean / alg)
