@@ -152,12 +152,13 @@ class Engine:
             with torch.cuda.device(self.device):
                 self.ctx = Context(self.cap_bytes, self.cap_blocks, self.device)
 
-    def _batches(self, bounds: Sequence[Tuple[int, int]]):
-        """Consecutive blocks grouped so that a batch holds <= batch_bytes (a single larger block forms its own batch)."""
+    def _batches(self, bounds: Sequence[Tuple[int, int]], limit: Optional[int] = None):
+        """Consecutive blocks grouped so that a batch holds <= limit (default batch_bytes) bytes (a single larger block forms its own batch)."""
+        limit = self.batch_bytes if limit is None else max(1, int(limit))
         i, n = 0, len(bounds)
         while i < n:
             j, tot = i, 0
-            while j < n and (j == i or tot + (bounds[j][1] - bounds[j][0]) <= self.batch_bytes) and j - i < (1 << 20):
+            while j < n and (j == i or tot + (bounds[j][1] - bounds[j][0]) <= limit) and j - i < (1 << 20):
                 tot += bounds[j][1] - bounds[j][0]
                 j += 1
             yield i, j
@@ -249,12 +250,12 @@ class Engine:
     def encode_kolr_area(self, data: bytes, bounds: Sequence[Tuple[int, int]], names: Sequence[str]):
         """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLR candidate list `names`."""
         mids_all, lens_all, areas = [], [], []
-        for i, j in self._batches(bounds):
+        v2 = self.enable_v2_new and "v2_new" in names
+        for i, j in self._batches(bounds, self.batch_bytes // 8 if v2 else None):   # v2_new sorts 8 planes per block: same scratch per batch
             a, b = bounds[i][0], bounds[j - 1][1]
             nb = j - i
             off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
             lens = np.diff(off)
-            v2 = self.enable_v2_new and "v2_new" in names
             if v2:                                                   # the eight bit planes of every block are sorted as one batch
                 self._ensure(max(8 * (b - a) + 64, 1024 * nb), 8 * nb)
             else:
@@ -385,10 +386,17 @@ class Engine:
             base_off = int(ends[i] - ols[i])
             with torch.cuda.device(self.device):
                 dev_out = torch.empty(max(tot, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
-                groups: Dict[str, List[int]] = {}
+                groups: Dict[Tuple[str, int], List[int]] = {}
+                v2_tot, v2_part = 0, 0
                 for idx in range(i, j):
-                    groups.setdefault(blocks[idx][0], []).append(idx)
-                for nme, sub in groups.items():
+                    part = 0
+                    if blocks[idx][0] == "v2_new":                 # eight planes per block are sorted: keep these sub-batches 8x smaller
+                        if v2_tot and v2_tot + blocks[idx][2] > self.batch_bytes // 8:
+                            v2_part, v2_tot = v2_part + 1, 0
+                        v2_tot += blocks[idx][2]
+                        part = v2_part
+                    groups.setdefault((blocks[idx][0], part), []).append(idx)
+                for (nme, _part), sub in groups.items():
                     pays = [blocks[t][1] for t in sub]
                     sol = ols[sub]
                     poff = np.zeros(len(sub) + 1, dtype=np.int64)
