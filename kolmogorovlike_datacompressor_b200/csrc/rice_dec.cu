@@ -26,12 +26,20 @@ struct RdecArgs {
 
 struct BitWin {                                 // MSB-first bit window over one payload
     const u8* p; u64 nbits;
-    __device__ __forceinline__ u32 peek32(u64 pos) const {           // 32 bits starting at pos (zero beyond the end)
-        u64 byte = pos >> 3; u32 sh = (u32)pos & 7;
-        u64 v = 0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) { u64 b = (byte + i) * 8 < nbits ? p[byte + i] : 0; v = (v << 8) | b; }
-        return (u32)(v >> (8 - sh));
+    // 32 bits starting at pos (zero beyond the end).  Two ALIGNED 32-bit loads and a funnel shift: an aligned word that holds at
+    // least one byte of the payload lies in the same page as that byte, so the loads cannot fault even when the payload itself
+    // is not 4-byte aligned; bits that belong to the neighbouring payload are masked off.
+    __device__ __forceinline__ u32 peek32(u64 pos) const {
+        if (pos >= nbits) return 0;
+        const u64 byte = pos >> 3; const u32 sh = (u32)pos & 7u;
+        const uintptr_t a = (uintptr_t)(p + byte); const u32 off = (u32)a & 3u;
+        const u32* w = reinterpret_cast<const u32*>(a - off);
+        const u32 w0 = __byte_perm(w[0], 0, 0x0123);
+        const u32 w1 = ((byte + 4 - off) * 8 < nbits) ? __byte_perm(w[1], 0, 0x0123) : 0u;
+        u32 v = __funnelshift_l(w1, w0, off * 8 + sh);
+        const u64 valid = nbits - pos;
+        if (valid < 32) v &= 0xffffffffu << (32 - (u32)valid);
+        return v;
     }
     // length of the run of `want` bits starting at pos (stops at the end of the payload)
     __device__ __forceinline__ u64 run(u64 pos, u32 want) const {

@@ -67,3 +67,45 @@ def test_bbwt_forward_fixture_blocks_64k():
     out = G.unbatch(G.ctx().bbwt_forward(t, off), off)
     for i, (b, o) in enumerate(zip(blocks, out)):
         assert o == O.bbwt_forward(b), i
+
+
+def _small_alphabet_cases():
+    rnd = random.Random(11)
+    c = {}
+    text = datasets.medium_cases()["text_big"]
+    c["text_20k"] = text
+    c["text_70k"] = (text * 4)[:70001]
+    c["dna_50k"] = bytes(rnd.choice(b"ACGT") for _ in range(50000))
+    c["binary_9k"] = bytes(rnd.randrange(2) for _ in range(9001))
+    c["ones_5k"] = b"\x01" * 5000
+    c["desc_letters"] = bytes(range(122, 96, -1)) * 200                  # many Lyndon factors (descending runs)
+    c["period7"] = b"abcabca" * 3000
+    c["two"] = b"ba"
+    c["one"] = b"z"
+    c["empty"] = b""
+    c["six_bit_64"] = bytes(32 + rnd.randrange(64) for _ in range(30000))   # exactly the largest compressed alphabet (6 bits -> h0 = 5)
+    return c
+
+
+def test_bbwt_forward_deep_bootstrap_batch():
+    """Batches whose alphabets all fit 6 bits take the deep bootstrap (two 32-bit sorts, k_rerank<2>): ragged batch vs the oracle."""
+    import gpu_util as G
+    cases = _small_alphabet_cases()
+    names = sorted(cases)
+    blocks = [cases[k] for k in names]
+    t, off = G.batch(blocks)
+    out = G.unbatch(G.ctx().bbwt_forward(t, off), off)
+    for k, b, o in zip(names, blocks, out):
+        assert o == O.bbwt_forward(b), k
+
+
+def test_bbwt_forward_deep_bootstrap_forced():
+    """KOLM_DEEP_BOOT=2 (deep bootstrap for every alphabet, read once per process): the ragged mixed batch in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, KOLM_DEEP_BOOT="2")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_bbwt.py"), "-k",
+                        "ragged_batch or single_blocks or fixture_blocks"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
