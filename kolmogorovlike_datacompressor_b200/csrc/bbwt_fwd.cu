@@ -139,9 +139,22 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_alpha_mask(const u8* __restric
     __syncthreads();
     const u8* src = in + bi.ioff + (td.start - bi.pbase);
     u32 loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) { u32 b = src[x]; 
+    auto add = [&](u32 b) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if ((b >> 5) == (u32)k) loc[k] |= 1u << (b & 31); }
+        for (int k = 0; k < 8; ++k) if ((b >> 5) == (u32)k) loc[k] |= 1u << (b & 31);
+    };
+    if (((uintptr_t)src & 15) == 0) {                          // 16 bytes per load
+        const u32 nv = td.count >> 4;
+        for (u32 x = threadIdx.x; x < nv; x += KOLM_THREADS) {
+            const uint4 q = reinterpret_cast<const uint4*>(src)[x];
+            const u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) add((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+        }
+        for (u32 x = (nv << 4) + threadIdx.x; x < td.count; x += KOLM_THREADS) add(src[x]);
+    } else {
+        for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) add(src[x]);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) { u32 v = __reduce_or_sync(FULL, loc[k]); if ((threadIdx.x & 31) == 0 && v) atomicOr(&m[k], v); }
     __syncthreads();

@@ -39,9 +39,29 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_mtf_last(const u8* __restrict_
     __syncthreads();
     u32 t0 = start - bi.pbase;
     const u8* src = in + bi.ioff + t0;
-    for (u32 x = threadIdx.x; x < count; x += KOLM_THREADS) {
-        u8 s = src[x];
-        if (x + 1 == count || src[x + 1] != s) atomicMax(&last[s], t0 + x + 1);
+    if ((((uintptr_t)src) & 15) == 0) {                        // 16 bytes per thread and load: only run ends touch shared memory
+        for (u32 x = threadIdx.x * 16; x < count; x += KOLM_THREADS * 16) {
+            const u32 nb = min(16u, count - x);
+            u32 w[5] = {0, 0, 0, 0, 0};
+            if (nb == 16) { const uint4 q = *reinterpret_cast<const uint4*>(src + x); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+            else for (u32 i = 0; i < nb; ++i) w[i >> 2] |= (u32)src[x + i] << (8 * (i & 3));
+            const bool more = x + nb < count;                   // the byte after mine decides whether my last byte ends a run
+            if (more) w[4] = src[x + nb];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if ((u32)i < nb) {
+                    const u32 sb = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    const bool last_of_mine = (u32)i + 1 == nb;
+                    const u32 nx = last_of_mine ? (w[4] & 0xFFu) : ((w[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xFFu);
+                    if ((last_of_mine && !more) || nx != sb) atomicMax(&last[sb], t0 + x + i + 1);
+                }
+            }
+        }
+    } else {
+        for (u32 x = threadIdx.x; x < count; x += KOLM_THREADS) {
+            u8 s = src[x];
+            if (x + 1 == count || src[x + 1] != s) atomicMax(&last[s], t0 + x + 1);
+        }
     }
     __syncthreads();
     const u32 v = last[threadIdx.x];
