@@ -369,80 +369,96 @@ class Engine:
     # ------------------------------------------------------------------
     # decode: blocks = [(method name, payload, orig_len)]
     def decode_area(self, blocks: Sequence[Tuple[str, bytes, int]]) -> np.ndarray:
-        """All blocks decoded back to back (uint8 array of sum(orig_len) bytes).  Each method group is decoded as one batch
-        into a temporary device buffer and copied to its blocks' final offsets on the device; one D2H per output batch."""
-        nb = len(blocks)
-        ols = np.array([b[2] for b in blocks], dtype=np.int64)
+        """All blocks decoded back to back (uint8 array of sum(orig_len) bytes); blocks = [(method name, payload, orig_len)]."""
+        names = [b[0] for b in blocks]
+        plens = np.array([len(b[1]) for b in blocks], dtype=np.int64)
+        starts = np.zeros(len(blocks), dtype=np.int64)
+        if len(blocks):
+            starts[1:] = np.cumsum(plens)[:-1]
+        parts = self._decode_spans(b"".join(b[1] for b in blocks), names, starts, plens, np.array([b[2] for b in blocks], dtype=np.int64))
+        return np.frombuffer(parts[0] if len(parts) == 1 else b"".join(parts), dtype=np.uint8)
+
+    def decode_container(self, blob: bytes, names: Sequence[str], starts, plens, orig_lens) -> bytes:
+        """Container decode: payload k is blob[starts[k] : starts[k] + plens[k]] (container order).  The payload bytes of an
+        output batch travel to the device in ONE copy; each method group is compacted there (`kolm_gather_payloads`), decoded
+        as one batch and copied to its blocks' final offsets; one D2H per output batch."""
+        parts = self._decode_spans(blob, list(names), np.asarray(starts, dtype=np.int64), np.asarray(plens, dtype=np.int64),
+                                   np.asarray(orig_lens, dtype=np.int64))
+        return parts[0] if len(parts) == 1 else b"".join(parts)
+
+    def _decode_spans(self, blob, names: List[str], starts: np.ndarray, plens: np.ndarray, ols: np.ndarray) -> List[bytes]:
+        nb = len(names)
+        if nb == 0:
+            return [b""]
         ends = np.cumsum(ols)
-        total = int(ends[-1]) if nb else 0
-        out = np.empty(total, dtype=np.uint8)
-        # output batches of <= batch_bytes
+        parts: List[bytes] = []
         i = 0
-        while i < nb:
+        while i < nb:                                                # output batches of <= batch_bytes
             j, tot = i, 0
-            while j < nb and (j == i or tot + blocks[j][2] <= self.batch_bytes):
-                tot += blocks[j][2]
+            while j < nb and (j == i or tot + int(ols[j]) <= self.batch_bytes):
+                tot += int(ols[j])
                 j += 1
             base_off = int(ends[i] - ols[i])
+            span0, span1 = int(starts[i]), int((starts[i:j] + plens[i:j]).max())
             with torch.cuda.device(self.device):
                 dev_out = torch.empty(max(tot, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
+                span = self._upload(blob, span0, max(span0, span1))
                 groups: Dict[Tuple[str, int], List[int]] = {}
                 v2_tot, v2_part = 0, 0
                 for idx in range(i, j):
                     part = 0
-                    if blocks[idx][0] == "v2_new":                 # eight planes per block are sorted: keep these sub-batches 8x smaller
-                        if v2_tot and v2_tot + blocks[idx][2] > self.batch_bytes // 8:
+                    if names[idx] == "v2_new":                       # eight planes per block are sorted: keep these sub-batches 8x smaller
+                        if v2_tot and v2_tot + int(ols[idx]) > self.batch_bytes // 8:
                             v2_part, v2_tot = v2_part + 1, 0
-                        v2_tot += blocks[idx][2]
+                        v2_tot += int(ols[idx])
                         part = v2_part
-                    groups.setdefault((blocks[idx][0], part), []).append(idx)
+                    groups.setdefault((names[idx], part), []).append(idx)
                 for (nme, _part), sub in groups.items():
-                    pays = [blocks[t][1] for t in sub]
-                    sol = ols[sub]
-                    poff = np.zeros(len(sub) + 1, dtype=np.int64)
-                    poff[1:] = np.cumsum([len(p) for p in pays])
+                    sub = np.asarray(sub, dtype=np.int64)
+                    sol, spl = ols[sub], plens[sub]
                     off = np.zeros(len(sub) + 1, dtype=np.int64)
                     off[1:] = np.cumsum(sol)
                     dst = np.uint64(dev_out.data_ptr()) + (ends[sub] - sol - base_off).astype(np.uint64)
-                    blob = b"".join(pays)
-                    self._ensure(max(int(off[-1]), len(blob), 1), len(sub))
+                    src_pay = np.uint64(span.data_ptr()) + (starts[sub] - span0).astype(np.uint64)
+                    ptot = int(spl.sum())
+                    self._ensure(max(int(off[-1]), ptot, 1), len(sub))
                     c = self.ctx
-                    pt = self._upload(blob, 0, len(blob))
                     if nme == "raw":
-                        for t in sub:
-                            assert len(blocks[t][1]) == blocks[t][2], "Payload length mismatch for RAW"
-                        y = pt
-                    else:
-                        try:
-                            if nme in ("kf_xor", "xor", "lfsr_pred"):
-                                y = c.residual_decode(pt, poff, off, {"kf_xor": 0, "xor": 1, "lfsr_pred": 2}[nme])
-                            elif nme == "kf_bbwt":
-                                y = c.bbwt_inverse(c.mtf_decode(c.rice_kf_decode(pt, poff, off), off), off)
-                            elif nme in K2_FLAG_OF:
-                                y = c.bbwt_inverse(c.mtf_decode(c.rice_k2_decode(pt, poff, off, K2_FLAG_OF[nme]), off), off)
-                            elif nme == "kf_lz77":
-                                y = c.lz77_decode(pt, poff, off, 0)
-                            elif nme == "lz77":
-                                y = c.lz77_decode(pt, poff, off, 4096)
-                            elif nme == "repair":
-                                y = c.repair_decode(pt, poff, off)
-                            elif nme == "v2_new":
-                                self._ensure(8 * int(off[-1]) + 64, 8 * len(sub))   # the eight bit planes of every block form one batch
-                                c = self.ctx
-                                y = c.v2new_decode(pt, poff, off)
-                            else:
-                                raise NotImplementedError("decoder for method '%s' is outside the GPU hot path (SURVEY §8 row a17)" % nme)
-                        except _lib.KolmError as err:
-                            if err.code == -4 and not nme.startswith("kf_"):
-                                raise ValueError(str(err)) from err     # V22's readers raise ValueError on truncation (v2-2.py:131-132, 1437-1447)
-                            raise_like_reference(err)
+                        assert bool((spl == sol).all()), "Payload length mismatch for RAW"
+                        c.copy_blocks(src_pay, dst, sol)
+                        torch.cuda.current_stream().synchronize()
+                        continue
+                    pt = torch.empty(max(ptot, 4) + 16, dtype=torch.uint8, device=span.device)
+                    poff = c.gather_payloads(src_pay, spl, pt)
+                    try:
+                        if nme in ("kf_xor", "xor", "lfsr_pred"):
+                            y = c.residual_decode(pt, poff, off, {"kf_xor": 0, "xor": 1, "lfsr_pred": 2}[nme])
+                        elif nme == "kf_bbwt":
+                            y = c.bbwt_inverse(c.mtf_decode(c.rice_kf_decode(pt, poff, off), off), off)
+                        elif nme in K2_FLAG_OF:
+                            y = c.bbwt_inverse(c.mtf_decode(c.rice_k2_decode(pt, poff, off, K2_FLAG_OF[nme]), off), off)
+                        elif nme == "kf_lz77":
+                            y = c.lz77_decode(pt, poff, off, 0)
+                        elif nme == "lz77":
+                            y = c.lz77_decode(pt, poff, off, 4096)
+                        elif nme == "repair":
+                            y = c.repair_decode(pt, poff, off)
+                        elif nme == "v2_new":
+                            self._ensure(8 * int(off[-1]) + 64, 8 * len(sub))   # the eight bit planes of every block form one batch
+                            c = self.ctx
+                            y = c.v2new_decode(pt, poff, off)
+                        else:
+                            raise NotImplementedError("no decoder for method '%s'" % nme)
+                    except _lib.KolmError as err:
+                        if err.code == -4 and not nme.startswith("kf_"):
+                            raise ValueError(str(err)) from err     # V22's readers raise ValueError on truncation (v2-2.py:131-132, 1437-1447)
+                        raise_like_reference(err)
                     src = np.uint64(y.data_ptr()) + off[:-1].astype(np.uint64)
                     self.ctx.copy_blocks(src, dst, sol)
                     torch.cuda.current_stream().synchronize()        # y / pt may be freed when the loop moves on
-                if tot:
-                    out[base_off:base_off + tot] = self._home(dev_out, tot)
+                parts.append(self._home(dev_out, tot).tobytes() if tot else b"")
             i = j
-        return out
+        return parts
 
     def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:
         area = self.decode_area(blocks)

@@ -136,17 +136,14 @@ def compress(data: bytes, target_block: int = 8192) -> bytes:
     if not cuts:                                          # nblocks wraps silently like the reference (kolm_final.py:889-890)
         return head
     mids, lens, area = _engine().encode_kolm_area(data, cuts)
-    out = bytearray(18 + 9 * len(cuts) + int(lens.sum()))
-    out[:18] = head
-    view, src = memoryview(out), memoryview(area)
-    p = 18
+    src = memoryview(area)                                # one copy: the pieces are joined straight into the result
+    pieces = [head]
     q = 0
     for (a, b), mid, ln in zip(cuts, mids.tolist(), lens.tolist()):
-        struct.pack_into("<BII", out, p, mid & 0xFF, (b - a) & 0xFFFFFFFF, ln & 0xFFFFFFFF)
-        view[p + 9:p + 9 + ln] = src[q:q + ln]
-        p += 9 + ln
+        pieces.append(struct.pack("<BII", mid & 0xFF, (b - a) & 0xFFFFFFFF, ln & 0xFFFFFFFF))
+        pieces.append(src[q:q + ln])
         q += ln
-    return bytes(out)
+    return b"".join(pieces)
 
 
 def decompress(blob: bytes) -> bytes:
@@ -161,7 +158,7 @@ def decompress(blob: bytes) -> bytes:
     p += 8
     nblocks = struct.unpack_from("<H", blob, p)[0]
     p += 2
-    todo = []
+    names, starts, plens, olens = [], [], [], []
     for _ in range(nblocks):
         if p >= len(blob):
             raise EOFError("Truncated block header")
@@ -175,9 +172,9 @@ def decompress(blob: bytes) -> bytes:
         p += 8
         if p + payload_len > len(blob):
             raise EOFError("Truncated payload")
-        todo.append((_NAMES[method_id], blob[p:p + payload_len], orig_len))
+        names.append(_NAMES[method_id]); starts.append(p); plens.append(payload_len); olens.append(orig_len)
         p += payload_len
-    out = _engine().decode_area(todo).tobytes() if todo else b""      # every decoder yields exactly orig_len bytes or raises
+    out = _engine().decode_container(blob, names, starts, plens, olens) if names else b""   # every decoder yields exactly orig_len bytes or raises
     if len(out) != total_len:
         raise ValueError(f"Total decoded length mismatch: expected {total_len}, got {len(out)}")
     return out

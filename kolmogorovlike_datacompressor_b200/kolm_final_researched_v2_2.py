@@ -341,8 +341,7 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int) -> bytes:
     out += uleb128_encode(total_payload)
     out += toc_header
     out += toc_bits
-    out += memoryview(area)
-    return bytes(out)
+    return b"".join((bytes(out), memoryview(area)))     # one copy of the payload area
 
 
 def compress_blocks_fixed(data: bytes, block_size: int = 8192) -> bytes:
@@ -428,18 +427,20 @@ def decompress(container: bytes) -> bytes:
         raise ValueError("Payload EF sum mismatch")
     if pos + total_payload > len(container):
         raise ValueError("Truncated payload area")
-    area = container[pos:pos + total_payload]
+    area0 = pos
     pos += total_payload
-    todo = []
-    start = 0
+    names = []
     for i in range(nblocks):
         mid = method_ids[i]
         if mid < 0 or mid >= len(KOLR_NAMES):
             raise ValueError(f"Unknown method_id {mid}")
-        todo.append((KOLR_NAMES[mid], area[start:P[i]], orig_lens[i]))
-        start = P[i]
+        names.append(KOLR_NAMES[mid])
+    starts = [area0] + [area0 + x for x in P[:-1]] if nblocks else []
+    plens = [P[0]] + [P[i] - P[i - 1] for i in range(1, nblocks)] if nblocks else []
+    if any(x < 0 for x in plens):
+        raise ValueError("Payload EF offsets not monotone")
     _print_progress("DECOMPRESS", 0, nblocks)
-    out = _engine().decode_area(todo).tobytes() if todo else b""
+    out = _engine().decode_container(container, names, starts, plens, orig_lens) if nblocks else b""
     _print_progress("DECOMPRESS", nblocks, nblocks, final=True)
     if len(out) != total_len:
         raise ValueError(f"Length mismatch: got {len(out)}, expect {total_len}")
