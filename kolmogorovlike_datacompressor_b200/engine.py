@@ -35,6 +35,37 @@ def raise_like_reference(e: _lib.KolmError):
     raise e
 
 
+_COPY_POOL = None
+
+
+def _par_copy(dst: np.ndarray, src: np.ndarray) -> None:
+    """dst[:] = src with several threads for large buffers: a fresh result buffer is all page faults on first touch (~2 GB/s
+    from one thread), numpy releases the GIL inside the copy."""
+    n = int(dst.shape[0])
+    if n < (16 << 20):
+        dst[:] = src
+        return
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="kolm-copy")
+    step = max(4 << 20, (n + 7) // 8)
+    futs = [_COPY_POOL.submit(np.copyto, dst[a:min(n, a + step)], src[a:min(n, a + step)]) for a in range(0, n, step)]
+    for f in futs:
+        f.result()
+
+
+def _new_bytes(n: int):
+    """(bytes object of n bytes, writable uint8 view of its storage).  The object is filled in place before anyone else can see
+    it (CPython: a fresh `bytes(n)` is not shared, interned or hashed), which saves one full copy of every decompressed output."""
+    out = bytes(n)
+    if n < 2:
+        return out, None
+    import ctypes
+    addr = ctypes.cast(ctypes.c_char_p(out), ctypes.c_void_p).value
+    return out, np.ctypeslib.as_array((ctypes.c_ubyte * n).from_address(addr))
+
+
 def cdc_boundaries(which: str, data: bytes, mn: int, avg: int, mx: int) -> List[Tuple[int, int]]:
     n = len(data)
     if n == 0:
@@ -180,12 +211,14 @@ class Engine:
 
     # ------------------------------------------------------------------
     # KOLM profile
-    def _gather_home(self, c: Context, addr: np.ndarray, lens: np.ndarray):
-        """Winners' payloads -> one device buffer in block order -> host memory.  Returns a uint8 numpy array."""
+    def _gather_home(self, c: Context, addr: np.ndarray, lens: np.ndarray, keep: bool = True):
+        """Winners' payloads -> one device buffer in block order -> host memory.  Returns a uint8 numpy array; with keep=False it
+        is a view of the pinned staging buffer, valid until the next engine call (the caller joins it into the container at once)."""
         total = int(lens.sum())
         dev = torch.empty(max(total, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
         c.gather_payloads(addr, lens, dev)
-        return self._home(dev, total).copy()
+        v = self._home(dev, total)
+        return v.copy() if keep else v
 
     def encode_kolm_area(self, data: bytes, bounds: Sequence[Tuple[int, int]]):
         """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLM candidates."""
@@ -214,7 +247,7 @@ class Engine:
                 base[:, 2] = np.uint64(kfp.data_ptr()) + kfo[:-1].astype(np.uint64)
                 base[:, 3] = np.uint64(lzp.data_ptr()) + lzo[:-1].astype(np.uint64)
                 plen = sizes[np.arange(nb), mids].astype(np.int64)
-                areas.append(self._gather_home(c, base[np.arange(nb), mids], plen))
+                areas.append(self._gather_home(c, base[np.arange(nb), mids], plen, keep=j < len(bounds)))
             mids_all.append(mids.astype(np.int64))
             lens_all.append(plen)
         if not areas:
@@ -329,7 +362,7 @@ class Engine:
                     keep.append(p)
                     base[:, mid] = np.uint64(p.data_ptr()) + o[:-1].astype(np.uint64)
                 plen = sizes[np.arange(nb), mids].astype(np.int64)
-                areas.append(self._gather_home(c, base[np.arange(nb), mids], plen))
+                areas.append(self._gather_home(c, base[np.arange(nb), mids], plen, keep=j < len(bounds)))
             mids_all.append(mids.astype(np.int64))
             lens_all.append(plen)
         if not areas:
@@ -375,23 +408,24 @@ class Engine:
         starts = np.zeros(len(blocks), dtype=np.int64)
         if len(blocks):
             starts[1:] = np.cumsum(plens)[:-1]
-        parts = self._decode_spans(b"".join(b[1] for b in blocks), names, starts, plens, np.array([b[2] for b in blocks], dtype=np.int64))
-        return np.frombuffer(parts[0] if len(parts) == 1 else b"".join(parts), dtype=np.uint8)
+        out = self._decode_spans(b"".join(b[1] for b in blocks), names, starts, plens, np.array([b[2] for b in blocks], dtype=np.int64))
+        return np.frombuffer(out, dtype=np.uint8)
 
     def decode_container(self, blob: bytes, names: Sequence[str], starts, plens, orig_lens) -> bytes:
         """Container decode: payload k is blob[starts[k] : starts[k] + plens[k]] (container order).  The payload bytes of an
         output batch travel to the device in ONE copy; each method group is compacted there (`kolm_gather_payloads`), decoded
-        as one batch and copied to its blocks' final offsets; one D2H per output batch."""
-        parts = self._decode_spans(blob, list(names), np.asarray(starts, dtype=np.int64), np.asarray(plens, dtype=np.int64),
-                                   np.asarray(orig_lens, dtype=np.int64))
-        return parts[0] if len(parts) == 1 else b"".join(parts)
+        as one batch and copied to its blocks' final offsets; one D2H per output batch, straight into the result."""
+        return self._decode_spans(blob, list(names), np.asarray(starts, dtype=np.int64), np.asarray(plens, dtype=np.int64),
+                                  np.asarray(orig_lens, dtype=np.int64))
 
-    def _decode_spans(self, blob, names: List[str], starts: np.ndarray, plens: np.ndarray, ols: np.ndarray) -> List[bytes]:
+    def _decode_spans(self, blob, names: List[str], starts: np.ndarray, plens: np.ndarray, ols: np.ndarray) -> bytes:
         nb = len(names)
         if nb == 0:
-            return [b""]
+            return b""
         ends = np.cumsum(ols)
-        parts: List[bytes] = []
+        result, sink = _new_bytes(int(ends[-1]))
+        if sink is None:                                             # 0 or 1 byte: CPython shares these objects, build them the ordinary way
+            sink = np.zeros(int(ends[-1]), dtype=np.uint8)
         i = 0
         while i < nb:                                                # output batches of <= batch_bytes
             j, tot = i, 0
@@ -456,9 +490,10 @@ class Engine:
                     src = np.uint64(y.data_ptr()) + off[:-1].astype(np.uint64)
                     self.ctx.copy_blocks(src, dst, sol)
                     torch.cuda.current_stream().synchronize()        # y / pt may be freed when the loop moves on
-                parts.append(self._home(dev_out, tot).tobytes() if tot else b"")
+                if tot:
+                    _par_copy(sink[base_off:base_off + tot], self._home(dev_out, tot))
             i = j
-        return parts
+        return result if len(result) >= 2 else sink.tobytes()
 
     def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:
         area = self.decode_area(blocks)
