@@ -12,6 +12,8 @@ import ctypes as C
 import warnings
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import numpy as np
 import torch
 
@@ -102,6 +104,14 @@ class Engine:
         self.repair_max = int(_lib.lib().kolm_repair_max_block())
         self.enable_v2_new = False     # method 10 as an encode candidate (dead in the shipped reference; see kolm_final_researched_v2_2.G_ENABLE_V2_NEW)
         self._pin: Optional[torch.Tensor] = None
+        # the LZ77 candidate runs beside the BBWT chain: own context, own (non-blocking) stream, one worker thread — its kernels
+        # are latency bound (class walks, one parse CTA per block) and fill the gaps of the sort rounds (KOLM_LZ_ASYNC=0: inline)
+        self.lz_async = os.environ.get("KOLM_LZ_ASYNC", "1") != "0"
+        self.ctx2: Optional[Context] = None
+        self.cap2_bytes = 0
+        self.cap2_blocks = 0
+        self._side: Optional[torch.cuda.Stream] = None
+        self._worker = None
 
     def _home(self, dev: torch.Tensor, n: int) -> np.ndarray:
         """Device bytes -> host through a persistent pinned staging buffer (pageable D2H runs at ~2 GB/s, pinned at PCIe speed)."""
@@ -183,6 +193,35 @@ class Engine:
             with torch.cuda.device(self.device):
                 self.ctx = Context(self.cap_bytes, self.cap_blocks, self.device)
 
+    def _lz_submit(self, x: torch.Tensor, off: np.ndarray, window: int, max_len: int):
+        """Start lz77_encode(x, off) and return a callable that yields (payload, offsets).  x must have been produced on the
+        current stream; the side stream waits for it."""
+        nbytes, nblocks = int(off[-1] - off[0]), len(off) - 1
+        if not self.lz_async:
+            res = self.ctx.lz77_encode(x, off, window, max_len)
+            return lambda: res
+        if self.ctx2 is None or nbytes > self.cap2_bytes or nblocks > self.cap2_blocks:
+            if self.ctx2 is not None:
+                self.ctx2.close()
+                self.ctx2 = None
+            self.cap2_bytes = max(nbytes, min(self.batch_bytes, 1 << 22), self.cap2_bytes)
+            self.cap2_blocks = max(nblocks, 1024, self.cap2_blocks)
+            self.ctx2 = Context(self.cap2_bytes, self.cap2_blocks, self.device)
+        if self._side is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._side = torch.cuda.Stream(device=self.device)
+            self._worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="kolm-lz")
+        ready = torch.cuda.Event()
+        ready.record()
+        ctx2, side, dev = self.ctx2, self._side, self.device
+
+        def work():
+            with torch.cuda.device(dev), torch.cuda.stream(side):
+                side.wait_event(ready)
+                return ctx2.lz77_encode(x, off, window, max_len)    # returns after its stream finished (payload offsets come home)
+        fut = self._worker.submit(work)
+        return fut.result
+
     def _batches(self, bounds: Sequence[Tuple[int, int]], limit: Optional[int] = None):
         """Consecutive blocks grouped so that a batch holds <= limit (default batch_bytes) bytes (a single larger block forms its own batch)."""
         limit = self.batch_bytes if limit is None else max(1, int(limit))
@@ -232,11 +271,12 @@ class Engine:
             with torch.cuda.device(self.device):
                 c = self.ctx
                 x = self._upload(data, a, b)
+                lz = self._lz_submit(x, off, 255, 127)
                 sx = c.residual_sizes(x, off)[:, 0]
                 L = c.bbwt_forward(x, off)
                 m = c.mtf_encode(L, off)
                 kfp, kfo = c.rice_kf_encode(m, off)
-                lzp, lzo = c.lz77_encode(x, off, 255, 127)
+                lzp, lzo = lz()
                 sizes = np.stack([lens, sx, np.diff(kfo), np.diff(lzo)], axis=1)
                 mids = np.argmin(sizes, axis=1)                      # first minimum == lowest id on ties (KF.py:857)
                 base = np.zeros((nb, 4), dtype=np.uint64)
@@ -300,6 +340,7 @@ class Engine:
                 v2p = v2o = None
                 if v2:
                     v2p, v2o = c.v2new_encode(x, off)
+                lz = self._lz_submit(x, off, 4096, 0) if "lz77" in names else None
                 need_res = any(n in ("xor", "lfsr_pred") for n in names)
                 rs = c.residual_sizes(x, off) if need_res else None
                 need_bbwt = any(n in K2_FLAG_OF for n in names)
@@ -308,8 +349,8 @@ class Engine:
                     m = c.mtf_encode(c.bbwt_forward(x, off), off)
                     k2p, k2o, k2s = c.rice_k2_encode(m, off, 0)
                 lzp = lzo = None
-                if "lz77" in names:
-                    lzp, lzo = c.lz77_encode(x, off, 4096, 0)
+                if lz is not None:
+                    lzp, lzo = lz()
                 rpp = rpo = None
                 if "repair" in names:
                     if int(lens.max(initial=0)) <= self.repair_max:
