@@ -159,3 +159,18 @@ def test_command_lines(tmp_path, capsys):
     assert (tmp_path / "c.out").read_bytes() == d
     assert V.main(["-i", str(src), "--fastcdc", "-b", "4096"]) == 0 and V.G_ONLY_METHOD is None
     assert V.decompress((tmp_path / "in.bin.kolr").read_bytes()) == d
+
+
+def test_corpus_as_sequence_of_containers():
+    """Inputs beyond one container's header limits become a sequence of containers, each the reference's bytes for its span."""
+    from kolmogorovlike_datacompressor_b200 import corpus, kolm_final as K, kolm_final_researched_v2_2 as V
+    data = (datasets.fixture("pattern")[:150000] + datasets.fixture("sine")[:100000] + datasets.medium_cases()["text_big"] * 3)
+    parts = corpus.compress_corpus(data, 2048, "kolr", max_blocks=40)
+    spans = corpus.container_spans(len(data), 2048, max_blocks=40)
+    assert len(parts) == len(spans) > 3
+    for (a, b), c in zip(spans, parts):
+        assert c == V.compress_blocks_fixed(data[a:b], 2048)
+    assert corpus.decompress_corpus(parts, "kolr") == data
+    parts = corpus.compress_corpus(data, 4096, "kolm", max_bytes=100000)
+    assert len(parts) >= 3 and corpus.decompress_corpus(parts, "kolm") == data
+    assert parts[0] == K.compress(data[:corpus.container_spans(len(data), 2048, max_bytes=100000)[0][1]], 4096)
