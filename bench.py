@@ -161,7 +161,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1000 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "bbwt+mtf+rice, S1 text-like corpus (bounded CPU sample)", "block_bytes": 8192 if kind == "reference" else MIB},
+            "config": {"workload": "cfg2: BBWT+MTF+Rice stage, 1 MiB blocks, 256 MiB S1 text-like corpus per GPU",
+                       "reference_sample": "bounded CPU sample of the same corpus; kolm_final.cpp cuts its own 8 KiB CDC blocks (hard-coded) and runs its "
+                                           "full model selection" if kind == "reference" else "bounded CPU sample of the same corpus, 1 MiB blocks",
+                       "block_bytes": 8192 if kind == "reference" else MIB},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
