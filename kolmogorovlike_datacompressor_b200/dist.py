@@ -82,19 +82,106 @@ def sharded_encode(data: bytes, bounds: Bounds, encode_fn: Callable[[bytes, Boun
     return out
 
 
+def sharded_encode_area(data: bytes, bounds: Bounds, area_fn, group=None, dst: int = 0):
+    """Array form of sharded_encode for whole containers.  area_fn(data, bounds_slice) -> (method ids, payload lengths, payload
+    area); the area is a device tensor under NCCL (it goes GPU -> GPU into its final place in one buffer on `dst`, which then
+    comes home in a single copy) and a numpy array / CPU tensor under gloo.  Returns (ids, lengths, area as uint8 numpy array)
+    in block order on `dst`, None elsewhere."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = partition_blocks(bounds, world)
+    b0, b1 = parts[rank]
+    dev = _dev(group)
+    if b1 > b0:
+        mids, lens, area = area_fn(data, bounds[b0:b1])
+    else:
+        mids, lens, area = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
+    if not isinstance(area, torch.Tensor):
+        area = torch.from_numpy(np.ascontiguousarray(np.frombuffer(memoryview(area), dtype=np.uint8)).copy())
+    area = area.to(dev)
+    nloc = b1 - b0
+    maxn = max(e - s for s, e in parts)
+    table = torch.zeros((max(maxn, 1), 2), dtype=torch.int64, device=dev)
+    if nloc:
+        table[:nloc, 0] = torch.as_tensor(np.asarray(mids, dtype=np.int64), device=dev)
+        table[:nloc, 1] = torch.as_tensor(np.asarray(lens, dtype=np.int64), device=dev)
+    tables = [torch.empty_like(table) for _ in range(world)]
+    dist.all_gather(tables, table, group=group)
+    tabs = [tables[r][:parts[r][1] - parts[r][0]].cpu().numpy() for r in range(world)]
+    nbytes = [int(t[:, 1].sum()) if len(t) else 0 for t in tabs]
+    if rank != dst:
+        if nbytes[rank]:
+            dist.send(area[:nbytes[rank]].contiguous(), dst=dst, group=group)
+        return None
+    total = sum(nbytes)
+    buf = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    p = 0
+    for r in range(world):
+        if nbytes[r]:
+            if r == dst:
+                buf[p:p + nbytes[r]].copy_(area[:nbytes[r]])
+            else:
+                dist.recv(buf[p:p + nbytes[r]], src=r, group=group)
+        p += nbytes[r]
+    if buf.is_cuda:
+        host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        host.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out_area = host[:total].numpy()
+    else:
+        out_area = buf[:total].numpy()
+    allm = np.concatenate([t[:, 0] for t in tabs]) if tabs else np.zeros(0, np.int64)
+    alll = np.concatenate([t[:, 1] for t in tabs]) if tabs else np.zeros(0, np.int64)
+    return allm, alll, out_area
+
+
+def _engine_area(eng, fn):
+    """Call eng.<encode_*_area> with the payload area left on the device (NCCL sends it from there)."""
+    def run(d, b):
+        eng._device_out = True
+        try:
+            return fn(d, b)
+        finally:
+            eng._device_out = False
+    return run
+
+
 def compress_kolm(data: bytes, target_block: int = 8192, group=None) -> Optional[bytes]:
     """kolm_final.compress with its blocks sharded over the group's GPUs; the container is returned on rank 0."""
     import struct
     from . import kolm_final as KF
     data = bytes(data)
     cuts = KF.cdc_fast_boundaries(data, target_block // 2, target_block, target_block * 2)
-    enc = sharded_encode(data, cuts, lambda d, b: KF._engine().encode_kolm(d, b), group)
+    head = b"KOLM" + struct.pack("<I", target_block & 0xFFFFFFFF) + struct.pack("<Q", len(data)) + struct.pack("<H", len(cuts) & 0xFFFF)
+    if not cuts:
+        return head if dist.get_rank(group) == 0 else None
+    eng = KF._engine()
+    enc = sharded_encode_area(data, cuts, _engine_area(eng, eng.encode_kolm_area), group)
     if enc is None:
         return None
-    out = bytearray(b"KOLM")
-    out += struct.pack("<I", target_block & 0xFFFFFFFF) + struct.pack("<Q", len(data)) + struct.pack("<H", len(cuts) & 0xFFFF)
-    for (a, b), (mid, payload) in zip(cuts, enc):
-        out.append(mid & 0xFF)
-        out += struct.pack("<II", (b - a) & 0xFFFFFFFF, len(payload) & 0xFFFFFFFF)
-        out += payload
-    return bytes(out)
+    return KF._container(head, cuts, enc[0], enc[1], enc[2])
+
+
+def _compress_kolr(data: bytes, bounds, mode: int, size_field: int, group=None) -> Optional[bytes]:
+    from . import kolm_final_researched_v2_2 as V
+    names = V._candidate_names()
+    if not bounds:
+        return V._assemble(data, bounds, mode, size_field) if dist.get_rank(group) == 0 else None
+    eng = V._engine()
+    enc = sharded_encode_area(data, bounds, _engine_area(eng, lambda d, b: eng.encode_kolr_area(d, b, names)), group)
+    if enc is None:
+        return None
+    return V._assemble(data, bounds, mode, size_field, encoded=enc)
+
+
+def compress_kolr_fixed(data: bytes, block_size: int = 8192, group=None) -> Optional[bytes]:
+    """compress_blocks_fixed with its blocks sharded over the group's GPUs; the container (TOC built on rank 0) is returned there."""
+    from . import kolm_final_researched_v2_2 as V
+    data = bytes(data)
+    return _compress_kolr(data, V.fixed_boundaries(data, block_size), V.MODE_FIXED, block_size, group)
+
+
+def compress_kolr_cdc(data: bytes, min_size: int = 4096, avg_size: int = 8192, max_size: int = 16384, group=None) -> Optional[bytes]:
+    """compress_blocks_cdc, sharded the same way."""
+    from . import kolm_final_researched_v2_2 as V
+    data = bytes(data)
+    return _compress_kolr(data, V.cdc_fast_boundaries_strict(data, min_size, avg_size, max_size), V.MODE_CDC, avg_size, group)

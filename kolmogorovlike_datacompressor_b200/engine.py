@@ -104,6 +104,7 @@ class Engine:
         self.repair_max = int(_lib.lib().kolm_repair_max_block())
         self.enable_v2_new = False     # method 10 as an encode candidate (dead in the shipped reference; see kolm_final_researched_v2_2.G_ENABLE_V2_NEW)
         self._pin: Optional[torch.Tensor] = None
+        self._device_out = False       # encode_*_area return the payload area as a device tensor (set by dist.* around its calls)
         # the LZ77 candidate runs beside the BBWT chain: own context, own (non-blocking) stream, one worker thread — its kernels
         # are latency bound (class walks, one parse CTA per block) and fill the gaps of the sort rounds (KOLM_LZ_ASYNC=0: inline)
         self.lz_async = os.environ.get("KOLM_LZ_ASYNC", "1") != "0"
@@ -252,12 +253,24 @@ class Engine:
     # KOLM profile
     def _gather_home(self, c: Context, addr: np.ndarray, lens: np.ndarray, keep: bool = True):
         """Winners' payloads -> one device buffer in block order -> host memory.  Returns a uint8 numpy array; with keep=False it
-        is a view of the pinned staging buffer, valid until the next engine call (the caller joins it into the container at once)."""
+        is a view of the pinned staging buffer, valid until the next engine call (the caller joins it into the container at once).
+        With self._device_out set (dist.*: the payloads travel GPU -> GPU over NCCL) the device tensor is returned instead."""
         total = int(lens.sum())
         dev = torch.empty(max(total, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
         c.gather_payloads(addr, lens, dev)
+        if self._device_out:
+            torch.cuda.current_stream().synchronize()                # the candidates' payload tensors die when the caller moves on
+            return dev[:total]
         v = self._home(dev, total)
         return v.copy() if keep else v
+
+    @staticmethod
+    def _cat(areas):
+        if not areas:
+            return np.zeros(0, np.uint8)
+        if len(areas) == 1:
+            return areas[0]
+        return torch.cat(areas) if isinstance(areas[0], torch.Tensor) else np.concatenate(areas)
 
     def encode_kolm_area(self, data: bytes, bounds: Sequence[Tuple[int, int]]):
         """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLM candidates."""
@@ -292,7 +305,7 @@ class Engine:
             lens_all.append(plen)
         if not areas:
             return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
-        return np.concatenate(mids_all), np.concatenate(lens_all), (areas[0] if len(areas) == 1 else np.concatenate(areas))
+        return np.concatenate(mids_all), np.concatenate(lens_all), self._cat(areas)
 
     def encode_kolm(self, data: bytes, bounds: Sequence[Tuple[int, int]]) -> List[Tuple[int, bytes]]:
         mids, lens, area = self.encode_kolm_area(data, bounds)
@@ -408,7 +421,7 @@ class Engine:
             lens_all.append(plen)
         if not areas:
             return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
-        return np.concatenate(mids_all), np.concatenate(lens_all), (areas[0] if len(areas) == 1 else np.concatenate(areas))
+        return np.concatenate(mids_all), np.concatenate(lens_all), self._cat(areas)
 
     def encode_kolr(self, data: bytes, bounds: Sequence[Tuple[int, int]], names: Sequence[str]) -> List[Tuple[int, bytes]]:
         mids, lens, area = self.encode_kolr_area(data, bounds, names)

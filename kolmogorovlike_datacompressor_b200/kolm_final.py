@@ -136,10 +136,15 @@ def compress(data: bytes, target_block: int = 8192) -> bytes:
     if not cuts:                                          # nblocks wraps silently like the reference (kolm_final.py:889-890)
         return head
     mids, lens, area = _engine().encode_kolm_area(data, cuts)
+    return _container(head, cuts, mids, lens, area)
+
+
+def _container(head: bytes, cuts, mids, lens, area) -> bytes:
+    """head + per block (method u8, orig_len u32, payload_len u32, payload) (kolm_final.py:892-901); `area` = payloads back to back."""
     src = memoryview(area)                                # one copy: the pieces are joined straight into the result
     pieces = [head]
     q = 0
-    for (a, b), mid, ln in zip(cuts, mids.tolist(), lens.tolist()):
+    for (a, b), mid, ln in zip(cuts, [int(x) for x in mids], [int(x) for x in lens]):
         pieces.append(struct.pack("<BII", mid & 0xFF, (b - a) & 0xFFFFFFFF, ln & 0xFFFFFFFF))
         pieces.append(src[q:q + ln])
         q += ln

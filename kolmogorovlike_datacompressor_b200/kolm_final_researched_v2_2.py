@@ -268,7 +268,9 @@ def _pack_mode_and_size(mode: int, size: int) -> int:
     return ((mode & 1) << 31) | (size & 0x7FFFFFFF)
 
 
-def _assemble(data: bytes, boundaries, mode: int, size_field: int) -> bytes:
+def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None) -> bytes:
+    """Container for `boundaries`.  encoded = (method ids, payload lengths, payload area) when the blocks were already encoded
+    elsewhere (dist.compress_kolr_*: block ranges sharded over several GPUs); otherwise they are encoded here."""
     out = bytearray(b"KOLR")
     out += struct.pack("<I", _pack_mode_and_size(mode, size_field))
     out += struct.pack("<I", len(data))                 # struct.error beyond 4 GiB-1 / 65535 blocks, like the reference
@@ -277,7 +279,9 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int) -> bytes:
     nblocks = len(boundaries)
     label = "FIXED" if mode == MODE_FIXED else "Fast CDC"
     _print_progress(label, 0, nblocks)
-    if nblocks:
+    if nblocks and encoded is not None:
+        method_ids, payload_lens, area = [int(x) for x in encoded[0]], [int(x) for x in encoded[1]], encoded[2]
+    elif nblocks:
         mids_np, lens_np, area = _engine().encode_kolr_area(data, boundaries, names)
         method_ids, payload_lens = mids_np.tolist(), lens_np.tolist()
     else:

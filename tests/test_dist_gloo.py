@@ -71,3 +71,44 @@ def test_partition_balanced_and_total():
         sizes = [e - s for s, e in parts]
         assert max(sizes) - min(sizes) <= 1 or world > 37
     assert kd.partition_blocks([], 4) == [(0, 0)] * 4
+
+
+def _worker_area(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+    from kolmogorovlike_datacompressor_b200 import dist as kd
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = datasets.fixture("pattern")[:50000] + datasets.medium_cases()["text_big"]
+    bounds = [(a, min(len(data), a + 2048)) for a in range(0, len(data), 2048)]
+
+    def area_fn(d, bs):
+        enc = [O.encode_block(O.PROFILE_KOLR, d[a:b])[:2] for a, b in bs]
+        return (np.array([m for m, _ in enc], dtype=np.int64), np.array([len(p) for _, p in enc], dtype=np.int64),
+                np.frombuffer(b"".join(p for _, p in enc), dtype=np.uint8))
+
+    got = kd.sharded_encode_area(data, bounds, area_fn)
+    if rank == 0:
+        want = area_fn(data, bounds)
+        q.put(("ok", all(np.array_equal(g, w) for g, w in zip(got, want)), len(bounds)))
+    else:
+        q.put(("none", got is None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_encode_area_three_ranks():
+    """Array form used by dist.compress_kolm / compress_kolr_*: ids, lengths and the payload area arrive in block order on rank 0."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_area, args=(r, 3, port, q)) for r in range(3)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r for r in res if r[0] == "ok"][0][1] is True
+    assert sum(1 for r in res if r[0] == "none" and r[1]) == 2
