@@ -185,3 +185,68 @@ def compress_kolr_cdc(data: bytes, min_size: int = 4096, avg_size: int = 8192, m
     from . import kolm_final_researched_v2_2 as V
     data = bytes(data)
     return _compress_kolr(data, V.cdc_fast_boundaries_strict(data, min_size, avg_size, max_size), V.MODE_CDC, avg_size, group)
+
+
+def _sharded_decode(blob: bytes, names, starts, plens, olens, decode_fn, group=None, dst: int = 0, piece: int = 256 << 20) -> Optional[bytes]:
+    """Blocks of one container decoded on the group's GPUs: contiguous block ranges balanced by decoded bytes; every rank holds
+    the container, decodes its range with decode_fn(blob, names, starts, plens, olens) -> uint8 tensor of the range's bytes
+    (device tensor under NCCL), and the ranges are collected in order on `dst` (send/recv in pieces of `piece` bytes)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ol = np.asarray(olens, dtype=np.int64)
+    ends = np.cumsum(ol)
+    bounds = [(int(e - l), int(e)) for e, l in zip(ends, ol)]
+    parts = partition_blocks(bounds, world)
+    b0, b1 = parts[rank]
+    dev = _dev(group)
+    mine = decode_fn(blob, names[b0:b1], starts[b0:b1], plens[b0:b1], olens[b0:b1]) if b1 > b0 else torch.empty(0, dtype=torch.uint8, device=dev)
+    nbytes = [int(ol[s:e].sum()) for s, e in parts]
+    if rank != dst:
+        for a in range(0, nbytes[rank], piece):
+            dist.send(mine[a:min(nbytes[rank], a + piece)].contiguous(), dst=dst, group=group)
+        return None
+    from .engine import _new_bytes, _par_copy
+    total = int(ol.sum())
+    out, sink = _new_bytes(total)                            # filled in place: no second copy of the decoded data
+    if sink is None:
+        sink = np.zeros(total, dtype=np.uint8)
+    host = torch.empty(max(1, min(piece, max(nbytes))), dtype=torch.uint8)
+    if dev.type == "cuda":
+        host = host.pin_memory()
+    p = 0
+    for r in range(world):
+        for a in range(0, nbytes[r], piece):
+            n = min(nbytes[r], a + piece) - a
+            if r == dst:
+                t = mine[a:a + n]
+            else:
+                t = torch.empty(n, dtype=torch.uint8, device=dev)
+                dist.recv(t, src=r, group=group)
+            host[:n].copy_(t)
+            _par_copy(sink[p:p + n], host[:n].numpy())
+            p += n
+    return out if total >= 2 else sink.tobytes()
+
+
+def decompress_kolm(blob: bytes, group=None) -> Optional[bytes]:
+    """kolm_final.decompress with the container's blocks decoded across the group's GPUs; the data is returned on rank 0."""
+    from . import kolm_final as KF
+    blob = bytes(blob)
+    names, starts, plens, olens, total_len = KF._parse(blob)
+    out = _sharded_decode(blob, names, starts, plens, olens, KF._engine().decode_to_device, group)
+    if out is not None and len(out) != total_len:
+        raise ValueError(f"Total decoded length mismatch: expected {total_len}, got {len(out)}")
+    return out
+
+
+def decompress_kolr(container: bytes, group=None) -> Optional[bytes]:
+    """kolm_final_researched_v2_2.decompress, sharded the same way (every rank parses the TOC)."""
+    from . import kolm_final_researched_v2_2 as V
+    container = bytes(container)
+    names, starts, plens, olens, total_len, pos = V._parse(container)
+    out = _sharded_decode(container, names, starts, plens, olens, V._engine().decode_to_device, group)
+    if out is not None:
+        if len(out) != total_len:
+            raise ValueError(f"Length mismatch: got {len(out)}, expect {total_len}")
+        if pos != len(container):
+            raise ValueError(f"Extra trailing {len(container) - pos} bytes after container end")
+    return out

@@ -472,13 +472,23 @@ class Engine:
         return self._decode_spans(blob, list(names), np.asarray(starts, dtype=np.int64), np.asarray(plens, dtype=np.int64),
                                   np.asarray(orig_lens, dtype=np.int64))
 
-    def _decode_spans(self, blob, names: List[str], starts: np.ndarray, plens: np.ndarray, ols: np.ndarray) -> bytes:
+    def decode_to_device(self, blob, names: Sequence[str], starts, plens, orig_lens) -> torch.Tensor:
+        """Like decode_container, but the decoded bytes stay on the device (one uint8 tensor; dist.decompress_* sends it over NCCL)."""
+        ols = np.asarray(orig_lens, dtype=np.int64)
+        out = torch.empty(max(int(ols.sum()), 1), dtype=torch.uint8, device=torch.device("cuda", self.device))
+
+        def keep(base_off, dev_out, tot):
+            out[base_off:base_off + tot].copy_(dev_out[:tot])
+        self._decode_spans(blob, list(names), np.asarray(starts, dtype=np.int64), np.asarray(plens, dtype=np.int64), ols, on_batch=keep)
+        return out[:int(ols.sum())]
+
+    def _decode_spans(self, blob, names: List[str], starts: np.ndarray, plens: np.ndarray, ols: np.ndarray, on_batch=None) -> bytes:
         nb = len(names)
         if nb == 0:
             return b""
         ends = np.cumsum(ols)
-        result, sink = _new_bytes(int(ends[-1]))
-        if sink is None:                                             # 0 or 1 byte: CPython shares these objects, build them the ordinary way
+        result, sink = (b"", None) if on_batch is not None else _new_bytes(int(ends[-1]))
+        if sink is None and on_batch is None:                        # 0 or 1 byte: CPython shares these objects, build them the ordinary way
             sink = np.zeros(int(ends[-1]), dtype=np.uint8)
         i = 0
         while i < nb:                                                # output batches of <= batch_bytes
@@ -544,9 +554,14 @@ class Engine:
                     src = np.uint64(y.data_ptr()) + off[:-1].astype(np.uint64)
                     self.ctx.copy_blocks(src, dst, sol)
                     torch.cuda.current_stream().synchronize()        # y / pt may be freed when the loop moves on
-                if tot:
+                if tot and on_batch is not None:
+                    on_batch(base_off, dev_out, tot)
+                    torch.cuda.current_stream().synchronize()
+                elif tot:
                     _par_copy(sink[base_off:base_off + tot], self._home(dev_out, tot))
             i = j
+        if on_batch is not None:
+            return b""
         return result if len(result) >= 2 else sink.tobytes()
 
     def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:

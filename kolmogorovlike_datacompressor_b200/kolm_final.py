@@ -151,8 +151,8 @@ def _container(head: bytes, cuts, mids, lens, area) -> bytes:
     return b"".join(pieces)
 
 
-def decompress(blob: bytes) -> bytes:
-    blob = bytes(blob)
+def _parse(blob: bytes):
+    """Container walk of decompress (kolm_final.py:904-945): -> (method names, payload starts, payload lengths, orig lengths, total_len)."""
     p = 0
     if blob[p:p + 4] != b"KOLM":
         raise ValueError("Bad magic header")
@@ -179,6 +179,12 @@ def decompress(blob: bytes) -> bytes:
             raise EOFError("Truncated payload")
         names.append(_NAMES[method_id]); starts.append(p); plens.append(payload_len); olens.append(orig_len)
         p += payload_len
+    return names, starts, plens, olens, total_len
+
+
+def decompress(blob: bytes) -> bytes:
+    blob = bytes(blob)
+    names, starts, plens, olens, total_len = _parse(blob)
     out = _engine().decode_container(blob, names, starts, plens, olens) if names else b""   # every decoder yields exactly orig_len bytes or raises
     if len(out) != total_len:
         raise ValueError(f"Total decoded length mismatch: expected {total_len}, got {len(out)}")

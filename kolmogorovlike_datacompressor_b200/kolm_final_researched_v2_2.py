@@ -358,8 +358,9 @@ def compress_blocks_cdc(data: bytes, min_size: int = 4096, avg_size: int = 8192,
     return _assemble(data, cdc_fast_boundaries_strict(data, min_size, avg_size, max_size), MODE_CDC, avg_size)
 
 
-def decompress(container: bytes) -> bytes:
-    container = bytes(container)
+def _parse(container: bytes):
+    """Header + TOC walk of decompress (v2-2.py:2451-2530): -> (method names, payload starts, payload lengths, orig lengths,
+    total_len, end position of the payload area)."""
     if len(container) < 4 or container[:4] != b"KOLR":
         raise ValueError("Invalid magic")
     pos = 4
@@ -443,6 +444,13 @@ def decompress(container: bytes) -> bytes:
     plens = [P[0]] + [P[i] - P[i - 1] for i in range(1, nblocks)] if nblocks else []
     if any(x < 0 for x in plens):
         raise ValueError("Payload EF offsets not monotone")
+    return names, starts, plens, orig_lens, total_len, pos
+
+
+def decompress(container: bytes) -> bytes:
+    container = bytes(container)
+    names, starts, plens, orig_lens, total_len, pos = _parse(container)
+    nblocks = len(names)
     _print_progress("DECOMPRESS", 0, nblocks)
     out = _engine().decode_container(container, names, starts, plens, orig_lens) if nblocks else b""
     _print_progress("DECOMPRESS", nblocks, nblocks, final=True)

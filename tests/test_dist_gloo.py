@@ -112,3 +112,41 @@ def test_sharded_encode_area_three_ranks():
         assert p.exitcode == 0
     assert [r for r in res if r[0] == "ok"][0][1] is True
     assert sum(1 for r in res if r[0] == "none" and r[1]) == 2
+
+
+def _worker_dec(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from kolmogorovlike_datacompressor_b200 import dist as kd, kolm_final as KF
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = datasets.fixture("pattern")[:40000] + datasets.medium_cases()["text_big"] + bytes(3000)
+    blob = O.kf_compress(data, 2048)
+    names, starts, plens, olens, total = KF._parse(blob)
+    ids = {"raw": 0, "kf_xor": 1, "kf_bbwt": 2, "kf_lz77": 3}
+
+    def dec(b, nm, st, pl, ol):
+        out = b"".join(O.decode_model(O.PROFILE_KOLM, ids[n], b[s:s + l], o) for n, s, l, o in zip(nm, st, pl, ol))
+        return torch.frombuffer(bytearray(out), dtype=torch.uint8)
+
+    got = kd._sharded_decode(blob, names, starts, plens, olens, dec, piece=7000)
+    q.put(("ok", got == data and total == len(data)) if rank == 0 else ("none", got is None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_decode_two_ranks():
+    """dist.decompress_*: block ranges decoded on different ranks arrive in order on rank 0 (pieces smaller than a range)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_dec, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] is True for r in res)
