@@ -200,6 +200,23 @@ __device__ __forceinline__ u32 scan_last_nonzero(u32 mine, u64* lb, u32 tile, bo
     return r;
 }
 
+// the same with the tile's exclusive value already known (recorded by the cost pass): no look-back, no ticket
+__device__ __forceinline__ u32 scan_last_nonzero_known(u32 mine, u32 excl, u64* s_warp, u64* s_last) {
+    const u32 tid = threadIdx.x;
+    u64 tot;
+    u64 incl = block_scan_incl((u64)mine, 0ull, OpMax(), s_warp, &tot);
+    u64 prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if ((tid & 31) == 31) s_last[tid >> 5] = incl;
+    __syncthreads();
+    if ((tid & 31) == 0) prev = (tid >> 5) ? s_last[(tid >> 5) - 1] : 0ull;
+    __syncthreads();
+    return (u32)max((u64)excl, prev);
+}
+
+// per-tile scratch slots next to the 25 cost sums (tacc[tile*32 + slot])
+#define RT_LN0 25      // KF: last non-zero position (1-based, block-local) before the tile
+#define RT_BITOFF 26   // exclusive bit offset of the tile inside its block's token stream (k_rice_tile_offsets)
+
 // ---------------------------------------------------------------------------------------------
 // cost pass: every candidate parameterisation in one read of the MTF bytes
 // ---------------------------------------------------------------------------------------------
@@ -210,6 +227,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
     __shared__ u64 s_last[KOLM_THREADS / 32];
     __shared__ u64 s_excl;
     __shared__ unsigned long long s_acc[25];
+    __shared__ u32 s_ln0;
     const u32 tid = threadIdx.x;
     const u32 tile = KF ? lb_take_ticket(lb) : blockIdx.x;
     if (tile == LB_NO_TILE) return;
@@ -243,6 +261,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
 #pragma unroll
         for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
         u32 ln = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
+        if (tid == 0) s_ln0 = ln;                          // thread 0's exclusive value = the tile's: the pack pass starts from it
 #pragma unroll
         for (int i = 0; i < KOLM_IPT; ++i) {
             u32 r = tid * KOLM_IPT + i;
@@ -309,7 +328,40 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
     }
     __syncthreads();
     // per-tile partial sums; k_tile_reduce adds them per block (same-address global atomics from 256 tiles serialise in L2)
-    if (tid < 32) tacc[(size_t)tile * 32 + tid] = tid < 25 ? s_acc[tid] : 0ull;
+    if (tid < 32) tacc[(size_t)tile * 32 + tid] = tid < 25 ? s_acc[tid] : (KF && tid == RT_LN0) ? (u64)s_ln0 : 0ull;
+}
+
+// After the plan: every tile's bit count under the chosen parameters from its cost sums, exclusive scan over the block's tiles
+// -> tacc[tile*32 + RT_BITOFF].  mode 1 = KF (bacc[RB_PARAM] holds k0, k1, Rice-vs-gamma flags), 2 = K2 (slot of the chosen variant).
+__global__ void __launch_bounds__(256) k_rice_tile_offsets(u64* __restrict__ tacc, const u32* __restrict__ tile0, const u32* __restrict__ tilen,
+                                                           const u64* __restrict__ bacc, int mode, int k2slot) {
+    __shared__ u64 s_w[8];
+    __shared__ u64 s_carry;
+    const u32 b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const u32 t0 = tile0[b], nt = tilen[b];
+    const u32 prm = (u32)bacc[(size_t)b * RB_STRIDE + RB_PARAM];
+    const u32 k0 = prm & 0xff, k1 = (prm >> 8) & 0xff; const bool urz = (prm >> 16) & 1, urn = (prm >> 17) & 1;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < nt; base += 256) {
+        const u32 t = base + tid;
+        u64 bits = 0;
+        if (t < nt) {
+            const u64* a = tacc + (size_t)(t0 + t) * 32;
+            bits = mode == 1 ? a[RB_KF_NZ] + a[RB_KF_NN] + (urz ? a[RB_KF_Z + k0] : a[RB_KF_Z + 7]) + (urn ? a[RB_KF_N + k1] : a[RB_KF_N + 7]) : a[RB_K2 + k2slot];
+        }
+        u64 v = bits;
+        for (int o = 1; o < 32; o <<= 1) { u64 n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v += n; }
+        if (lane == 31) s_w[w] = v;
+        __syncthreads();
+        u64 pre = 0;
+        for (u32 i = 0; i < w; ++i) pre += s_w[i];
+        const u64 carry = s_carry;
+        if (t < nt) tacc[(size_t)(t0 + t) * 32 + RT_BITOFF] = carry + pre + v - bits;
+        __syncthreads();
+        if (tid == 255) s_carry = carry + pre + v;
+        __syncthreads();
+    }
 }
 
 // bacc[b*64 + slot] (+)= sum over the tiles of block b of tacc[tile*32 + slot], slot < 32
@@ -382,15 +434,13 @@ __global__ void k_zero_words(u32* __restrict__ out, const i64* __restrict__ tota
 // KF pack (KF.py:662-684)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
-                                                               const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
+                                                               const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
                                                                u32* __restrict__ out) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_last[KOLM_THREADS / 32];
-    __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
-    const u32 tile = lb_take_ticket(lb);
-    if (tile == LB_NO_TILE) return;
-    u64* lb2 = lb + gridDim.x;                              // second look-back (bit offsets)
+    const u32 tile = blockIdx.x;                            // no ticket, no look-back: entry state and bit offset were recorded per tile
+    const u64* trec = tacc + (size_t)tile * 32;
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
     const u64* a = bacc + (size_t)td.block * RB_STRIDE;
@@ -403,7 +453,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
     u32 lastnz = 0;
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
-    const u32 ln0 = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
+    const u32 ln0 = scan_last_nonzero_known(lastnz, (u32)trec[RT_LN0], s_warp, s_last);
     // token of item i (KF.py:670-684): tag bit, then Rice(k) of x or gamma of x.  non-zero v -> tag 1, x = v-1 (Rice) / v (gamma);
     // a zero that ends a run -> tag 0, x = run length.  The parameters are uniform over the block, so every token with a
     // value below 256 (all non-zeros, almost all runs) comes from one of two 256-entry tables built per CTA:
@@ -451,16 +501,12 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
     }
     u64 btot;
     u64 bincl = block_scan_incl(mybits, 0ull, OpAdd(), s_warp, &btot);
-    if (tid < 32) {
-        u64 e = lb_exclusive(lb2, tile, (td.flags & 1u) != 0, btot, 0ull, OpAdd());
-        if (tid == 0) s_excl = e;
-    }
-    __syncthreads();
-    const u64 bp0 = bitbase + 10 + s_excl + (bincl - mybits);
+    const u64 texcl = trec[RT_BITOFF];
+    const u64 bp0 = bitbase + 10 + texcl + (bincl - mybits);
     __shared__ u32 s_stage[STAGE_WORDS];
     BitStage st;
     {   // this tile's bit range (the first tile of a block also owns the 10 header bits)
-        u64 tb0 = bitbase + 10 + s_excl, tbn = btot;
+        u64 tb0 = bitbase + 10 + texcl, tbn = btot;
         if (td.flags & 1u) { tb0 = bitbase; tbn += 10; }
         st.begin(s_stage, out, tb0, tbn);
     }
@@ -493,13 +539,11 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
 // V22 Rice(k=2) pack of T_flags(mtf)  (V22.py:1413-1421)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_k2_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
-                                                               const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
+                                                               const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
                                                                u32* __restrict__ out, int flags) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
-    __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
-    const u32 tile = lb_take_ticket(lb);
-    if (tile == LB_NO_TILE) return;
+    const u32 tile = blockIdx.x;                            // bit offset of the tile from k_rice_tile_offsets: no look-back
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
     const u64 bitbase = bacc[(size_t)td.block * RB_STRIDE + RB_OFF] * 8;
@@ -525,15 +569,11 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_k2_pack(const u8* __re
     }
     u64 btot;
     u64 bincl = block_scan_incl(mybits, 0ull, OpAdd(), s_warp, &btot);
-    if (tid < 32) {
-        u64 e = lb_exclusive(lb, tile, (td.flags & 1u) != 0, btot, 0ull, OpAdd());
-        if (tid == 0) s_excl = e;
-    }
-    __syncthreads();
-    const u64 bp0 = bitbase + s_excl + (bincl - mybits);
+    const u64 texcl = tacc[(size_t)tile * 32 + RT_BITOFF];
+    const u64 bp0 = bitbase + texcl + (bincl - mybits);
     __shared__ u32 s_stage[STAGE_WORDS];
     BitStage st;
-    st.begin(s_stage, out, bitbase + s_excl, btot);
+    st.begin(s_stage, out, bitbase + texcl, btot);
     BitAcc ba; ba.init(st, bp0);
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
@@ -583,8 +623,8 @@ int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
-        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out));
+        KL(c, KC_RICE_PLAN, (i64)nt * 64, s, k_rice_tile_offsets<<<nb, 256, 0, s>>>((u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 1, 0));
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, params, nullptr, out_cap, s);
@@ -605,9 +645,8 @@ int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 2, slot));
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
-        int lgrid = nt;
-        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
-        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, (u32*)out, flags));
+        KL(c, KC_RICE_PLAN, (i64)nt * 64, s, k_rice_tile_offsets<<<nb, 256, 0, s>>>((u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 2, slot));
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, flags));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, nullptr, sizes, out_cap, s);
