@@ -216,6 +216,9 @@ __device__ __forceinline__ u32 scan_last_nonzero_known(u32 mine, u32 excl, u64* 
 // per-tile scratch slots next to the 25 cost sums (tacc[tile*32 + slot])
 #define RT_LN0 25      // KF: last non-zero position (1-based, block-local) before the tile
 #define RT_BITOFF 26   // exclusive bit offset of the tile inside its block's token stream (k_rice_tile_offsets)
+#define RT_LEAD 27     // KF: in-tile length of the zero run that ends in the tile with no non-zero before it in the tile (0: none)
+#define RT_TRAIL 28    // KF: zeros at the end of the tile whose run does not end in the tile
+#define RT_ANYNZ 29    // KF: the tile holds a non-zero
 
 // ---------------------------------------------------------------------------------------------
 // cost pass: every candidate parameterisation in one read of the MTF bytes
@@ -225,17 +228,16 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
                                                             const BlockInfo* __restrict__ binfo, u64* lb, u64* __restrict__ tacc) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_last[KOLM_THREADS / 32];
-    __shared__ u64 s_excl;
     __shared__ unsigned long long s_acc[25];
-    __shared__ u32 s_ln0;
+    __shared__ u32 s_ln0, s_lead, s_trail;
     const u32 tid = threadIdx.x;
-    const u32 tile = KF ? lb_take_ticket(lb) : blockIdx.x;
-    if (tile == LB_NO_TILE) return;
+    const u32 tile = blockIdx.x;                            // no look-back: runs that cross tiles are settled by k_rice_kf_fixup
     const TileDesc td = tiles[tile];
     const BlockInfo bi = binfo[td.block];
     const u32 t0 = td.start - bi.pbase;
     const u8* src = mtf + bi.ioff + t0;
     if (tid < 25) s_acc[tid] = 0;
+    if (tid == 0) { s_ln0 = 0; s_lead = 0; s_trail = 0; }
     // s_ptab[x] = (x>>0) | (x>>1)<<12 | (x>>2)<<23 | (x>>3)<<33 | (x>>4)<<42 | (x>>5)<<50 | (x>>6)<<57 : field k is wide enough for
     // the sum of a thread's 16 items (x <= 254), so one 64-bit add per non-zero symbol replaces seven shift/add pairs
     __shared__ u64 s_ptab[256];
@@ -260,8 +262,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
         u32 lastnz = 0;
 #pragma unroll
         for (int i = 0; i < KOLM_IPT; ++i) { u32 r = tid * KOLM_IPT + i; if (r < td.count && v[i]) lastnz = t0 + r + 1; }
-        u32 ln = scan_last_nonzero(lastnz, lb, tile, (td.flags & 1u) != 0, s_warp, s_last, &s_excl);
-        if (tid == 0) s_ln0 = ln;                          // thread 0's exclusive value = the tile's: the pack pass starts from it
+        u32 ln = scan_last_nonzero_known(lastnz, 0u, s_warp, s_last);     // last non-zero of THIS tile before my items (0: none)
 #pragma unroll
         for (int i = 0; i < KOLM_IPT; ++i) {
             u32 r = tid * KOLM_IPT + i;
@@ -273,6 +274,10 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
                     accn[7] += 2 * bitlen32(v[i]) - 1;
                     ++nnt;
                 } else if (v[i + 1] != 0) {                 // zero run ends here (next is non-zero or end of block)
+                    if (ln == 0) {                          // it began before the tile (or at its start): length known only to the fix-up
+                        s_lead = pos1 - t0;                 // at most one such run end per tile: a single writer
+                        continue;
+                    }
                     u32 run = pos1 - ln;
                     if (run < 256u) packz += s_ptab[run];   // same packed quotient sums as the non-zeros
                     else {
@@ -282,6 +287,17 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
                     accz[7] += 2 * bitlen32(run) - 1;
                     ++nzt;
                 }
+            }
+        }
+        {   // the thread that owns the tile's last byte describes the tile's tail (ln now covers its own items too)
+            const u32 rl = td.count - 1;
+            if (rl / KOLM_IPT == tid) {
+                const int il = (int)(rl % KOLM_IPT);
+                u32 vl = 0, vn = 0;
+#pragma unroll
+                for (int i = 0; i < KOLM_IPT; ++i) if (i == il) { vl = v[i]; vn = v[i + 1]; }
+                s_ln0 = ln;                                 // 0: the tile holds no non-zero
+                s_trail = (vl != 0 || vn != 0) ? 0u : (ln ? t0 + td.count - ln : td.count);
             }
         }
     }
@@ -328,7 +344,44 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_cost(const u8* __restr
     }
     __syncthreads();
     // per-tile partial sums; k_tile_reduce adds them per block (same-address global atomics from 256 tiles serialise in L2)
-    if (tid < 32) tacc[(size_t)tile * 32 + tid] = tid < 25 ? s_acc[tid] : (KF && tid == RT_LN0) ? (u64)s_ln0 : 0ull;
+    if (tid < 32) tacc[(size_t)tile * 32 + tid] = tid < 25 ? s_acc[tid] : !KF ? 0ull : tid == RT_LEAD ? (u64)s_lead : tid == RT_TRAIL ? (u64)s_trail :
+                                                  tid == RT_ANYNZ ? (u64)(s_ln0 != 0) : 0ull;
+}
+
+// KF: zero runs that cross tile boundaries.  One thread per block walks its tiles in order with the number of pending zeros:
+// the run that ends in a tile with no non-zero before it there (RT_LEAD) gets its full length and its costs are added to that
+// tile's sums; every tile learns the position of the last non-zero before it (RT_LN0, what the pack pass starts from).
+__global__ void k_rice_kf_fixup(u64* __restrict__ tacc, const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
+                                const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks) {
+    // one WARP per block: 32 tiles' records are loaded at once (the walk itself is a short serial chain over registers)
+    const u32 lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const u32 t0 = tile0[b], nt = tilen[b], pbase = binfo[b].pbase;
+    u32 carry = 0;
+    for (u32 base = 0; base < nt; base += 32) {
+        const u32 t = base + lane;
+        u32 lead = 0, trail = 0, any = 0, cnt = 0, start = 0;
+        u64* a = tacc + (size_t)(t0 + (t < nt ? t : 0)) * 32;
+        if (t < nt) { const TileDesc td = tiles[t0 + t]; lead = (u32)a[RT_LEAD]; trail = (u32)a[RT_TRAIL]; any = a[RT_ANYNZ] != 0; cnt = td.count; start = td.start - pbase; }
+        const u32 n = min(32u, nt - base);
+        u32 my_carry = 0;
+        for (u32 k = 0; k < n; ++k) {                       // carry entering tile base+k, broadcast from the lanes' registers
+            if (lane == k) my_carry = carry;
+            const u32 l = __shfl_sync(0xffffffffu, lead, k), tr = __shfl_sync(0xffffffffu, trail, k);
+            const u32 an = __shfl_sync(0xffffffffu, any, k), c = __shfl_sync(0xffffffffu, cnt, k);
+            carry = (!l && !an) ? carry + c : tr;
+        }
+        if (t < nt) {
+            a[RT_LN0] = (u64)(start - my_carry);
+            if (lead) {
+                const u32 run = my_carry + lead;
+                for (int k = 0; k < 7; ++k) a[RB_KF_Z + k] += (u64)(run >> k) + 1 + k;
+                a[RB_KF_Z + 7] += 2 * bitlen32(run) - 1;
+                a[RB_KF_NZ] += 1;
+            }
+        }
+    }
 }
 
 // After the plan: every tile's bit count under the chosen parameters from its cost sums, exclusive scan over the block's tiles
@@ -611,13 +664,12 @@ static int rice_finish(kolm_ctx* c, i64* out_off, int* params, i64* sizes, size_
 
 int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i64* out_off, int* params, cudaStream_t s) {
     const int nb = c->nblocks, nt = c->ntiles;
-    int lgrid = nt;
     if (((uintptr_t)out & 3) != 0) return KOLM_E_ARG;
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * RB_STRIDE * 8, s));
     if (nt) {
-        KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
-        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<lgrid, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, (u64*)c->d_thist));
+        KL(c, KC_RICE_COST, c->total_bytes, s, k_rice_cost<true, false><<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, c->d_lb, (u64*)c->d_thist));
+        KL(c, KC_RICE_COST, (i64)nt * 64, s, k_rice_kf_fixup<<<(nb + 3) / 4, 128, 0, s>>>((u64*)c->d_thist, c->d_tiles, c->d_binfo, c->d_btile0, c->d_btilen, nb));
         KL(c, KC_RICE_COST, (i64)nt * 256, s, k_tile_reduce<<<nb, 256, 0, s>>>((const u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 0, 20));
     }
     KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, 1, 0));
