@@ -21,6 +21,7 @@ void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
 #include "lz77.cu"
 #include "residual.cu"
 #include "repair.cu"
+#include "repair_big.cu"
 #include "v2new.cu"
 
 static size_t padded_capacity(size_t max_batch_bytes, int max_blocks) {
@@ -97,7 +98,7 @@ void kolm_destroy(kolm_ctx* c) {
     cudaSetDevice(c->device);
     void* dptrs[] = {c->d_binfo, c->d_btile0, c->d_btilen, c->d_atile0, c->d_atilen, c->d_active, c->d_newcls, c->d_done, c->d_nfac,
                      c->d_stats, c->d_bacc, c->d_tiles, c->d_atiles, c->d_lb, c->d_thist, c->d_k0, c->d_v0, c->d_k1, c->d_v1,
-                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes, c->d_jump, c->d_err};
+                     c->d_sa, c->d_rank, c->d_nr, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes, c->d_jump, c->d_err, c->d_rpb};
     for (void* p : dptrs) if (p) cudaFree(p);
     if (c->prof_ev) { for (int i = 0; i < 2 * KOLM_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]); delete[] c->prof_ev; }
     if (c->h_binfo) cudaFreeHost(c->h_binfo);
@@ -264,7 +265,7 @@ int kolm_repair_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off,
     return kolm_repair_dec_impl(c, payload, pay_off, out, s);
 }
 
-int kolm_repair_max_block(void) { return REPAIR_MAX; }
+int kolm_repair_max_block(void) { return REPAIR_MAX; }          // shared-memory kernel; longer blocks take the incremental kernel (repair_big.cu)
 
 int kolm_v2new_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
                    kolm_stream_t stream) {

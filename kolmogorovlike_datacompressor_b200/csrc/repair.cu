@@ -180,6 +180,8 @@ __global__ void k_repair_gather(const u8* __restrict__ tmp, const BlockInfo* __r
     for (u64 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+int kolm_repair_big_impl(kolm_ctx* c, const u8* in, u8* tmp, cudaStream_t s);
+
 // decode (v0): one thread per block; iterative expansion with an explicit stack in global scratch
 __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo, u8* __restrict__ out,
                              u32* __restrict__ scratch_rules, u32* __restrict__ scratch_stack, int* __restrict__ err, int nblocks) {
@@ -188,7 +190,7 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
     BlockInfo bi = binfo[b];
     const u8* d = pay + pay_off[b];
     i64 n = pay_off[b + 1] - pay_off[b], p = 2;
-    u32* rules = scratch_rules + bi.pbase;       // capacity len (+pad) entries of (a<<16|b): enough for encoder output (<= len/2 rules)
+    u32* rules = scratch_rules + bi.pbase;       // capacity len (+pad) words = len/2 rules of two 32-bit symbols (what the encoder can emit)
     u32* stack = scratch_stack + bi.pbase;
     u32 cap = ((bi.len + KOLM_PAD - 1) / KOLM_PAD) * KOLM_PAD;
     if (cap < KOLM_PAD) cap = KOLM_PAD;
@@ -200,12 +202,12 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
     if (!e && !get(term)) e = KOLM_E_TRUNCATED;
     if (!e && term != 256) e = KOLM_E_CORRUPT;
     if (!e && !get(nr)) e = KOLM_E_TRUNCATED;
-    if (!e && nr > cap) e = KOLM_E_UNSUPPORTED;
+    if (!e && 2 * nr > cap) e = KOLM_E_UNSUPPORTED;           // the encoder emits at most len/2 rules
     for (u64 r = 0; r < nr && !e; ++r) {
         u64 x, y;
         if (!get(x) || !get(y)) { e = KOLM_E_TRUNCATED; break; }
-        if (x >= 256 + r || y >= 256 + r || x > 0xffff || y > 0xffff) { e = KOLM_E_CORRUPT; break; }
-        rules[r] = ((u32)x << 16) | (u32)y;
+        if (x >= 256 + r || y >= 256 + r) { e = KOLM_E_CORRUPT; break; }
+        rules[2 * r] = (u32)x; rules[2 * r + 1] = (u32)y;
     }
     if (!e && !get(sl)) e = KOLM_E_TRUNCATED;
     u32 o = 0;
@@ -217,7 +219,7 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
         while (sp) {
             u32 x = stack[--sp];
             if (x < 256) { if (o >= bi.len) { e = KOLM_E_CORRUPT; break; } dst[o++] = (u8)x; }
-            else { if (sp + 2 > cap) { e = KOLM_E_UNSUPPORTED; break; } u32 k = rules[x - 256]; stack[sp++] = k & 0xffff; stack[sp++] = k >> 16; }
+            else { if (sp + 2 > cap) { e = KOLM_E_UNSUPPORTED; break; } stack[sp++] = rules[2 * (x - 256) + 1]; stack[sp++] = rules[2 * (x - 256)]; }
         }
     }
     if (!e && o != bi.len) e = KOLM_E_CORRUPT;
@@ -227,7 +229,9 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
 int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
     const int nb = c->nblocks;
     if (!nb) { out_off[0] = 0; return KOLM_OK; }
-    if (c->max_len > REPAIR_MAX) return KOLM_E_UNSUPPORTED;
+    static long long big_max = -1;                            // KOLM_REPAIR_BIG_MAX: largest block (bytes) the incremental kernel takes (0: none)
+    if (big_max < 0) { const char* e = getenv("KOLM_REPAIR_BIG_MAX"); big_max = e ? atoll(e) : (1ll << 30); }
+    if (c->max_len > REPAIR_MAX && (long long)c->max_len > big_max) return KOLM_E_UNSUPPORTED;
     static bool attr_set[64];
     if (c->device < 64 && !attr_set[c->device]) {
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
@@ -236,6 +240,7 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * 64 * 8, s));
     u8* tmp = (u8*)c->d_k0;                                   // 4 bytes per padded element
     KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+    if (c->max_len > REPAIR_MAX) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out));
     CUDA_TRY(cudaGetLastError());

@@ -101,7 +101,12 @@ class Engine:
         self.ctx: Optional[Context] = None
         self.cap_bytes = 0
         self.cap_blocks = 0
-        self.repair_max = int(_lib.lib().kolm_repair_max_block())
+        # Re-Pair candidate: blocks up to kolm_repair_max_block() bytes run in shared memory, longer ones through the incremental
+        # kernel (exact, but a serial chain of ~10^5 rounds per MiB: tens of MB/s).  KOLM_REPAIR_MAX_BLOCK / this attribute caps
+        # the block length for which the candidate is evaluated; capped blocks are skipped with a RuntimeWarning and the container
+        # can then differ from the reference's wherever Re-Pair would have won.  Default: no cap (byte-exact).
+        env = os.environ.get("KOLM_REPAIR_MAX_BLOCK")
+        self.repair_max = int(env) if env else (1 << 30)
         self.enable_v2_new = False     # method 10 as an encode candidate (dead in the shipped reference; see kolm_final_researched_v2_2.G_ENABLE_V2_NEW)
         self._pin: Optional[torch.Tensor] = None
         self._device_out = False       # encode_*_area return the payload area as a device tensor (set by dist.* around its calls)
@@ -369,8 +374,9 @@ class Engine:
                     if int(lens.max(initial=0)) <= self.repair_max:
                         rpp, rpo = c.repair_encode(x, off)
                     else:
-                        warnings.warn("Re-Pair candidate skipped: block longer than %d bytes (GPU kernel limit; the reference's own "
-                                      "algorithm is O(rounds*n) there)" % self.repair_max, RuntimeWarning, stacklevel=3)
+                        warnings.warn("Re-Pair candidate skipped: block longer than the configured cap of %d bytes (Engine.repair_max / "
+                                      "KOLM_REPAIR_MAX_BLOCK); the container can differ from the reference's where Re-Pair would win" % self.repair_max,
+                                      RuntimeWarning, stacklevel=3)
                 for nme in names:
                     if nme == "raw":
                         cols.append(lens)

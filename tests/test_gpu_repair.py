@@ -41,10 +41,54 @@ def test_repair_encode_decode():
         assert d == b, k
 
 
-def test_repair_rejects_large_blocks():
+def _big_cases():
+    rnd = random.Random(77)
+    text = datasets.medium_cases()["text_big"]
+    c = {}
+    c["text_20k"] = text
+    c["text_50k"] = (text * 3)[:50001]
+    c["sine_40k"] = datasets.fixture("sine")[1000:41000]
+    c["pattern_64k"] = datasets.fixture("pattern")[60000:60000 + 65536]
+    c["gradient_30k"] = datasets.fixture("gradient")[5000:35000]
+    c["checker_33k"] = datasets.fixture("checker")[:33000]
+    c["zeros_9k"] = bytes(9001)
+    c["zeros_even"] = bytes(16384)
+    c["aab_10k"] = b"aab" * 3400
+    c["abab_9k"] = b"ab" * 4600
+    c["alpha2_12k"] = bytes(rnd.randrange(2) for _ in range(12000))
+    c["alpha4_10k"] = bytes(rnd.randrange(4) for _ in range(10000))
+    c["alpha16_9k"] = bytes(rnd.randrange(16) for _ in range(9000))
+    c["random_9k"] = bytes(rnd.randrange(256) for _ in range(9000))
+    c["runs_mixed"] = b"".join(bytes([rnd.randrange(3)]) * rnd.randrange(1, 40) for _ in range(900))
+    c["aaa_tail"] = b"xy" * 5000 + b"aaa"                       # count 2, one replacement: the reference stops there
+    return c
+
+
+def test_repair_large_blocks_incremental_kernel():
+    """Blocks beyond the shared-memory kernel (> 8192 bytes) take the incremental kernel: payloads equal the literal oracle's."""
     import gpu_util as G
-    from kolmogorovlike_datacompressor_b200._lib import KolmError
-    t, off = G.batch([bytes(9000)])
-    with pytest.raises(KolmError) as e:
-        G.ctx().repair_encode(t, off)
-    assert e.value.code == -6
+    cases = _big_cases()
+    cases["small_mixed_in"] = b"abracadabra" * 50               # small and large blocks in one batch
+    names = sorted(cases)
+    blocks = [cases[k] for k in names]
+    t, off = G.batch(blocks)
+    out, out_off = G.ctx().repair_encode(t, off)
+    got = out.cpu().numpy().tobytes()
+    for i, k in enumerate(names):
+        assert got[out_off[i]:out_off[i + 1]] == O.repair_compress(blocks[i]), k
+    dec = G.unbatch(G.ctx().repair_decode(out, out_off, off), off)
+    for k, b, d in zip(names, blocks, dec):
+        assert d == b, k
+
+
+def test_repair_one_mib_roundtrip():
+    """Full-size property check (the literal oracle needs minutes here): 1 MiB blocks round-trip through the grammar."""
+    import gpu_util as G
+    from kolmogorovlike_datacompressor_b200 import synth
+    d = synth.s3_mix(4 << 20).tobytes()
+    blocks = [d[i << 20:(i + 1) << 20] for i in (0, 2, 3)]     # text, gradient, sine
+    t, off = G.batch(blocks)
+    out, out_off = G.ctx().repair_encode(t, off)
+    dec = G.unbatch(G.ctx().repair_decode(out, out_off, off), off)
+    assert dec == blocks
+    assert all(out_off[i + 1] - out_off[i] < len(blocks[i]) for i in range(3))
