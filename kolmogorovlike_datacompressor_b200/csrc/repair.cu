@@ -184,9 +184,10 @@ int kolm_repair_big_impl(kolm_ctx* c, const u8* in, u8* tmp, cudaStream_t s);
 
 // decode (v0): one thread per block; iterative expansion with an explicit stack in global scratch
 __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo, u8* __restrict__ out,
-                             u32* __restrict__ scratch_rules, u32* __restrict__ scratch_stack, int* __restrict__ err, int nblocks) {
+                             u32* __restrict__ scratch_rules, u32* __restrict__ scratch_stack, int* __restrict__ err, int nblocks, const int* __restrict__ todo) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
+    if (todo && !todo[b]) return;                            // the parallel decoder (k_repair_dec2) already produced this block
     BlockInfo bi = binfo[b];
     const u8* d = pay + pay_off[b];
     i64 n = pay_off[b + 1] - pay_off[b], p = 2;
@@ -226,6 +227,132 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
     err[b] = e;
 }
 
+// decode, parallel (one CTA per block).  The payload after 'RP' is one stream of ULEB128 values (256, nrules, 2*nrules rule
+// symbols, the sequence length, the sequence), and a byte ends a value iff its high bit is clear — so the values are found with a
+// prefix count over the bytes, the rules' expansion lengths by relaxation in creation order (a rule only names earlier rules), the
+// sequence symbols' output offsets by a scan, and the output is produced in chunks of 128 bytes: binary search for the sequence
+// symbol that covers the chunk start, a length-guided descent to the exact byte, then an in-order walk with a small stack.
+// Anything unusual (malformed stream, grammar deeper than the stack, length mismatch) leaves the block to the serial decoder
+// above, which also owns the error codes: todo[b] = 1.
+#define RD2_THREADS 256
+#define RD2_STACK 96
+__global__ void __launch_bounds__(RD2_THREADS) k_repair_dec2(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo,
+                                                            u8* __restrict__ out, u32* __restrict__ g_ra, u32* __restrict__ g_rb, u32* __restrict__ g_rl,
+                                                            u32* __restrict__ g_sq, u32* __restrict__ g_so, int* __restrict__ err, int* __restrict__ todo) {
+    __shared__ u32 s_scan[RD2_THREADS / 32];
+    __shared__ u32 s_R, s_start, s_seqlen, s_bad;
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5, b = blockIdx.x;
+    const BlockInfo bi = binfo[b];
+    const u32 L = bi.len;
+    const u8* d = pay + pay_off[b];
+    const u32 n = (u32)(pay_off[b + 1] - pay_off[b]);
+    const u32 cap = max(((L + KOLM_PAD - 1) / KOLM_PAD) * KOLM_PAD, (u32)KOLM_PAD);
+    u32* ra = g_ra + bi.pbase; u32* rb = g_rb + bi.pbase; u32* rl = g_rl + bi.pbase; u32* sq = g_sq + bi.pbase; u32* so = g_so + bi.pbase;
+    auto exscan = [&](u32 v, u32* total) -> u32 {
+        u32 x = v;
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (u32)o) x += t; }
+        if (lane == 31) s_scan[w] = x;
+        __syncthreads();
+        u32 pre = 0, tot = 0;
+        for (int i = 0; i < RD2_THREADS / 32; ++i) { u32 t = s_scan[i]; if ((u32)i < w) pre += t; tot += t; }
+        __syncthreads();
+        *total = tot;
+        return pre + x - v;
+    };
+    if (tid == 0) {
+        s_bad = 0; s_R = 0; s_start = 0; s_seqlen = 0xffffffffu;
+        u32 p = 2; u64 v0 = 0, v1 = 0; bool ok = L > 0 && n >= 4 && d[0] == 'R' && d[1] == 'P';
+        auto get = [&](u64& v) { v = 0; int sh = 0; for (;;) { if (p >= n) return false; u8 x = d[p++]; if (sh < 35) v |= (u64)(x & 0x7F) << sh; else if (x & 0x7F) return false; if (!(x & 0x80)) return true; sh += 7; } };
+        ok = ok && get(v0) && v0 == 256 && get(v1) && 2 * v1 <= cap;
+        if (!ok) s_bad = 1; else { s_R = (u32)v1; s_start = p; }
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) todo[b] = 1; return; }
+    const u32 R = s_R, start = s_start;
+    // ---- values
+    u32 nvals = 0;
+    for (u32 base = start; base < n; base += RD2_THREADS * 16) {
+        const u32 i0 = base + tid * 16;
+        u32 mask = 0;
+#pragma unroll
+        for (u32 k = 0; k < 16; ++k) if (i0 + k < n && !(d[i0 + k] & 0x80)) mask |= 1u << k;
+        u32 tot;
+        u32 j = nvals + exscan(__popc(mask), &tot);
+        while (mask) {
+            const u32 k = __ffs(mask) - 1; mask &= mask - 1;
+            const u32 e = i0 + k;                              // last byte of the value; its first byte follows the previous terminator
+            u32 f = e;
+            while (f > start && (d[f - 1] & 0x80) && e - f < 5) --f;
+            u64 v = 0;
+            if (e - f >= 5) v = ~0ull;                         // longer than any 32-bit value
+            else for (u32 x = f; x <= e; ++x) v |= (u64)(d[x] & 0x7F) << (7 * (x - f));
+            if (j < 2 * R) { const u32 r = j >> 1; if (v >= 256ull + r) s_bad = 1; else if (j & 1) rb[r] = (u32)v; else ra[r] = (u32)v; }
+            else if (j == 2 * R) { if (v > L) s_bad = 1; else s_seqlen = (u32)v; }
+            else { const u32 q = j - 2 * R - 1; if (q < cap) { if (v >= 256ull + R) { if (q < s_seqlen || s_seqlen == 0xffffffffu) sq[q] = 0xffffffffu; } else sq[q] = (u32)v; } }
+            ++j;
+        }
+        nvals += tot;
+    }
+    __syncthreads();
+    const u32 seqlen = s_seqlen;
+    if (s_bad || seqlen == 0xffffffffu || nvals < 2 * R + 1 + seqlen) { if (tid == 0) todo[b] = 1; return; }
+    // ---- expansion length of every rule (0 = not known yet): chunks in creation order, relaxation inside a chunk
+    for (u32 base = 0; base < R; base += RD2_THREADS) {
+        const u32 r = base + tid;
+        if (r < R) rl[r] = 0;
+        __syncthreads();
+        for (u32 it = 0; it <= RD2_THREADS; ++it) {
+            int pending = 0;
+            if (r < R && rl[r] == 0) {
+                const u32 a = ra[r], bb = rb[r];
+                const u32 la = a < 256 ? 1u : rl[a - 256], lb = bb < 256 ? 1u : rl[bb - 256];
+                if (la && lb) { const u64 t = (u64)la + lb; if (t > L) s_bad = 1; rl[r] = t > L ? 1u : (u32)t; } else pending = 1;
+            }
+            if (!__syncthreads_or(pending)) break;
+        }
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) todo[b] = 1; return; }
+    // ---- output offset of every sequence symbol
+    u32 total = 0;
+    for (u32 base = 0; base < seqlen; base += RD2_THREADS) {
+        const u32 i = base + tid;
+        u32 len = 0;
+        if (i < seqlen) { const u32 v = sq[i]; if (v == 0xffffffffu) s_bad = 1; else len = v < 256 ? 1u : rl[v - 256]; }
+        u32 tot; const u32 ex = exscan(len, &tot);
+        if (i < seqlen) so[i] = total + ex;
+        if ((u64)total + tot > L) s_bad = 1;
+        total += tot;
+    }
+    __syncthreads();
+    if (s_bad || total != L) { if (tid == 0) todo[b] = 1; return; }
+    // ---- expand, 128 output bytes per thread and step
+    u8* dst = out + bi.ioff;
+    for (u32 c0 = tid * 128; c0 < L; c0 += RD2_THREADS * 128) {
+        const u32 cend = min(L, c0 + 128);
+        u32 lo = 0, hi = seqlen;                               // last symbol whose offset is <= c0
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (so[mid] <= c0) lo = mid; else hi = mid; }
+        u32 i = lo, k = c0 - so[lo], o = c0, sp = 0;
+        u32 stack[RD2_STACK];
+        u32 cur = sq[i];
+        bool over = false;
+        while (cur >= 256) {                                    // guided descent to byte k of the symbol
+            const u32 a = ra[cur - 256], bb = rb[cur - 256];
+            const u32 la = a < 256 ? 1u : rl[a - 256];
+            if (k < la) { if (sp >= RD2_STACK) { over = true; break; } stack[sp++] = bb; cur = a; } else { k -= la; cur = bb; }
+        }
+        while (!over) {
+            dst[o++] = (u8)cur;
+            if (o >= cend) break;
+            if (sp) cur = stack[--sp]; else cur = sq[++i];
+            while (cur >= 256) { if (sp >= RD2_STACK) { over = true; break; } stack[sp++] = rb[cur - 256]; cur = ra[cur - 256]; }
+        }
+        if (over) s_bad = 1;
+    }
+    __syncthreads();
+    if (tid == 0) { if (s_bad) todo[b] = 1; else err[b] = KOLM_OK; }
+}
+
 int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
     const int nb = c->nblocks;
     if (!nb) { out_off[0] = 0; return KOLM_OK; }
@@ -256,7 +383,10 @@ int kolm_repair_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u8* out
     if (!nb) return KOLM_OK;
     memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
     CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
-    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_k0, c->d_v0, c->d_err, nb));
+    int* todo = (int*)c->d_done;                             // blocks the parallel decoder leaves to the serial one
+    CUDA_TRY(cudaMemsetAsync(todo, 0, (size_t)nb * 4, s));
+    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_dec2<<<nb, RD2_THREADS, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_k0, c->d_k1, c->d_v0, c->d_v1, c->d_sa, c->d_err, todo));
+    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_k0, c->d_v0, c->d_err, nb, todo));
     CUDA_TRY(cudaGetLastError());
     return rice_dec_finish(c, s);
 }

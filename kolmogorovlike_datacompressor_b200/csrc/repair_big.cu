@@ -230,17 +230,24 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             const u64 cp = sh.cur_pair; const u32 A = (u32)(cp >> 32), B = (u32)cp, cslot = sh.cur_slot;
             const u32 newsym = 256 + nrules;
             const u32 st_seen = round * 4 + 1, st_take = round * 4 + 2, st_part = round * 4 + 3;
-            // ---- valid occurrences (one thread follows the list; nodes are position hints)
+            // ---- valid occurrences: one thread follows the list (a single dependent load per node) and only collects the
+            //      position hints; all threads then check them against the live sequence and claim each position once
             if (tid == 0) {
                 u32 k = 0;
-                for (u32 node = S.hhead[cslot]; node != RPB_NIL; node = S.onext[node]) {
-                    const u32 p = S.opos[node];
-                    if (S.sym[p] != A || S.stamp[p] == st_seen) continue;
+                for (u32 node = S.hhead[cslot]; node != RPB_NIL; node = S.onext[node]) S.tk[k++] = S.opos[node];   // tk as staging: <= n nodes... see below
+                sh.total = k;
+            }
+            __syncthreads();
+            {
+                const u32 nh = sh.total;
+                for (u32 i = tid; i < nh; i += RPB_THREADS) {
+                    const u32 p = S.tk[i];
+                    if (S.sym[p] != A) continue;
                     const u32 q = S.nxt[p];
                     if (q == RPB_NIL || S.sym[q] != B) continue;
-                    S.stamp[p] = st_seen; S.occ[k++] = p;
+                    if (atomicExch(&S.stamp[p], st_seen) == st_seen) continue;       // the same position can be hinted twice
+                    S.occ[atomicAdd(&sh.n_occ, 1u)] = p;
                 }
-                sh.n_occ = k;
             }
             __syncthreads();
             const u32 nocc = sh.n_occ;
