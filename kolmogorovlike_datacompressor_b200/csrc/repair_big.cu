@@ -26,7 +26,9 @@
 // text) times a few microseconds of dependent global-memory steps.
 #include "common.cuh"
 
-#define RPB_THREADS 512
+#ifndef RPB_THREADS
+#define RPB_THREADS 128
+#endif
 #define RPB_PMAX 8192u
 #define RPB_NIL 0xffffffffu
 #define RPB_EMPTY 0xffffffffffffffffull
@@ -406,8 +408,8 @@ int kolm_repair_big_impl(kolm_ctx* c, const u8* in, u8* tmp, cudaStream_t s) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = free_b + c->rpb_bytes;                   // what the pool may use: what is free now plus what it already holds
-    budget = budget / 2 < ((size_t)64 << 30) ? budget / 2 : ((size_t)64 << 30);
-    int grid = nbig < c->sm_count ? nbig : c->sm_count;
+    budget = budget / 2 < ((size_t)96 << 30) ? budget / 2 : ((size_t)96 << 30);
+    int grid = nbig < 2 * c->sm_count ? nbig : 2 * c->sm_count;   // the CTAs mostly wait on dependent loads: two per SM overlap well
     if ((size_t)grid * need > budget) grid = (int)(budget / need);
     if (grid < 1) return KOLM_E_CAPACITY;
     if ((size_t)grid * need > c->rpb_bytes) {

@@ -199,12 +199,15 @@ class Engine:
             with torch.cuda.device(self.device):
                 self.ctx = Context(self.cap_bytes, self.cap_blocks, self.device)
 
-    def _lz_submit(self, x: torch.Tensor, off: np.ndarray, window: int, max_len: int):
-        """Start lz77_encode(x, off) and return a callable that yields (payload, offsets).  x must have been produced on the
-        current stream; the side stream waits for it."""
+    def _lz_submit(self, x: torch.Tensor, off: np.ndarray, window: int, max_len: int, with_repair: bool = False):
+        """Start lz77_encode(x, off) and return a callable that yields (payload, offsets) — with_repair: (payload, offsets,
+        (repair payload, repair offsets)), the Re-Pair candidate runs after it on the same side stream.  x must have been
+        produced on the current stream; the side stream waits for it."""
         nbytes, nblocks = int(off[-1] - off[0]), len(off) - 1
         if not self.lz_async:
             res = self.ctx.lz77_encode(x, off, window, max_len)
+            if with_repair:
+                res = res + (self.ctx.repair_encode(x, off),)
             return lambda: res
         if self.ctx2 is None or nbytes > self.cap2_bytes or nblocks > self.cap2_blocks:
             if self.ctx2 is not None:
@@ -224,7 +227,8 @@ class Engine:
         def work():
             with torch.cuda.device(dev), torch.cuda.stream(side):
                 side.wait_event(ready)
-                return ctx2.lz77_encode(x, off, window, max_len)    # returns after its stream finished (payload offsets come home)
+                res = ctx2.lz77_encode(x, off, window, max_len)     # returns after its stream finished (payload offsets come home)
+                return res + (ctx2.repair_encode(x, off),) if with_repair else res
         fut = self._worker.submit(work)
         return fut.result
 
@@ -358,7 +362,13 @@ class Engine:
                 v2p = v2o = None
                 if v2:
                     v2p, v2o = c.v2new_encode(x, off)
-                lz = self._lz_submit(x, off, 4096, 0) if "lz77" in names else None
+                want_rp = "repair" in names and int(lens.max(initial=0)) <= self.repair_max
+                if "repair" in names and not want_rp:
+                    warnings.warn("Re-Pair candidate skipped: block longer than the configured cap of %d bytes (Engine.repair_max / "
+                                  "KOLM_REPAIR_MAX_BLOCK); the container can differ from the reference's where Re-Pair would win" % self.repair_max,
+                                  RuntimeWarning, stacklevel=3)
+                rp_side = want_rp and "lz77" in names and self.lz_async     # both latency-bound candidates share the side stream
+                lz = self._lz_submit(x, off, 4096, 0, with_repair=rp_side) if "lz77" in names else None
                 need_res = any(n in ("xor", "lfsr_pred") for n in names)
                 rs = c.residual_sizes(x, off) if need_res else None
                 need_bbwt = any(n in K2_FLAG_OF for n in names)
@@ -366,17 +376,14 @@ class Engine:
                 if need_bbwt:
                     m = c.mtf_encode(c.bbwt_forward(x, off), off)
                     k2p, k2o, k2s = c.rice_k2_encode(m, off, 0)
-                lzp = lzo = None
+                lzp = lzo = rpp = rpo = None
                 if lz is not None:
-                    lzp, lzo = lz()
-                rpp = rpo = None
-                if "repair" in names:
-                    if int(lens.max(initial=0)) <= self.repair_max:
-                        rpp, rpo = c.repair_encode(x, off)
-                    else:
-                        warnings.warn("Re-Pair candidate skipped: block longer than the configured cap of %d bytes (Engine.repair_max / "
-                                      "KOLM_REPAIR_MAX_BLOCK); the container can differ from the reference's where Re-Pair would win" % self.repair_max,
-                                      RuntimeWarning, stacklevel=3)
+                    got = lz()
+                    lzp, lzo = got[0], got[1]
+                    if rp_side:
+                        rpp, rpo = got[2]
+                if want_rp and rpo is None:
+                    rpp, rpo = c.repair_encode(x, off)
                 for nme in names:
                     if nme == "raw":
                         cols.append(lens)
