@@ -10,9 +10,12 @@
 // One CTA per block, everything in a per-CTA slab of global memory:
 //   sequence      doubly linked list over the original positions (sym / prv / nxt); positions never move, so the index order
 //                 is the sequence order;
-//   pair table    open addressing, key = a << 32 | b, exact count, head of an occurrence list (nodes = positions where the pair
-//                 started when it was created; stale nodes are skipped on traversal, a pair is processed at most once because a
-//                 replaced pair can never re-form);
+//   pair table    open addressing, key = a << 32 | b, exact count, base of an occurrence ARRAY (the positions where the pair
+//                 started when it was created: every occurrence of a pair is created in ONE round — the one that creates its
+//                 newer symbol, or the initial count — so the array is sized from that round's count and filled behind a
+//                 cursor; pairs created with a single occurrence can never be chosen and get none; stale entries are skipped
+//                 when the array is read — by all threads at once —, and a pair is processed at most once because a replaced
+//                 pair can never re-form);
 //   priority      a list M sorted by (count desc, pair asc) walked by a cursor + an unsorted pending list P of the pairs whose
 //                 count changed since the last merge (only decrements of old pairs and new pairs containing the newest symbol,
 //                 so counts never rise after a pair's creation round and an entry is valid iff its count is still current);
@@ -30,13 +33,16 @@
 #define RPB_THREADS 128
 #endif
 #define RPB_PMAX 8192u
+#ifndef RPB_V
+#define RPB_V 14            // experiment mask: 1 parallel M skip, 2 warp pbest update, 4 unrolled rescan, 8 small hash
+#endif
 #define RPB_NIL 0xffffffffu
 #define RPB_EMPTY 0xffffffffffffffffull
 
 struct RpbSlab {
     u32 *sym, *prv, *nxt, *stamp;                       // [n]
     u64* hkey; u32 *hcnt, *hhead, *hstamp; u32 hmask;   // [H]
-    u32 *opos, *onext; u32 ocap;                        // occurrence nodes
+    u32* opos; u32 ocap;                                // occurrence arrays: [base] = entries filled, [base+1 ...] = positions
     u64 *mpair, *tpair; u32 *mcnt, *tcnt, *mslot, *tslot; u32 mcap;   // sorted list + merge target
     u64* ppair; u32 *pcnt, *pslot; u32 pcap;            // pending
     u32 *occ, *tk, *touched; u32 tcap;                  // per-round lists
@@ -47,11 +53,11 @@ __host__ __device__ inline u32 rpb_pow2_at_least(u64 v) { u32 p = 1024; while ((
 __host__ __device__ inline size_t rpb_align(size_t x) { return (x + 255) & ~(size_t)255; }
 // slab bytes for a block of n bytes (n >= 2)
 __host__ __device__ inline size_t rpb_need(u64 n) {
-    const u64 H = rpb_pow2_at_least(4 * n + 131072), oc = 3 * n + 64, mc = 2 * n + 2 * RPB_PMAX + 64, pc = 2 * n + RPB_PMAX + 64, tc = 2 * n + 64;
+    const u64 H = (RPB_V & 8) ? rpb_pow2_at_least(3 * n + 65536) : rpb_pow2_at_least(4 * n + 131072), oc = 9 * n / 2 + 64, mc = 2 * n + 2 * RPB_PMAX + 64, pc = 2 * n + RPB_PMAX + 64, tc = 2 * n + 64;
     size_t b = 0;
     b += 4 * rpb_align(n * 4);
     b += rpb_align(H * 8) + 3 * rpb_align(H * 4);
-    b += 2 * rpb_align(oc * 4);
+    b += rpb_align(oc * 4);
     b += 2 * rpb_align(mc * 8) + 4 * rpb_align(mc * 4);
     b += rpb_align(pc * 8) + 2 * rpb_align(pc * 4);
     b += 2 * rpb_align(n * 4) + rpb_align(tc * 4);
@@ -59,12 +65,12 @@ __host__ __device__ inline size_t rpb_need(u64 n) {
     return b + 1024;
 }
 __device__ inline void rpb_carve(u8* base, u64 n, RpbSlab& S) {
-    const u64 H = rpb_pow2_at_least(4 * n + 131072), oc = 3 * n + 64, mc = 2 * n + 2 * RPB_PMAX + 64, pc = 2 * n + RPB_PMAX + 64, tc = 2 * n + 64;
+    const u64 H = (RPB_V & 8) ? rpb_pow2_at_least(3 * n + 65536) : rpb_pow2_at_least(4 * n + 131072), oc = 9 * n / 2 + 64, mc = 2 * n + 2 * RPB_PMAX + 64, pc = 2 * n + RPB_PMAX + 64, tc = 2 * n + 64;
     u8* p = base;
     auto take = [&](size_t bytes) { u8* r = p; p += rpb_align(bytes); return r; };
     S.sym = (u32*)take(n * 4); S.prv = (u32*)take(n * 4); S.nxt = (u32*)take(n * 4); S.stamp = (u32*)take(n * 4);
     S.hkey = (u64*)take(H * 8); S.hcnt = (u32*)take(H * 4); S.hhead = (u32*)take(H * 4); S.hstamp = (u32*)take(H * 4); S.hmask = (u32)H - 1;
-    S.opos = (u32*)take(oc * 4); S.onext = (u32*)take(oc * 4); S.ocap = (u32)oc;
+    S.opos = (u32*)take(oc * 4); S.ocap = (u32)oc;
     S.mpair = (u64*)take(mc * 8); S.tpair = (u64*)take(mc * 8);
     S.mcnt = (u32*)take(mc * 4); S.tcnt = (u32*)take(mc * 4); S.mslot = (u32*)take(mc * 4); S.tslot = (u32*)take(mc * 4); S.mcap = (u32)mc;
     S.ppair = (u64*)take(pc * 8); S.pcnt = (u32*)take(pc * 4); S.pslot = (u32*)take(pc * 4); S.pcap = (u32)pc;
@@ -179,12 +185,20 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             const u64 key = ((u64)src[i] << 32) | src[i + 1];
             const u32 s = rpb_slot(S, key);
             atomicAdd(&S.hcnt[s], 1u);
-            const u32 node = atomicAdd(&sh.n_occ_nodes, 1u);
-            S.opos[node] = i; S.onext[node] = atomicExch(&S.hhead[s], node);
+            S.tk[i] = s;
         }
         __syncthreads();
         for (u32 i = tid; i < H; i += RPB_THREADS) {
-            if (S.hkey[i] != RPB_EMPTY && S.hcnt[i] >= 2) { const u32 o = atomicAdd(&sh.mlen, 1u); S.mpair[o] = S.hkey[i]; S.mcnt[o] = S.hcnt[i]; S.mslot[o] = i; }
+            const u32 c = S.hcnt[i];
+            if (c >= 2) {
+                const u32 o = atomicAdd(&sh.mlen, 1u); S.mpair[o] = S.hkey[i]; S.mcnt[o] = c; S.mslot[o] = i;
+                const u32 base = atomicAdd(&sh.n_occ_nodes, c + 1u); S.hhead[i] = base; S.opos[base] = 0;
+            }
+        }
+        __syncthreads();
+        for (u32 i = tid; i + 1 < n; i += RPB_THREADS) {
+            const u32 base = S.hhead[S.tk[i]];
+            if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = i;
         }
         __syncthreads();
         rpb_sort(S.mpair, S.mcnt, S.mslot, sh.mlen, sh);
@@ -195,9 +209,19 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             // pending list: (re)find its best valid entry when the cached one is gone
             if (sh.n_p && !sh.pbest_ok) {
                 u32 bc = 0, bidx = RPB_NIL; u64 bp = RPB_EMPTY;
-                for (u32 i = tid; i < sh.n_p; i += RPB_THREADS) {
-                    const u32 c = S.pcnt[i];
-                    if (c >= 2 && S.hcnt[S.pslot[i]] == c && rpb_better(c, S.ppair[i], bc, bp)) { bc = c; bp = S.ppair[i]; bidx = i; }
+                const u32 npend = sh.n_p;
+                if (RPB_V & 4) {
+#pragma unroll 4
+                    for (u32 i = tid; i < npend; i += RPB_THREADS) {
+                        const u32 c = S.pcnt[i], sl = S.pslot[i]; const u64 p = S.ppair[i];
+                        const u32 hc = S.hcnt[sl];
+                        if (c >= 2 && hc == c && rpb_better(c, p, bc, bp)) { bc = c; bp = p; bidx = i; }
+                    }
+                } else {
+                    for (u32 i = tid; i < npend; i += RPB_THREADS) {
+                        const u32 c = S.pcnt[i];
+                        if (c >= 2 && S.hcnt[S.pslot[i]] == c && rpb_better(c, S.ppair[i], bc, bp)) { bc = c; bp = S.ppair[i]; bidx = i; }
+                    }
                 }
                 for (int o = 16; o > 0; o >>= 1) {
                     const u32 oc = __shfl_xor_sync(0xffffffffu, bc, o), oi = __shfl_xor_sync(0xffffffffu, bidx, o); const u64 op = __shfl_xor_sync(0xffffffffu, bp, o);
@@ -211,10 +235,24 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
                 }
                 __syncthreads();
             }
+            if (!(RPB_V & 1)) {
+                if (tid == 0) { u32 mp = sh.mpos; while (mp < sh.mlen && !(S.mcnt[mp] >= 2 && S.hcnt[S.mslot[mp]] == S.mcnt[mp])) ++mp; sh.mpos = mp; }
+            } else if (tid < 32) {
+                u32 mp = sh.mpos; const u32 ml = sh.mlen;          // warp 0 skips the entries whose count moved on, 32 at a time
+                __syncwarp();
+                for (;;) {
+                    const u32 i = mp + tid; bool ok = false;
+                    if (i < ml) { const u32 c = S.mcnt[i]; ok = c >= 2 && S.hcnt[S.mslot[i]] == c; }
+                    const u32 m = __ballot_sync(0xffffffffu, ok);
+                    if (m) { mp += (u32)__ffs((int)m) - 1u; break; }
+                    if (mp + 32u >= ml) { mp = ml; break; }
+                    mp += 32u;
+                }
+                if (tid == 0) sh.mpos = mp;
+                __syncwarp();
+            }
             if (tid == 0) {
-                u32 mp = sh.mpos;
-                while (mp < sh.mlen && !(S.mcnt[mp] >= 2 && S.hcnt[S.mslot[mp]] == S.mcnt[mp])) ++mp;     // skip entries whose count moved on
-                sh.mpos = mp;
+                const u32 mp = sh.mpos;
                 u32 c = 0, s = 0; u64 p = RPB_EMPTY; int from_p = 0;
                 if (mp < sh.mlen) { c = S.mcnt[mp]; p = S.mpair[mp]; s = S.mslot[mp]; }
                 if (sh.n_p && sh.pbest != RPB_NIL) {
@@ -232,18 +270,13 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             const u64 cp = sh.cur_pair; const u32 A = (u32)(cp >> 32), B = (u32)cp, cslot = sh.cur_slot;
             const u32 newsym = 256 + nrules;
             const u32 st_seen = round * 4 + 1, st_take = round * 4 + 2, st_part = round * 4 + 3;
-            // ---- valid occurrences: one thread follows the list (a single dependent load per node) and only collects the
-            //      position hints; all threads then check them against the live sequence and claim each position once
-            if (tid == 0) {
-                u32 k = 0;
-                for (u32 node = S.hhead[cslot]; node != RPB_NIL; node = S.onext[node]) S.tk[k++] = S.opos[node];   // tk as staging: <= n nodes... see below
-                sh.total = k;
-            }
-            __syncthreads();
+            // ---- valid occurrences: all threads read the pair's occurrence array (position hints), check the hints against the
+            //      live sequence and claim each position once
             {
-                const u32 nh = sh.total;
+                const u32 obase = S.hhead[cslot];
+                const u32 nh = obase == RPB_NIL ? 0u : S.opos[obase];
                 for (u32 i = tid; i < nh; i += RPB_THREADS) {
-                    const u32 p = S.tk[i];
+                    const u32 p = S.opos[obase + 1u + i];
                     if (S.sym[p] != A) continue;
                     const u32 q = S.nxt[p];
                     if (q == RPB_NIL || S.sym[q] != B) continue;
@@ -291,21 +324,15 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
                 if (y != RPB_NIL) S.prv[y] = p;
             }
             __syncthreads();
-            // ---- new neighbours (new links): left pair always, right pair unless the right neighbour was replaced too
+            // ---- new neighbours (new links): left pair always, right pair unless the right neighbour was replaced too.  Counted
+            //      now (slots remembered: occ is free again and ntk <= n/2), their occurrence arrays are filled once sized.
+            u32* const lslot = S.occ; u32* const rslot = S.occ + (n >> 1);
             for (u32 i = tid; i < ntk; i += RPB_THREADS) {
                 const u32 p = S.tk[i], x = S.prv[p], y = S.nxt[p];
-                if (x != RPB_NIL) {
-                    const u32 s = rpb_slot(S, ((u64)S.sym[x] << 32) | newsym);
-                    atomicAdd(&S.hcnt[s], 1u); touch(s);
-                    const u32 node = atomicAdd(&sh.n_occ_nodes, 1u);
-                    if (node < S.ocap) { S.opos[node] = x; S.onext[node] = atomicExch(&S.hhead[s], node); }
-                }
-                if (y != RPB_NIL && S.stamp[y] != st_take) {
-                    const u32 s = rpb_slot(S, ((u64)newsym << 32) | S.sym[y]);
-                    atomicAdd(&S.hcnt[s], 1u); touch(s);
-                    const u32 node = atomicAdd(&sh.n_occ_nodes, 1u);
-                    if (node < S.ocap) { S.opos[node] = p; S.onext[node] = atomicExch(&S.hhead[s], node); }
-                }
+                u32 sl = RPB_NIL, sr = RPB_NIL;
+                if (x != RPB_NIL) { sl = rpb_slot(S, ((u64)S.sym[x] << 32) | newsym); atomicAdd(&S.hcnt[sl], 1u); touch(sl); }
+                if (y != RPB_NIL && S.stamp[y] != st_take) { sr = rpb_slot(S, ((u64)newsym << 32) | S.sym[y]); atomicAdd(&S.hcnt[sr], 1u); touch(sr); }
+                lslot[i] = sl; rslot[i] = sr;
             }
             if (tid == 0) { S.hcnt[cslot] = 0; S.rules[nrules] = cp; }
             ++nrules;
@@ -316,18 +343,49 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             __syncthreads();                                     // everyone has read the old length before anyone appends
             for (u32 i = tid; i < ntouch; i += RPB_THREADS) {
                 const u32 s = S.touched[i], c = S.hcnt[s];
-                if (c >= 2) { const u32 o = atomicAdd(&sh.n_p, 1u); if (o < S.pcap) { S.ppair[o] = S.hkey[s]; S.pcnt[o] = c; S.pslot[o] = s; } }
+                if (c >= 2) {
+                    const u64 key = S.hkey[s];
+                    const u32 o = atomicAdd(&sh.n_p, 1u); if (o < S.pcap) { S.ppair[o] = key; S.pcnt[o] = c; S.pslot[o] = s; }
+                    if ((u32)(key >> 32) == newsym || (u32)key == newsym) {       // a pair born this round: all its occurrences exist now
+                        const u32 base = atomicAdd(&sh.n_occ_nodes, c + 1u);
+                        if (base + c + 1u <= S.ocap) { S.hhead[s] = base; S.opos[base] = 0; }
+                    }
+                }
             }
             __syncthreads();
-            if (tid == 0) {
-                const u32 np = min(sh.n_p, S.pcap);
-                sh.n_p = np;
-                if (sh.pbest_ok) {                               // new entries can only improve the cached best
-                    u32 bi2 = sh.pbest;
-                    for (u32 i = p0; i < np; ++i) if (bi2 == RPB_NIL || rpb_better(S.pcnt[i], S.ppair[i], S.pcnt[bi2], S.ppair[bi2])) bi2 = i;
-                    // the cached best may have been decremented this round: then it is stale and a rescan is due
-                    if (bi2 != RPB_NIL && !(S.pcnt[bi2] >= 2 && S.hcnt[S.pslot[bi2]] == S.pcnt[bi2])) sh.pbest_ok = 0; else sh.pbest = bi2;
+            for (u32 i = tid; i < ntk; i += RPB_THREADS) {
+                const u32 sl = lslot[i], sr = rslot[i];
+                if (sl != RPB_NIL) { const u32 base = S.hhead[sl]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = S.prv[S.tk[i]]; }
+                if (sr != RPB_NIL) { const u32 base = S.hhead[sr]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = S.tk[i]; }
+            }
+            if (!(RPB_V & 2)) {
+                if (tid == 0) {
+                    const u32 np = min(sh.n_p, S.pcap);
+                    sh.n_p = np;
+                    if (sh.pbest_ok) {
+                        u32 bi2 = sh.pbest;
+                        for (u32 i = p0; i < np; ++i) if (bi2 == RPB_NIL || rpb_better(S.pcnt[i], S.ppair[i], S.pcnt[bi2], S.ppair[bi2])) bi2 = i;
+                        if (bi2 != RPB_NIL && !(S.pcnt[bi2] >= 2 && S.hcnt[S.pslot[bi2]] == S.pcnt[bi2])) sh.pbest_ok = 0; else sh.pbest = bi2;
+                    }
                 }
+            } else if (tid < 32) {                               // warp 0: the new pending entries against the cached best
+                const u32 np = min(sh.n_p, S.pcap);
+                const int ok = sh.pbest_ok; const u32 cur = sh.pbest;
+                __syncwarp();
+                if (ok) {                                        // new entries can only improve the cached best
+                    u32 bc = 0, bidx = RPB_NIL; u64 bp = RPB_EMPTY;
+                    for (u32 i = p0 + tid; i < np; i += 32) { const u32 c = S.pcnt[i]; const u64 p = S.ppair[i]; if (rpb_better(c, p, bc, bp)) { bc = c; bp = p; bidx = i; } }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const u32 oc = __shfl_xor_sync(0xffffffffu, bc, o), oi = __shfl_xor_sync(0xffffffffu, bidx, o); const u64 op = __shfl_xor_sync(0xffffffffu, bp, o);
+                        if (rpb_better(oc, op, bc, bp)) { bc = oc; bp = op; bidx = oi; }
+                    }
+                    if (tid == 0) {
+                        if (cur != RPB_NIL) { const u32 cc = S.pcnt[cur]; const u64 cq = S.ppair[cur]; if (bidx == RPB_NIL || !rpb_better(bc, bp, cc, cq)) { bc = cc; bp = cq; bidx = cur; } }
+                        // the cached best may have been decremented this round: then it is stale and a rescan is due
+                        if (bidx != RPB_NIL && !(bc >= 2 && S.hcnt[S.pslot[bidx]] == bc)) sh.pbest_ok = 0; else sh.pbest = bidx;
+                    }
+                }
+                if (tid == 0) sh.n_p = np;
             }
             __syncthreads();
             // ---- merge the pending list into the unread rest of M

@@ -118,6 +118,16 @@ class Engine:
         self.cap2_blocks = 0
         self._side: Optional[torch.cuda.Stream] = None
         self._worker = None
+        # Re-Pair on long blocks (> kolm_repair_max_block() bytes: the incremental kernel, one CTA per block and seconds per MiB)
+        # is run AHEAD of the batch loop over groups of up to repair_group_bytes on a third context / stream / worker thread: a
+        # group offers enough blocks for two CTAs on every SM and a work queue that evens out fast and slow blocks, and the BBWT /
+        # LZ77 chains of all batches run beside it (KOLM_REPAIR_GROUP_MIB, 0: per batch on the LZ77 side stream)
+        self.repair_group_bytes = int(os.environ.get("KOLM_REPAIR_GROUP_MIB", "512")) << 20
+        self.ctx3: Optional[Context] = None
+        self.cap3_bytes = 0
+        self.cap3_blocks = 0
+        self._side3: Optional[torch.cuda.Stream] = None
+        self._worker3 = None
 
     def _home(self, dev: torch.Tensor, n: int) -> np.ndarray:
         """Device bytes -> host through a persistent pinned staging buffer (pageable D2H runs at ~2 GB/s, pinned at PCIe speed)."""
@@ -231,6 +241,48 @@ class Engine:
                 return res + (ctx2.repair_encode(x, off),) if with_repair else res
         fut = self._worker.submit(work)
         return fut.result
+
+    def _repair_ahead(self, data, bounds: Sequence[Tuple[int, int]]):
+        """Queue repair_encode over the whole input in groups of <= repair_group_bytes on the Re-Pair context.  Returns a function
+        (i, j) -> (sizes int64[j-i], absolute device addresses uint64[j-i]) that waits for the groups holding blocks [i, j); the
+        payload tensors stay alive as long as the returned function does."""
+        groups = list(self._batches(bounds, self.repair_group_bytes))
+        need_bytes = max(bounds[j - 1][1] - bounds[i][0] for i, j in groups)
+        need_blocks = max(j - i for i, j in groups)
+        if self._side3 is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._side3 = torch.cuda.Stream(device=self.device)
+            self._worker3 = ThreadPoolExecutor(max_workers=1, thread_name_prefix="kolm-repair")
+        dev, side = self.device, self._side3
+
+        def work(i, j):
+            with torch.cuda.device(dev), torch.cuda.stream(side):
+                if self.ctx3 is None or need_bytes > self.cap3_bytes or need_blocks > self.cap3_blocks:
+                    if self.ctx3 is not None:
+                        self.ctx3.close()
+                        self.ctx3 = None
+                    self.cap3_bytes = max(need_bytes, 1 << 22, self.cap3_bytes)
+                    self.cap3_blocks = max(need_blocks, 1024, self.cap3_blocks)
+                    self.ctx3 = Context(self.cap3_bytes, self.cap3_blocks, dev)
+                a, b = bounds[i][0], bounds[j - 1][1]
+                off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
+                x = self._upload(data, a, b)
+                p, o = self.ctx3.repair_encode(x, off)                 # returns after its stream finished
+                return p, np.asarray(o, dtype=np.int64)
+        futs = [(i, j, self._worker3.submit(work, i, j)) for i, j in groups]
+
+        def take(i, j):
+            sizes = np.zeros(j - i, dtype=np.int64)
+            addr = np.zeros(j - i, dtype=np.uint64)
+            for gi, gj, f in futs:
+                lo, hi = max(i, gi), min(j, gj)
+                if lo >= hi:
+                    continue
+                pt, o = f.result()
+                sizes[lo - i:hi - i] = np.diff(o)[lo - gi:hi - gi]
+                addr[lo - i:hi - i] = np.uint64(pt.data_ptr()) + o[lo - gi:hi - gi].astype(np.uint64)
+            return sizes, addr
+        return take
 
     def _batches(self, bounds: Sequence[Tuple[int, int]], limit: Optional[int] = None):
         """Consecutive blocks grouped so that a batch holds <= limit (default batch_bytes) bytes (a single larger block forms its own batch)."""
@@ -346,6 +398,11 @@ class Engine:
         """-> (method ids int64[nb], payload lengths int64[nb], payload area uint8[sum]) for the KOLR candidate list `names`."""
         mids_all, lens_all, areas = [], [], []
         v2 = self.enable_v2_new and "v2_new" in names
+        longest = max((b - a for a, b in bounds), default=0)
+        rp_take = None
+        if ("repair" in names and self.lz_async and self.repair_group_bytes > 0 and
+                _lib.lib().kolm_repair_max_block() < longest <= self.repair_max):
+            rp_take = self._repair_ahead(data, bounds)
         for i, j in self._batches(bounds, self.batch_bytes // 8 if v2 else None):   # v2_new sorts 8 planes per block: same scratch per batch
             a, b = bounds[i][0], bounds[j - 1][1]
             nb = j - i
@@ -367,7 +424,7 @@ class Engine:
                     warnings.warn("Re-Pair candidate skipped: block longer than the configured cap of %d bytes (Engine.repair_max / "
                                   "KOLM_REPAIR_MAX_BLOCK); the container can differ from the reference's where Re-Pair would win" % self.repair_max,
                                   RuntimeWarning, stacklevel=3)
-                rp_side = want_rp and "lz77" in names and self.lz_async     # both latency-bound candidates share the side stream
+                rp_side = want_rp and rp_take is None and "lz77" in names and self.lz_async   # both latency-bound candidates share the side stream
                 lz = self._lz_submit(x, off, 4096, 0, with_repair=rp_side) if "lz77" in names else None
                 need_res = any(n in ("xor", "lfsr_pred") for n in names)
                 rs = c.residual_sizes(x, off) if need_res else None
@@ -382,7 +439,10 @@ class Engine:
                     lzp, lzo = got[0], got[1]
                     if rp_side:
                         rpp, rpo = got[2]
-                if want_rp and rpo is None:
+                rp_sizes = rp_addr = None
+                if want_rp and rp_take is not None:
+                    rp_sizes, rp_addr = rp_take(i, j)
+                elif want_rp and rpo is None:
                     rpp, rpo = c.repair_encode(x, off)
                 for nme in names:
                     if nme == "raw":
@@ -395,6 +455,8 @@ class Engine:
                         cols.append(k2s[:, K2_SLOT[K2_FLAG_OF[nme]]])
                     elif nme == "lz77":
                         cols.append(np.diff(lzo))
+                    elif nme == "repair" and rp_sizes is not None:
+                        cols.append(rp_sizes)
                     elif nme == "repair" and rpo is not None:
                         cols.append(np.diff(rpo))
                     elif nme == "v2_new" and v2o is not None:
@@ -420,6 +482,9 @@ class Engine:
                         p, o, _ = c.rice_k2_encode(m, off, K2_FLAG_OF[nme])
                     elif nme == "lz77":
                         p, o = lzp, lzo
+                    elif nme == "repair" and rp_addr is not None:
+                        base[:, mid] = rp_addr                       # the groups' payload tensors live in rp_take
+                        continue
                     elif nme == "repair":
                         p, o = rpp, rpo
                     elif nme == "v2_new":

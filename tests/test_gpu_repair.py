@@ -92,3 +92,32 @@ def test_repair_one_mib_roundtrip():
     dec = G.unbatch(G.ctx().repair_decode(out, out_off, off), off)
     assert dec == blocks
     assert all(out_off[i + 1] - out_off[i] < len(blocks[i]) for i in range(3))
+
+
+def test_kolr_selection_with_repair_ahead_of_the_batches(monkeypatch):
+    """Long blocks: the engine runs Re-Pair ahead of its batch loop in groups on a third context.  (method, payload) of every
+    block must equal the oracle's selection over all ten candidates — small groups and batches so that groups span batches."""
+    import numpy as np
+    from kolmogorovlike_datacompressor_b200 import synth
+    from kolmogorovlike_datacompressor_b200.engine import Engine
+    from kolmogorovlike_datacompressor_b200.kolm_final_researched_v2_2 import KOLR_NAMES
+    rnd = random.Random(5)
+    bs = 12 << 10
+    parts = [synth.s1_text(3 * bs).tobytes(), bytes(rnd.randrange(4) for _ in range(bs)), b"abcabcabd" * (2 * bs // 9),
+             synth.s2_mixed(2 * bs).tobytes(), bytes(rnd.randrange(256) for _ in range(bs // 2))]
+    data = b"".join(parts)
+    bounds = [(a, min(a + bs, len(data))) for a in range(0, len(data), bs)]
+    eng = Engine(batch_bytes=3 * bs)
+    eng.repair_group_bytes = 4 * bs
+    names = [n for n in KOLR_NAMES if n != "v2_new"]
+    got = eng.encode_kolr(data, bounds, names)
+    assert eng.ctx3 is not None                                  # the ahead path ran
+    two = eng.encode_kolr(data, bounds, ["raw", "repair"])      # Re-Pair against raw only: its payloads reach the container
+    wins = 0
+    for k, (a, b) in enumerate(bounds):
+        mid, payload, _ = O.encode_block(O.PROFILE_KOLR, data[a:b])
+        assert got[k][0] == mid and got[k][1] == payload, k
+        mid2, payload2, _ = O.encode_block(O.PROFILE_KOLR, data[a:b], models_mask=(1 << 0) | (1 << 9))
+        assert two[k][0] == (1 if mid2 == 9 else 0) and two[k][1] == payload2, k
+        wins += mid2 == 9
+    assert wins >= 4
