@@ -29,12 +29,15 @@
 // text) times a few microseconds of dependent global-memory steps.
 #include "common.cuh"
 
+#ifndef RPB_CTAS_PER_SM
+#define RPB_CTAS_PER_SM 4
+#endif
 #ifndef RPB_THREADS
 #define RPB_THREADS 128
 #endif
 #define RPB_PMAX 8192u
 #ifndef RPB_V
-#define RPB_V 14            // experiment mask: 1 parallel M skip, 2 warp pbest update, 4 unrolled rescan, 8 small hash
+#define RPB_V 30            // experiment mask: 1 parallel M skip, 2 warp pbest update, 4 unrolled rescan, 8 small hash, 16 register-resident small rounds
 #endif
 #define RPB_NIL 0xffffffffu
 #define RPB_EMPTY 0xffffffffffffffffull
@@ -49,11 +52,14 @@ struct RpbSlab {
     u64* rules;                                          // [n/2 + 1]
 };
 
+// Capacities.  Pairs whose count is >= 2 are distinct and share the sequence's < n adjacent positions, so fewer than n/2 exist at
+// any time: that bounds the valid entries of the sorted list, of a merge, and what one round can append to the pending list
+// (appended entries are distinct pairs with a current count >= 2); the pending list is merged once it holds RPB_PMAX entries.
 __host__ __device__ inline u32 rpb_pow2_at_least(u64 v) { u32 p = 1024; while ((u64)p < v) p <<= 1; return p; }
 __host__ __device__ inline size_t rpb_align(size_t x) { return (x + 255) & ~(size_t)255; }
 // slab bytes for a block of n bytes (n >= 2)
 __host__ __device__ inline size_t rpb_need(u64 n) {
-    const u64 H = (RPB_V & 8) ? rpb_pow2_at_least(3 * n + 65536) : rpb_pow2_at_least(4 * n + 131072), oc = 9 * n / 2 + 64, mc = 2 * n + 2 * RPB_PMAX + 64, pc = 2 * n + RPB_PMAX + 64, tc = 2 * n + 64;
+    const u64 H = (RPB_V & 8) ? rpb_pow2_at_least(3 * n + 65536) : rpb_pow2_at_least(4 * n + 131072), oc = 9 * n / 2 + 64, mc = n / 2 + 64, pc = n / 2 + RPB_PMAX + 64, tc = 2 * n + 64;
     size_t b = 0;
     b += 4 * rpb_align(n * 4);
     b += rpb_align(H * 8) + 3 * rpb_align(H * 4);
@@ -65,7 +71,7 @@ __host__ __device__ inline size_t rpb_need(u64 n) {
     return b + 1024;
 }
 __device__ inline void rpb_carve(u8* base, u64 n, RpbSlab& S) {
-    const u64 H = (RPB_V & 8) ? rpb_pow2_at_least(3 * n + 65536) : rpb_pow2_at_least(4 * n + 131072), oc = 9 * n / 2 + 64, mc = 2 * n + 2 * RPB_PMAX + 64, pc = 2 * n + RPB_PMAX + 64, tc = 2 * n + 64;
+    const u64 H = (RPB_V & 8) ? rpb_pow2_at_least(3 * n + 65536) : rpb_pow2_at_least(4 * n + 131072), oc = 9 * n / 2 + 64, mc = n / 2 + 64, pc = n / 2 + RPB_PMAX + 64, tc = 2 * n + 64;
     u8* p = base;
     auto take = [&](size_t bytes) { u8* r = p; p += rpb_align(bytes); return r; };
     S.sym = (u32*)take(n * 4); S.prv = (u32*)take(n * 4); S.nxt = (u32*)take(n * 4); S.stamp = (u32*)take(n * 4);
@@ -97,7 +103,7 @@ __device__ __forceinline__ bool rpb_better(u32 ca, u64 pa, u32 cb, u64 pb) { ret
 struct RpbShared {
     u32 scan[RPB_THREADS / 32];
     u64 red_pair[RPB_THREADS / 32]; u32 red_cnt[RPB_THREADS / 32]; u32 red_idx[RPB_THREADS / 32];
-    u32 n_occ_nodes, n_occ, n_tk, n_touched, n_p, mpos, mlen;
+    u32 n_occ_nodes, n_occ, n_tk, n_touched, n_p, mpos, mlen, n_alloc;
     u32 pbest; int pbest_ok;                             // index of the best pending entry (valid when pbest_ok)
     u64 cur_pair; u32 cur_cnt, cur_slot; int stop;
     u32 total;
@@ -270,11 +276,53 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             const u64 cp = sh.cur_pair; const u32 A = (u32)(cp >> 32), B = (u32)cp, cslot = sh.cur_slot;
             const u32 newsym = 256 + nrules;
             const u32 st_seen = round * 4 + 1, st_take = round * 4 + 2, st_part = round * 4 + 3;
+            const u32 p0 = sh.n_p;                               // pending entries before this round's (appended after the next barriers)
+            auto touch = [&](u32 s) { if (atomicExch(&S.hstamp[s], round) != round) { const u32 o = atomicAdd(&sh.n_touched, 1u); if (o < S.tcap) S.touched[o] = s; } };
+            const u32 obase = S.hhead[cslot];
+            const u32 nh = obase == RPB_NIL ? 0u : S.opos[obase];
+            const bool fast = (RPB_V & 16) && A != B && nh <= RPB_THREADS;
+            u32 ntk;
+            u32 f_p = RPB_NIL, f_xpos = RPB_NIL, f_sl = RPB_NIL, f_sr = RPB_NIL;      // fast rounds: my occurrence lives in registers
+            u32* const lslot = S.occ; u32* const rslot = S.occ + (n >> 1);
+            if (fast) {
+                // ---- small round (one position hint per thread, a != b so occurrences cannot overlap): the occurrence, its
+                //      neighbours and their symbols are read once, under the OLD links, and kept in registers
+                u32 q = RPB_NIL, x = RPB_NIL, y = RPB_NIL, sx = 0, sy = 0; bool valid = false;
+                if (tid < nh) {
+                    const u32 p = S.opos[obase + 1u + tid];
+                    const bool fresh = atomicExch(&S.stamp[p], st_seen) != st_seen;   // the same position can be hinted twice
+                    const u32 sp = S.sym[p]; q = S.nxt[p]; x = S.prv[p];
+                    if (sp == A && q != RPB_NIL) {
+                        const u32 sq = S.sym[q]; y = S.nxt[q];
+                        if (x != RPB_NIL) sx = S.sym[x];
+                        if (sq == B && fresh) { valid = true; f_p = p; if (y != RPB_NIL) sy = S.sym[y]; }
+                    }
+                }
+                ntk = (u32)__syncthreads_count(valid);
+                if (ntk < 2) break;                              // V22.py:1880-1882: the rule is not recorded, the sequence stays
+                if (valid) { S.stamp[f_p] = st_take; S.stamp[q] = st_part; }
+                __syncthreads();
+                if (valid) {
+                    const u32 stx = x != RPB_NIL ? S.stamp[x] : 0u, sty = y != RPB_NIL ? S.stamp[y] : 0u;
+                    const bool right = y != RPB_NIL && sty != st_take;
+                    // old neighbours lose an occurrence; a != b: neither (sx, a) nor (b, sy) can be the round's pair
+                    if (x != RPB_NIL) { const u32 s = rpb_slot(S, ((u64)sx << 32) | A); atomicSub(&S.hcnt[s], 1u); touch(s); }
+                    if (right) { const u32 s = rpb_slot(S, ((u64)B << 32) | sy); atomicSub(&S.hcnt[s], 1u); touch(s); }
+                    // new neighbours: a left neighbour that is the second half of a replaced occurrence stands for that occurrence
+                    if (x != RPB_NIL) {
+                        const bool part = stx == st_part;
+                        f_xpos = part ? S.prv[x] : x;
+                        f_sl = rpb_slot(S, ((u64)(part ? newsym : sx) << 32) | newsym); atomicAdd(&S.hcnt[f_sl], 1u); touch(f_sl);
+                    }
+                    if (right) { f_sr = rpb_slot(S, ((u64)newsym << 32) | sy); atomicAdd(&S.hcnt[f_sr], 1u); touch(f_sr); }
+                    // relink: nobody reads these words in this phase (prv[x] above is only read for second halves, which no one writes)
+                    S.sym[f_p] = newsym; S.sym[q] = RPB_NIL; S.nxt[f_p] = y;
+                    if (y != RPB_NIL) S.prv[y] = f_p;
+                }
+            } else {
             // ---- valid occurrences: all threads read the pair's occurrence array (position hints), check the hints against the
             //      live sequence and claim each position once
             {
-                const u32 obase = S.hhead[cslot];
-                const u32 nh = obase == RPB_NIL ? 0u : S.opos[obase];
                 for (u32 i = tid; i < nh; i += RPB_THREADS) {
                     const u32 p = S.opos[obase + 1u + i];
                     if (S.sym[p] != A) continue;
@@ -305,11 +353,10 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
                 }
             }
             __syncthreads();
-            const u32 ntk = sh.n_tk;
+            ntk = sh.n_tk;
             if (ntk < 2) break;                                  // V22.py:1880-1882: the rule is not recorded, the sequence stays
             for (u32 i = tid; i < ntk; i += RPB_THREADS) { const u32 p = S.tk[i]; S.stamp[p] = st_take; S.stamp[S.nxt[p]] = st_part; }
             __syncthreads();
-            auto touch = [&](u32 s) { if (atomicExch(&S.hstamp[s], round) != round) { const u32 o = atomicAdd(&sh.n_touched, 1u); if (o < S.tcap) S.touched[o] = s; } };
             // ---- old neighbours lose an occurrence (old links)
             for (u32 i = tid; i < ntk; i += RPB_THREADS) {
                 const u32 p = S.tk[i], q = S.nxt[p], x = S.prv[p], y = S.nxt[q];
@@ -326,7 +373,6 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             __syncthreads();
             // ---- new neighbours (new links): left pair always, right pair unless the right neighbour was replaced too.  Counted
             //      now (slots remembered: occ is free again and ntk <= n/2), their occurrence arrays are filled once sized.
-            u32* const lslot = S.occ; u32* const rslot = S.occ + (n >> 1);
             for (u32 i = tid; i < ntk; i += RPB_THREADS) {
                 const u32 p = S.tk[i], x = S.prv[p], y = S.nxt[p];
                 u32 sl = RPB_NIL, sr = RPB_NIL;
@@ -334,13 +380,12 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
                 if (y != RPB_NIL && S.stamp[y] != st_take) { sr = rpb_slot(S, ((u64)newsym << 32) | S.sym[y]); atomicAdd(&S.hcnt[sr], 1u); touch(sr); }
                 lslot[i] = sl; rslot[i] = sr;
             }
-            if (tid == 0) { S.hcnt[cslot] = 0; S.rules[nrules] = cp; }
+            }
+            if (tid == 0) { S.hcnt[cslot] = 0; S.rules[nrules] = cp; sh.n_alloc = 0; }
             ++nrules;
             __syncthreads();
             // ---- touched pairs whose count is still >= 2 become pending
             const u32 ntouch = min(sh.n_touched, S.tcap);
-            const u32 p0 = sh.n_p;
-            __syncthreads();                                     // everyone has read the old length before anyone appends
             for (u32 i = tid; i < ntouch; i += RPB_THREADS) {
                 const u32 s = S.touched[i], c = S.hcnt[s];
                 if (c >= 2) {
@@ -348,15 +393,22 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
                     const u32 o = atomicAdd(&sh.n_p, 1u); if (o < S.pcap) { S.ppair[o] = key; S.pcnt[o] = c; S.pslot[o] = s; }
                     if ((u32)(key >> 32) == newsym || (u32)key == newsym) {       // a pair born this round: all its occurrences exist now
                         const u32 base = atomicAdd(&sh.n_occ_nodes, c + 1u);
-                        if (base + c + 1u <= S.ocap) { S.hhead[s] = base; S.opos[base] = 0; }
+                        if (base + c + 1u <= S.ocap) { S.hhead[s] = base; S.opos[base] = 0; sh.n_alloc = 1; }
                     }
                 }
             }
             __syncthreads();
-            for (u32 i = tid; i < ntk; i += RPB_THREADS) {
-                const u32 sl = lslot[i], sr = rslot[i];
-                if (sl != RPB_NIL) { const u32 base = S.hhead[sl]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = S.prv[S.tk[i]]; }
-                if (sr != RPB_NIL) { const u32 base = S.hhead[sr]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = S.tk[i]; }
+            if (sh.n_alloc) {                                    // some pair born this round occurs twice or more: fill its array
+                if (fast) {
+                    if (f_sl != RPB_NIL) { const u32 base = S.hhead[f_sl]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = f_xpos; }
+                    if (f_sr != RPB_NIL) { const u32 base = S.hhead[f_sr]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = f_p; }
+                } else {
+                    for (u32 i = tid; i < ntk; i += RPB_THREADS) {
+                        const u32 sl = lslot[i], sr = rslot[i];
+                        if (sl != RPB_NIL) { const u32 base = S.hhead[sl]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = S.prv[S.tk[i]]; }
+                        if (sr != RPB_NIL) { const u32 base = S.hhead[sr]; if (base != RPB_NIL) S.opos[base + 1u + atomicAdd(&S.opos[base], 1u)] = S.tk[i]; }
+                    }
+                }
             }
             if (!(RPB_V & 2)) {
                 if (tid == 0) {
@@ -466,8 +518,10 @@ int kolm_repair_big_impl(kolm_ctx* c, const u8* in, u8* tmp, cudaStream_t s) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = free_b + c->rpb_bytes;                   // what the pool may use: what is free now plus what it already holds
-    budget = budget / 2 < ((size_t)96 << 30) ? budget / 2 : ((size_t)96 << 30);
-    int grid = nbig < 2 * c->sm_count ? nbig : 2 * c->sm_count;   // the CTAs mostly wait on dependent loads: two per SM overlap well
+    budget = budget * 3 / 5 < ((size_t)100 << 30) ? budget * 3 / 5 : ((size_t)100 << 30);
+    static int per_sm = -1;                                  // KOLM_REPAIR_CTAS_PER_SM: the CTAs mostly wait on dependent loads, several per SM overlap
+    if (per_sm < 0) { const char* e = getenv("KOLM_REPAIR_CTAS_PER_SM"); per_sm = e ? atoi(e) : RPB_CTAS_PER_SM; if (per_sm < 1) per_sm = 1; }
+    int grid = nbig < per_sm * c->sm_count ? nbig : per_sm * c->sm_count;
     if ((size_t)grid * need > budget) grid = (int)(budget / need);
     if (grid < 1) return KOLM_E_CAPACITY;
     if ((size_t)grid * need > c->rpb_bytes) {
