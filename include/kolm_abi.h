@@ -51,6 +51,11 @@ const char* kolm_last_cuda_error(void);
 /* context: scratch for batches of up to max_batch_bytes bytes in up to max_blocks blocks */
 size_t kolm_scratch_bytes(size_t max_batch_bytes, int max_blocks);
 int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** out);
+/* flags = KOLM_CTX_REPAIR_ONLY: a context on which only kolm_repair_enc may run (every other operator returns
+ * KOLM_E_UNSUPPORTED); it holds 8 instead of 38 bytes of scratch per element, so one context can take a whole container's
+ * long blocks for the Re-Pair candidate (repair_compress, V22.py:1841-1911) beside the contexts of the other candidates. */
+#define KOLM_CTX_REPAIR_ONLY 1u
+int kolm_create_ex(int device, size_t max_batch_bytes, int max_blocks, unsigned flags, kolm_ctx** out);
 void kolm_destroy(kolm_ctx* ctx);
 
 /* ---- stage operators (batched) ------------------------------------------------------------- */

@@ -13,7 +13,7 @@ KOLM_PROFILE_KOLM = 1
 KOLM_PROFILE_KOLR = 2
 
 EXPORTS = [
-    "kolm_abi_version", "kolm_strerror", "kolm_last_cuda_error", "kolm_scratch_bytes", "kolm_create", "kolm_destroy",
+    "kolm_abi_version", "kolm_strerror", "kolm_last_cuda_error", "kolm_scratch_bytes", "kolm_create", "kolm_create_ex", "kolm_destroy",
     "kolm_lyndon", "kolm_bbwt_fwd", "kolm_bbwt_inv", "kolm_mtf_enc", "kolm_mtf_dec",
     "kolm_rice_kf_enc", "kolm_rice_kf_dec", "kolm_rice_k2_enc", "kolm_rice_k2_dec", "kolm_last_counters",
     "kolm_lz77_enc", "kolm_lz77_dec", "kolm_residual_sizes", "kolm_residual_enc", "kolm_residual_dec",
@@ -53,6 +53,7 @@ def lib():
     L.kolm_scratch_bytes.restype = C.c_size_t
     L.kolm_scratch_bytes.argtypes = [C.c_size_t, C.c_int]
     L.kolm_create.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.kolm_create_ex.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
     L.kolm_destroy.argtypes = [C.c_void_p]
     p, i64p, ip = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int)
     L.kolm_lyndon.argtypes = [p, p, i64p, C.c_int, p, p]

@@ -56,14 +56,19 @@ size_t kolm_scratch_bytes(size_t max_batch_bytes, int max_blocks) {
     return e * (4 * 8 + 4 / 8 + 2) + tiles * (sizeof(TileDesc) * 2 + 16 + 1024) + (size_t)max_blocks * (sizeof(BlockInfo) + 4 * 9 + 64 * 8);
 }
 
-int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** out) {
-    if (!out || max_blocks < 1 || max_batch_bytes < 1) return KOLM_E_ARG;
+int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** out) { return kolm_create_ex(device, max_batch_bytes, max_blocks, 0u, out); }
+
+// flags & KOLM_CTX_REPAIR_ONLY: a context for kolm_repair_enc alone — block tables and the two staging arrays it uses (8 instead of
+// 38 bytes per element), so that one context can hold a whole container's worth of long blocks next to the slab pool
+int kolm_create_ex(int device, size_t max_batch_bytes, int max_blocks, unsigned flags, kolm_ctx** out) {
+    if (!out || max_blocks < 1 || max_batch_bytes < 1 || (flags & ~(unsigned)KOLM_CTX_REPAIR_ONLY)) return KOLM_E_ARG;
+    const bool light = (flags & KOLM_CTX_REPAIR_ONLY) != 0;
     size_t e = padded_capacity(max_batch_bytes, max_blocks);
     if (e >= (1ull << 31)) return KOLM_E_ARG;     // 31-bit positions / ranks
     CUDA_TRY(cudaSetDevice(device));
     kolm_ctx* c = new kolm_ctx();
     memset(c, 0, sizeof *c);
-    c->device = device; c->max_elems = e; c->max_blocks = max_blocks;
+    c->device = device; c->max_elems = e; c->max_blocks = max_blocks; c->light = light ? 1 : 0;
     c->max_tiles = (int)(e / KOLM_TILE) + max_blocks + 2;
     cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -74,10 +79,13 @@ int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** o
     CUDA_TRY(dalloc(&c->d_stats, 16)); CUDA_TRY(dalloc(&c->d_bacc, nb * 64));
     CUDA_TRY(dalloc(&c->d_tiles, nt)); CUDA_TRY(dalloc(&c->d_atiles, nt));
     CUDA_TRY(dalloc(&c->d_lb, 32 + 8 * nt)); CUDA_TRY(dalloc(&c->d_thist, nt * 256));
-    CUDA_TRY(dalloc(&c->d_k0, e)); CUDA_TRY(dalloc(&c->d_v0, e)); CUDA_TRY(dalloc(&c->d_k1, e)); CUDA_TRY(dalloc(&c->d_v1, e));
-    CUDA_TRY(dalloc(&c->d_sa, e)); CUDA_TRY(dalloc(&c->d_rank, e)); CUDA_TRY(dalloc(&c->d_nr, e));
-    CUDA_TRY(dalloc(&c->d_single, e / 32 + 8)); CUDA_TRY(dalloc(&c->d_fstart, e));
-    CUDA_TRY(dalloc(&c->d_tmp8a, e)); CUDA_TRY(dalloc(&c->d_tmp8b, e));
+    CUDA_TRY(dalloc(&c->d_k0, e)); CUDA_TRY(dalloc(&c->d_v0, e));
+    if (!light) {
+        CUDA_TRY(dalloc(&c->d_k1, e)); CUDA_TRY(dalloc(&c->d_v1, e));
+        CUDA_TRY(dalloc(&c->d_sa, e)); CUDA_TRY(dalloc(&c->d_rank, e)); CUDA_TRY(dalloc(&c->d_nr, e));
+        CUDA_TRY(dalloc(&c->d_single, e / 32 + 8)); CUDA_TRY(dalloc(&c->d_fstart, e));
+        CUDA_TRY(dalloc(&c->d_tmp8a, e)); CUDA_TRY(dalloc(&c->d_tmp8b, e));
+    }
     CUDA_TRY(cudaMallocHost((void**)&c->h_binfo, nb * sizeof(BlockInfo)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_u32, nb * 4 * sizeof(u32)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_stats, 16 * sizeof(u32)));
@@ -118,6 +126,7 @@ void kolm_destroy(kolm_ctx* c) {
 int kolm_set_batch(kolm_ctx* c, const i64* off, int nblocks, cudaStream_t s) {
     if (!c || !off || nblocks < 0) return KOLM_E_ARG;
     if (nblocks > c->max_blocks) return KOLM_E_CAPACITY;
+    if (c->light && !c->light_ok) return KOLM_E_UNSUPPORTED;   // a Re-Pair-only context has no scratch for the other operators
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(s));           // pinned staging below may still be in flight from the previous call
     u64 p = 0; u32 t = 0, maxlen = 0, rows = 0;
@@ -254,7 +263,11 @@ int kolm_residual_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_of
 int kolm_repair_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
                     kolm_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    if (!c) return KOLM_E_ARG;
+    c->light_ok = 1;
+    const int rc = kolm_set_batch(c, off, nblocks, s);
+    c->light_ok = 0;
+    KOLM_TRY(rc);
     return kolm_repair_enc_impl(c, in, out, out_cap, out_off, s);
 }
 

@@ -83,6 +83,7 @@ struct kolm_ctx {
     u32 *d_fstart;           // Lyndon factor starts, front-packed per block (block-local positions)
     u8  *d_tmp8a, *d_tmp8b;  // byte staging (bbwt out -> mtf -> rice)
     void* d_jump;            // inverse BBWT pointer-jumping nodes (2 x 16 B / element), allocated on first decode
+    int light, light_ok;             // KOLM_CTX_REPAIR_ONLY context (kolm_create_ex): only kolm_repair_enc may run on it
     void* d_rpb; size_t rpb_bytes;   // slab pool of the incremental Re-Pair kernel (repair_big.cu), allocated on first use
     int* d_err; int* h_err;  // [max_blocks] per-block decode status
     // host mirrors

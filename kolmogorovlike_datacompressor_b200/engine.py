@@ -119,10 +119,11 @@ class Engine:
         self._side: Optional[torch.cuda.Stream] = None
         self._worker = None
         # Re-Pair on long blocks (> kolm_repair_max_block() bytes: the incremental kernel, one CTA per block and seconds per MiB)
-        # is run AHEAD of the batch loop over groups of up to repair_group_bytes on a third context / stream / worker thread: a
-        # group offers enough blocks for two CTAs on every SM and a work queue that evens out fast and slow blocks, and the BBWT /
-        # LZ77 chains of all batches run beside it (KOLM_REPAIR_GROUP_MIB, 0: per batch on the LZ77 side stream)
-        self.repair_group_bytes = int(os.environ.get("KOLM_REPAIR_GROUP_MIB", "512")) << 20
+        # is run AHEAD of the batch loop over groups of up to repair_group_bytes on a third (Re-Pair-only, 8 bytes of scratch per
+        # byte) context / stream / worker thread: a group offers enough blocks for four CTAs on every SM and a work queue that
+        # evens out fast and slow blocks (every group ends with a tail as long as its slowest block, so the larger the better),
+        # and the BBWT / LZ77 chains of all batches run beside it (KOLM_REPAIR_GROUP_MIB, 0: per batch on the LZ77 side stream)
+        self.repair_group_bytes = min(int(os.environ.get("KOLM_REPAIR_GROUP_MIB", "1792")), 1920) << 20
         self.ctx3: Optional[Context] = None
         self.cap3_bytes = 0
         self.cap3_blocks = 0
@@ -263,11 +264,13 @@ class Engine:
                         self.ctx3 = None
                     self.cap3_bytes = max(need_bytes, 1 << 22, self.cap3_bytes)
                     self.cap3_blocks = max(need_blocks, 1024, self.cap3_blocks)
-                    self.ctx3 = Context(self.cap3_bytes, self.cap3_blocks, dev)
+                    self.ctx3 = Context(self.cap3_bytes, self.cap3_blocks, dev, repair_only=True)
                 a, b = bounds[i][0], bounds[j - 1][1]
                 off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
                 x = self._upload(data, a, b)
                 p, o = self.ctx3.repair_encode(x, off)                 # returns after its stream finished
+                p = p[:max(int(o[-1]), 4)].clone()                      # the capacity is 4x the input: keep what was used
+                side.synchronize()
                 return p, np.asarray(o, dtype=np.int64)
         futs = [(i, j, self._worker3.submit(work, i, j)) for i, j in groups]
 

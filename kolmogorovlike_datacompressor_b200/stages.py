@@ -23,14 +23,15 @@ def _offsets(off: Sequence[int]):
 class Context:
     """Owns the device scratch for batches up to (max_batch_bytes, max_blocks) on one device."""
 
-    def __init__(self, max_batch_bytes: int, max_blocks: int, device: Optional[int] = None):
+    def __init__(self, max_batch_bytes: int, max_blocks: int, device: Optional[int] = None, repair_only: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("kolmogorovlike_datacompressor_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.max_batch_bytes = int(max_batch_bytes)
         self.max_blocks = int(max_blocks)
         h = C.c_void_p()
-        _lib.check(_lib.lib().kolm_create(self.device, max(1, self.max_batch_bytes), max(1, self.max_blocks), C.byref(h)))
+        # repair_only: KOLM_CTX_REPAIR_ONLY — only repair_encode works on such a context (8 instead of 38 bytes of scratch per byte)
+        _lib.check(_lib.lib().kolm_create_ex(self.device, max(1, self.max_batch_bytes), max(1, self.max_blocks), 1 if repair_only else 0, C.byref(h)))
         self._h = h
 
     def close(self):
