@@ -159,6 +159,13 @@ int64_t kolm_cdc_walk_kf(const uint8_t* data, int64_t n, int64_t min_size, int64
 int64_t kolm_cdc_walk_v22(const uint8_t* data, int64_t n, int64_t min_size, int64_t avg_size, int64_t max_size, uint64_t* cand, int64_t ncand,
                           int64_t* ends, int64_t cap);
 
+/* Per-block model selection: _encode_block KF.py:821-864 (ids 0..3 in order, keep `plen < best`) and the selection loops of
+ * V22.py:2233-2252 / 2350-2369 over _select_encoders() (strict '<'): the winner is the FIRST minimum of the candidates' exact
+ * payload sizes — the lowest id on ties.  sizes: HOST array, row-major [nblocks][ncand], as produced by the candidates'
+ * encoders / cost kernels (a candidate the reference skips — it raised — carries a huge size); method[b] (HOST) receives the
+ * winner's index, best[b] its size.  The comparison runs on the device (one thread per block). */
+int kolm_select_blocks(kolm_ctx* ctx, const int64_t* sizes, int nblocks, int ncand, int32_t* method, int64_t* best, kolm_stream_t stream);
+
 /* Payload gather after model selection: block b's winning payload is len[b] bytes at DEVICE address src_addr[b] (any of
  * the per-model payload buffers, or the input itself for RAW); they are laid out back to back at `out` in block order —
  * the payload area of a container (KF.py:896-901; V22.py:2443-2444).  src_addr/len: HOST arrays; out_off (HOST, nblocks+1)

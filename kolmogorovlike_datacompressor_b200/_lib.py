@@ -17,7 +17,7 @@ EXPORTS = [
     "kolm_lyndon", "kolm_bbwt_fwd", "kolm_bbwt_inv", "kolm_mtf_enc", "kolm_mtf_dec",
     "kolm_rice_kf_enc", "kolm_rice_kf_dec", "kolm_rice_k2_enc", "kolm_rice_k2_dec", "kolm_last_counters",
     "kolm_lz77_enc", "kolm_lz77_dec", "kolm_residual_sizes", "kolm_residual_enc", "kolm_residual_dec",
-    "kolm_repair_enc", "kolm_repair_dec", "kolm_repair_max_block", "kolm_v2new_enc", "kolm_v2new_dec", "kolm_cdc_kf", "kolm_cdc_v22", "kolm_cdc_candidates", "kolm_cdc_walk_kf", "kolm_cdc_walk_v22", "kolm_gather_payloads", "kolm_copy_blocks",
+    "kolm_repair_enc", "kolm_repair_dec", "kolm_repair_max_block", "kolm_v2new_enc", "kolm_v2new_dec", "kolm_cdc_kf", "kolm_cdc_v22", "kolm_cdc_candidates", "kolm_cdc_walk_kf", "kolm_cdc_walk_v22", "kolm_select_blocks", "kolm_gather_payloads", "kolm_copy_blocks",
     "kolm_profile_categories", "kolm_profile_name", "kolm_profile_enable", "kolm_profile_reset", "kolm_profile_read",
 ]
 
@@ -73,6 +73,7 @@ def lib():
     for f in ("kolm_cdc_walk_kf", "kolm_cdc_walk_v22"):
         getattr(L, f).restype = C.c_int64
         getattr(L, f).argtypes = [p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, p, C.c_int64, i64p, C.c_int64]
+    L.kolm_select_blocks.argtypes = [p, i64p, C.c_int, C.c_int, C.POINTER(C.c_int32), i64p, p]
     L.kolm_gather_payloads.argtypes = [p, C.POINTER(C.c_uint64), i64p, C.c_int, p, i64p, p]
     L.kolm_copy_blocks.argtypes = [p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), i64p, C.c_int, p]
     L.kolm_repair_enc.argtypes = [p, p, i64p, C.c_int, p, C.c_size_t, i64p, p]

@@ -439,6 +439,37 @@ extern "C" int kolm_gather_payloads(kolm_ctx* c, const uint64_t* src_addr, const
     return KOLM_OK;
 }
 
+// Per-block model selection (_encode_block kolm_final.py:821-864: ids in order, keep `plen < best`; the selection loops of
+// kolm_final_researched_v2-2.py:2233-2252 / 2350-2369: strict '<'): the winner is the FIRST minimum of the candidates' payload
+// sizes, i.e. the lowest id on ties.  One thread per block; sizes row-major [nblocks][ncand].
+__global__ void __launch_bounds__(256) k_select_blocks(const i64* __restrict__ sizes, int nblocks, int ncand, i64* __restrict__ method, i64* __restrict__ best) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const i64* row = sizes + (size_t)b * ncand;
+    i64 bs = row[0]; int bm = 0;
+    for (int m = 1; m < ncand; ++m) { const i64 v = row[m]; if (v < bs) { bs = v; bm = m; } }
+    method[b] = bm; best[b] = bs;
+}
+
+extern "C" int kolm_select_blocks(kolm_ctx* c, const int64_t* sizes, int nblocks, int ncand, int32_t* method, int64_t* best, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!c || !sizes || !method || !best || nblocks < 0 || nblocks > c->max_blocks || ncand < 1 || ncand > 62) return KOLM_E_ARG;
+    if (!nblocks) return KOLM_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(s));                    // pinned staging reuse
+    const size_t nin = (size_t)nblocks * ncand;
+    i64* hin = (i64*)c->h_bacc; i64* hout = hin + nin;     // [sizes | method | best] in the pinned accumulator mirror (64 words per block)
+    memcpy(hin, sizes, nin * 8);
+    i64* din = (i64*)c->d_bacc; i64* dout = din + nin;
+    CUDA_TRY(cudaMemcpyAsync(din, hin, nin * 8, cudaMemcpyHostToDevice, s));
+    KL(c, KC_PLAN, (i64)nin * 8, s, k_select_blocks<<<(nblocks + 255) / 256, 256, 0, s>>>(din, nblocks, ncand, dout, dout + nblocks));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(hout, dout, (size_t)nblocks * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int b = 0; b < nblocks; ++b) { method[b] = (int32_t)hout[b]; best[b] = hout[nblocks + b]; }
+    return KOLM_OK;
+}
+
 // general batched device-to-device copy: block b = len[b] bytes from src_addr[b] to dst_addr[b] (absolute device addresses, HOST arrays)
 __global__ void __launch_bounds__(256) k_copy_blocks(const u64* __restrict__ src, const u64* __restrict__ dst, const i64* __restrict__ len, int nblocks) {
     for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {

@@ -355,7 +355,7 @@ class Engine:
                 kfp, kfo = c.rice_kf_encode(m, off)
                 lzp, lzo = lz()
                 sizes = np.stack([lens, sx, np.diff(kfo), np.diff(lzo)], axis=1)
-                mids = np.argmin(sizes, axis=1)                      # first minimum == lowest id on ties (KF.py:857)
+                mids, _ = c.select_blocks(sizes)                     # first minimum == lowest id on ties (KF.py:857)
                 base = np.zeros((nb, 4), dtype=np.uint64)
                 base[:, 0] = np.uint64(x.data_ptr()) + off[:-1].astype(np.uint64)
                 if (mids == 1).any():
@@ -467,7 +467,7 @@ class Engine:
                     else:                                            # v2_new raises NameError in the shipped reference; skipped repair
                         cols.append(np.full(nb, _BIG, dtype=np.int64))
                 sizes = np.stack(cols, axis=1)
-                mids = np.argmin(sizes, axis=1)                      # strict '<' in the reference == first minimum
+                mids, _ = c.select_blocks(sizes)                     # strict '<' in the reference == first minimum
                 base = np.zeros((nb, len(names)), dtype=np.uint64)
                 keep = [x]                                           # keep every payload tensor alive until the gather ran
                 for mid in sorted(set(int(v) for v in mids)):

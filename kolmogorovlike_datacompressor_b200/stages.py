@@ -184,6 +184,19 @@ class Context:
         """decode_new_pipeline per block (method 10).  The context must hold 8x the batch (the bit planes are one batch)."""
         return self._dec("kolm_v2new_dec", payload, pay_off, off, (), out)
 
+    def select_blocks(self, sizes: np.ndarray):
+        """_encode_block / the KOLR selection loops: sizes int64[nblocks, ncand] -> (winner index int64[nblocks], its size
+        int64[nblocks]); first minimum, i.e. the lowest id on ties (strict '<' in the reference).  Compared on the device."""
+        sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+        nb, nc = sizes.shape
+        mids = np.zeros(nb, dtype=np.int32)
+        best = np.zeros(nb, dtype=np.int64)
+        if nb:
+            _lib.check(_lib.lib().kolm_select_blocks(self._h, sizes.ctypes.data_as(C.POINTER(C.c_int64)), nb, nc,
+                                                     mids.ctypes.data_as(C.POINTER(C.c_int32)), best.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                     self._stream()), "kolm_select_blocks")
+        return mids.astype(np.int64), best
+
     def gather_payloads(self, src_addr: np.ndarray, lens: np.ndarray, out: torch.Tensor):
         """Winning payloads (device addresses + lengths per block) -> back to back in `out`; returns out_off."""
         nb = len(lens)
