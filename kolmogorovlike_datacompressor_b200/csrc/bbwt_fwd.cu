@@ -861,11 +861,32 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_lyn_cand(const u8* __restrict_
     const u32 t0 = td.start - bi.pbase;
     u64 key[KOLM_IPT];
     u64 mn = LYN_KEY_INF;
+    {
+        // my 16 positions and the 5 bytes after them: one 16-byte and one 8-byte load when the window lies inside the block and
+        // is aligned (byte loads at a 16-byte lane stride cost 4 L1 wavefronts each, 96 of them per thread), funnel shifts
+        // cut the 6-byte prefixes out of the registers; threads at the end of a block or on unaligned input build them bytewise
+        const u32 r0 = tid * KOLM_IPT;
+        const u8* p = src + t0 + r0;
+        if (KOLM_IPT == 16 && r0 + KOLM_IPT <= td.count && t0 + r0 + 24u <= bi.len && ((uintptr_t)p & 15) == 0) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p);
+            const uint2 b = *reinterpret_cast<const uint2*>(p + 16);
+            const u32 w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
 #pragma unroll
-    for (int i = 0; i < KOLM_IPT; ++i) {
-        u32 r = tid * KOLM_IPT + i;
-        key[i] = r < td.count ? lyn_key(src, t0 + r, bi.len) : LYN_KEY_INF;
-        mn = key[i] < mn ? key[i] : mn;
+            for (int i = 0; i < KOLM_IPT; ++i) {
+                const int q = i >> 2, sh = 8 * (i & 3);
+                const u32 x0 = __funnelshift_r(w[q], w[q + 1], sh), x1 = __funnelshift_r(w[q + 1], w[(q + 2) < 6 ? q + 2 : 5], sh);
+                const u64 k = ((u64)__byte_perm(x0, 0, 0x0123) << 16) | (u64)__byte_perm(x1, 0, 0x4401);
+                key[i] = (k << 3) | 7ull;                    // at least 9 bytes remain: length code 7
+                mn = key[i] < mn ? key[i] : mn;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KOLM_IPT; ++i) {
+                u32 r = r0 + i;
+                key[i] = r < td.count ? lyn_key(src, t0 + r, bi.len) : LYN_KEY_INF;
+                mn = key[i] < mn ? key[i] : mn;
+            }
+        }
     }
     struct OpMin { __device__ __forceinline__ u64 operator()(u64 a, u64 b) const { return a < b ? a : b; } };
     u64 tot;
@@ -1053,11 +1074,24 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_bbwt_emit(const u8* __restrict
     BlockInfo bi = binfo[td.block];
     const u8* src = in + bi.ioff;
     u32 nf = nfac[td.block];
-    for (u32 x = threadIdx.x; x < td.count; x += KOLM_THREADS) {
+    // four consecutive outputs per thread: one 16-byte load of the order, four independent byte gathers in flight, one word store
+    // (td.start is a multiple of 32 elements, so the order is 16-byte aligned; the output is word aligned when the block is)
+    u8* const dst = out + bi.ioff + (td.start - bi.pbase);
+    const u32 n4 = (((uintptr_t)dst & 3) == 0) ? (td.count & ~3u) : 0u;
+    for (u32 x = threadIdx.x * 4; x < n4; x += KOLM_THREADS * 4) {
+        const uint4 s4 = *reinterpret_cast<const uint4*>(sa + td.start + x);
+        const u32 lp[4] = {s4.x - bi.pbase, s4.y - bi.pbase, s4.z - bi.pbase, s4.w - bi.pbase};
+        u32 pp[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { u32 fs, fl; find_factor(fstart + bi.pbase, nf, bi.len, lp[k], fs, fl); pp[k] = (lp[k] == fs) ? fs + fl - 1 : lp[k] - 1; }
+        const u32 b0 = src[pp[0]], b1 = src[pp[1]], b2 = src[pp[2]], b3 = src[pp[3]];
+        *reinterpret_cast<u32*>(dst + x) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    for (u32 x = n4 + threadIdx.x; x < td.count; x += KOLM_THREADS) {
         u32 lp = sa[td.start + x] - bi.pbase, fs, fl;
         find_factor(fstart + bi.pbase, nf, bi.len, lp, fs, fl);
         u32 pp = (lp == fs) ? fs + fl - 1 : lp - 1;
-        out[bi.ioff + (td.start + x - bi.pbase)] = src[pp];
+        dst[x] = src[pp];
     }
 }
 

@@ -285,6 +285,21 @@ class Engine:
                 sizes[lo - i:hi - i] = np.diff(o)[lo - gi:hi - gi]
                 addr[lo - i:hi - i] = np.uint64(pt.data_ptr()) + o[lo - gi:hi - gi].astype(np.uint64)
             return sizes, addr
+
+        def release():
+            """After the container: a Re-Pair context sized for GiB groups and its slab pool (up to 100 GB) go back to the
+            device; small ones stay for the next call."""
+            for _, _, f in futs:
+                f.exception()                                          # wait; errors surface where the results are taken
+            if self.ctx3 is not None and self.cap3_bytes > (256 << 20):
+                def close():
+                    with torch.cuda.device(dev):
+                        side.synchronize()
+                        self.ctx3.close()
+                        self.ctx3 = None
+                        self.cap3_bytes = self.cap3_blocks = 0
+                self._worker3.submit(close).result()
+        take.release = release
         return take
 
     def _batches(self, bounds: Sequence[Tuple[int, int]], limit: Optional[int] = None):
@@ -500,6 +515,8 @@ class Engine:
                 areas.append(self._gather_home(c, base[np.arange(nb), mids], plen, keep=j < len(bounds)))
             mids_all.append(mids.astype(np.int64))
             lens_all.append(plen)
+        if rp_take is not None:
+            rp_take.release()
         if not areas:
             return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
         return np.concatenate(mids_all), np.concatenate(lens_all), self._cat(areas)
