@@ -121,3 +121,21 @@ def test_kolr_selection_with_repair_ahead_of_the_batches(monkeypatch):
         assert two[k][0] == (1 if mid2 == 9 else 0) and two[k][1] == payload2, k
         wins += mid2 == 9
     assert wins >= 4
+
+
+def test_kolr_container_where_repair_wins_on_long_blocks():
+    """The sine fixture at 32 KiB blocks: Re-Pair (method 9) is the reference's choice on such blocks.  Every block of the drop-in's
+    container carries the oracle's method and payload, and the container round-trips."""
+    from kolmogorovlike_datacompressor_b200 import kolm_final_researched_v2_2 as V
+    from kolmogorovlike_datacompressor_b200.engine import KOLR_NAMES
+    d = datasets.fixture("sine")[:4 * 32768 + 1000]
+    blob = V.compress_blocks_fixed(d, 32768)
+    names, starts, plens, orig_lens, total_len, _ = V._parse(blob)
+    assert total_len == len(d) and len(names) == 5
+    nine = 0
+    for k, (nm, st, pl, ol) in enumerate(zip(names, starts, plens, orig_lens)):
+        mid, payload, _ = O.encode_block(O.PROFILE_KOLR, d[k * 32768:k * 32768 + ol])
+        assert nm == KOLR_NAMES[mid] and blob[st:st + pl] == payload, k
+        nine += mid == 9
+    assert nine >= 3
+    assert V.decompress(blob) == d
