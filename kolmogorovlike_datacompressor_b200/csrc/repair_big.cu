@@ -105,7 +105,7 @@ struct RpbShared {
     u64 red_pair[RPB_THREADS / 32]; u32 red_cnt[RPB_THREADS / 32]; u32 red_idx[RPB_THREADS / 32];
     u32 n_occ_nodes, n_occ, n_tk, n_touched, n_p, mpos, mlen, n_alloc;
     u32 pbest; int pbest_ok;                             // index of the best pending entry (valid when pbest_ok)
-    u64 cur_pair; u32 cur_cnt, cur_slot; int stop;
+    u64 cur_pair; u32 cur_cnt, cur_slot, cur_base; int stop;
     u32 total;
 };
 
@@ -260,12 +260,15 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             if (tid == 0) {
                 const u32 mp = sh.mpos;
                 u32 c = 0, s = 0; u64 p = RPB_EMPTY; int from_p = 0;
-                if (mp < sh.mlen) { c = S.mcnt[mp]; p = S.mpair[mp]; s = S.mslot[mp]; }
-                if (sh.n_p && sh.pbest != RPB_NIL) {
-                    const u32 i = sh.pbest;
-                    if (rpb_better(S.pcnt[i], S.ppair[i], c, p)) { c = S.pcnt[i]; p = S.ppair[i]; s = S.pslot[i]; from_p = 1; }
-                }
-                sh.cur_cnt = c; sh.cur_pair = p; sh.cur_slot = s;
+                const bool hasm = mp < sh.mlen, hasp = sh.n_p && sh.pbest != RPB_NIL;
+                if (hasm) { c = S.mcnt[mp]; p = S.mpair[mp]; s = S.mslot[mp]; }
+                u32 pc = 0, ps = 0; u64 pp = RPB_EMPTY;
+                if (hasp) { const u32 i = sh.pbest; pc = S.pcnt[i]; pp = S.ppair[i]; ps = S.pslot[i]; }
+                // both candidates' occurrence-array bases are fetched now (two loads in flight) so the round does not start with one
+                const u32 hbm = hasm ? S.hhead[s] : RPB_NIL, hbp = hasp ? S.hhead[ps] : RPB_NIL;
+                u32 hb = hbm;
+                if (hasp && rpb_better(pc, pp, c, p)) { c = pc; p = pp; s = ps; hb = hbp; from_p = 1; }
+                sh.cur_cnt = c; sh.cur_pair = p; sh.cur_slot = s; sh.cur_base = hb;
                 if (c < 2) sh.stop = 1;
                 else if (from_p) { S.pcnt[sh.pbest] = 0; sh.pbest_ok = 0; }   // consumed
                 else sh.mpos = mp + 1;
@@ -277,9 +280,12 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             const u32 newsym = 256 + nrules;
             const u32 st_seen = round * 4 + 1, st_take = round * 4 + 2, st_part = round * 4 + 3;
             const u32 p0 = sh.n_p;                               // pending entries before this round's (appended after the next barriers)
-            auto touch = [&](u32 s) { if (atomicExch(&S.hstamp[s], round) != round) { const u32 o = atomicAdd(&sh.n_touched, 1u); if (o < S.tcap) S.touched[o] = s; } };
-            const u32 obase = S.hhead[cslot];
+            // touched pairs are only listed here (a pair can be listed up to four times per replaced occurrence: 4 * ntk <= 2n
+            // entries); the pass over the list below claims each pair once — no atomic with a return value inside this chain
+            auto touch = [&](u32 s) { const u32 o = atomicAdd(&sh.n_touched, 1u); if (o < S.tcap) S.touched[o] = s; };
+            const u32 obase = sh.cur_base;
             const u32 nh = obase == RPB_NIL ? 0u : S.opos[obase];
+            const u32 pspec = (obase != RPB_NIL && tid < 2) ? S.opos[obase + 1u + tid] : 0u;   // every array holds >= 2 hints: no need to wait for nh
             const bool fast = (RPB_V & 16) && A != B && nh <= RPB_THREADS;
             u32 ntk;
             u32 f_p = RPB_NIL, f_xpos = RPB_NIL, f_sl = RPB_NIL, f_sr = RPB_NIL;      // fast rounds: my occurrence lives in registers
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
                 //      neighbours and their symbols are read once, under the OLD links, and kept in registers
                 u32 q = RPB_NIL, x = RPB_NIL, y = RPB_NIL, sx = 0, sy = 0; bool valid = false;
                 if (tid < nh) {
-                    const u32 p = S.opos[obase + 1u + tid];
+                    const u32 p = tid < 2 ? pspec : S.opos[obase + 1u + tid];
                     const bool fresh = atomicExch(&S.stamp[p], st_seen) != st_seen;   // the same position can be hinted twice
                     const u32 sp = S.sym[p]; q = S.nxt[p]; x = S.prv[p];
                     if (sp == A && q != RPB_NIL) {
@@ -387,9 +393,10 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
             // ---- touched pairs whose count is still >= 2 become pending
             const u32 ntouch = min(sh.n_touched, S.tcap);
             for (u32 i = tid; i < ntouch; i += RPB_THREADS) {
-                const u32 s = S.touched[i], c = S.hcnt[s];
-                if (c >= 2) {
-                    const u64 key = S.hkey[s];
+                const u32 s = S.touched[i];
+                const u32 seen = atomicExch(&S.hstamp[s], round);       // claim: a pair listed several times is handled once
+                const u32 c = S.hcnt[s]; const u64 key = S.hkey[s];
+                if (seen != round && c >= 2) {
                     const u32 o = atomicAdd(&sh.n_p, 1u); if (o < S.pcap) { S.ppair[o] = key; S.pcnt[o] = c; S.pslot[o] = s; }
                     if ((u32)(key >> 32) == newsym || (u32)key == newsym) {       // a pair born this round: all its occurrences exist now
                         const u32 base = atomicAdd(&sh.n_occ_nodes, c + 1u);
