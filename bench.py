@@ -335,11 +335,12 @@ def run_ours(args):
 
 def ncu_traffic(category, args):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, from the committed
-    `ncu --set full` capture of this same command (profiles/r1c_traffic.json, written by tools/make_profile_summary.py).
+    `ncu --set full` capture of this same command (profiles/r1d_traffic.json, else r1c; written by tools/make_profile_summary.py).
     ncu captured only the largest launches of the category, so the figure is their mean; it is not measured by this run."""
     kname = {"rerank": "k_rerank", "radix_scatter": "k_radix_scatter", "gather": "k_gather"}.get(category)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1c_traffic.json")
-    if kname is None or not os.path.isfile(path) or args.mib != 256 or args.block_kib != 1024:
+    pdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    path = next((os.path.join(pdir, t + "_traffic.json") for t in ("r1d", "r1c") if os.path.isfile(os.path.join(pdir, t + "_traffic.json"))), "")
+    if kname is None or not path or args.mib != 256 or args.block_kib != 1024:
         return None, "no ncu capture for this kernel/workload"
     doc = json.load(open(path))
     rows = [(k, r) for k, v in doc["kernels"].items() if k.startswith(kname) for r in v]
@@ -353,7 +354,7 @@ def ncu_traffic(category, args):
     per_rec = {"k_rerank": lambda k: 16 if k.startswith("k_rerank<1") else 20, "k_radix_scatter": lambda k: 16, "k_gather": lambda k: 4}[kname]
     alg = sum(r["grid"] * 4096 * per_rec(k) for k, r in rows) / len(rows)
     return int(mean), "mean of the %d full-size launches in %s (%s): DRAM %.2f GB vs %.2f GB algorithmic for those launches (ratio %.2f)" % (
-        len(rows), "profiles/r1c_traffic.json", doc["source"], mean / 1e9, alg / 1e9, mean / alg)
+        len(rows), "profiles/" + os.path.basename(path), doc["source"], mean / 1e9, alg / 1e9, mean / alg)
 
 
 def main():
