@@ -212,38 +212,32 @@ __global__ void __launch_bounds__(RPB_THREADS) k_repair_big(const u8* __restrict
         // ---- rounds
         for (;;) {
             ++round;
-            // pending list: (re)find its best valid entry when the cached one is gone.  The same pass drops the entries whose count
-            // moved on (a pair touched k times has k entries, only the last is valid) and the consumed ones: the list shrinks to its
-            // valid entries — through the merge target T and back — so the next rescans and the next merge come cheaper
+            // pending list: (re)find its best valid entry when the cached one is gone
             if (sh.n_p && !sh.pbest_ok) {
-                u32 bc = 0; u64 bp = RPB_EMPTY;
+                u32 bc = 0, bidx = RPB_NIL; u64 bp = RPB_EMPTY;
                 const u32 npend = sh.n_p;
-                if (tid == 0) sh.n_tk = 0;                       // free here: the round's lists are reset when the pair is chosen
-                __syncthreads();
+                if (RPB_V & 4) {
 #pragma unroll 4
-                for (u32 i = tid; i < npend; i += RPB_THREADS) {
-                    const u32 c = S.pcnt[i], sl = S.pslot[i]; const u64 p = S.ppair[i];
-                    const u32 hc = S.hcnt[sl];
-                    if (c >= 2 && hc == c) {
-                        const u32 o = atomicAdd(&sh.n_tk, 1u);
-                        S.tpair[o] = p; S.tcnt[o] = c; S.tslot[o] = sl;
-                        if (rpb_better(c, p, bc, bp)) { bc = c; bp = p; }
+                    for (u32 i = tid; i < npend; i += RPB_THREADS) {
+                        const u32 c = S.pcnt[i], sl = S.pslot[i]; const u64 p = S.ppair[i];
+                        const u32 hc = S.hcnt[sl];
+                        if (c >= 2 && hc == c && rpb_better(c, p, bc, bp)) { bc = c; bp = p; bidx = i; }
+                    }
+                } else {
+                    for (u32 i = tid; i < npend; i += RPB_THREADS) {
+                        const u32 c = S.pcnt[i];
+                        if (c >= 2 && S.hcnt[S.pslot[i]] == c && rpb_better(c, S.ppair[i], bc, bp)) { bc = c; bp = S.ppair[i]; bidx = i; }
                     }
                 }
                 for (int o = 16; o > 0; o >>= 1) {
-                    const u32 oc = __shfl_xor_sync(0xffffffffu, bc, o); const u64 op = __shfl_xor_sync(0xffffffffu, bp, o);
-                    if (rpb_better(oc, op, bc, bp)) { bc = oc; bp = op; }
+                    const u32 oc = __shfl_xor_sync(0xffffffffu, bc, o), oi = __shfl_xor_sync(0xffffffffu, bidx, o); const u64 op = __shfl_xor_sync(0xffffffffu, bp, o);
+                    if (rpb_better(oc, op, bc, bp)) { bc = oc; bp = op; bidx = oi; }
                 }
-                if ((tid & 31) == 0) { sh.red_cnt[tid >> 5] = bc; sh.red_pair[tid >> 5] = bp; }
+                if ((tid & 31) == 0) { sh.red_cnt[tid >> 5] = bc; sh.red_pair[tid >> 5] = bp; sh.red_idx[tid >> 5] = bidx; }
                 __syncthreads();
-                for (int i = 0; i < RPB_THREADS / 32; ++i) if (rpb_better(sh.red_cnt[i], sh.red_pair[i], bc, bp)) { bc = sh.red_cnt[i]; bp = sh.red_pair[i]; }
-                const u32 nv = sh.n_tk;
-                if (tid == 0) { sh.pbest = RPB_NIL; sh.pbest_ok = 1; sh.n_p = nv; }   // RPB_NIL: nothing valid is pending
-                __syncthreads();
-                for (u32 i = tid; i < nv; i += RPB_THREADS) {
-                    const u64 p = S.tpair[i]; const u32 c = S.tcnt[i];
-                    S.ppair[i] = p; S.pcnt[i] = c; S.pslot[i] = S.tslot[i];
-                    if (p == bp && c == bc) sh.pbest = i;        // a pair has one valid entry
+                if (tid == 0) {
+                    for (int i = 1; i < RPB_THREADS / 32; ++i) if (rpb_better(sh.red_cnt[i], sh.red_pair[i], bc, bp)) { bc = sh.red_cnt[i]; bp = sh.red_pair[i]; bidx = sh.red_idx[i]; }
+                    sh.pbest = bidx; sh.pbest_ok = 1;         // RPB_NIL: nothing valid is pending
                 }
                 __syncthreads();
             }
