@@ -112,7 +112,9 @@ int kolm_residual_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_
                       uint8_t* out, kolm_stream_t stream);
 
 /* Re-Pair grammar candidate: repair_compress / repair_decompress (V22.py:1841-1911, 1916-1978).
- * Blocks longer than kolm_repair_max_block() bytes return KOLM_E_UNSUPPORTED (one CTA keeps the sequence in shared memory). */
+ * Blocks of up to kolm_repair_max_block() bytes are coded by one CTA with the sequence in shared memory; longer blocks take the
+ * exact incremental kernel (one CTA per block in a slab of global memory, ~150 bytes per input byte, allocated on first use and
+ * kept by the context; KOLM_E_CAPACITY when not even one slab fits in free memory). */
 int kolm_repair_enc(kolm_ctx* ctx, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
                     kolm_stream_t stream);
 int kolm_repair_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* out,

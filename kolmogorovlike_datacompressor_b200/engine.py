@@ -268,7 +268,14 @@ class Engine:
                 a, b = bounds[i][0], bounds[j - 1][1]
                 off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
                 x = self._upload(data, a, b)
-                p, o = self.ctx3.repair_encode(x, off)                 # returns after its stream finished
+                try:
+                    p, o = self.ctx3.repair_encode(x, off)             # returns after its stream finished
+                except _lib.KolmError as e:
+                    if e.code == -3:                                   # KOLM_E_CAPACITY: not one slab of the incremental kernel fits
+                        raise RuntimeError("Re-Pair candidate: a block of %d bytes needs more device memory than is free; set "
+                                           "KOLM_REPAIR_MAX_BLOCK (Engine.repair_max) to skip the candidate on such blocks — the "
+                                           "container can then differ from the reference's where Re-Pair would win" % int(np.diff(off).max())) from e
+                    raise
                 p = p[:max(int(o[-1]), 4)].clone()                      # the capacity is 4x the input: keep what was used
                 side.synchronize()
                 return p, np.asarray(o, dtype=np.int64)
