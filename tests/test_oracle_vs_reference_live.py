@@ -86,3 +86,56 @@ def test_kolr_models_and_selection(d):
     if d:
         got = O.encode_block(O.PROFILE_KOLR, d)
         assert (got[0], got[1]) == (best_id, best)
+
+
+# ---- container / TOC host code of the drop-ins, no GPU involved ---------------------------------------------
+@st.composite
+def corpora(draw):
+    parts = draw(st.lists(blocks(), min_size=1, max_size=12))
+    return b"".join(parts)
+
+
+@seed(20251021)
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(corpora(), st.sampled_from([64, 100, 256, 512]))
+def test_kolr_toc_assembly_and_parse_match_the_reference(d, bs):
+    """The reference's container is taken apart by OUR _parse and put together again by OUR _assemble (RLE + canonical Huffman with
+    the reference's heapq ties, Rice, Elias-Fano — V22.py:2256-2445): the bytes must come back, in FIXED and in CDC mode."""
+    import numpy as np
+    from kolmogorovlike_datacompressor_b200 import kolm_final_researched_v2_2 as OURS
+    V = R.load_v22()
+    for mode in ("fixed", "cdc"):
+        if mode == "fixed":
+            ref = V.compress_blocks_fixed(d, bs)
+            bounds, size_field, m = OURS.fixed_boundaries(d, bs), bs, OURS.MODE_FIXED
+            assert bounds == V.fixed_boundaries(d, bs)
+        else:
+            mn, avg, mx = max(1, bs // 2), max(64, bs), max(64, bs) * 2
+            ref = V.compress_blocks_cdc(d, mn, avg, mx)
+            bounds, size_field, m = OURS.cdc_fast_boundaries_strict(d, mn, avg, mx), avg, OURS.MODE_CDC
+            assert [tuple(b) for b in bounds] == [tuple(b) for b in V.cdc_fast_boundaries_strict(d, mn, avg, mx)]
+        names, starts, plens, orig_lens, total_len, pos = OURS._parse(ref)
+        assert total_len == len(d) and pos == len(ref) and list(orig_lens) == [b - a for a, b in bounds]
+        mids = [OURS.KOLR_NAMES.index(nm) for nm in names]
+        area = b"".join(ref[s:s + l] for s, l in zip(starts, plens))
+        again = OURS._assemble(d, bounds, m, size_field, encoded=(mids, list(plens), np.frombuffer(area, dtype=np.uint8)))
+        assert again == ref, mode
+
+
+@seed(20251022)
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(corpora(), st.sampled_from([64, 128, 512]))
+def test_kolm_container_and_parse_match_the_reference(d, tb):
+    import numpy as np
+    from kolmogorovlike_datacompressor_b200 import kolm_final as OURS
+    KF = R.load_kf()
+    ref = KF.compress(d, tb)
+    cuts = OURS.cdc_fast_boundaries(d, min_size=tb // 2, avg_size=tb, max_size=tb * 2)
+    assert [tuple(c) for c in cuts] == [tuple(c) for c in KF.cdc_fast_boundaries(d, tb // 2, tb, tb * 2)]
+    if not cuts:
+        return
+    names, starts, plens, olens, total = OURS._parse(ref)
+    assert total == len(d) and list(olens) == [b - a for a, b in cuts]
+    mids = [list(OURS._NAMES).index(nm) if not isinstance(OURS._NAMES, dict) else {v: k for k, v in OURS._NAMES.items()}[nm] for nm in names]
+    area = b"".join(ref[s:s + l] for s, l in zip(starts, plens))
+    assert OURS._container(ref[:18], cuts, mids, list(plens), np.frombuffer(area, dtype=np.uint8)) == ref
