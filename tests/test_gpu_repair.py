@@ -139,3 +139,17 @@ def test_kolr_container_where_repair_wins_on_long_blocks():
         nine += mid == 9
     assert nine >= 3
     assert V.decompress(blob) == d
+
+
+def test_repair_one_mib_blocks_equal_the_incremental_oracle():
+    """BASELINE's block size: the payloads of six 1 MiB blocks of the S3 mix (text, gradient, sine, patterns, checker, random) equal
+    the oracle's incremental Re-Pair byte for byte (tests/test_oracle_repair_fast.py ties that one to the literal restatement)."""
+    import gpu_util as G
+    from kolmogorovlike_datacompressor_b200 import synth
+    mix = synth.s3_mix(8 << 20)
+    blocks = [mix[t << 20:(t + 1) << 20].tobytes() for t in (0, 2, 3, 4, 5, 7)]
+    t, off = G.batch(blocks)
+    out, oo = G.ctx().repair_encode(t, off)
+    got = out.cpu().numpy().tobytes()
+    for i, b in enumerate(blocks):
+        assert got[oo[i]:oo[i + 1]] == O.repair_compress_fast(b), i
