@@ -12,7 +12,7 @@
 //   argmax          = 64-bit atomicMax of (count << 32 | ~pair)   -> max count, smallest pair
 //   replacement     = inside a maximal run of overlapping matches (only when a == b) every other one
 //                     from the run start is taken; then a block-wide compaction.
-// Larger blocks return KOLM_E_UNSUPPORTED (the reference's own algorithm is O(rounds * n) there).
+// Larger blocks are passed over here and taken by the incremental kernel of repair_big.cu (same output, global-memory slabs).
 #include "common.cuh"
 
 #define REPAIR_MAX 8192
