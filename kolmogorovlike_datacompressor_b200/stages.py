@@ -170,7 +170,8 @@ class Context:
         return self._dec("kolm_residual_dec", payload, pay_off, off, (C.c_int(kind),), out)
 
     def repair_encode(self, x, off, out=None):
-        """repair_compress per block (blocks <= kolm_repair_max_block() bytes)."""
+        """repair_compress per block (V22.py:1841-1911): blocks <= kolm_repair_max_block() bytes in shared memory, longer ones through
+        the incremental kernel (exact at any length)."""
         return self._enc("kolm_repair_enc", x, off, (), 4, out)
 
     def repair_decode(self, payload, pay_off, off, out=None):
