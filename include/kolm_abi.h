@@ -18,6 +18,11 @@
  *     in the hot path; all scratch lives in the context.
  *   - a context is bound to one device and must not be used from two threads at once;
  *     distinct contexts are independent.
+ *   - encoders with an `out_cap`: the exact total payload size is known on the device before any byte is
+ *     emitted; when it exceeds out_cap (the Rice packers, which store whole words, want 8 bytes of slack) the
+ *     emit kernels write NOTHING and the call returns KOLM_E_CAPACITY with out_off filled in, so the caller can
+ *     retry with out_off[nblocks] (+ 8) bytes.  Worst cases: residual / LZ77 2n, KF model 2 ~2.2n, V22 Rice 8.25n + 8
+ *     per block, Re-Pair 5n + 16 per block (ULEB128 symbols of blocks >= 512 MiB need five bytes).
  */
 #ifndef KOLM_ABI_H
 #define KOLM_ABI_H

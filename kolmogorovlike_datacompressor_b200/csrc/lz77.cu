@@ -178,7 +178,8 @@ __global__ void k_lz_mark(LzArgs a, u32 total_chunks, const u32* __restrict__ ch
 
 // sizes per block (pass 0) or byte scatter (pass 1)
 template <bool EMIT>
-__global__ void __launch_bounds__(KOLM_THREADS) k_lz_emit(LzArgs a, u64* lb, u64* __restrict__ bacc, u8* __restrict__ out) {
+__global__ void __launch_bounds__(KOLM_THREADS) k_lz_emit(LzArgs a, u64* lb, u64* __restrict__ bacc, u8* __restrict__ out, const i64* __restrict__ cap_total, u64 cap) {
+    if (EMIT && (u64)*cap_total > cap) return;              // exact total known before any byte is emitted: never write past the caller's buffer
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x;
@@ -271,7 +272,14 @@ __global__ void k_lz_dec(const u8* __restrict__ pay, const i64* __restrict__ pay
             }
             if (e) break;
             u64 len = v[0], dist = v[1];
-            if (dist == 0) { e = KOLM_E_CORRUPT; break; }
+            if (dist == 0) {
+                // V22 rejects distance 0 (V22.py:1794-1795); KF has no such check: `out[-0]` is out[0], so the token repeats the
+                // first output byte, and raises IndexError only while the output is still empty (KF.py:745-752)
+                if (window_check) { e = KOLM_E_CORRUPT; break; }
+                if (len && o == 0 && bi.len) { e = KOLM_E_INDEX; break; }
+                for (u64 t = 0; t < len && o < bi.len; ++t) dst[o++] = dst[0];
+                continue;
+            }
             for (u64 t = 0; t < len && o < bi.len; ++t) {
                 u32 avail = window_check ? min(o, window_check) : o;
                 if (dist > avail) { e = KOLM_E_CORRUPT; break; }
@@ -314,10 +322,19 @@ __global__ void __launch_bounds__(128) k_lz_dec_warp(const u8* __restrict__ pay,
             }
             if (e) break;
             u64 len = v[0], dist = v[1];
-            if (dist == 0) { e = KOLM_E_CORRUPT; break; }
             u32 avail = window_check ? min(o, window_check) : o;
             u64 room = (u64)(bi.len - o);
             u32 cnt = (u32)(len < room ? len : room);
+            if (dist == 0) {                                                // see k_lz_dec: V22 rejects, KF repeats out[0] (IndexError on empty output)
+                if (window_check) { e = KOLM_E_CORRUPT; break; }
+                if (cnt && o == 0) { e = KOLM_E_INDEX; break; }
+                __syncwarp();
+                const u8 first = dst[0];
+                for (u32 k = lane; k < cnt; k += 32) dst[o + k] = first;
+                o += cnt;
+                __syncwarp();
+                continue;
+            }
             if (cnt && dist > avail) { e = KOLM_E_CORRUPT; break; }       // reference: "distance beyond window" / "Invalid LZ77 distance"
             __syncwarp();                                                  // earlier literal / match stores are visible to all lanes
             const u32 dd = (u32)dist;
@@ -364,11 +381,11 @@ int kolm_lz77_enc_impl(kolm_ctx* c, const u8* in, u32 window, u32 maxlen, u8* ou
         KL(c, KC_MISC, N * 16, s, k_lz_chunks<<<(total_chunks + 127) / 128, 128, 0, s>>>(a, nb, total_chunks, d_cblock, d_cfirst));
         KL(c, KC_MISC, N, s, k_lz_parse<<<nb, 256, 0, s>>>(a, d_cfirst));
         KL(c, KC_MISC, N * 9, s, k_lz_mark<<<(total_chunks + 127) / 128, 128, 0, s>>>(a, total_chunks, d_cblock, d_cfirst));
-        KL(c, KC_MISC, N, s, k_lz_emit<false><<<nt, KOLM_THREADS, 0, s>>>(a, c->d_lb, c->d_bacc, out));
+        KL(c, KC_MISC, N, s, k_lz_emit<false><<<nt, KOLM_THREADS, 0, s>>>(a, c->d_lb, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));
         KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
         int lgrid = nt;
         KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
-        KL(c, KC_MISC, N * 10, s, k_lz_emit<true><<<lgrid, KOLM_THREADS, 0, s>>>(a, c->d_lb, c->d_bacc, out));
+        KL(c, KC_MISC, N * 10, s, k_lz_emit<true><<<lgrid, KOLM_THREADS, 0, s>>>(a, c->d_lb, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));
     } else {
         KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     }

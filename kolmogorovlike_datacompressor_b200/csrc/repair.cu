@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __re
     if (tid == 0) { bacc[(size_t)b * 64 + 32] = (u64)s_hdr + stot; err[b] = KOLM_OK; }
 }
 
-__global__ void k_repair_gather(const u8* __restrict__ tmp, const BlockInfo* __restrict__ binfo, const u64* __restrict__ bacc, u8* __restrict__ out) {
+__global__ void k_repair_gather(const u8* __restrict__ tmp, const BlockInfo* __restrict__ binfo, const u64* __restrict__ bacc, u8* __restrict__ out,
+                                const i64* __restrict__ cap_total, u64 cap) {
+    if ((u64)*cap_total > cap) return;                      // exact total known before any byte is emitted: never write past the caller's buffer
     const u32 b = blockIdx.x;
     const u8* src = tmp + (size_t)binfo[b].pbase * 4;
     u8* dst = out + bacc[(size_t)b * 64 + 33];
@@ -369,7 +371,7 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
     if (c->max_len > REPAIR_MAX) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
-    KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out));
+    KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(c->h_poff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));

@@ -488,9 +488,10 @@ __global__ void k_zero_words(u32* __restrict__ out, const i64* __restrict__ tota
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                                const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
-                                                               u32* __restrict__ out) {
+                                                               u32* __restrict__ out, const i64* __restrict__ cap_total, u64 cap) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_last[KOLM_THREADS / 32];
+    if ((u64)*cap_total + 8 > cap) return;                  // exact total known before any bit is packed (words are written whole: 8 bytes of slack)
     const u32 tid = threadIdx.x;
     const u32 tile = blockIdx.x;                            // no ticket, no look-back: entry state and bit offset were recorded per tile
     const u64* trec = tacc + (size_t)tile * 32;
@@ -593,8 +594,9 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_kf_pack(const u8* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rice_k2_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                                const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
-                                                               u32* __restrict__ out, int flags) {
+                                                               u32* __restrict__ out, int flags, const i64* __restrict__ cap_total, u64 cap) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
+    if ((u64)*cap_total + 8 > cap) return;                  // exact total known before any bit is packed (words are written whole: 8 bytes of slack)
     const u32 tid = threadIdx.x;
     const u32 tile = blockIdx.x;                            // bit offset of the tile from k_rice_tile_offsets: no look-back
     const TileDesc td = tiles[tile];
@@ -657,7 +659,7 @@ static int rice_finish(kolm_ctx* c, i64* out_off, int* params, i64* sizes, size_
     memcpy(out_off, c->h_poff, (size_t)(nb + 1) * 8);
     if (params) memcpy(params, c->h_params, (size_t)nb * 16);
     if (sizes) memcpy(sizes, c->h_sizes, (size_t)nb * 40);
-    if ((size_t)out_off[nb] > out_cap) return KOLM_E_CAPACITY;
+    if ((size_t)out_off[nb] + 8 > out_cap) return KOLM_E_CAPACITY;   // the pack kernels did not run (device-side guard)
     c->algbytes[KC_RICE_PACK] += out_off[nb];                 // payload bytes written
     return KOLM_OK;
 }
@@ -676,7 +678,7 @@ int kolm_rice_kf_enc_impl(kolm_ctx* c, const u8* mtf, u8* out, size_t out_cap, i
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
         KL(c, KC_RICE_PLAN, (i64)nt * 64, s, k_rice_tile_offsets<<<nb, 256, 0, s>>>((u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 1, 0));
-        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out));
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_kf_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, c->d_poff + nb, (u64)out_cap));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, params, nullptr, out_cap, s);
@@ -698,7 +700,7 @@ int kolm_rice_k2_enc_impl(kolm_ctx* c, const u8* mtf, int flags, u8* out, size_t
     KL(c, KC_ZERO, 0, s, k_zero_words<<<4 * c->sm_count, 256, 0, s>>>((u32*)out, c->d_poff + nb, out_cap / 4));
     if (nt) {
         KL(c, KC_RICE_PLAN, (i64)nt * 64, s, k_rice_tile_offsets<<<nb, 256, 0, s>>>((u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, 2, slot));
-        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, flags));
+        KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice_k2_pack<<<nt, KOLM_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, flags, c->d_poff + nb, (u64)out_cap));
     }
     CUDA_TRY(cudaGetLastError());
     return rice_finish(c, out_off, nullptr, sizes, out_cap, s);

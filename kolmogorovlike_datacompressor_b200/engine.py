@@ -57,6 +57,20 @@ def _par_copy(dst: np.ndarray, src: np.ndarray) -> None:
         f.result()
 
 
+def _ro_tensor(arr: np.ndarray) -> torch.Tensor:
+    """CPU uint8 tensor sharing the memory of a read-only numpy view (the caller only reads it).  torch.from_numpy warns on
+    read-only arrays; the array interface of a ctypes view of the same address does not, and no filter state is touched."""
+    import ctypes
+    n = int(arr.shape[0])
+    if n == 0:
+        return torch.empty(0, dtype=torch.uint8)
+    addr = arr.__array_interface__["data"][0]
+    view = np.ctypeslib.as_array((ctypes.c_ubyte * n).from_address(addr))
+    t = torch.from_numpy(view)
+    t._kolm_keepalive = arr                                     # the bytes object must outlive the tensor
+    return t
+
+
 def _new_bytes(n: int):
     """(bytes object of n bytes, writable uint8 view of its storage).  The object is filled in place before anyone else can see
     it (CPython: a fresh `bytes(n)` is not shared, interned or hashed), which saves one full copy of every decompressed output."""
@@ -324,11 +338,10 @@ class Engine:
     def _upload(self, data, a: int, b: int) -> torch.Tensor:
         t = torch.empty(max(4, b - a + 4), dtype=torch.uint8, device=torch.device("cuda", self.device))
         if b > a:
-            import warnings as _w
-            with _w.catch_warnings():
-                _w.simplefilter("ignore")                   # read-only buffer: we only read it
-                src = torch.frombuffer(data, dtype=torch.uint8, count=b - a, offset=a)
-            t[:b - a].copy_(src)
+            # numpy view of the (read-only) bytes -> torch: no warning to filter (warnings.catch_warnings is not thread-safe and
+            # _upload runs on the main thread and on the side-stream workers at once)
+            arr = np.frombuffer(data, dtype=np.uint8, count=b - a, offset=a)
+            t[:b - a].copy_(_ro_tensor(arr))
         return t
 
     @staticmethod
@@ -592,8 +605,15 @@ class Engine:
         if nb == 0:
             return b""
         ends = np.cumsum(ols)
-        result, sink = (b"", None) if on_batch is not None else _new_bytes(int(ends[-1]))
-        if sink is None and on_batch is None:                        # 0 or 1 byte: CPython shares these objects, build them the ordinary way
+        # untrusted header: every coder here expands a payload byte into a bounded number of output bytes except the run /
+        # match / grammar coders, so only sanity-bound the allocation (the reference builds its output incrementally and
+        # fails on the first bad block instead of a MemoryError)
+        # lengths are allocated up front only when plausible; an implausible header (the lengths are untrusted) is decoded batch by
+        # batch into a growing buffer, so a bad block fails with the reference's exception instead of a MemoryError
+        lazy = on_batch is None and int(ends[-1]) > max(1 << 30, 4096 * len(blob))
+        grow = bytearray() if lazy else None
+        result, sink = (b"", None) if (on_batch is not None or lazy) else _new_bytes(int(ends[-1]))
+        if sink is None and on_batch is None and not lazy:           # 0 or 1 byte: CPython shares these objects, build them the ordinary way
             sink = np.zeros(int(ends[-1]), dtype=np.uint8)
         i = 0
         while i < nb:                                                # output batches of <= batch_bytes
@@ -627,7 +647,8 @@ class Engine:
                     self._ensure(max(int(off[-1]), ptot, 1), len(sub))
                     c = self.ctx
                     if nme == "raw":
-                        assert bool((spl == sol).all()), "Payload length mismatch for RAW"
+                        if not bool((spl == sol).all()):             # untrusted container: never an `assert` (gone under python -O)
+                            raise AssertionError("Payload length mismatch for RAW")
                         c.copy_blocks(src_pay, dst, sol)
                         torch.cuda.current_stream().synchronize()
                         continue
@@ -662,11 +683,15 @@ class Engine:
                 if tot and on_batch is not None:
                     on_batch(base_off, dev_out, tot)
                     torch.cuda.current_stream().synchronize()
+                elif tot and lazy:
+                    grow += self._home(dev_out, tot).tobytes()
                 elif tot:
                     _par_copy(sink[base_off:base_off + tot], self._home(dev_out, tot))
             i = j
         if on_batch is not None:
             return b""
+        if lazy:
+            return bytes(grow)
         return result if len(result) >= 2 else sink.tobytes()
 
     def decode_blocks(self, blocks: Sequence[Tuple[str, bytes, int]]) -> List[bytes]:

@@ -172,7 +172,7 @@ class Context:
     def repair_encode(self, x, off, out=None):
         """repair_compress per block (V22.py:1841-1911): blocks <= kolm_repair_max_block() bytes in shared memory, longer ones through
         the incremental kernel (exact at any length)."""
-        return self._enc("kolm_repair_enc", x, off, (), 4, out)
+        return self._enc("kolm_repair_enc", x, off, (), 4 if int(np.asarray(off)[-1]) < (1 << 28) else 5, out)
 
     def repair_decode(self, payload, pay_off, off, out=None):
         return self._dec("kolm_repair_dec", payload, pay_off, off, (), out)

@@ -60,6 +60,12 @@ XOR_IN = bytes([5, 3, 131])
 KF_XOR = bytes([5, 5 ^ 3]) + bytes([((3 ^ 131) & 0x7F) | 0x80, 1])          # 3^131 = 128 -> 80 01
 V22_DELTA = bytes([5]) + bytes([((3 - 5) & 0x7F) | 0x80, 1]) + bytes([128 & 0x7F | 0x80, 1])   # 254 -> FE 01; 131-3 = 128 -> 80 01
 
+# LZ77 distance 0 (not in Appendix B; found by the round-1 review): KF's decoder has no check, `out[-0]` is out[0] (KF.py:745-752), so
+# literal 'a', literal 'b', match(len 3, dist 0) decodes to 'ab' + 'aaa'; with nothing decoded yet out[0] raises IndexError.
+# V22's decoder raises ValueError("distance 0") (V22.py:1794-1795).
+LZ_DIST0 = (bytes([0, 97, 0, 98, 1, 3, 0]), 5, b"abaaa")
+LZ_DIST0_EMPTY = (bytes([1, 3, 0]), 3)
+
 EMPTY_KOLM = bytes.fromhex("4b4f4c4d" "00200000" "0000000000000000" "0000")                 # quirk 10
 EMPTY_KOLR = bytes.fromhex("4b4f4c520008000000000000000004000000000000")
 ONE_KOLM = bytes.fromhex("4b4f4c4d002000000100000000000000010000010000000100000041")
@@ -137,6 +143,17 @@ def test_oracle_selection_ties_quirk_8():
     assert mid == 0 and sizes[0] == sizes[1] == 1
 
 
+def test_oracle_lz77_distance_zero():
+    pay, n, want = LZ_DIST0
+    assert O.lz77_decode(pay, n, 0) == want
+    with pytest.raises(O.OracleError) as e:
+        O.lz77_decode(LZ_DIST0_EMPTY[0], LZ_DIST0_EMPTY[1], 0)
+    assert e.value.code == -5                                      # IndexError in the reference
+    with pytest.raises(O.OracleError) as e:
+        O.lz77_decode(pay, n, 4096)
+    assert e.value.code == -2                                      # ValueError in the reference
+
+
 def test_oracle_empty_and_one_byte_kolm_quirk_10():
     assert O.kf_compress(b"") == EMPTY_KOLM
     assert O.kf_compress(b"A") == ONE_KOLM
@@ -164,6 +181,11 @@ def test_reference_agrees_with_the_hand_derived_vectors():
         assert V.repair_compress(d)[0] == want
     assert KF.compress(b"") == EMPTY_KOLM and KF.compress(b"A") == ONE_KOLM
     assert V.compress_blocks_fixed(b"", 2048) == EMPTY_KOLR and V.compress_blocks_fixed(b"A", 2048) == ONE_KOLR
+    assert KF.decode_model_lz77(LZ_DIST0[0], LZ_DIST0[1]) == LZ_DIST0[2]
+    with pytest.raises(IndexError):
+        KF.decode_model_lz77(*LZ_DIST0_EMPTY)
+    with pytest.raises(ValueError):
+        V.decode_lz77(LZ_DIST0[0], LZ_DIST0[1])
     assert KF.decompress(ONE_KOLM + b"junk") == b"A"               # quirk 9: KF ignores trailing bytes ...
     with pytest.raises(ValueError):
         V.decompress(ONE_KOLR + b"\0")                              # ... V22 rejects them (V22.py:2547-2549)
@@ -198,6 +220,18 @@ def test_gpu_stage_quirks():
     p, o = c.lz77_encode(t, off, 255, 127)
     b = p.cpu().numpy().tobytes()
     assert lz_tokens(b[o[1]:o[2]])[0] == (127, 1) and max(l for l, _ in lz_tokens(b[o[1]:o[2]])) == 127
+    import numpy as np
+    import torch
+    from kolmogorovlike_datacompressor_b200 import _lib
+    pay = torch.from_numpy(np.frombuffer(LZ_DIST0[0] + LZ_DIST0_EMPTY[0], dtype=np.uint8).copy()).cuda()
+    po = np.array([0, len(LZ_DIST0[0]), len(LZ_DIST0[0]) + len(LZ_DIST0_EMPTY[0])], dtype=np.int64)
+    assert c.lz77_decode(pay, po[:2], np.array([0, 5]), 0).cpu().numpy().tobytes()[:5] == LZ_DIST0[2]
+    with pytest.raises(_lib.KolmError) as e:
+        c.lz77_decode(pay[po[1]:].clone(), po[1:] - po[1], np.array([0, 3]), 0)
+    assert e.value.code == -7                                      # KOLM_E_INDEX -> IndexError in the drop-in
+    with pytest.raises(_lib.KolmError) as e:
+        c.lz77_decode(pay, po[:2], np.array([0, 5]), 4096)
+    assert e.value.code == -5                                      # KOLM_E_CORRUPT -> ValueError
     t, off = G.batch([RP_TIE[0], RP_DROP[0]])
     p, o = c.repair_encode(t, off)
     b = p.cpu().numpy().tobytes()
