@@ -82,19 +82,50 @@ def sharded_encode(data: bytes, bounds: Bounds, encode_fn: Callable[[bytes, Boun
     return out
 
 
-def sharded_encode_area(data: bytes, bounds: Bounds, area_fn, group=None, dst: int = 0):
+class _Clock:
+    """Phase timer of the sharded calls: seconds per phase, taken after the device finished the phase's work."""
+
+    def __init__(self, stats, dev):
+        import time
+        self.stats, self.dev, self.t = stats, dev, time.perf_counter()
+
+    def lap(self, name):
+        if self.stats is None:
+            return
+        import time
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        now = time.perf_counter()
+        self.stats[name] = self.stats.get(name, 0.0) + (now - self.t)
+        self.t = now
+
+
+def _exchange(sends, recvs, group):
+    """All payload transfers of one gather as ONE group of point-to-point operations (NCCL fuses them into a single launch and
+    the receives need no order): sends = [(tensor, peer)], recvs = [(tensor, peer)]."""
+    ops = [dist.P2POp(dist.isend, t, peer, group) for t, peer in sends] + [dist.P2POp(dist.irecv, t, peer, group) for t, peer in recvs]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def sharded_encode_area(data: bytes, bounds: Bounds, area_fn, group=None, dst: int = 0, data_base: int = 0, stats: Optional[dict] = None):
     """Array form of sharded_encode for whole containers.  area_fn(data, bounds_slice) -> (method ids, payload lengths, payload
     area); the area is a device tensor under NCCL (it goes GPU -> GPU into its final place in one buffer on `dst`, which then
     comes home in a single copy) and a numpy array / CPU tensor under gloo.  Returns (ids, lengths, area as uint8 numpy array)
-    in block order on `dst`, None elsewhere."""
+    in block order on `dst`, None elsewhere.  `data` may be just this rank's slice of the input: data[0] is byte `data_base` of
+    the input the (global) `bounds` refer to.  stats (dict) receives seconds per phase."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     parts = partition_blocks(bounds, world)
     b0, b1 = parts[rank]
     dev = _dev(group)
+    clk = _Clock(stats, dev)
     if b1 > b0:
-        mids, lens, area = area_fn(data, bounds[b0:b1])
+        mine = bounds[b0:b1] if not data_base else [(a - data_base, b - data_base) for a, b in bounds[b0:b1]]
+        mids, lens, area = area_fn(data, mine)
     else:
         mids, lens, area = np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
+    clk.lap("encode_s")
     if not isinstance(area, torch.Tensor):
         area = torch.from_numpy(np.ascontiguousarray(np.frombuffer(memoryview(area), dtype=np.uint8)).copy())
     area = area.to(dev)
@@ -108,20 +139,23 @@ def sharded_encode_area(data: bytes, bounds: Bounds, area_fn, group=None, dst: i
     dist.all_gather(tables, table, group=group)
     tabs = [tables[r][:parts[r][1] - parts[r][0]].cpu().numpy() for r in range(world)]
     nbytes = [int(t[:, 1].sum()) if len(t) else 0 for t in tabs]
+    clk.lap("table_allgather_s")
     if rank != dst:
-        if nbytes[rank]:
-            dist.send(area[:nbytes[rank]].contiguous(), dst=dst, group=group)
+        _exchange([(area[:nbytes[rank]].contiguous(), dst)] if nbytes[rank] else [], [], group)
+        clk.lap("payload_exchange_s")
         return None
     total = sum(nbytes)
     buf = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
-    p = 0
+    p, recvs = 0, []
     for r in range(world):
         if nbytes[r]:
             if r == dst:
                 buf[p:p + nbytes[r]].copy_(area[:nbytes[r]])
             else:
-                dist.recv(buf[p:p + nbytes[r]], src=r, group=group)
+                recvs.append((buf[p:p + nbytes[r]], r))
         p += nbytes[r]
+    _exchange([], recvs, group)                               # every rank's area straight into its final place, one group
+    clk.lap("payload_exchange_s")
     if buf.is_cuda:
         host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
         host.copy_(buf, non_blocking=True)
@@ -129,6 +163,7 @@ def sharded_encode_area(data: bytes, bounds: Bounds, area_fn, group=None, dst: i
         out_area = host[:total].numpy()
     else:
         out_area = buf[:total].numpy()
+    clk.lap("d2h_s")
     allm = np.concatenate([t[:, 0] for t in tabs]) if tabs else np.zeros(0, np.int64)
     alll = np.concatenate([t[:, 1] for t in tabs]) if tabs else np.zeros(0, np.int64)
     return allm, alll, out_area
@@ -250,3 +285,232 @@ def decompress_kolr(container: bytes, group=None) -> Optional[bytes]:
         if pos != len(container):
             raise ValueError(f"Extra trailing {len(container) - pos} bytes after container end")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Corpora of several containers (SURVEY §8e: "multi-container corpora additionally shard by container"; a KOLR container holds
+# < 4 GiB and <= 65535 blocks, V22.py:2336-2339).  The blocks of ALL containers form one list in container order; it is cut into
+# contiguous ranges balanced by bytes, every rank loads only the bytes of its own blocks, and ONE exchange (table all_gather +
+# one group of sends/receives) brings every container's payload area to the assembling rank.
+# ------------------------------------------------------------------------------------------------------------------------------
+def corpus_blocks(sizes: Sequence[int], block_size: int) -> List[Tuple[int, int, int]]:
+    """[(container, start, end)] of the fixed-size blocks of every container (V22.py:314-320), container-major."""
+    out = []
+    for k, n in enumerate(sizes):
+        out.extend((k, a, min(n, a + block_size)) for a in range(0, n, block_size))
+    return out
+
+
+def _virtual_bounds(blocks):
+    out, p = [], 0
+    for _, a, b in blocks:
+        out.append((p, p + (b - a)))
+        p += b - a
+    return out
+
+
+def _my_runs(blocks, b0, b1):
+    """Blocks [b0, b1) grouped into runs of one container each: [(container, first block index, last + 1)]."""
+    runs, i = [], b0
+    while i < b1:
+        j = i
+        while j < b1 and blocks[j][0] == blocks[i][0]:
+            j += 1
+        runs.append((blocks[i][0], i, j))
+        i = j
+    return runs
+
+
+def compress_kolr_fixed_corpus(sizes: Sequence[int], load: Callable[[int, int, int], bytes], block_size: int = 8192, group=None, dst: int = 0,
+                               stats: Optional[dict] = None, area_fn=None) -> Optional[List[bytes]]:
+    """compress_blocks_fixed (V22.py:2332-2445) of every container of a corpus, block-sharded over the group's GPUs.
+    sizes[k] = input length of container k; load(k, a, b) -> the bytes [a, b) of container k's input (called on the rank that
+    encodes them, once per container it touches).  area_fn(data, bounds) -> (ids, lengths, payload area) is the per-rank encoder
+    (default: this GPU's engine with the reference's candidate list); the containers are returned as a list on `dst`, None
+    elsewhere.  stats (dict) receives seconds per phase and the exchanged byte count."""
+    from . import kolm_final_researched_v2_2 as V
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = _dev(group)
+    clk = _Clock(stats, dev)
+    blocks = corpus_blocks(sizes, block_size)
+    parts = partition_blocks(_virtual_bounds(blocks), world)
+    b0, b1 = parts[rank]
+    if area_fn is None:
+        eng, names = V._engine(), V._candidate_names()
+        area_fn = _engine_area(eng, lambda d, b: eng.encode_kolr_area(d, b, names))
+    mids_l, lens_l, areas = [], [], []
+    for k, i, j in _my_runs(blocks, b0, b1):
+        lo, hi = blocks[i][1], blocks[j - 1][2]
+        d = load(k, lo, hi)
+        clk.lap("load_s")
+        m, l, ar = area_fn(d, [(a - lo, b - lo) for _, a, b in blocks[i:j]])
+        if not isinstance(ar, torch.Tensor):
+            ar = torch.from_numpy(np.ascontiguousarray(np.frombuffer(memoryview(ar), dtype=np.uint8)).copy())
+        mids_l.append(np.asarray(m, dtype=np.int64)); lens_l.append(np.asarray(l, dtype=np.int64)); areas.append(ar.to(dev))
+        clk.lap("encode_s")
+    nloc = b1 - b0
+    maxn = max(e - s for s, e in parts)
+    table = torch.zeros((max(maxn, 1), 2), dtype=torch.int64, device=dev)
+    if nloc:
+        table[:nloc, 0] = torch.as_tensor(np.concatenate(mids_l), device=dev)
+        table[:nloc, 1] = torch.as_tensor(np.concatenate(lens_l), device=dev)
+    tables = [torch.empty_like(table) for _ in range(world)]
+    dist.all_gather(tables, table, group=group)
+    tabs = [tables[r][:parts[r][1] - parts[r][0]].cpu().numpy() for r in range(world)]
+    nbytes = [int(t[:, 1].sum()) if len(t) else 0 for t in tabs]
+    clk.lap("table_allgather_s")
+    mine = torch.cat(areas) if len(areas) > 1 else (areas[0] if areas else torch.empty(0, dtype=torch.uint8, device=dev))
+    if stats is not None:
+        stats["exchanged_bytes"] = int(sum(nbytes) - nbytes[dst])
+    if rank != dst:
+        _exchange([(mine[:nbytes[rank]].contiguous(), dst)] if nbytes[rank] else [], [], group)
+        clk.lap("payload_exchange_s")
+        return None
+    total = sum(nbytes)
+    buf = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    p, recvs = 0, []
+    for r in range(world):
+        if nbytes[r]:
+            if r == dst:
+                buf[p:p + nbytes[r]].copy_(mine[:nbytes[r]])
+            else:
+                recvs.append((buf[p:p + nbytes[r]], r))
+        p += nbytes[r]
+    _exchange([], recvs, group)
+    clk.lap("payload_exchange_s")
+    if buf.is_cuda:
+        host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        host.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        area = host[:total].numpy()
+    else:
+        area = buf[:total].numpy()
+    clk.lap("d2h_s")
+    allm = np.concatenate([t[:, 0] for t in tabs]) if blocks else np.zeros(0, np.int64)
+    alll = np.concatenate([t[:, 1] for t in tabs]) if blocks else np.zeros(0, np.int64)
+    ends = np.cumsum(alll)
+    out, i = [], 0
+    for k, n in enumerate(sizes):
+        j = i
+        while j < len(blocks) and blocks[j][0] == k:
+            j += 1
+        a0 = int(ends[i] - alll[i]) if j > i else 0
+        a1 = int(ends[j - 1]) if j > i else 0
+        out.append(V._assemble(int(n), [(a, b) for _, a, b in blocks[i:j]], V.MODE_FIXED, block_size,
+                               encoded=(allm[i:j], alll[i:j], area[a0:a1]) if j > i else None))
+        i = j
+    clk.lap("assemble_s")
+    return out
+
+
+def decompress_kolr_corpus(containers: Optional[Sequence[bytes]], group=None, src: int = 0, gather: bool = True, stats: Optional[dict] = None,
+                           decode_fn=None):
+    """decompress (V22.py:2451-2550) of every container of a corpus, block-sharded over the group's GPUs.  The containers live on
+    rank `src` (None elsewhere): it walks the TOCs, broadcasts the block table, uploads the payload areas once and sends every
+    rank the payload span of its block range (one group of sends/receives); the ranks decode their ranges.
+    gather=True : the decoded bytes travel back to `src` (one group), which returns [bytes per container]; others return None.
+    gather=False: every rank returns [(container, first byte, end byte, uint8 tensor of those decoded bytes)] for its own range
+                  (the sharded output SURVEY §8e describes when no single-device result is needed).
+    decode_fn(span tensor, names, starts, plens, olens) -> uint8 tensor (default: this GPU's engine)."""
+    from . import kolm_final_researched_v2_2 as V
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = _dev(group)
+    clk = _Clock(stats, dev)
+    box = [None]
+    if rank == src:
+        metas, p = [], 0
+        for c in containers:
+            c = bytes(c) if not isinstance(c, bytes) else c
+            names, starts, plens, olens, total_len, pos = V._parse(c)
+            if pos != len(c):
+                raise ValueError(f"Extra trailing {len(c) - pos} bytes after container end")
+            if sum(olens) != total_len:
+                raise ValueError(f"Length mismatch: got {sum(olens)}, expect {total_len}")
+            a0 = starts[0] if starts else pos
+            metas.append(dict(names=names, rel=[x - a0 for x in starts], plens=plens, olens=olens, area0=a0, area_len=pos - a0, gbase=p))
+            p += pos - a0
+        box = [[{k: v for k, v in m.items() if k != "area0"} for m in metas]]
+    dist.broadcast_object_list(box, src=src, group=group)
+    table = box[0]
+    clk.lap("toc_s")
+    blocks, gstart, plen, olen, names = [], [], [], [], []           # flat, container-major
+    for k, m in enumerate(table):
+        o = 0
+        for i, ol in enumerate(m["olens"]):
+            blocks.append((k, o, o + ol)); o += ol
+            gstart.append(m["gbase"] + m["rel"][i]); plen.append(m["plens"][i]); olen.append(ol); names.append(m["names"][i])
+    parts = partition_blocks(_virtual_bounds(blocks), world)
+    spans = []
+    for s0, s1 in parts:                                             # payload span (in the concatenated areas) of every rank's range
+        if s1 > s0:
+            spans.append((min(gstart[s0:s1]), max(g + l for g, l in zip(gstart[s0:s1], plen[s0:s1]))))
+        else:
+            spans.append((0, 0))
+    b0, b1 = parts[rank]
+    lo, hi = spans[rank]
+    if rank == src:
+        total_area = sum(m["area_len"] for m in table)
+        allp = torch.empty(max(total_area, 1), dtype=torch.uint8, device=dev)
+        for c, m in zip(containers, metas):
+            if m["area_len"]:
+                view = np.frombuffer(c, dtype=np.uint8, count=m["area_len"], offset=m["area0"])
+                from .engine import _ro_tensor
+                allp[m["gbase"]:m["gbase"] + m["area_len"]].copy_(_ro_tensor(view))
+        clk.lap("h2d_s")
+        _exchange([(allp[spans[r][0]:spans[r][1]], r) for r in range(world) if r != src and spans[r][1] > spans[r][0]], [], group)
+        span = allp[lo:hi]
+    else:
+        span = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=dev)
+        _exchange([], [(span[:hi - lo], src)] if hi > lo else [], group)
+    clk.lap("payload_scatter_s")
+    if decode_fn is None:
+        decode_fn = V._engine().decode_to_device
+    pieces = []
+    for k, i, j in _my_runs(blocks, b0, b1):
+        st = [g - lo for g in gstart[i:j]]
+        y = decode_fn(span, names[i:j], st, plen[i:j], olen[i:j])
+        pieces.append((k, blocks[i][1], blocks[j - 1][2], y))
+    clk.lap("decode_s")
+    if not gather:
+        return pieces
+    nbytes = [sum(olen[s0:s1]) for s0, s1 in parts]
+    mine = torch.cat([y for *_, y in pieces]) if len(pieces) > 1 else (pieces[0][3] if pieces else torch.empty(0, dtype=torch.uint8, device=dev))
+    if rank != src:
+        _exchange([(mine[:nbytes[rank]].contiguous(), src)] if nbytes[rank] else [], [], group)
+        clk.lap("output_gather_s")
+        return None
+    total = sum(nbytes)
+    buf = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    p, recvs = 0, []
+    for r in range(world):
+        if nbytes[r]:
+            if r == src:
+                buf[p:p + nbytes[r]].copy_(mine[:nbytes[r]])
+            else:
+                recvs.append((buf[p:p + nbytes[r]], r))
+        p += nbytes[r]
+    _exchange([], recvs, group)
+    clk.lap("output_gather_s")
+    from .engine import _new_bytes, _par_copy
+    outs, p = [], 0
+    host = None
+    for m in table:
+        n = sum(m["olens"])
+        ob, sink = _new_bytes(n)
+        if n:
+            if buf.is_cuda:
+                if host is None or host.numel() < n:
+                    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+                host[:n].copy_(buf[p:p + n], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                srcv = host[:n].numpy()
+            else:
+                srcv = buf[p:p + n].numpy()
+            if sink is None:
+                ob = srcv.tobytes()
+            else:
+                _par_copy(sink, srcv)
+        outs.append(ob)
+        p += n
+    clk.lap("d2h_s")
+    return outs

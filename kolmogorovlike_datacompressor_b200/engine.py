@@ -336,6 +336,12 @@ class Engine:
             i = j
 
     def _upload(self, data, a: int, b: int) -> torch.Tensor:
+        if isinstance(data, torch.Tensor) and data.is_cuda:        # already on the device (dist.*_corpus: payload spans arrive over NCCL)
+            if b - a >= 4 and a + max(4, b - a + 4) <= data.numel():
+                return data[a:a + max(4, b - a + 4)]
+            t = torch.zeros(max(4, b - a + 4), dtype=torch.uint8, device=data.device)
+            t[:b - a].copy_(data[a:b])
+            return t
         t = torch.empty(max(4, b - a + 4), dtype=torch.uint8, device=torch.device("cuda", self.device))
         if b > a:
             # numpy view of the (read-only) bytes -> torch: no warning to filter (warnings.catch_warnings is not thread-safe and
@@ -610,7 +616,8 @@ class Engine:
         # fails on the first bad block instead of a MemoryError)
         # lengths are allocated up front only when plausible; an implausible header (the lengths are untrusted) is decoded batch by
         # batch into a growing buffer, so a bad block fails with the reference's exception instead of a MemoryError
-        lazy = on_batch is None and int(ends[-1]) > max(1 << 30, 4096 * len(blob))
+        blob_len = blob.numel() if isinstance(blob, torch.Tensor) else len(blob)
+        lazy = on_batch is None and int(ends[-1]) > max(1 << 30, 4096 * blob_len)
         grow = bytearray() if lazy else None
         result, sink = (b"", None) if (on_batch is not None or lazy) else _new_bytes(int(ends[-1]))
         if sink is None and on_batch is None and not lazy:           # 0 or 1 byte: CPython shares these objects, build them the ordinary way

@@ -273,7 +273,8 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
     elsewhere (dist.compress_kolr_*: block ranges sharded over several GPUs); otherwise they are encoded here."""
     out = bytearray(b"KOLR")
     out += struct.pack("<I", _pack_mode_and_size(mode, size_field))
-    out += struct.pack("<I", len(data))                 # struct.error beyond 4 GiB-1 / 65535 blocks, like the reference
+    # dist.*_corpus pass the input LENGTH when the blocks were encoded elsewhere (the assembling rank holds no input bytes)
+    out += struct.pack("<I", data if isinstance(data, int) else len(data))   # struct.error beyond 4 GiB-1 / 65535 blocks, like the reference
     out += struct.pack("<H", len(boundaries))
     names = _candidate_names()
     nblocks = len(boundaries)

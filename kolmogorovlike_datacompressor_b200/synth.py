@@ -23,8 +23,22 @@ def _vocab(rng):
     return table, lens
 
 
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(16, len(os.sched_getaffinity(0)))), thread_name_prefix="kolm-synth")
+    return _POOL
+
+
 def s1_text(n: int, seed: int = 0xC0FFEE) -> np.ndarray:
-    """Words sampled with p(i) ~ 1/(i+1), joined by ' ', '\\n' after every 12th word, truncated to n bytes."""
+    """Words sampled with p(i) ~ 1/(i+1), joined by ' ', '\n' after every 12th word, truncated to n bytes.
+    The random stream is drawn sequentially (the corpus is a function of (n, seed) only); the table lookups and the expansion of
+    word ids into bytes run on a thread pool, slice by slice (numpy releases the GIL in all of them)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     table, lens = _vocab(rng)
     ext = np.zeros((4096, 11), dtype=np.uint8)            # letters, then one separator slot
@@ -38,20 +52,40 @@ def s1_text(n: int, seed: int = 0xC0FFEE) -> np.ndarray:
     filled = 0
     widx = 0
     chunk = 1 << 21
+    pool = _pool()
+    nsl = 16
+    step = chunk // nsl
     while filled < n:
-        ids = np.searchsorted(cdf, rng.random(chunk), side="right").clip(0, 4095)
+        u = rng.random(chunk)
+        ids = np.empty(chunk, dtype=np.int64)
+
+        def look(k):
+            ids[k * step:(k + 1) * step] = np.searchsorted(cdf, u[k * step:(k + 1) * step], side="right").clip(0, 4095)
+        list(pool.map(look, range(nsl)))
         wl = wl_tab[ids]
         ends = np.cumsum(wl)
         tot = int(ends[-1])
-        word_of = np.repeat(np.arange(chunk, dtype=np.int64), wl)
-        within = np.arange(tot, dtype=np.int64) - np.repeat(ends - wl, wl)
-        buf = flat[ids[word_of] * 11 + within]
-        sep = np.full(chunk, 0x20, dtype=np.uint8)
-        sep[(np.arange(widx, widx + chunk) % 12) == 11] = 0x0A
-        buf[ends - 1] = sep
-        widx += chunk
         take = min(tot, n - filled)
-        out[filled:filled + take] = buf[:take]
+        base_w, base_o = widx, filled
+
+        def expand(k):
+            a, b = k * step, (k + 1) * step
+            o0 = int(ends[a] - wl[a])                       # byte offset of word a inside this chunk
+            if o0 >= take:
+                return
+            w = wl[a:b]
+            e = ends[a:b] - o0
+            m = int(e[-1])
+            word_of = np.repeat(np.arange(b - a, dtype=np.int64), w)
+            within = np.arange(m, dtype=np.int64) - np.repeat(e - w, w)
+            buf = flat[ids[a:b][word_of] * 11 + within]
+            sep = np.full(b - a, 0x20, dtype=np.uint8)
+            sep[(np.arange(base_w + a, base_w + b) % 12) == 11] = 0x0A
+            buf[e - 1] = sep
+            m = min(m, take - o0)
+            out[base_o + o0:base_o + o0 + m] = buf[:m]
+        list(pool.map(expand, range(nsl)))
+        widx += chunk
         filled += take
     return out
 

@@ -46,7 +46,7 @@ def dir_exports():
     return ["ko_duval", "ko_bbwt_forward_literal", "ko_bbwt_forward", "ko_bbwt_inverse", "ko_mtf_encode", "ko_mtf_decode",
             "ko_kf_rice_pack", "ko_kf_rice_unpack", "ko_v22_rice_pack", "ko_v22_rice_unpack", "ko_lz77_encode", "ko_lz77_decode",
             "ko_residual_encode", "ko_residual_decode", "ko_repair_compress", "ko_repair_decompress", "ko_kf_cdc", "ko_v22_cdc",
-            "ko_v2new_encode", "ko_v2new_decode", "ko_v2new_encode_forced", "ko_encode_model", "ko_decode_model", "ko_encode_block", "ko_kf_compress", "ko_kf_decompress"]
+            "ko_lz77_encode_fast", "ko_encode_block_fast", "ko_v2new_encode", "ko_v2new_decode", "ko_v2new_encode_forced", "ko_encode_model", "ko_decode_model", "ko_encode_block", "ko_kf_compress", "ko_kf_decompress"]
 
 
 def _buf(n):
@@ -123,6 +123,15 @@ def lz77_encode(data, window, cap_len):
     cap = 2 * n + 16
     out = _buf(cap)
     r = _chk(lib().ko_lz77_encode(p, C.c_int64(n), C.c_uint32(window), C.c_uint32(cap_len), out, C.c_int64(cap)))
+    return bytes(out[:r])
+
+
+def lz77_encode_fast(data, window, cap_len):
+    """lz77_encode through trigram chains (exact; for long blocks).  tests/test_oracle_lz77_fast.py ties it to lz77_encode."""
+    p, n = _in(data)
+    cap = 2 * n + 16
+    out = _buf(cap)
+    r = _chk(lib().ko_lz77_encode_fast(p, C.c_int64(n), C.c_uint32(window), C.c_uint32(cap_len), out, C.c_int64(cap)))
     return bytes(out[:r])
 
 
@@ -231,8 +240,8 @@ def decode_model(profile, mid, payload, orig_len):
     return bytes(out[:orig_len])
 
 
-def encode_block(profile, data, models_mask=None):
-    """-> (method, payload, sizes[list])"""
+def encode_block(profile, data, models_mask=None, fast=False):
+    """-> (method, payload, sizes[list]).  fast: LZ77 and Re-Pair through lz77_encode_fast / repair_compress_fast (long blocks)."""
     nm = 4 if profile == PROFILE_KOLM else 10
     if models_mask is None:
         models_mask = (1 << nm) - 1
@@ -241,7 +250,7 @@ def encode_block(profile, data, models_mask=None):
     out = _buf(cap)
     method = C.c_int()
     sizes = (C.c_int64 * 16)()
-    r = _chk(lib().ko_encode_block(C.c_int(profile), p, C.c_int64(n), C.c_uint32(models_mask), out, C.c_int64(cap), C.byref(method), sizes))
+    r = _chk((lib().ko_encode_block_fast if fast else lib().ko_encode_block)(C.c_int(profile), p, C.c_int64(n), C.c_uint32(models_mask), out, C.c_int64(cap), C.byref(method), sizes))
     return method.value, bytes(out[:r]), [s if s >= 0 else None for s in sizes[:nm]]
 
 

@@ -150,3 +150,83 @@ def test_sharded_decode_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] is True for r in res)
+
+
+def _corpus_parts():
+    a = datasets.fixture("pattern")[:30000] + datasets.medium_cases()["text_big"]
+    b = datasets.fixture("checker")[:9000]
+    c = b""
+    d = datasets.fixture("sine")[:12345] + bytes(5000)
+    return [a, b, c, d]
+
+
+def _kolr_area_fn(d, bs):
+    import numpy as np
+    from oracle import oracle as O
+    enc = [O.encode_block(O.PROFILE_KOLR, bytes(d[a:b]))[:2] for a, b in bs]
+    return (np.array([m for m, _ in enc], dtype=np.int64), np.array([len(p) for _, p in enc], dtype=np.int64),
+            np.frombuffer(b"".join(p for _, p in enc), dtype=np.uint8))
+
+
+def _worker_corpus(rank, world, port, q):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from kolmogorovlike_datacompressor_b200 import dist as kd, kolm_final_researched_v2_2 as V
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    parts = _corpus_parts()
+    loads = []
+
+    def load(k, a, b):
+        loads.append((k, a, b))
+        return parts[k][a:b]
+
+    st = {}
+    got = kd.compress_kolr_fixed_corpus([len(p) for p in parts], load, 2048, stats=st, area_fn=_kolr_area_fn)
+    ids = {n: i for i, n in enumerate(V.KOLR_NAMES)}
+
+    def dec(span, nm, stt, pl, ol):
+        raw = span.numpy().tobytes()
+        out = b"".join(O.decode_model(O.PROFILE_KOLR, ids[n], raw[s:s + l], o) for n, s, l, o in zip(nm, stt, pl, ol))
+        return torch.frombuffer(bytearray(out), dtype=torch.uint8) if out else torch.empty(0, dtype=torch.uint8)
+
+    back = kd.decompress_kolr_corpus(got, decode_fn=dec)
+    shard = kd.decompress_kolr_corpus(got, decode_fn=dec, gather=False)
+    shard_ok = all(parts[k][a:b] == y.numpy().tobytes() for k, a, b, y in shard)
+    loaded = sum(b - a for _, a, b in loads)
+    if rank == 0:
+        want = []
+        for p in parts:
+            bounds = [(a, min(len(p), a + 2048)) for a in range(0, len(p), 2048)]
+            want.append(V._assemble(len(p), bounds, V.MODE_FIXED, 2048, encoded=_kolr_area_fn(p, bounds) if bounds else None))
+        q.put(("ok", got == want, back == parts, shard_ok, loaded, sorted(st)))
+    else:
+        q.put(("none", got is None and back is None, shard_ok, loaded))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_corpus_of_containers_sharded(world):
+    """dist.compress_kolr_fixed_corpus / decompress_kolr_corpus: four containers (one empty) cut into block ranges over the ranks;
+    every rank loads only its own bytes; rank 0 gets byte-identical containers and the round trip, gathered and sharded."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_corpus, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ok = [r for r in res if r[0] == "ok"][0]
+    assert ok[1] is True and ok[2] is True and ok[3] is True
+    assert {"encode_s", "table_allgather_s", "payload_exchange_s", "d2h_s", "assemble_s"} <= set(ok[5])
+    others = [r for r in res if r[0] == "none"]
+    assert len(others) == world - 1 and all(r[1] and r[2] for r in others)
+    total = sum(len(p) for p in _corpus_parts())
+    assert ok[4] + sum(r[3] for r in others) == total          # every input byte was loaded exactly once, by the rank that encodes it
+    assert max([ok[4]] + [r[3] for r in others]) < total * 0.75
