@@ -163,12 +163,13 @@ def s2_mixed(n: int) -> np.ndarray:
     return out
 
 
-def s3_mix(n: int, seed: int = 7) -> np.ndarray:
-    """1 MiB segments in the repeating pattern [S1, S1, S2g, S2s, S2p, S2c, S1, random]."""
+def s3_mix(n: int, seed: int = 7, text_seed: int = 0xC0FFEE) -> np.ndarray:
+    """1 MiB segments in the repeating pattern [S1, S1, S2g, S2s, S2p, S2c, S1, random]; `seed` drives the random segments,
+    `text_seed` the S1 text (the containers of a multi-container corpus use different seeds)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     nseg = (n + MIB - 1) // MIB
     n_s1 = sum(1 for k in range(nseg) if k % 8 in (0, 1, 6))
-    text = s1_text(max(1, n_s1) * MIB)
+    text = s1_text(max(1, n_s1) * MIB, seed=text_seed)
     out = np.empty(n, dtype=np.uint8)
     ti = 0
     for k in range(nseg):
