@@ -94,6 +94,11 @@ int kolm_rice_kf_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_o
  * order flags {0,1,4,8,16}; the variant `flags` is packed. */
 int kolm_rice_k2_enc(kolm_ctx* ctx, const uint8_t* mtf, const int64_t* off, int nblocks, int flags, uint8_t* out, size_t out_cap,
                      int64_t* out_off, int64_t* sizes, kolm_stream_t stream);
+/* Both coders of one MTF batch in one call: the cost pass reads the MTF bytes ONCE for the KF parameters / size and for the five
+ * V22 variants' sizes (what one iteration of both references' selection loops needs, KF.py:821-864 / V22.py:2350-2369), then the KF
+ * payload and the V22 variant `k2_flags` are packed.  Arguments as in kolm_rice_kf_enc / kolm_rice_k2_enc. */
+int kolm_rice_dual_enc(kolm_ctx* ctx, const uint8_t* mtf, const int64_t* off, int nblocks, int k2_flags, uint8_t* kf_out, size_t kf_cap,
+                       int64_t* kf_off, int* kf_params, uint8_t* k2_out, size_t k2_cap, int64_t* k2_off, int64_t* k2_sizes, kolm_stream_t stream);
 int kolm_rice_k2_dec(kolm_ctx* ctx, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int flags,
                      uint8_t* mtf_out, kolm_stream_t stream);
 

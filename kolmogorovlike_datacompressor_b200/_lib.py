@@ -63,6 +63,7 @@ def lib():
     L.kolm_rice_kf_dec.argtypes = [p, p, i64p, i64p, C.c_int, p, p]
     L.kolm_rice_k2_enc.argtypes = [p, p, i64p, C.c_int, C.c_int, p, C.c_size_t, i64p, i64p, p]
     L.kolm_rice_k2_dec.argtypes = [p, p, i64p, i64p, C.c_int, C.c_int, p, p]
+    L.kolm_rice_dual_enc.argtypes = [p, p, i64p, C.c_int, C.c_int, p, C.c_size_t, i64p, ip, p, C.c_size_t, i64p, i64p, p]
     L.kolm_last_counters.argtypes = [p, i64p]
     L.kolm_lz77_enc.argtypes = [p, p, i64p, C.c_int, C.c_uint32, C.c_uint32, p, C.c_size_t, i64p, p]
     L.kolm_lz77_dec.argtypes = [p, p, i64p, i64p, C.c_int, C.c_uint32, p, p]

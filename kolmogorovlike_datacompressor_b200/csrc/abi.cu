@@ -17,6 +17,7 @@ void kolm_set_cuda_error(cudaError_t e, const char* file, int line) {
 #include "bbwt_inv.cu"
 #include "mtf.cu"
 #include "rice.cu"
+#include "rice2.cu"
 #include "rice_dec.cu"
 #include "lz77.cu"
 #include "residual.cu"
@@ -162,6 +163,9 @@ static const char* KC_NAMES[KC_COUNT] = {"build_tiles", "boot_keys", "radix_hist
 
 extern "C" {
 
+// KOLM_RICE_V1=1: the first (CTA-per-tile) Rice encoders of rice.cu instead of the warp-per-tile ones of rice2.cu (A/B runs)
+static bool rice_v1() { static int v = -1; if (v < 0) { const char* e = getenv("KOLM_RICE_V1"); v = e ? atoi(e) : 0; } return v != 0; }
+
 int kolm_lyndon(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* start_flags, kolm_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
@@ -202,7 +206,8 @@ int kolm_rice_kf_enc(kolm_ctx* c, const uint8_t* mtf, const int64_t* off, int nb
                      int* params, kolm_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
-    return kolm_rice_kf_enc_impl(c, mtf, out, out_cap, out_off, params, s);
+    if (rice_v1()) return kolm_rice_kf_enc_impl(c, mtf, out, out_cap, out_off, params, s);
+    return kolm_rice2_kf_enc_impl(c, mtf, out, out_cap, out_off, params, s);
 }
 
 int kolm_rice_kf_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, uint8_t* mtf_out,
@@ -216,7 +221,16 @@ int kolm_rice_k2_enc(kolm_ctx* c, const uint8_t* mtf, const int64_t* off, int nb
                      int64_t* out_off, int64_t* sizes, kolm_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
-    return kolm_rice_k2_enc_impl(c, mtf, flags, out, out_cap, out_off, sizes, s);
+    if (rice_v1()) return kolm_rice_k2_enc_impl(c, mtf, flags, out, out_cap, out_off, sizes, s);
+    return kolm_rice2_k2_enc_impl(c, mtf, flags, out, out_cap, out_off, sizes, s);
+}
+
+int kolm_rice_dual_enc(kolm_ctx* c, const uint8_t* mtf, const int64_t* off, int nblocks, int k2_flags, uint8_t* kf_out, size_t kf_cap,
+                       int64_t* kf_off, int* kf_params, uint8_t* k2_out, size_t k2_cap, int64_t* k2_off, int64_t* k2_sizes, kolm_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!kf_off || !k2_off) return KOLM_E_ARG;
+    KOLM_TRY(kolm_set_batch(c, off, nblocks, s));
+    return kolm_rice2_dual_enc_impl(c, mtf, k2_flags, kf_out, kf_cap, kf_off, kf_params, k2_out, k2_cap, k2_off, k2_sizes, s);
 }
 
 int kolm_rice_k2_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off, const int64_t* off, int nblocks, int flags,

@@ -205,7 +205,7 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
     if (!e && !get(term)) e = KOLM_E_TRUNCATED;
     if (!e && term != 256) e = KOLM_E_CORRUPT;
     if (!e && !get(nr)) e = KOLM_E_TRUNCATED;
-    if (!e && 2 * nr > cap) e = KOLM_E_UNSUPPORTED;           // the encoder emits at most len/2 rules
+    if (!e && 2 * nr > cap) e = KOLM_E_CORRUPT;               // more rules than any block of this length needs (the encoder emits <= len/2): cannot expand to len bytes with every rule used
     for (u64 r = 0; r < nr && !e; ++r) {
         u64 x, y;
         if (!get(x) || !get(y)) { e = KOLM_E_TRUNCATED; break; }
@@ -222,7 +222,7 @@ __global__ void k_repair_dec(const u8* __restrict__ pay, const i64* __restrict__
         while (sp) {
             u32 x = stack[--sp];
             if (x < 256) { if (o >= bi.len) { e = KOLM_E_CORRUPT; break; } dst[o++] = (u8)x; }
-            else { if (sp + 2 > cap) { e = KOLM_E_UNSUPPORTED; break; } stack[sp++] = rules[2 * (x - 256) + 1]; stack[sp++] = rules[2 * (x - 256)]; }
+            else { if (sp + 2 > cap) { e = KOLM_E_CORRUPT; break; } stack[sp++] = rules[2 * (x - 256) + 1]; stack[sp++] = rules[2 * (x - 256)]; }
         }
     }
     if (!e && o != bi.len) e = KOLM_E_CORRUPT;

@@ -82,6 +82,17 @@ def sharded_encode(data: bytes, bounds: Bounds, encode_fn: Callable[[bytes, Boun
     return out
 
 
+_PIN = {}
+
+
+def _pinned(n: int) -> torch.Tensor:
+    """Persistent pinned staging buffer (allocating and pinning a GB of host memory costs about a second each time)."""
+    t = _PIN.get("buf")
+    if t is None or t.numel() < n:
+        _PIN["buf"] = t = torch.empty(max(n + (n >> 3), 1 << 20), dtype=torch.uint8).pin_memory()
+    return t
+
+
 class _Clock:
     """Phase timer of the sharded calls: seconds per phase, taken after the device finished the phase's work."""
 
@@ -157,8 +168,8 @@ def sharded_encode_area(data: bytes, bounds: Bounds, area_fn, group=None, dst: i
     _exchange([], recvs, group)                               # every rank's area straight into its final place, one group
     clk.lap("payload_exchange_s")
     if buf.is_cuda:
-        host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
-        host.copy_(buf, non_blocking=True)
+        host = _pinned(max(total, 1))
+        host[:max(total, 1)].copy_(buf, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         out_area = host[:total].numpy()
     else:
@@ -379,8 +390,8 @@ def compress_kolr_fixed_corpus(sizes: Sequence[int], load: Callable[[int, int, i
     _exchange([], recvs, group)
     clk.lap("payload_exchange_s")
     if buf.is_cuda:
-        host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
-        host.copy_(buf, non_blocking=True)
+        host = _pinned(max(total, 1))
+        host[:max(total, 1)].copy_(buf, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         area = host[:total].numpy()
     else:

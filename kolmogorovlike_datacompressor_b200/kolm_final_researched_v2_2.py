@@ -346,7 +346,17 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
     out += uleb128_encode(total_payload)
     out += toc_header
     out += toc_bits
-    return b"".join((bytes(out), memoryview(area)))     # one copy of the payload area
+    head = bytes(out)
+    n_area = len(area)
+    if n_area < (32 << 20):
+        return b"".join((head, memoryview(area)))       # one copy of the payload area
+    # large payload areas: the container is filled in place by several threads (one copy, page faults spread over the cores)
+    from .engine import _new_bytes, _par_copy
+    import numpy as np
+    blob, sink = _new_bytes(len(head) + n_area)
+    sink[:len(head)] = np.frombuffer(head, dtype=np.uint8)
+    _par_copy(sink[len(head):], np.frombuffer(memoryview(area), dtype=np.uint8))
+    return blob
 
 
 def compress_blocks_fixed(data: bytes, block_size: int = 8192) -> bytes:

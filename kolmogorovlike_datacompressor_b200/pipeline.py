@@ -58,9 +58,12 @@ class BlockPipeline:
             c.bbwt_forward(x, off[b0:b1 + 1], out=self.d_bbwt)
             b0 = b1
         c.mtf_encode(self.d_bbwt, off, out=self.d_mtf)
-        if self.profile_kf:
+        if self.profile_kf and self.profile_k2:                     # one cost read for both references' coders
+            (r["kf_payload"], r["kf_off"], r["kf_params"], r["k2_payload"], r["k2_off"], r["k2_sizes"]) = c.rice_dual_encode(
+                self.d_mtf, off, k2_flags, kf_out=self.d_kf, k2_out=self.d_k2)
+        elif self.profile_kf:
             r["kf_payload"], r["kf_off"], r["kf_params"] = c.rice_kf_encode(self.d_mtf, off, out=self.d_kf, want_params=True)
-        if self.profile_k2:
+        elif self.profile_k2:
             r["k2_payload"], r["k2_off"], r["k2_sizes"] = c.rice_k2_encode(self.d_mtf, off, k2_flags, out=self.d_k2)
         r["bbwt"], r["mtf"] = self.d_bbwt, self.d_mtf
         return r

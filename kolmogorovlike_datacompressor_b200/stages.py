@@ -116,6 +116,27 @@ class Context:
                                                self._stream()), "kolm_rice_k2_enc")
         return out, out_off, sizes.reshape(-1, 5)[:nb]
 
+    def rice_dual_encode(self, mtf, off, k2_flags: int, kf_out: Optional[torch.Tensor] = None, k2_out: Optional[torch.Tensor] = None):
+        """KF model 2 and the V22 Rice variants of one MTF batch from ONE cost read (kolm_rice_dual_enc) ->
+        (kf payload, kf_off, kf params[nb,4], k2 payload, k2_off, k2 sizes[nb,5])."""
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        n = int(oa[-1] - oa[0])
+        if kf_out is None:
+            kf_out = torch.empty(3 * n + 16 * nb + 64, dtype=torch.uint8, device=mtf.device)
+        if k2_out is None:
+            k2_out = torch.empty(9 * n + 16 * nb + 64, dtype=torch.uint8, device=mtf.device)
+        kf_off = np.zeros(nb + 1, dtype=np.int64)
+        k2_off = np.zeros(nb + 1, dtype=np.int64)
+        params = np.zeros(4 * max(1, nb), dtype=np.int32)
+        sizes = np.zeros(5 * max(1, nb), dtype=np.int64)
+        _lib.check(_lib.lib().kolm_rice_dual_enc(self._h, C.c_void_p(mtf.data_ptr()), op, nb, int(k2_flags),
+                                                 C.c_void_p(kf_out.data_ptr()), kf_out.numel(), kf_off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 params.ctypes.data_as(C.POINTER(C.c_int)),
+                                                 C.c_void_p(k2_out.data_ptr()), k2_out.numel(), k2_off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 sizes.ctypes.data_as(C.POINTER(C.c_int64)), self._stream()), "kolm_rice_dual_enc")
+        return kf_out, kf_off, params.reshape(-1, 4)[:nb], k2_out, k2_off, sizes.reshape(-1, 5)[:nb]
+
     def rice_k2_decode(self, payload, pay_off, off, flags: int, out=None):
         pa, pp = _offsets(pay_off)
         oa, op = _offsets(off)
