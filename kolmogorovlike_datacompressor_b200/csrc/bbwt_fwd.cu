@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_boot_keys_alpha(const u8* __re
 // 256 MiB text batch); four more plain passes and the re-key cost about 8.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KOLM_THREADS) k_boot_lo(const u32* __restrict__ KH, const BlockInfo* __restrict__ binfo, const TileDesc* __restrict__ tiles,
-                                                          const u32* __restrict__ fstart, const u32* __restrict__ nfac, u32 h0, u32* __restrict__ K0) {
+                                                          const u32* __restrict__ fstart, const u32* __restrict__ nfac, u32 h0, u32* __restrict__ K0,
+                                                          u32* __restrict__ LO) {
     const TileDesc td = tiles[blockIdx.x];
     const BlockInfo bi = binfo[td.block];
     const u32 r0 = threadIdx.x * KOLM_IPT;
@@ -286,13 +287,18 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_boot_lo(const u32* __restrict_
             keys[i] = kh[fs + o];
         }
     }
+    // the same keys twice: K0 is the first sort's key column (scrambled by the passes), LO stays by position for k_rerank<2>
     u32* dst = K0 + td.start + r0;
+    u32* dlo = LO + td.start + r0;
     if (nmine == KOLM_IPT) {
 #pragma unroll
-        for (int i = 0; i < KOLM_IPT; i += 4) *reinterpret_cast<uint4*>(dst + i) = make_uint4(keys[i], keys[i + 1], keys[i + 2], keys[i + 3]);
+        for (int i = 0; i < KOLM_IPT; i += 4) {
+            const uint4 q = make_uint4(keys[i], keys[i + 1], keys[i + 2], keys[i + 3]);
+            *reinterpret_cast<uint4*>(dst + i) = q; *reinterpret_cast<uint4*>(dlo + i) = q;
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < KOLM_IPT; ++i) if ((u32)i < nmine) dst[i] = keys[i];
+        for (int i = 0; i < KOLM_IPT; ++i) if ((u32)i < nmine) { dst[i] = keys[i]; dlo[i] = keys[i]; }
     }
 }
 
@@ -493,6 +499,7 @@ struct RerankArgs {
     const u32* fstart; const u32* nfac; u64* lb;
     u32* sa; u32* rank; u32* nr; u32* single; u32* newcls; u32 h;
     u32* survivors;                     // [1] records that remain unsettled after this round (non-BOOT only)
+    const u32* lo;                      // BOOT 2: low key half by position (k_boot_lo), so the rerank needs no factor search
 };
 
 template <int BOOT, bool CYCLIC>
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rerank(RerankArgs a) {
     {
         constexpr int NS = KOLM_IPT + 1;                   // slot x = i*THREADS + tid, i < NS covers count+2 <= TILE+2
         u32 kk[NS], vv[NS]; bool ok[NS];
-        const u32 nf = (BOOT != 1 && CYCLIC) ? a.nfac[td.block] : 0;
+        const u32 nf = (BOOT == 0 && CYCLIC) ? a.nfac[td.block] : 0;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             u32 x = i * KOLM_THREADS + tid;
@@ -531,6 +538,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rerank(RerankArgs a) {
         for (int i = 0; i < NS; ++i) {
             k2[i] = 0xffffffffu;
             if (BOOT == 1) { if (ok[i]) { k2[i] = kk[i]; kk[i] = 0; } }
+            else if (BOOT == 2) { /* second key = lo[position]: no successor arithmetic */ }
             else if (ok[i]) {
                 u32 lp = vv[i] - bi.pbase, sp;
                 if (CYCLIC) { u32 fs, fl; find_factor(a.fstart + bi.pbase, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
@@ -539,7 +547,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rerank(RerankArgs a) {
             }
         }
         if (BOOT != 1) {
-            const u32* second = BOOT == 2 ? a.nr : a.rank;
+            const u32* second = BOOT == 2 ? a.lo : a.rank;
 #pragma unroll
             for (int i = 0; i < NS; ++i) if (ok[i]) k2[i] = second[vv[i]];
         }
@@ -1175,6 +1183,9 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     CUDA_TRY(cudaMemsetAsync(c->d_single, 0, words * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->d_done, 0, (size_t)nb * 4, s));
     CUDA_TRY(cudaMemsetAsync(c->d_newcls, 0, (size_t)nb * 4, s));
+    // k_gather / k_ls_build write a block's active count from its LAST TILE: a block without tiles (empty) is never written, and
+    // the array doubles as scratch of the Lyndon pass — without this an empty block enters k_plan_active with whatever the memory held
+    CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
     int bgrid = nb < 1024 ? nb : 1024;
     // ---- bootstrap
     const i64 N = c->total_bytes;
@@ -1201,7 +1212,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     else KL(c, KC_BOOT, N * 9, s, k_boot_keys<false><<<nt, KOLM_THREADS, 0, s>>>(in, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, c->d_k0, c->d_v0));
     u32 *K, *V;
     if (deep) {
-        KL(c, KC_BOOT, N * 8, s, k_boot_lo<<<nt, KOLM_THREADS, 0, s>>>(c->d_nr, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, h0, c->d_k0));
+        KL(c, KC_BOOT, N * 12, s, k_boot_lo<<<nt, KOLM_THREADS, 0, s>>>(c->d_nr, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, h0, c->d_k0, c->d_lo));
         KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, 32, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
         KL(c, KC_BOOT, N * 12, s, k_boot_rekey<<<nt, KOLM_THREADS, 0, s>>>(c->d_nr, V, c->d_tiles, K));
         u32* Ko = (K == c->d_k0) ? c->d_k1 : c->d_k0;
@@ -1214,7 +1225,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
     RerankArgs ra;
     ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
-    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0;
+    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0; ra.lo = c->d_lo;
     if (deep) { KL(c, KC_RERANK, N * 20, s, k_rerank<2, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra)); h0 *= 2; c->counters[4] += N; }   // second full sort
     else if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<1, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
     else KL(c, KC_RERANK, N * 16, s, k_rerank<1, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));

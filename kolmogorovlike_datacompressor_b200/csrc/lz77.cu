@@ -349,9 +349,10 @@ __global__ void __launch_bounds__(128) k_lz_dec_warp(const u8* __restrict__ pay,
     if (lane == 0) err[b] = e;
 }
 
+// out_off == nullptr: device mode (kolm_encode_blocks) — the offsets stay in c->d_poff, nothing comes home, no synchronisation
 int kolm_lz77_enc_impl(kolm_ctx* c, const u8* in, u32 window, u32 maxlen, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
     const int nb = c->nblocks, nt = c->ntiles;
-    if (!nb) { out_off[0] = 0; return KOLM_OK; }
+    if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     if (window == 0) return KOLM_E_ARG;
     const i64 N = c->total_bytes;
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * 64 * 8, s));
@@ -390,6 +391,7 @@ int kolm_lz77_enc_impl(kolm_ctx* c, const u8* in, u32 window, u32 maxlen, u8* ou
         KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     }
     CUDA_TRY(cudaGetLastError());
+    if (!out_off) return KOLM_OK;
     CUDA_TRY(cudaMemcpyAsync(c->h_poff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     memcpy(out_off, c->h_poff, (size_t)(nb + 1) * 8);

@@ -355,9 +355,10 @@ __global__ void __launch_bounds__(RD2_THREADS) k_repair_dec2(const u8* __restric
     if (tid == 0) { if (s_bad) todo[b] = 1; else err[b] = KOLM_OK; }
 }
 
+// out_off == nullptr: device mode (kolm_encode_blocks) — the offsets stay in c->d_poff, nothing comes home
 int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
     const int nb = c->nblocks;
-    if (!nb) { out_off[0] = 0; return KOLM_OK; }
+    if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     static long long big_max = -1;                            // KOLM_REPAIR_BIG_MAX: largest block (bytes) the incremental kernel takes (0: none)
     if (big_max < 0) { const char* e = getenv("KOLM_REPAIR_BIG_MAX"); big_max = e ? atoll(e) : (1ll << 30); }
     if (c->max_len > REPAIR_MAX && (long long)c->max_len > big_max) return KOLM_E_UNSUPPORTED;
@@ -373,6 +374,7 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));
     CUDA_TRY(cudaGetLastError());
+    if (!out_off) return KOLM_OK;
     CUDA_TRY(cudaMemcpyAsync(c->h_poff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     memcpy(out_off, c->h_poff, (size_t)(nb + 1) * 8);

@@ -59,7 +59,8 @@ __global__ void k_res_plan_sizes(u64* __restrict__ bacc, const BlockInfo* __rest
 
 __global__ void __launch_bounds__(KOLM_THREADS) k_res_emit(const u8* __restrict__ in, const TileDesc* __restrict__ tiles,
                                                            const BlockInfo* __restrict__ binfo, u64* lb, const u64* __restrict__ bacc,
-                                                           u8* __restrict__ out, int kind, const i64* __restrict__ cap_total, u64 cap) {
+                                                           u8* __restrict__ out, int kind, const i64* __restrict__ cap_total, u64 cap,
+                                                           const int* __restrict__ method, int want) {
     __shared__ u64 s_warp[KOLM_THREADS / 32];
     __shared__ u64 s_excl;
     if ((u64)*cap_total > cap) return;                      // exact total known before any byte is emitted: never write past the caller's buffer
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_res_emit(const u8* __restrict_
     const u32 tile = lb_take_ticket(lb);
     if (tile == LB_NO_TILE) return;
     const TileDesc td = tiles[tile];
+    if (method && method[td.block] != want) return;         // whole blocks drop out together: no tile of another block looks back at them
     const BlockInfo bi = binfo[td.block];
     const u8* src = in + bi.ioff;
     const u32 t0 = td.start - bi.pbase;
@@ -139,7 +141,7 @@ int kolm_residual_enc_impl(kolm_ctx* c, const u8* in, int kind, u8* out, size_t 
     if (nt) {
         int lgrid = nt;
         KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
-        KL(c, KC_MISC, c->total_bytes * 2, s, k_res_emit<<<lgrid, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, out, kind, c->d_poff + nb, (u64)out_cap));
+        KL(c, KC_MISC, c->total_bytes * 2, s, k_res_emit<<<lgrid, KOLM_THREADS, 0, s>>>(in, c->d_tiles, c->d_binfo, c->d_lb, c->d_bacc, out, kind, c->d_poff + nb, (u64)out_cap, nullptr, 0));
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(c->h_poff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));

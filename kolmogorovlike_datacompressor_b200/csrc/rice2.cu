@@ -348,7 +348,8 @@ __device__ __forceinline__ void r2_kf_emit(const WStage& st, WAcc& ba, bool rice
 
 __global__ void __launch_bounds__(R2_THREADS) k_rice2_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                               const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
-                                                              u32* __restrict__ out, int ntiles, const i64* __restrict__ cap_total, u64 cap) {
+                                                              u32* __restrict__ out, int ntiles, const i64* __restrict__ cap_total, u64 cap,
+                                                              const int* __restrict__ method, int want) {
     __shared__ u32 s_stage[R2_WARPS][R2_STAGE];
     if ((u64)*cap_total + 8 > cap) return;                  // exact total known before any bit is packed (words are written whole: 8 bytes of slack)
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(R2_THREADS) k_rice2_kf_pack(const u8* __restri
     if (tile >= ntiles) return;
     const u64* trec = tacc + (size_t)tile * 32;
     const TileDesc td = tiles[tile];
+    if (method && method[td.block] != want) return;         // kolm_encode_blocks: only the blocks this coder won are packed
     const BlockInfo bi = binfo[td.block];
     const u64* a = bacc + (size_t)td.block * RB_STRIDE;
     const u32 prm = (u32)a[RB_PARAM];
@@ -435,13 +437,15 @@ __device__ __forceinline__ u32 r2_xform4(u32 x, int flags) {
 
 __global__ void __launch_bounds__(R2_THREADS) k_rice2_k2_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                               const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
-                                                              u32* __restrict__ out, int flags, int ntiles, const i64* __restrict__ cap_total, u64 cap) {
+                                                              u32* __restrict__ out, int flags, int ntiles, const i64* __restrict__ cap_total, u64 cap,
+                                                              const int* __restrict__ method, int want) {
     __shared__ u32 s_stage[R2_WARPS][R2_STAGE];
     if ((u64)*cap_total + 8 > cap) return;
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tile = blockIdx.x * R2_WARPS + w;
     if (tile >= ntiles) return;
     const TileDesc td = tiles[tile];
+    if (method && method[td.block] != want) return;
     const BlockInfo bi = binfo[td.block];
     const u32 t0 = td.start - bi.pbase, count = td.count;
     const u8* src = mtf + bi.ioff + t0;
@@ -519,8 +523,8 @@ static int rice2_pack(kolm_ctx* c, const u8* mtf, int mode, int slot, int flags,
     if (nt) {
         const int g = (nt + R2_WARPS - 1) / R2_WARPS;
         KL(c, KC_RICE_PLAN, (i64)nt * 64, s, k_rice_tile_offsets<<<nb, 256, 0, s>>>((u64*)c->d_thist, c->d_btile0, c->d_btilen, c->d_bacc, mode, slot));
-        if (mode == 1) KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice2_kf_pack<<<g, R2_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, nt, c->d_poff + nb, (u64)out_cap));
-        else KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice2_k2_pack<<<g, R2_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, flags, nt, c->d_poff + nb, (u64)out_cap));
+        if (mode == 1) KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice2_kf_pack<<<g, R2_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, nt, c->d_poff + nb, (u64)out_cap, nullptr, 0));
+        else KL(c, KC_RICE_PACK, c->total_bytes, s, k_rice2_k2_pack<<<g, R2_THREADS, 0, s>>>(mtf, c->d_tiles, c->d_binfo, (const u64*)c->d_thist, c->d_bacc, (u32*)out, flags, nt, c->d_poff + nb, (u64)out_cap, nullptr, 0));
     }
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;

@@ -9,6 +9,10 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# contexts created by the tests start with poisoned scratch (see kolm_create_ex): reads of never-written scratch fail reproducibly
+os.environ.setdefault("KOLM_POISON", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     config.addinivalue_line("markers", "slow: minutes of CPU")
