@@ -189,6 +189,37 @@ int kolm_gather_payloads(kolm_ctx* ctx, const uint64_t* src_addr, const int64_t*
  * Used on the decode side to put each method group's decoded blocks at their final offsets. */
 int kolm_copy_blocks(kolm_ctx* ctx, const uint64_t* src_addr, const uint64_t* dst_addr, const int64_t* len, int nblocks, kolm_stream_t stream);
 
+/* ---- fused hot path: what compress() / decompress() call per batch ---------------- */
+/* Per-block model selection with every candidate evaluated on the device: _encode_block (KF.py:821-864, ids 0..3 = raw, xor,
+ * bbwt+mtf+model 2, lz77) for KOLM_PROFILE_KOLM; the selection loops of V22.py:2233-2252 / 2350-2369 over _select_encoders()
+ * (V22.py:2152-2178, ids 0..9 = raw, xor[delta], bbwt, bbwt_bp, bbwt_nib, bbwt_br, bbwt_gray, lz77, lfsr_pred, repair; id 10 = v2_new
+ * raises in the shipped reference and is never selected) for KOLM_PROFILE_KOLR.  The winner is the first minimum of the exact
+ * payload sizes (strict '<': the lowest id on ties).  Sizes, offsets and method ids stay in device memory until the single copy home
+ * at the end; only the winners are emitted, directly at their final offsets.
+ *   off[0] must be 0.  cand_mask: bit id = candidate offered (0 = all; raw is always offered).
+ *   ext_id >= 0: candidate ext_id was computed elsewhere (e.g. Re-Pair of long blocks on a KOLM_CTX_REPAIR_ONLY context): ext_sizes
+ *                (HOST int64[nblocks]) and ext_addr (HOST: DEVICE address of each block's payload); -1 = none.
+ *   scratch (DEVICE, 256-byte aligned, kolm_encode_blocks_scratch(profile, batch bytes, nblocks) bytes).
+ *   payload_out (DEVICE, cap bytes, 8 bytes of slack wanted): the winners' payloads back to back in block order (KF.py:896-901;
+ *                V22.py:2443-2444); payload_off (HOST, nblocks+1); method_ids (HOST u8[nblocks]); sizes_out (HOST, may be NULL):
+ *                every candidate's size, row-major [nblocks][4 or 10], 2^62-1 for a candidate that was not offered. */
+size_t kolm_encode_blocks_scratch(int profile, size_t batch_bytes, int nblocks);
+int kolm_encode_blocks(kolm_ctx* ctx, int profile, const uint8_t* in, const int64_t* off, int nblocks, uint32_t cand_mask,
+                       int ext_id, const int64_t* ext_sizes, const uint64_t* ext_addr, uint8_t* scratch, size_t scratch_bytes,
+                       uint8_t* payload_out, size_t cap, int64_t* payload_off, uint8_t* method_ids, int64_t* sizes_out,
+                       kolm_stream_t stream);
+/* The decode loops of decompress (KF.py:925-949 over _DECODERS; V22.py:2530-2540 over _select_decoders()): block b's payload is
+ * payload[payload_start[b] .. + payload_len[b]) (DEVICE buffer, HOST arrays — KOLM containers interleave 9-byte block headers with
+ * the payloads, so starts and lengths are separate), its method method_ids[b], and it decodes to
+ * out[out_off[b] .. out_off[b+1]) (DEVICE).  Blocks are grouped by method and each group runs as one batch.  On a bad block the
+ * reference's error class comes back (KOLM_E_TRUNCATED / CORRUPT / INDEX) and *bad_block (may be NULL) is the lowest failing block
+ * index; an unknown method id is KOLM_E_CORRUPT.  Method 10 (v2_new) -> KOLM_E_UNSUPPORTED here (kolm_v2new_dec needs its own,
+ * 8x larger context).  scratch: DEVICE, kolm_decode_blocks_scratch(payload bytes, output bytes, nblocks) bytes. */
+size_t kolm_decode_blocks_scratch(size_t payload_bytes, size_t out_bytes, int nblocks);
+int kolm_decode_blocks(kolm_ctx* ctx, int profile, const uint8_t* payload, const int64_t* payload_start, const int64_t* payload_len,
+                       const uint8_t* method_ids, const int64_t* out_off, int nblocks, uint8_t* scratch, size_t scratch_bytes,
+                       uint8_t* out, int* bad_block, kolm_stream_t stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* counters of the last call on this context: [0] plain-suffix doubling rounds, [1] rotation doubling
  * rounds, [2] kernels launched since the last profile reset, [3] records sorted (sum over rounds) */

@@ -530,3 +530,5 @@ extern "C" int kolm_copy_blocks(kolm_ctx* c, const uint64_t* src_addr, const uin
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;
 }
+
+#include "fused.cu"

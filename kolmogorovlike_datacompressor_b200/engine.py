@@ -24,6 +24,8 @@ KOLR_NAMES = ["raw", "xor", "bbwt", "bbwt_bp", "bbwt_nib", "bbwt_br", "bbwt_gray
 K2_FLAG_OF = {"bbwt": 0, "bbwt_bp": 1, "bbwt_nib": 4, "bbwt_br": 8, "bbwt_gray": 16}
 K2_SLOT = {0: 0, 1: 1, 4: 2, 8: 3, 16: 4}
 _BIG = np.iinfo(np.int64).max
+_KOLR_IDS = {n: i for i, n in enumerate(KOLR_NAMES)}
+_KOLM_IDS = {"raw": 0, "kf_xor": 1, "kf_bbwt": 2, "kf_lz77": 3}
 
 
 def raise_like_reference(e: _lib.KolmError):
@@ -127,6 +129,9 @@ class Engine:
         # the LZ77 candidate runs beside the BBWT chain: own context, own (non-blocking) stream, one worker thread — its kernels
         # are latency bound (class walks, one parse CTA per block) and fill the gaps of the sort rounds (KOLM_LZ_ASYNC=0: inline)
         self.lz_async = os.environ.get("KOLM_LZ_ASYNC", "1") != "0"
+        # kolm_encode_blocks / kolm_decode_blocks: one C-ABI call per batch, sizes / offsets / method ids stay on the device
+        # (KOLM_FUSED=0: the stage-by-stage path below, kept for A/B runs and for the candidate lists the fused call does not cover)
+        self.fused = os.environ.get("KOLM_FUSED", "1") != "0"
         self.ctx2: Optional[Context] = None
         self.cap2_bytes = 0
         self.cap2_blocks = 0
@@ -369,6 +374,14 @@ class Engine:
         v = self._home(dev, total)
         return v.copy() if keep else v
 
+    def _area_home(self, dev: torch.Tensor, total: int, keep: bool = True):
+        """Payload area of a fused call -> host (or the device tensor itself for dist.*, see _gather_home)."""
+        if self._device_out:
+            torch.cuda.current_stream().synchronize()
+            return dev[:total]
+        v = self._home(dev, total)
+        return v.copy() if keep else v
+
     @staticmethod
     def _cat(areas):
         if not areas:
@@ -386,6 +399,14 @@ class Engine:
             off = np.array([bounds[k][0] - a for k in range(i, j)] + [b - a], dtype=np.int64)
             lens = np.diff(off)
             self._ensure(b - a, nb)
+            if self.fused:
+                with torch.cuda.device(self.device):
+                    x = self._upload(data, a, b)
+                    out, poff, mids = self.ctx.encode_blocks(_lib.KOLM_PROFILE_KOLM, x, off)
+                    areas.append(self._area_home(out, int(poff[-1]), keep=j < len(bounds)))
+                mids_all.append(mids.astype(np.int64))
+                lens_all.append(np.diff(poff))
+                continue
             with torch.cuda.device(self.device):
                 c = self.ctx
                 x = self._upload(data, a, b)
@@ -456,6 +477,25 @@ class Engine:
                 self._ensure(max(8 * (b - a) + 64, 1024 * nb), 8 * nb)
             else:
                 self._ensure(b - a, nb)
+            want_rp_f = "repair" in names and int(lens.max(initial=0)) <= self.repair_max
+            if self.fused and not v2 and list(names) == KOLR_NAMES:      # the reference's full candidate list: ids are list indices
+                if "repair" in names and not want_rp_f:
+                    warnings.warn("Re-Pair candidate skipped: block longer than the configured cap of %d bytes (Engine.repair_max / "
+                                  "KOLM_REPAIR_MAX_BLOCK); the container can differ from the reference's where Re-Pair would win" % self.repair_max,
+                                  RuntimeWarning, stacklevel=3)
+                with torch.cuda.device(self.device):
+                    x = self._upload(data, a, b)
+                    ext, mask = None, 0x3FF
+                    if not want_rp_f:
+                        mask = 0x1FF
+                    elif rp_take is not None:                        # Re-Pair of long blocks ran ahead on its own context
+                        rs_, ra_ = rp_take(i, j)
+                        ext = (9, rs_, ra_)
+                    out, poff, mids = self.ctx.encode_blocks(_lib.KOLM_PROFILE_KOLR, x, off, cand_mask=mask, ext=ext)
+                    areas.append(self._area_home(out, int(poff[-1]), keep=j < len(bounds)))
+                mids_all.append(mids.astype(np.int64))
+                lens_all.append(np.diff(poff))
+                continue
             with torch.cuda.device(self.device):
                 c = self.ctx
                 x = self._upload(data, a, b)
@@ -633,6 +673,35 @@ class Engine:
             with torch.cuda.device(self.device):
                 dev_out = torch.empty(max(tot, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
                 span = self._upload(blob, span0, max(span0, span1))
+                if self.fused and "v2_new" not in names[i:j]:
+                    # one kolm_decode_blocks call for the output batch (groups by method inside)
+                    kolm_prof = any(nm.startswith("kf_") for nm in names[i:j])
+                    ids = _KOLM_IDS if kolm_prof else _KOLR_IDS
+                    try:
+                        mids = np.array([ids[nm] for nm in names[i:j]], dtype=np.uint8)
+                    except KeyError as ke:
+                        raise NotImplementedError("no decoder for method '%s'" % ke.args[0])
+                    ooff = np.zeros(j - i + 1, dtype=np.int64)
+                    ooff[1:] = np.cumsum(ols[i:j])
+                    self._ensure(max(tot, int(plens[i:j].sum()), 1), j - i)
+                    try:
+                        self.ctx.decode_blocks(_lib.KOLM_PROFILE_KOLM if kolm_prof else _lib.KOLM_PROFILE_KOLR, span, starts[i:j] - span0, plens[i:j], mids, ooff, out=dev_out)
+                    except _lib.KolmError as err:
+                        blk = getattr(err, "block", -1)
+                        if blk >= 0 and names[i + blk] == "raw" and err.code == -5:
+                            raise AssertionError("Payload length mismatch for RAW") from err
+                        if err.code == -4 and not kolm_prof:
+                            raise ValueError(str(err)) from err     # V22's readers raise ValueError on truncation (v2-2.py:131-132, 1437-1447)
+                        raise_like_reference(err)
+                    if tot and on_batch is not None:
+                        on_batch(base_off, dev_out, tot)
+                        torch.cuda.current_stream().synchronize()
+                    elif tot and lazy:
+                        grow += self._home(dev_out, tot).tobytes()
+                    elif tot:
+                        _par_copy(sink[base_off:base_off + tot], self._home(dev_out, tot))
+                    i = j
+                    continue
                 groups: Dict[Tuple[str, int], List[int]] = {}
                 v2_tot, v2_part = 0, 0
                 for idx in range(i, j):

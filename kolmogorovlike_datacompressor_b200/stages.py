@@ -206,6 +206,69 @@ class Context:
         """decode_new_pipeline per block (method 10).  The context must hold 8x the batch (the bit planes are one batch)."""
         return self._dec("kolm_v2new_dec", payload, pay_off, off, (), out)
 
+    # ---- fused hot path ---------------------------------------------------
+    def _scratch(self, nbytes: int, device) -> torch.Tensor:
+        """Device scratch of the fused calls, kept between calls (256-byte aligned: torch allocations are 512-byte aligned)."""
+        t = getattr(self, "_fused_scratch", None)
+        if t is None or t.numel() < nbytes or t.device != device:
+            self._fused_scratch = None
+            t = self._fused_scratch = torch.empty(int(nbytes) + (int(nbytes) >> 4) + 4096, dtype=torch.uint8, device=device)
+        return t
+
+    def encode_blocks(self, profile: int, x: torch.Tensor, off, cand_mask: int = 0, ext=None, out: Optional[torch.Tensor] = None,
+                      want_sizes: bool = False):
+        """kolm_encode_blocks: _encode_block (profile 1, KF.py:821-864) / the KOLR selection loops (profile 2, V22.py:2350-2369) for a
+        whole batch, every candidate on the device -> (payload area tensor, payload_off int64[nb+1], method ids uint8[nb]
+        [, sizes int64[nb, ncand]]).  ext = (candidate id, sizes int64[nb], device addresses uint64[nb]) for a candidate that was
+        computed elsewhere."""
+        oa, op = _offsets(off)
+        nb = len(oa) - 1
+        n = int(oa[-1] - oa[0])
+        L = _lib.lib()
+        scratch = self._scratch(L.kolm_encode_blocks_scratch(int(profile), max(n, 1), max(nb, 1)), x.device)
+        if out is None:
+            out = torch.empty(n + 16 * nb + 64, dtype=torch.uint8, device=x.device)      # a winner is never larger than the block (raw)
+        poff = np.zeros(nb + 1, dtype=np.int64)
+        mids = np.zeros(max(nb, 1), dtype=np.uint8)
+        ncand = 4 if int(profile) == 1 else 10
+        sizes = np.zeros(max(nb, 1) * ncand, dtype=np.int64) if want_sizes else None
+        ext_id, ext_sizes, ext_addr = -1, None, None
+        if ext is not None:
+            ext_id = int(ext[0])
+            ext_sizes = np.ascontiguousarray(ext[1], dtype=np.int64)
+            ext_addr = np.ascontiguousarray(ext[2], dtype=np.uint64)
+        _lib.check(L.kolm_encode_blocks(self._h, int(profile), C.c_void_p(x.data_ptr()), op, nb, int(cand_mask), ext_id,
+                                        ext_sizes.ctypes.data_as(C.POINTER(C.c_int64)) if ext_sizes is not None else None,
+                                        C.c_void_p(ext_addr.ctypes.data) if ext_addr is not None else None,
+                                        C.c_void_p(scratch.data_ptr()), scratch.numel(), C.c_void_p(out.data_ptr()), out.numel(),
+                                        poff.ctypes.data_as(C.POINTER(C.c_int64)), C.c_void_p(mids.ctypes.data),
+                                        sizes.ctypes.data_as(C.POINTER(C.c_int64)) if sizes is not None else None, self._stream()), "kolm_encode_blocks")
+        res = (out, poff, mids[:nb])
+        return res + (sizes.reshape(-1, ncand)[:nb],) if want_sizes else res
+
+    def decode_blocks(self, profile: int, payload: torch.Tensor, pay_start, pay_len, method_ids, out_off, out: Optional[torch.Tensor] = None):
+        """kolm_decode_blocks: the decode loop of decompress (KF.py:925-949 / V22.py:2530-2540) for a whole batch; block b's payload is
+        payload[pay_start[b] : pay_start[b] + pay_len[b]].  Raises KolmError with .block = the lowest failing block index."""
+        ps = np.ascontiguousarray(pay_start, dtype=np.int64)
+        pl = np.ascontiguousarray(pay_len, dtype=np.int64)
+        oa, op = _offsets(out_off)
+        nb = len(oa) - 1
+        mids = np.ascontiguousarray(method_ids, dtype=np.uint8)
+        L = _lib.lib()
+        nout = int(oa[-1])
+        scratch = self._scratch(L.kolm_decode_blocks_scratch(max(int(pl.sum()), 1), max(nout - int(oa[0]), 1), max(nb, 1)), payload.device)
+        if out is None:
+            out = torch.empty(max(nout, 1) + 16, dtype=torch.uint8, device=payload.device)
+        bad = C.c_int(-1)
+        rc = L.kolm_decode_blocks(self._h, int(profile), C.c_void_p(payload.data_ptr()), ps.ctypes.data_as(C.POINTER(C.c_int64)),
+                                  pl.ctypes.data_as(C.POINTER(C.c_int64)), C.c_void_p(mids.ctypes.data), op, nb,
+                                  C.c_void_p(scratch.data_ptr()), scratch.numel(), C.c_void_p(out.data_ptr()), C.byref(bad), self._stream())
+        if rc != 0:
+            e = _lib.KolmError(rc, "kolm_decode_blocks")
+            e.block = bad.value
+            raise e
+        return out
+
     def select_blocks(self, sizes: np.ndarray):
         """_encode_block / the KOLR selection loops: sizes int64[nblocks, ncand] -> (winner index int64[nblocks], its size
         int64[nblocks]); first minimum, i.e. the lowest id on ties (strict '<' in the reference).  Compared on the device."""
