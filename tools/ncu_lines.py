@@ -8,8 +8,8 @@ import sys
 
 rep, kre = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kre],
-                     capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kre],
+                     capture_output=True, text=True).stdout if len(sys.argv) < 5 else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kre, "-s", sys.argv[4], "-c", "1"], capture_output=True, text=True).stdout
 fpath, hdr, seen_fn, out = "", None, 0, []
 for r in csv.reader(raw.splitlines()):
     if not r:
