@@ -309,6 +309,19 @@ struct WAcc {
         acc = 0;
     }
 };
+// The same without the first-word bookkeeping: every completed word goes out with a shared-memory atomic OR (one instruction, like the
+// plain store it replaces) and the cursor is a shared-memory pointer, so a push is a 64-bit shift, two ORs and a predicated flush.
+struct WFast {
+    u32 hi, lo, fill; u32* wp;
+    __device__ __forceinline__ void init(const WStage& st, u32 rel) { wp = st.sm + (rel >> 5); fill = rel & 31u; hi = lo = 0; }   // rel: bits from the window's first word
+    __device__ __forceinline__ void push(u32 code, u32 n) {                          // n in 1..32, code < 2^n
+        const u64 v = (u64)code << (64u - fill - n);
+        hi |= (u32)(v >> 32); lo |= (u32)v; fill += n;
+        if (fill >= 32u) { atomicOr(wp, hi); ++wp; hi = lo; lo = 0; fill -= 32u; }
+    }
+    __device__ __forceinline__ u32 rel(const WStage& st) const { return (u32)(wp - st.sm) * 32u + fill; }
+    __device__ __forceinline__ void finish() { if (hi) atomicOr(wp, hi); hi = 0; }
+};
 // tokens longer than 32 bits, or any token of a step that does not fit the window: rare, kept out of line
 // (the window travels BY VALUE so that the callers' copy never has its address taken and stays in registers)
 __device__ __noinline__ void r2_long_rice(WStage st, u64 bp, u32 tagbits, u32 tag, u32 x, u32 k) {
@@ -320,6 +333,16 @@ __device__ __noinline__ void r2_long_gamma(WStage st, u64 bp, u32 tag, u32 x) {
     st.gamma(bp + 1, x);
 }
 
+__device__ __forceinline__ u32 r2_warp_incl_add32(u32 v) {
+    const u32 lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v += n; }
+    return v;
+}
+// one KF token of more than 32 bits at absolute bit position bp (tag, then Rice(k) of val - tag or gamma of val)
+__device__ __forceinline__ void r2_long_tok(const WStage& st, u64 bp, bool rice, u32 k, u32 tag, u32 val) {
+    if (rice) r2_long_rice(st, bp, 1, tag, val - tag, k); else r2_long_gamma(st, bp, tag, val);
+}
 // KF token (KF.py:670-684): tag bit, then Rice(k) of x or gamma of g.  Zero run of length r: tag 0, x = g = r.  Non-zero v: tag 1,
 // x = v - 1, g = v.  Returns the token's length in bits; code is valid when the length is <= 32.
 __device__ __forceinline__ u32 r2_kf_token(bool rice, u32 k, u32 tag, u32 val /* r or v */, u32& code) {
@@ -388,40 +411,86 @@ __global__ void __launch_bounds__(R2_THREADS) k_rice2_kf_pack(const u8* __restri
         carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
         const bool hdr = first_tile && base == 0 && lane == 0;
         const bool tail = last_tile && valid && o + valid == count;     // I hold the block's last byte
-        // pass 1: bits of my tokens
-        u64 mybits = hdr ? 10 : 0;
+        const u32 p0 = t0 + o;                                           // block-local position of my first byte
+        // run tokens end at the non-zeros that follow a zero: bit i of rz = a run ends before my byte i
+        const u32 rz = nzm0 & ~(nzm0 << 1) & ~((ln0 == p0) ? 1u : 0u);
+        // pass 1: bits of my tokens.  Non-zero tokens as SIMD-in-register sums (no loop), run tokens one by one (few)
+        u32 mybits = hdr ? 10u : 0u;
         {
-            u32 nzm = nzm0, ln = ln0, code;
-            while (nzm) {
-                const u32 i = __ffs(nzm) - 1; nzm &= nzm - 1;
-                const u32 b = r2_byte(wd, i), pos = t0 + o + i;            // block-local 0-based
-                if (pos > ln) mybits += r2_kf_token(urz, k0, 0, pos - ln, code);
-                mybits += r2_kf_token(urn, k1, 1, b, code);
-                ln = pos + 1;
+            const u32 cnt = __popc(nzm0);
+            if (urn) {                                       // Rice(k1) of x = v - 1: sum q + cnt * (2 + k1)
+                const u32 mk = (0xFFu >> k1) * 0x01010101u;
+                u32 q = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const u32 x = wd[j] - (__vcmpne4(wd[j], 0u) & 0x01010101u); q = __dp4a((x >> k1) & mk, 0x01010101u, q); }
+                mybits += q + cnt * (2u + k1);
+            } else {                                         // gamma of v: 2 * bitlen(v) per non-zero (tag included)
+                u32 bl = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    u32 x = wd[j];
+                    x |= (x >> 1) & 0x7F7F7F7Fu; x |= (x >> 2) & 0x3F3F3F3Fu; x |= (x >> 4) & 0x0F0F0F0Fu;   // smear: bitlen = popcount
+                    x = x - ((x >> 1) & 0x55555555u); x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u); x = (x + (x >> 4)) & 0x0F0F0F0Fu;
+                    bl = __dp4a(x, 0x01010101u, bl);
+                }
+                mybits += 2u * bl;
             }
-            if (tail && bi.len > ln) mybits += r2_kf_token(urz, k0, 0, bi.len - ln, code);
+            u32 m = rz, code;
+            while (m) {
+                const u32 i = __ffs(m) - 1; m &= m - 1;
+                const u32 below = nzm0 & ((1u << i) - 1u);
+                const u32 ln = below ? p0 + (32u - __clz(below)) : ln0;      // 1-based position of the previous non-zero
+                mybits += r2_kf_token(urz, k0, 0, p0 + i - ln, code);
+            }
+            if (tail) {
+                const u32 ln = nzm0 ? p0 + (32u - __clz(nzm0)) : ln0;
+                if (bi.len > ln) mybits += r2_kf_token(urz, k0, 0, bi.len - ln, code);
+            }
         }
-        const u64 incb = r2_warp_incl_add(mybits);
-        const u64 total = __shfl_sync(0xffffffffu, incb, 31);
+        const u32 incb = r2_warp_incl_add32(mybits);
+        const u32 total = __shfl_sync(0xffffffffu, incb, 31);
         WStage st;
         st.begin(s_stage[w], out, bitpos, total);
-        WAcc ba; ba.init(st, bitpos + (incb - mybits));
-        if (hdr) {                                           // KF.py:664-668: 2 bits (nz << 1 | zero), 4 bits k0, 4 bits k1
-            const u32 h = (((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1;
-            if (st.use) ba.push(st, h, 10); else { st.bits(bitpos, h, 10); ba.init(st, bitpos + 10); }
-        }
-        {
+        if (st.use) {
+            // the step fits the window: lean accumulator, positions relative to the window
+            WFast fa; fa.init(st, ((u32)bitpos & 31u) + (incb - mybits));
+            if (hdr) fa.push((((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1, 10);   // KF.py:664-668: flags, k0, k1
             u32 nzm = nzm0, ln = ln0;
             while (nzm) {
                 const u32 i = __ffs(nzm) - 1; nzm &= nzm - 1;
-                const u32 b = r2_byte(wd, i), pos = t0 + o + i;
+                const u32 b = r2_byte(wd, i), pos = p0 + i;
+                u32 code;
+                if (pos > ln) {
+                    const u32 n = r2_kf_token(urz, k0, 0, pos - ln, code);
+                    if (n <= 32) fa.push(code, n);
+                    else { fa.finish(); const u32 r = fa.rel(st); r2_long_tok(st, (st.first_word << 5) + r, urz, k0, 0, pos - ln); fa.init(st, r + n); }
+                }
+                const u32 n = r2_kf_token(urn, k1, 1, b, code);
+                if (n <= 32) fa.push(code, n);
+                else { fa.finish(); const u32 r = fa.rel(st); r2_long_tok(st, (st.first_word << 5) + r, urn, k1, 1, b); fa.init(st, r + n); }
+                ln = pos + 1;
+            }
+            if (tail && bi.len > ln) {
+                u32 code; const u32 n = r2_kf_token(urz, k0, 0, bi.len - ln, code);
+                if (n <= 32) fa.push(code, n);
+                else { fa.finish(); const u32 r = fa.rel(st); r2_long_tok(st, (st.first_word << 5) + r, urz, k0, 0, bi.len - ln); fa.init(st, r + n); }
+            }
+            fa.finish();
+        } else {
+            // a step whose bits exceed the window (long unary parts): every token straight to global memory
+            WAcc ba; ba.init(st, bitpos + (incb - mybits));
+            if (hdr) { st.bits(bitpos, (((urn ? 2u : 0u) | (urz ? 1u : 0u)) << 8) | (k0 << 4) | k1, 10); ba.init(st, bitpos + 10); }
+            u32 nzm = nzm0, ln = ln0;
+            while (nzm) {
+                const u32 i = __ffs(nzm) - 1; nzm &= nzm - 1;
+                const u32 b = r2_byte(wd, i), pos = p0 + i;
                 if (pos > ln) r2_kf_emit(st, ba, urz, k0, 0, pos - ln);
                 r2_kf_emit(st, ba, urn, k1, 1, b);
                 ln = pos + 1;
             }
             if (tail && bi.len > ln) r2_kf_emit(st, ba, urz, k0, 0, bi.len - ln);
+            ba.finish(st);
         }
-        ba.finish(st);
         st.flush();
         bitpos += total;
     }
@@ -474,25 +543,39 @@ __global__ void __launch_bounds__(R2_THREADS) k_rice2_k2_pack(const u8* __restri
             const u32 keep = nb == 4 ? 0xffffffffu : ((1u << (8 * nb)) - 1u);
             mybits = __dp4a((wd[j] >> 2) & 0x3F3F3F3Fu & keep, 0x01010101u, mybits) + 3u * nb;
         }
-        const u64 incb = r2_warp_incl_add((u64)mybits);
-        const u64 total = __shfl_sync(0xffffffffu, incb, 31);
+        const u32 incb = r2_warp_incl_add32(mybits);
+        const u32 total = __shfl_sync(0xffffffffu, incb, 31);
         WStage st;
         st.begin(s_stage[w], out, bitpos, total);
-        WAcc ba; ba.init(st, bitpos + (incb - mybits));
+        // q ones, the terminating 0, 2 remainder bits per symbol; a symbol below 120 codes in at most 32 bits
+        const bool allshort = ((__vcmpgeu4(wd[0], 0x78787878u) | __vcmpgeu4(wd[1], 0x78787878u) | __vcmpgeu4(wd[2], 0x78787878u) | __vcmpgeu4(wd[3], 0x78787878u)) == 0u);
+        if (st.use && allshort) {
+            WFast fa; fa.init(st, ((u32)bitpos & 31u) + (incb - mybits));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if ((u32)i < valid) {
-                const u32 t = (wd[i >> 2] >> (8 * (i & 3))) & 0xFFu, q = t >> 2, n = q + 3;   // q ones, the terminating 0, 2 remainder bits
-                if (n <= 32 && st.use) ba.push(st, ((((u32)1 << q) - 1u) << 3) | (t & 3u), n);
-                else {
-                    ba.finish(st);
-                    const u64 bp = ba.bitpos(st);
-                    r2_long_rice(st, bp, 0, 0, t, 2);
-                    ba.init(st, bp + n);
+            for (int i = 0; i < 16; ++i) {
+                if ((u32)i < valid) {
+                    const u32 t = (wd[i >> 2] >> (8 * (i & 3))) & 0xFFu, q = t >> 2;
+                    fa.push(((((u32)1 << q) - 1u) << 3) | (t & 3u), q + 3);
                 }
             }
+            fa.finish();
+        } else {
+            WAcc ba; ba.init(st, bitpos + (incb - mybits));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if ((u32)i < valid) {
+                    const u32 t = (wd[i >> 2] >> (8 * (i & 3))) & 0xFFu, q = t >> 2, n = q + 3;
+                    if (n <= 32 && st.use) ba.push(st, ((((u32)1 << q) - 1u) << 3) | (t & 3u), n);
+                    else {
+                        ba.finish(st);
+                        const u64 bp = ba.bitpos(st);
+                        r2_long_rice(st, bp, 0, 0, t, 2);
+                        ba.init(st, bp + n);
+                    }
+                }
+            }
+            ba.finish(st);
         }
-        ba.finish(st);
         st.flush();
         bitpos += total;
     }
