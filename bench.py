@@ -19,6 +19,7 @@ variants' exact costs + one packed variant (kolm_final_researched_v2-2.py models
                          gather of the compressed stream inside the timed region (strong scaling: the corpus does not grow with N);
                          at N = 1 also kolm_final compress/decompress (KOLM)
     cfg5_block_sweep     block sizes 64 KiB .. 16 MiB, encode and decode, S3 mix, per GPU (weak)
+    default_block_sizes  the reference's default block sizes (2 KiB KOLR, 8 KiB KOLM) through the drop-ins' fused per-batch call (N = 1)
 """
 from __future__ import annotations
 
@@ -709,15 +710,58 @@ def leg_cfg5(env, args):
     return out
 
 
+def leg_default_blocks(env, args):
+    """The reference's own default block sizes through the fused per-batch call (kolm_encode_blocks / kolm_decode_blocks behind the
+    drop-ins): compress_blocks_fixed(data, 2048) (V22 CLI default, V22.py:2650) and kolm_final.compress(data, 8192) (KF.py:866) on the
+    S3 mix, with the round trip and a sampled oracle comparison of whole containers (KOLM) / block selections (KOLR)."""
+    torch = env.torch
+    from kolmogorovlike_datacompressor_b200 import synth
+    from kolmogorovlike_datacompressor_b200 import kolm_final as KF
+    from kolmogorovlike_datacompressor_b200 import kolm_final_researched_v2_2 as V
+    from oracle import oracle as O
+    import concurrent.futures as cf
+    pool = cf.ThreadPoolExecutor(max_workers=8)
+    out = {"workload": "S3 mix at the reference's default block sizes, 1 GPU, host bytes in -> container bytes out"}
+    n_r = min(args.default_mib, 120) * MIB                           # <= 65 535 blocks of 2 KiB per KOLR container
+    data = synth.s3_mix(max(n_r, args.default_mib * MIB), seed=11, text_seed=0xC0FFEE + 11)
+    d_r = data[:n_r].tobytes()
+    # oracle expectation for sampled blocks (one 2 KiB block out of each of the eight segment kinds)
+    picks = [k * MIB // 2048 + 37 for k in range(8) if (k + 1) * MIB <= n_r]
+    futs = [pool.submit(O.encode_block, O.PROFILE_KOLR, d_r[i * 2048:(i + 1) * 2048]) for i in picks]
+    V.compress_blocks_fixed(d_r[:4 * MIB], 2048)
+    t0 = time.perf_counter(); blob = V.compress_blocks_fixed(d_r, 2048); torch.cuda.synchronize(); t1 = time.perf_counter()
+    back = V.decompress(blob); t2 = time.perf_counter()
+    names, starts, plens, olens, _, _ = V._parse(blob)
+    bad = [i for i, f in zip(picks, futs) if V.KOLR_NAMES[f.result()[0]] != names[i] or blob[starts[i]:starts[i] + plens[i]] != f.result()[1]]
+    hist = {}
+    for nme in names:
+        hist[nme] = hist.get(nme, 0) + 1
+    out["kolr_2KiB"] = {"bytes": n_r, "blocks": len(names), "compress_MBps": round(n_r / (t1 - t0) / 1e6, 1), "decompress_MBps": round(n_r / (t2 - t1) / 1e6, 1),
+                        "roundtrip_bit_exact": back == d_r, "container_bytes": len(blob), "methods": hist, "oracle_blocks": len(picks), "oracle_blocks_identical": not bad}
+    d_m = data[:args.default_mib * MIB].tobytes()
+    small = d_m[:2 * MIB]
+    fut_c = pool.submit(O.kf_compress, small, 8192)                  # the oracle's whole container for a 2 MiB prefix
+    KF.compress(d_m[:4 * MIB], 8192)
+    t0 = time.perf_counter(); blob = KF.compress(d_m, 8192); torch.cuda.synchronize(); t1 = time.perf_counter()
+    back = KF.decompress(blob); t2 = time.perf_counter()
+    same = KF.compress(small, 8192) == fut_c.result()
+    out["kolm_8KiB"] = {"bytes": len(d_m), "blocks": int.from_bytes(blob[16:18], "little"), "compress_MBps": round(len(d_m) / (t1 - t0) / 1e6, 1),
+                        "decompress_MBps": round(len(d_m) / (t2 - t1) / 1e6, 1), "roundtrip_bit_exact": back == d_m, "container_bytes": len(blob),
+                        "oracle_container_2MiB_identical": bool(same)}
+    out["ok"] = bool(out["kolr_2KiB"]["roundtrip_bit_exact"] and not bad and out["kolm_8KiB"]["roundtrip_bit_exact"] and same)
+    return out
+
+
 def run_ours(args):
     env = Env(args)
     fields, finish_parity = leg_cfg2(env, args)
     parity_fail = False
     legs = {}
-    want = set(args.legs.split(",")) if args.legs != "all" else {"cfg3", "cfg4", "cfg5"}
+    want = set(args.legs.split(",")) if args.legs != "all" else {"cfg3", "cfg4", "cfg5", "default"}
     if args.legs == "none":
         want = set()
     for name, fn, cond in (("cfg3_lz77", leg_cfg3, "cfg3" in want and env.world == 1),
+                           ("default_block_sizes", leg_default_blocks, "default" in want and env.world == 1),
                            ("cfg5_block_sweep", leg_cfg5, "cfg5" in want),
                            ("cfg4_full_pipeline", leg_cfg4, "cfg4" in want)):
         if not cond:
@@ -788,13 +832,14 @@ def main():
     ap.add_argument("--block-kib", type=int, default=1024)
     ap.add_argument("--cpu-blocks", type=int, default=16, help="blocks in the bounded cpu_baseline / parity sample (0 = skip)")
     ap.add_argument("--cpu-all-cores", type=int, default=1, help="also time the oracle port on every host core (N = 1)")
-    ap.add_argument("--legs", default="all", help="comma list of cfg3,cfg4,cfg5 | all | none")
+    ap.add_argument("--legs", default="all", help="comma list of cfg3,cfg4,cfg5,default | all | none")
     ap.add_argument("--leg-steps", type=int, default=2, help="timed repetitions inside the cfg 3 / cfg 5 legs")
     ap.add_argument("--cfg3-mib", type=int, default=256)
     ap.add_argument("--cfg4-containers", type=int, default=4, help="containers of the sharded S3 corpus (BASELINE cfg 4: 4 x 1 GiB)")
     ap.add_argument("--cfg4-container-mib", type=int, default=1024)
     ap.add_argument("--kolm-mib", type=int, default=256, help="KOLM drop-in leg on this many MiB (N = 1; 0 = skip)")
     ap.add_argument("--cfg5-mib", type=int, default=512, help="cfg 5 corpus MiB per GPU")
+    ap.add_argument("--default-mib", type=int, default=120, help="corpus MiB of the default-block-size leg (N = 1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

@@ -528,7 +528,10 @@ int kolm_repair_big_impl(kolm_ctx* c, const u8* in, u8* tmp, cudaStream_t s) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = free_b + c->rpb_bytes;                   // what the pool may use: what is free now plus what it already holds
-    budget = budget * 3 / 5 < ((size_t)100 << 30) ? budget * 3 / 5 : ((size_t)100 << 30);
+    static long long pool_gib = -1, pool_pct = -1;           // KOLM_REPAIR_POOL_GIB / KOLM_REPAIR_POOL_PCT: cap of the slab pool (absolute, share of free memory)
+    if (pool_gib < 0) { const char* e = getenv("KOLM_REPAIR_POOL_GIB"); pool_gib = e ? atoll(e) : 100; if (pool_gib < 1) pool_gib = 1; }
+    if (pool_pct < 0) { const char* e = getenv("KOLM_REPAIR_POOL_PCT"); pool_pct = e ? atoll(e) : 60; if (pool_pct < 5 || pool_pct > 95) pool_pct = 60; }
+    budget = budget / 100 * (size_t)pool_pct < ((size_t)pool_gib << 30) ? budget / 100 * (size_t)pool_pct : ((size_t)pool_gib << 30);
     static int per_sm = -1;                                  // KOLM_REPAIR_CTAS_PER_SM: the CTAs mostly wait on dependent loads, several per SM overlap
     if (per_sm < 0) { const char* e = getenv("KOLM_REPAIR_CTAS_PER_SM"); per_sm = e ? atoi(e) : RPB_CTAS_PER_SM; if (per_sm < 1) per_sm = 1; }
     int grid = nbig < per_sm * c->sm_count ? nbig : per_sm * c->sm_count;

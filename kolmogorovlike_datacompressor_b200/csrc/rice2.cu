@@ -369,7 +369,7 @@ __device__ __forceinline__ void r2_kf_emit(const WStage& st, WAcc& ba, bool rice
     }
 }
 
-__global__ void __launch_bounds__(R2_THREADS) k_rice2_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
+__global__ void __launch_bounds__(R2_THREADS, 4) k_rice2_kf_pack(const u8* __restrict__ mtf, const TileDesc* __restrict__ tiles,
                                                               const BlockInfo* __restrict__ binfo, const u64* __restrict__ tacc, const u64* __restrict__ bacc,
                                                               u32* __restrict__ out, int ntiles, const i64* __restrict__ cap_total, u64 cap,
                                                               const int* __restrict__ method, int want) {
