@@ -252,6 +252,292 @@ __global__ void __launch_bounds__(MTF2_THREADS) k_mtf_enc2(const u8* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// encode, v3 (default): local lists, list-prefix scan, miss fix-up.  No timestamp tables, no per-piece entry lists.
+//
+//   k_mtf3_walk   one THREAD per 1 KiB piece walks its bytes from the EMPTY list.  A symbol already seen in the piece has its true
+//                 MTF index (everything between its two occurrences lies inside the piece); a first occurrence ("miss") is
+//                 recorded (symbol, position) and patched later.  The walk alternates two warp-uniform phases per 32 bytes:
+//                   A  all lanes run the same branch-free code on the four front entries (one register): the entry is found
+//                      there (index 0..3) or not; either way the register word is final — a symbol not found in front is pushed
+//                      on the front and the fourth entry drops into the deep part — so the phase never waits for a deep search;
+//                   B  the deep searches of the group (packed words in shared memory, [word][thread]) are drained in order.
+//                 The divergence of the old walk (every byte step cost the warp its slowest lane) is confined to phase B.
+//   k_mtf3_agg    one warp per group of 32 pieces: the group's list = fold of its pieces' final lists under
+//                 later (+) earlier = later, then earlier without the symbols of later.
+//   k_mtf3_prefix one warp per block: entry list of every group (identity list at the block start).
+//   k_mtf3_fix    one warp per group: entry list E of every piece; the m-th miss of a piece (symbol c, entry index r in E) has
+//                 index r + #{earlier misses of the piece with a larger entry index} (the m symbols seen so far sit in front, the
+//                 rest of E keeps its order).
+// ---------------------------------------------------------------------------------------------
+#define M3_THREADS 128
+#define M3_SLOT 1024                                       // scratch bytes per piece: final list [256] | misses in order [256] | their positions [256] u16
+#define M3_GROUP_TILES 8                                   // tiles per scan group (32 pieces of 1 KiB)
+
+template <bool WHOLE>
+__device__ __forceinline__ void m3_byte(const u32 b, const u32 i, const u32 nb, u32& w0, u32& vmask, u32& dm, u32& ow) {
+    const u32 x = w0 ^ (b * 0x01010101u);
+    const u32 z = (x - 0x01010101u) & ~x & vmask;          // lowest set bit = the entry that equals b (bits above it may be false)
+    const bool ok = WHOLE || i < nb;
+    u32 M = z ^ (z - 1u);                                  // bytes 0..idx; all ones when b is not among the front entries
+    if (!WHOLE && !ok) M = 0u;
+    const u32 sh = __byte_perm(w0, b, 0x2104);            // (w0 << 8) | b
+    const u32 e = w0 >> 24;                                // the entry that drops out of the register when b is pushed
+    w0 = (w0 & ~M) | (sh & M);
+    const u32 val = z ? (u32)__popc(M & 0x01010100u) : e;
+    ow |= val << (8 * (i & 3));
+    if (ok && !z) { dm |= 1u << i; vmask = (vmask << 8) | 0x80u; }
+}
+
+__global__ void __launch_bounds__(M3_THREADS) k_mtf3_walk(const u8* __restrict__ in, u8* __restrict__ out, const TileDesc* __restrict__ tiles,
+                                                          const BlockInfo* __restrict__ binfo, u8* __restrict__ slots, u32* __restrict__ npc, int np) {
+    __shared__ u32 lst[63][M3_THREADS];                    // deep part: list word k (entries 4k..4k+3) of thread t at lst[k-1][t]
+    __shared__ u32 ist[8][M3_THREADS];                     // the group's input bytes
+    __shared__ u32 ost[8][M3_THREADS];                     // the group's output bytes (phase B patches them)
+    const u32 tid = threadIdx.x;
+    const int piece = blockIdx.x * M3_THREADS + tid;
+    u32 pcount = 0; const u8* src = nullptr; u8* dst = nullptr;
+    if (piece < np) {
+        const TileDesc td = tiles[(u32)piece >> 2];
+        const BlockInfo bi = binfo[td.block];
+        u32 pstart;
+        mtf_piece(td, (u32)piece, 2u, pstart, pcount);
+        const u32 t0 = pstart - bi.pbase;
+        src = in + bi.ioff + t0; dst = out + bi.ioff + t0;
+    }
+    u8* slot = slots + (size_t)(piece < np ? piece : 0) * M3_SLOT;
+    const bool al_in = (((uintptr_t)src) & 15) == 0, al_out = (((uintptr_t)dst) & 15) == 0;
+    u8* ib = reinterpret_cast<u8*>(&ist[0][0]) + 4 * tid;  // byte i of my group at ib[(i >> 2) * 4 * M3_THREADS + (i & 3)]
+    u8* ob = reinterpret_cast<u8*>(&ost[0][0]) + 4 * tid;
+    u32 w0 = 0, vmask = 0, n = 0;
+    const u32 maxc = __reduce_max_sync(0xffffffffu, pcount);
+    for (u32 x0 = 0; x0 < maxc; x0 += 32) {
+        const u32 nb = pcount > x0 ? min(32u, pcount - x0) : 0u;
+        u32 inw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) inw[j] = 0;
+        if (nb) {
+            const u8* g = src + x0;
+            if (al_in) {                                   // a 16-byte load that holds one valid byte stays inside the allocation
+                const uint4 q0 = *reinterpret_cast<const uint4*>(g);
+                inw[0] = q0.x; inw[1] = q0.y; inw[2] = q0.z; inw[3] = q0.w;
+                if (nb > 16) { const uint4 q1 = *reinterpret_cast<const uint4*>(g + 16); inw[4] = q1.x; inw[5] = q1.y; inw[6] = q1.z; inw[7] = q1.w; }
+            } else {                                       // aligned words + funnel shift (same argument for the words at the ends)
+                const u32 s = (u32)((uintptr_t)g & 3);
+                const u32* gw = reinterpret_cast<const u32*>(g - s);
+                u32 a[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) a[j] = (4u * j < nb + s) ? gw[j] : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) inw[j] = __funnelshift_r(a[j], a[j + 1], 8 * s);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ist[j][tid] = inw[j];
+        // ---- phase A
+        u32 dm = 0;
+        if (__all_sync(0xffffffffu, nb == 32)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                u32 ow = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) m3_byte<true>((inw[j] >> (8 * q)) & 0xFFu, 4 * j + q, 32u, w0, vmask, dm, ow);
+                ost[j][tid] = ow;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                u32 ow = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) m3_byte<false>((inw[j] >> (8 * q)) & 0xFFu, 4 * j + q, nb, w0, vmask, dm, ow);
+                ost[j][tid] = ow;
+            }
+        }
+        // ---- phase B: the group's deep searches, in order
+        while (__any_sync(0xffffffffu, dm != 0)) {
+            if (dm) {
+                const u32 i = __ffs(dm) - 1; dm &= dm - 1;
+                const u32 bo = (i >> 2) * (4 * M3_THREADS) + (i & 3);
+                const u32 c = ib[bo];
+                bool miss = true;
+                if (n >= 4) {                              // with fewer than four entries the deep part is empty and the register is already right
+                    const u32 bbbb = c * 0x01010101u, last = n >> 2;
+                    u32 carry = ob[bo];
+                    for (u32 k = 1;; ++k) {
+                        const u32 wk = lst[k - 1][tid];
+                        const u32 vm = k == last ? (0x00808080u >> (8 * (3 - (n & 3)))) : 0x80808080u;   // word `last` holds n & 3 entries
+                        const u32 x = wk ^ bbbb;
+                        const u32 z = (x - 0x01010101u) & ~x & vm;
+                        const u32 M = z ^ (z - 1u);
+                        const u32 sh = (wk << 8) | carry;
+                        lst[k - 1][tid] = (wk & ~M) | (sh & M);
+                        if (z) { ob[bo] = (u8)(4 * k + __popc(M & 0x01010100u)); miss = false; break; }
+                        if (k == last) break;
+                        carry = wk >> 24;
+                    }
+                }
+                if (miss) {                                // first occurrence in the piece: k_mtf3_fix writes its index
+                    slot[256 + n] = (u8)c;
+                    reinterpret_cast<u16*>(slot + 512)[n] = (u16)(x0 + i);
+                    ++n;
+                }
+            }
+        }
+        // ---- store
+        if (nb) {
+            u8* g = dst + x0;
+            if (al_out && nb == 32) {
+                *reinterpret_cast<uint4*>(g) = make_uint4(ost[0][tid], ost[1][tid], ost[2][tid], ost[3][tid]);
+                *reinterpret_cast<uint4*>(g + 16) = make_uint4(ost[4][tid], ost[5][tid], ost[6][tid], ost[7][tid]);
+            } else {
+                for (u32 i = 0; i < nb; ++i) g[i] = ob[(i >> 2) * (4 * M3_THREADS) + (i & 3)];
+            }
+        }
+    }
+    if (piece < np) {
+        npc[piece] = n;
+        u32* Lw = reinterpret_cast<u32*>(slot);
+        if (n) Lw[0] = w0;
+        for (u32 k = 1; 4 * k < n; ++k) Lw[k] = lst[k - 1][tid];
+    }
+}
+
+struct __align__(16) M3Warp { u8 a[256]; u8 b[256]; u8 inv[256]; u8 r[256]; u32 mask[8]; };
+
+// cur (cnt entries) <- L (n entries, all distinct) followed by the entries of cur that are not in L; l0 = L[lane] (prefetched, lane < n).
+// The current list is W.a or W.b, chosen by `sel` (an index, not a pair of swapped pointers: with the swap nvcc 12.9 addressed
+// W.mask relative to the loop-carried `cur`, i.e. 256 bytes too far in every second call, and cleared the next warp's list instead).
+__device__ __forceinline__ void m3_combine(M3Warp& W, u32& sel, u32& cnt, const u8* __restrict__ L, u32 n, u32 l0) {
+    const u32 lane = lane_id();
+    if (!n) return;
+    u8* const cur = sel ? W.b : W.a;
+    u8* const nxt = sel ? W.a : W.b;
+    u32* const mask = W.mask;
+    if (lane < 8) mask[lane] = 0;
+    __syncwarp();
+    if (lane < n) { nxt[lane] = (u8)l0; atomicOr(&mask[l0 >> 5], 1u << (l0 & 31)); }
+    for (u32 i = lane + 32; i < n; i += 32) { const u32 c = L[i]; nxt[i] = (u8)c; atomicOr(&mask[c >> 5], 1u << (c & 31)); }
+    __syncwarp();
+    const uint2 mine = *reinterpret_cast<const uint2*>(cur + 8 * lane);
+    u32 keep = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const u32 c = ((j < 4 ? mine.x : mine.y) >> (8 * (j & 3))) & 0xFFu;
+        if (8 * lane + j < cnt && !((mask[c >> 5] >> (c & 31)) & 1u)) keep |= 1u << j;
+    }
+    u32 incl = __popc(keep);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
+    u32 pos = n + incl - __popc(keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if ((keep >> j) & 1u) nxt[pos++] = (u8)(((j < 4 ? mine.x : mine.y) >> (8 * (j & 3))) & 0xFFu);
+    cnt = n + __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    sel ^= 1u;
+}
+
+// warp g looks at the tiles 8g .. 8g+7: every tile that starts a group (its distance from the block's first tile is a multiple of
+// eight) is folded by this warp — exactly one group per warp when blocks are whole multiples of 32 KiB, a few short ones otherwise
+__global__ void __launch_bounds__(256) k_mtf3_agg(const TileDesc* __restrict__ tiles, const u32* __restrict__ tile0, const u32* __restrict__ tilen,
+                                                  const u8* __restrict__ slots, const u32* __restrict__ npc, u8* __restrict__ agg, u32* __restrict__ aggn, int nt) {
+    __shared__ M3Warp sw[8];
+    const u32 lane = lane_id(), w = threadIdx.x >> 5;
+    const int g = blockIdx.x * 8 + w;
+    for (int t = g * M3_GROUP_TILES; t < nt && t < (g + 1) * M3_GROUP_TILES; ++t) {
+        const u32 b = tiles[t].block, rel = (u32)t - tile0[b];
+        if (rel % M3_GROUP_TILES) continue;
+        const u32 np = 4 * min((u32)M3_GROUP_TILES, tilen[b] - rel), p0 = 4 * (u32)t;
+        const u32 myn = lane < np ? npc[p0 + lane] : 0u;
+        u32 sel = 0, cnt = 0;
+        u32 n = __shfl_sync(0xffffffffu, myn, 0);
+        u32 l0 = lane < n ? slots[(size_t)p0 * M3_SLOT + lane] : 0u;
+        for (u32 q = 0; q < np; ++q) {
+            const u32 n1 = q + 1 < np ? __shfl_sync(0xffffffffu, myn, q + 1) : 0u;
+            const u32 l1 = lane < n1 ? slots[(size_t)(p0 + q + 1) * M3_SLOT + lane] : 0u;      // next piece's list, in flight during this fold
+            m3_combine(sw[w], sel, cnt, slots + (size_t)(p0 + q) * M3_SLOT, n, l0);
+            n = n1; l0 = l1;
+        }
+        const u8* cur = sel ? sw[w].b : sw[w].a;
+        for (u32 i = lane; i < cnt; i += 32) agg[(size_t)t * 256 + i] = cur[i];
+        if (lane == 0) aggn[t] = cnt;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mtf3_prefix(const u32* __restrict__ tile0, const u32* __restrict__ tilen, const u8* __restrict__ agg,
+                                                     const u32* __restrict__ aggn, u8* __restrict__ pre, int nblocks) {
+    __shared__ M3Warp sw[8];
+    const u32 lane = lane_id(), w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 8 + w;
+    if (b >= nblocks) return;
+    u32 sel = 0, cnt = 256;
+    for (u32 i = lane; i < 256; i += 32) sw[w].a[i] = (u8)i;
+    __syncwarp();
+    const u32 t0 = tile0[b], tn = tilen[b];
+    u32 n = tn ? aggn[t0] : 0u;
+    u32 l0 = lane < n ? agg[(size_t)t0 * 256 + lane] : 0u;
+    for (u32 rel = 0; rel < tn; rel += M3_GROUP_TILES) {
+        const size_t t = (size_t)t0 + rel;
+        const u32 n1 = rel + M3_GROUP_TILES < tn ? aggn[t + M3_GROUP_TILES] : 0u;
+        const u32 l1 = lane < n1 ? agg[(t + M3_GROUP_TILES) * 256 + lane] : 0u;
+        reinterpret_cast<uint2*>(pre + t * 256)[lane] = *reinterpret_cast<const uint2*>((sel ? sw[w].b : sw[w].a) + 8 * lane);
+        m3_combine(sw[w], sel, cnt, agg + t * 256, n, l0);
+        n = n1; l0 = l1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mtf3_fix(u8* __restrict__ out, const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
+                                                  const u32* __restrict__ tile0, const u32* __restrict__ tilen, const u8* __restrict__ slots,
+                                                  const u32* __restrict__ npc, const u8* __restrict__ pre, int nt) {
+    __shared__ M3Warp sw[8];
+    const u32 lane = lane_id(), w = threadIdx.x >> 5;
+    const int g = blockIdx.x * 8 + w;
+    M3Warp& W = sw[w];
+    for (int t = g * M3_GROUP_TILES; t < nt && t < (g + 1) * M3_GROUP_TILES; ++t) {
+        const TileDesc td0 = tiles[t];
+        const u32 b = td0.block, rel = (u32)t - tile0[b];
+        if (rel % M3_GROUP_TILES) continue;
+        const BlockInfo bi = binfo[b];
+        const u32 np = 4 * min((u32)M3_GROUP_TILES, tilen[b] - rel), p0 = 4 * (u32)t;
+        const u32 myn = lane < np ? npc[p0 + lane] : 0u;
+        u32 sel = 0, cnt = 256;
+        *reinterpret_cast<uint2*>(W.a + 8 * lane) = reinterpret_cast<const uint2*>(pre + (size_t)t * 256)[lane];
+        __syncwarp();
+        u8* dst0 = out + bi.ioff + (td0.start - bi.pbase);   // tiles of a block are consecutive and full except the last
+        u32 n = __shfl_sync(0xffffffffu, myn, 0);
+        u32 l0 = 0, f0 = 0, q0 = 0;
+        if (lane < n) { const u8* sl = slots + (size_t)p0 * M3_SLOT; l0 = sl[lane]; f0 = sl[256 + lane]; q0 = reinterpret_cast<const u16*>(sl + 512)[lane]; }
+        for (u32 q = 0; q < np; ++q) {
+            const u32 n1 = q + 1 < np ? __shfl_sync(0xffffffffu, myn, q + 1) : 0u;
+            u32 l1 = 0, f1 = 0, q1 = 0;                          // the next piece's first 32 entries, in flight during this step
+            if (lane < n1) { const u8* sl = slots + (size_t)(p0 + q + 1) * M3_SLOT; l1 = sl[lane]; f1 = sl[256 + lane]; q1 = reinterpret_cast<const u16*>(sl + 512)[lane]; }
+            if (n) {
+                const u8* slot = slots + (size_t)(p0 + q) * M3_SLOT;
+                const u16* Q = reinterpret_cast<const u16*>(slot + 512);
+                u8* dst = dst0 + (size_t)q * (KOLM_TILE / 4);
+                const uint2 mine = *reinterpret_cast<const uint2*>((sel ? W.b : W.a) + 8 * lane);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) W.inv[((j < 4 ? mine.x : mine.y) >> (8 * (j & 3))) & 0xFFu] = (u8)(8 * lane + j);
+                __syncwarp();
+                if (lane < n) W.r[lane] = W.inv[f0];
+                for (u32 i = lane + 32; i < n; i += 32) W.r[i] = W.inv[slot[256 + i]];
+                __syncwarp();
+                for (u32 i = lane; i < n; i += 32) {
+                    const u32 r = W.r[i], rrrr = r * 0x01010101u;
+                    u32 gt = 0, k = 0;
+                    for (; k + 4 <= i; k += 4) gt += __popc(__vcmpgtu4(*reinterpret_cast<const u32*>(W.r + k), rrrr)) >> 3;
+                    for (; k < i; ++k) gt += W.r[k] > r;
+                    dst[i < 32 ? q0 : (u32)Q[i]] = (u8)(r + gt);
+                }
+                __syncwarp();
+                m3_combine(W, sel, cnt, slot, n, l0);
+            }
+            n = n1; l0 = l1; f0 = f1; q0 = q1;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // decode
 // ---------------------------------------------------------------------------------------------
 // Replays the list operations of one tile on `list` (256 bytes in shared memory, private to the warp).
@@ -399,6 +685,70 @@ __global__ void __launch_bounds__(MTF2_THREADS) k_mtf_dec2(const u8* __restrict_
     }
 }
 
+
+// KOLM_MTF3_DBG=2: host re-computation of every intermediate of the v3 encode (pieces' local lists and misses, group lists,
+// group entry lists) compared with what the kernels left in scratch — a debugging aid, never on in production.
+#include <vector>
+static int m3_host_check(kolm_ctx* c, const u8* in, const u8* d_slots, const u32* d_npc, const u8* d_agg, const u32* d_aggn, const u8* d_pre, int stage) {
+    const int nb = c->nblocks, nt = c->ntiles, np = nt * 4;
+    std::vector<u8> slots((size_t)np * M3_SLOT), agg((size_t)nt * 256), pre((size_t)nt * 256);
+    std::vector<u32> npc(np), aggn(nt);
+    cudaMemcpy(slots.data(), d_slots, slots.size(), cudaMemcpyDeviceToHost);
+    cudaMemcpy(npc.data(), d_npc, npc.size() * 4, cudaMemcpyDeviceToHost);
+    if (stage >= 2) { cudaMemcpy(agg.data(), d_agg, agg.size(), cudaMemcpyDeviceToHost); cudaMemcpy(aggn.data(), d_aggn, aggn.size() * 4, cudaMemcpyDeviceToHost); }
+    if (stage >= 3) cudaMemcpy(pre.data(), d_pre, pre.size(), cudaMemcpyDeviceToHost);
+    int bad = 0; u32 t = 0;
+    auto fold = [](std::vector<u8>& cur, const u8* L, u32 n) {
+        std::vector<u8> nx(L, L + n); bool in[256] = {false};
+        for (u32 i = 0; i < n; ++i) in[L[i]] = true;
+        for (u8 x : cur) if (!in[x]) nx.push_back(x);
+        cur.swap(nx);
+    };
+    for (int b = 0; b < nb && bad < 8; ++b) {
+        const u32 len = c->h_binfo[b].len, tn = (len + KOLM_TILE - 1) / KOLM_TILE;
+        std::vector<u8> data(len);
+        if (len) cudaMemcpy(data.data(), in + c->h_binfo[b].ioff, len, cudaMemcpyDeviceToHost);
+        std::vector<u8> entry(256); for (int i = 0; i < 256; ++i) entry[i] = (u8)i;
+        for (u32 rel = 0; rel < tn && bad < 8; rel += M3_GROUP_TILES) {
+            const u32 gtiles = std::min<u32>(M3_GROUP_TILES, tn - rel), gp = 4 * gtiles, p0 = 4 * (t + rel);
+            std::vector<u8> g;
+            for (u32 q = 0; q < gp; ++q) {
+                const u32 a = (rel * 4 + q) * 1024, e = std::min<u32>(len, a + 1024), piece = p0 + q;
+                const u8* sl = slots.data() + (size_t)piece * M3_SLOT;
+                const u32 n = npc[piece];
+                if (stage == 1) {
+                    std::vector<u8> L, ms; std::vector<u16> mp;
+                    for (u32 i = a; i < e && a < len; ++i) {
+                        const u8 x = data[i]; size_t k = 0;
+                        while (k < L.size() && L[k] != x) ++k;
+                        if (k == L.size()) { ms.push_back(x); mp.push_back((u16)(i - a)); } else L.erase(L.begin() + k);
+                        L.insert(L.begin(), x);
+                    }
+                    bool ok = n == L.size();
+                    for (u32 i = 0; ok && i < n; ++i) ok = sl[i] == L[i] && sl[256 + i] == ms[i] && reinterpret_cast<const u16*>(sl + 512)[i] == mp[i];
+                    if (!ok) { ++bad; fprintf(stderr, "mtf3 check: walk piece %u (block %d len %u, bytes %u..%u): n gpu %u cpu %zu\n", piece, b, len, a, e, n, L.size()); }
+                }
+                if (n <= 256) fold(g, sl, n);
+            }
+            const u32 gt = t + rel;
+            if (stage == 2) {
+                bool ok = aggn[gt] == g.size();
+                for (size_t i = 0; ok && i < g.size(); ++i) ok = agg[(size_t)gt * 256 + i] == g[i];
+                if (!ok) { ++bad; fprintf(stderr, "mtf3 check: agg tile %u (block %d rel %u): n gpu %u cpu %zu\n", gt, b, rel, aggn[gt], g.size()); }
+            }
+            if (stage == 3) {
+                bool ok = true;
+                for (int i = 0; ok && i < 256; ++i) ok = pre[(size_t)gt * 256 + i] == entry[i];
+                if (!ok) { ++bad; fprintf(stderr, "mtf3 check: prefix tile %u (block %d rel %u)\n", gt, b, rel); }
+            }
+            fold(entry, g.data(), (u32)g.size());
+        }
+        t += tn;
+    }
+    fprintf(stderr, "mtf3 check stage %d: %s\n", stage, bad ? "MISMATCH" : "ok");
+    return bad;
+}
+
 int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t s) {
     const int nt = c->ntiles, nb = c->nblocks;
     if (!nt) return KOLM_OK;
@@ -406,8 +756,32 @@ int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t 
     int wgrid = (nt + MTF_WARPS - 1) / MTF_WARPS;
     if (!decode) {
         const i64 N = c->total_bytes;
-        static int v2 = -1, sub = -1;
+        static int v2 = -1, sub = -1, v3 = -1;
         if (v2 < 0) { const char* e = getenv("KOLM_MTF_V2"); v2 = e ? atoi(e) : 1; }
+        if (v3 < 0) { const char* e = getenv("KOLM_MTF_V3"); v3 = e ? atoi(e) : 1; }
+        if (v3 && v2 && (size_t)nt * 1024 <= c->max_elems) {
+            // scratch in the idle sort buffers: 1 KB per piece (d_k0), the pieces' list lengths (d_v0), per group of eight tiles its
+            // list (d_k1, indexed by the group's first tile), length (d_v1) and entry list (d_sa)
+            const int np = nt * 4;
+            u8* slots = (u8*)c->d_k0; u32* npc = c->d_v0; u8* agg = (u8*)c->d_k1; u32* aggn = c->d_v1; u8* pre = (u8*)c->d_sa;
+            static int dbg = -1;
+            if (dbg < 0) { const char* e = getenv("KOLM_MTF3_DBG"); dbg = e ? atoi(e) : 0; }
+#define M3_CHECK(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(s); if (e_ == cudaSuccess) e_ = cudaGetLastError(); \
+                                        fprintf(stderr, "mtf3 %s: %s (nt %d nb %d)\n", name, cudaGetErrorString(e_), nt, nb); if (e_ != cudaSuccess) return KOLM_E_CUDA; } } while (0)
+            KL(c, KC_MTF_MAIN, 2 * N, s, k_mtf3_walk<<<(np + M3_THREADS - 1) / M3_THREADS, M3_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, slots, npc, np));
+            M3_CHECK("walk");
+            if (dbg >= 2 && m3_host_check(c, in, slots, npc, agg, aggn, pre, 1)) return KOLM_E_CUDA;
+            KL(c, KC_MTF_SCAN, (i64)np * 64, s, k_mtf3_agg<<<((nt + M3_GROUP_TILES - 1) / M3_GROUP_TILES + 7) / 8, 256, 0, s>>>(c->d_tiles, c->d_btile0, c->d_btilen, slots, npc, agg, aggn, nt));
+            M3_CHECK("agg");
+            if (dbg >= 2 && m3_host_check(c, in, slots, npc, agg, aggn, pre, 2)) return KOLM_E_CUDA;
+            KL(c, KC_MTF_SCAN, (i64)nt * 64, s, k_mtf3_prefix<<<(nb + 7) / 8, 256, 0, s>>>(c->d_btile0, c->d_btilen, agg, aggn, pre, nb));
+            M3_CHECK("prefix");
+            if (dbg >= 2 && m3_host_check(c, in, slots, npc, agg, aggn, pre, 3)) return KOLM_E_CUDA;
+            KL(c, KC_MTF_PRE, (i64)np * 128, s, k_mtf3_fix<<<((nt + M3_GROUP_TILES - 1) / M3_GROUP_TILES + 7) / 8, 256, 0, s>>>(out, c->d_tiles, c->d_binfo, c->d_btile0, c->d_btilen, slots, npc, pre, nt));
+            M3_CHECK("fix");
+            CUDA_TRY(cudaGetLastError());
+            return KOLM_OK;
+        }
         if (sub < 0) { const char* e = getenv("KOLM_MTF_SUB"); sub = e ? atoi(e) : 2; if (sub < 0 || sub > 3) sub = 2; }
         // pieces of 4096 >> ss bytes; their last-occurrence tables (1 KB each) live in the idle sort buffer d_k0 when they
         // outgrow d_thist (batches of many tiny blocks keep whole tiles)
