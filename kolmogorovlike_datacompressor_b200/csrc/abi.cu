@@ -54,7 +54,7 @@ const char* kolm_last_cuda_error(void) { return g_cuda_err; }
 size_t kolm_scratch_bytes(size_t max_batch_bytes, int max_blocks) {
     size_t e = padded_capacity(max_batch_bytes, max_blocks);
     size_t tiles = e / KOLM_TILE + max_blocks + 2;
-    return e * (4 * 9 + 4 / 8 + 2) + tiles * (sizeof(TileDesc) * 2 + 16 + 1024) + (size_t)max_blocks * (sizeof(BlockInfo) + 4 * 9 + 64 * 8);
+    return e * (4 * 10 + 4 / 8 + 2) + tiles * (sizeof(TileDesc) * 2 + 16 + 1024) + (size_t)max_blocks * (sizeof(BlockInfo) + 4 * 9 + 64 * 8);
 }
 
 int kolm_create(int device, size_t max_batch_bytes, int max_blocks, kolm_ctx** out) { return kolm_create_ex(device, max_batch_bytes, max_blocks, 0u, out); }
@@ -85,6 +85,7 @@ int kolm_create_ex(int device, size_t max_batch_bytes, int max_blocks, unsigned 
         CUDA_TRY(dalloc(&c->d_k1, e)); CUDA_TRY(dalloc(&c->d_v1, e));
         CUDA_TRY(dalloc(&c->d_sa, e)); CUDA_TRY(dalloc(&c->d_rank, e)); CUDA_TRY(dalloc(&c->d_nr, e)); CUDA_TRY(dalloc(&c->d_lo, e));
         CUDA_TRY(dalloc(&c->d_single, e / 32 + 8)); CUDA_TRY(dalloc(&c->d_fstart, e));
+        CUDA_TRY(dalloc(&c->d_grp, e)); CUDA_TRY(dalloc(&c->d_live, nt)); CUDA_TRY(dalloc(&c->d_lact, nb));
         CUDA_TRY(dalloc(&c->d_tmp8a, e)); CUDA_TRY(dalloc(&c->d_tmp8b, e));
     }
     CUDA_TRY(cudaMallocHost((void**)&c->h_binfo, nb * sizeof(BlockInfo)));
@@ -105,7 +106,7 @@ int kolm_create_ex(int device, size_t max_batch_bytes, int max_blocks, unsigned 
                 {c->d_active, nb * 4}, {c->d_newcls, nb * 4}, {c->d_done, nb * 4}, {c->d_nfac, nb * 4}, {c->d_stats, 64}, {c->d_bacc, nb * 512},
                 {c->d_tiles, nt * sizeof(TileDesc)}, {c->d_atiles, nt * sizeof(TileDesc)}, {c->d_lb, (32 + 8 * nt) * 8}, {c->d_thist, nt * 1024},
                 {c->d_k0, e * 4}, {c->d_v0, e * 4}, {c->d_k1, e * 4}, {c->d_v1, e * 4}, {c->d_sa, e * 4}, {c->d_rank, e * 4}, {c->d_nr, e * 4},
-                {c->d_lo, e * 4}, {c->d_single, (e / 32 + 8) * 4}, {c->d_fstart, e * 4}, {c->d_tmp8a, e}, {c->d_tmp8b, e}, {c->d_err, nb * 4},
+                {c->d_lo, e * 4}, {c->d_grp, e * 4}, {c->d_live, nt}, {c->d_lact, nb * 4}, {c->d_single, (e / 32 + 8) * 4}, {c->d_fstart, e * 4}, {c->d_tmp8a, e}, {c->d_tmp8b, e}, {c->d_err, nb * 4},
                 {c->d_poff, (nb + 1) * 8}, {c->d_params, nb * 16}, {c->d_sizes, nb * 40}};
             for (auto& a : arr) if (a.p) CUDA_TRY(cudaMemset(a.p, 0xA5, a.n));
         }
@@ -121,7 +122,7 @@ void kolm_destroy(kolm_ctx* c) {
     cudaSetDevice(c->device);
     void* dptrs[] = {c->d_binfo, c->d_btile0, c->d_btilen, c->d_atile0, c->d_atilen, c->d_active, c->d_newcls, c->d_done, c->d_nfac,
                      c->d_stats, c->d_bacc, c->d_tiles, c->d_atiles, c->d_lb, c->d_thist, c->d_k0, c->d_v0, c->d_k1, c->d_v1,
-                     c->d_sa, c->d_rank, c->d_nr, c->d_lo, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes, c->d_jump, c->d_err, c->d_rpb};
+                     c->d_sa, c->d_rank, c->d_nr, c->d_lo, c->d_grp, c->d_live, c->d_lact, c->d_single, c->d_fstart, c->d_tmp8a, c->d_tmp8b, c->d_poff, c->d_params, c->d_sizes, c->d_jump, c->d_err, c->d_rpb};
     for (void* p : dptrs) if (p) cudaFree(p);
     if (c->prof_ev) { for (int i = 0; i < 2 * KOLM_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]); delete[] c->prof_ev; }
     if (c->h_binfo) cudaFreeHost(c->h_binfo);

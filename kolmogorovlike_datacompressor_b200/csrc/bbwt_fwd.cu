@@ -347,22 +347,43 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_hist(const u32* __restri
     thist[(size_t)blockIdx.x * 256 + tid] = tot;
 }
 
-// radix pass 2/3: per block, turn tile histograms into block-relative scatter bases (digit-major, tile-minor)
-__global__ void __launch_bounds__(256) k_radix_scan(u32* __restrict__ thist, const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks) {
-    __shared__ u32 tot[256];
+// radix pass 2/3: per block, turn tile histograms into block-relative scatter bases (digit-major, tile-minor).
+// 1024 threads = four row groups x 256 digits: every group owns a quarter of the block's tiles, sums its column first (loads
+// batched eight deep: the serial one-thread-per-digit walk over 256 tiles was pure latency, ~50 us per launch at 1 MiB blocks),
+// then rewrites it as running bases on top of (digit start + the earlier groups' column sums).
+#define RSCAN_GROUPS 4
+__global__ void __launch_bounds__(256 * RSCAN_GROUPS) k_radix_scan(u32* __restrict__ thist, const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks) {
+    __shared__ u32 part[RSCAN_GROUPS][256];
     __shared__ u32 excl[256];
+    const u32 d = threadIdx.x & 255u, q = threadIdx.x >> 8;
     for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        u32 nt = tilen[b];
+        const u32 nt = tilen[b];
         if (!nt) continue;
-        u32* base = thist + (size_t)tile0[b] * 256 + threadIdx.x;
-        u32 run = 0;
-        for (u32 t = 0; t < nt; ++t) { u32 v = base[(size_t)t * 256]; base[(size_t)t * 256] = run; run += v; }
-        tot[threadIdx.x] = run;
+        const u32 per = (nt + RSCAN_GROUPS - 1) / RSCAN_GROUPS;
+        const u32 ta = min(nt, q * per), tb = min(nt, ta + per);
+        u32* base = thist + (size_t)tile0[b] * 256 + d;
+        u32 sum = 0;
+        {
+            u32 t = ta;
+            for (; t + 8 <= tb; t += 8) {
+                u32 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = base[(size_t)(t + i) * 256];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sum += v[i];
+            }
+            for (; t < tb; ++t) sum += base[(size_t)t * 256];
+        }
+        part[q][d] = sum;
         __syncthreads();
         if (threadIdx.x < 32) {
             u32 s = 0, loc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { loc[i] = s; s += tot[threadIdx.x * 8 + i]; }
+            for (int i = 0; i < 8; ++i) {
+                loc[i] = s;
+#pragma unroll
+                for (int g = 0; g < RSCAN_GROUPS; ++g) s += part[g][threadIdx.x * 8 + i];
+            }
             u32 v = s;
             for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(FULL, v, o); if (threadIdx.x >= (u32)o) v += n; }
             u32 pre = v - s;
@@ -370,8 +391,19 @@ __global__ void __launch_bounds__(256) k_radix_scan(u32* __restrict__ thist, con
             for (int i = 0; i < 8; ++i) excl[threadIdx.x * 8 + i] = pre + loc[i];
         }
         __syncthreads();
-        u32 db = excl[threadIdx.x];
-        if (db) for (u32 t = 0; t < nt; ++t) base[(size_t)t * 256] += db;
+        u32 run = excl[d];
+        for (u32 g = 0; g < q; ++g) run += part[g][d];
+        {
+            u32 t = ta;
+            for (; t + 8 <= tb; t += 8) {
+                u32 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = base[(size_t)(t + i) * 256];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { base[(size_t)(t + i) * 256] = run; run += v[i]; }
+            }
+            for (; t < tb; ++t) { const u32 v = base[(size_t)t * 256]; base[(size_t)t * 256] = run; run += v; }
+        }
         __syncthreads();
     }
 }
@@ -500,6 +532,7 @@ struct RerankArgs {
     u32* sa; u32* rank; u32* nr; u32* single; u32* newcls; u32 h;
     u32* survivors;                     // [1] records that remain unsettled after this round (non-BOOT only)
     const u32* lo;                      // BOOT 2: low key half by position (k_boot_lo), so the rerank needs no factor search
+    u32* grp;                           // group start by order index (local refinement rounds), may be null
 };
 
 template <int BOOT, bool CYCLIC>
@@ -611,12 +644,27 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rerank(RerankArgs a) {
         nrk_[i] = key2r[i] + (ch - cf);
         if (((headbits >> i) & 1u) && ((nextbits >> i) & 1u)) singles |= 1u << i;
     }
+    // bootstrap reranks place record r of the tile at order index t0 + r: 16 consecutive words per thread, stored as four uint4
+    const bool vec = BOOT != 0 && tid * KOLM_IPT + KOLM_IPT <= td.count;
+    if (vec) {
+        uint4* d = reinterpret_cast<uint4*>(a.sa + td.start + tid * KOLM_IPT);
+#pragma unroll
+        for (int i = 0; i < KOLM_IPT; i += 4) d[i >> 2] = make_uint4(val2[i], val2[i + 1], val2[i + 2], val2[i + 3]);
+        if (a.grp) {
+            uint4* g = reinterpret_cast<uint4*>(a.grp + td.start + tid * KOLM_IPT);
+#pragma unroll
+            for (int i = 0; i < KOLM_IPT; i += 4) g[i >> 2] = make_uint4(nrk_[i], nrk_[i + 1], nrk_[i + 2], nrk_[i + 3]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < KOLM_IPT; ++i) {
         u32 r = tid * KOLM_IPT + i;
         if (r < td.count) {
             const bool single = (singles >> i) & 1u;
-            a.sa[bi.pbase + pos_[i]] = val2[i];
+            if (!vec) {
+                a.sa[bi.pbase + pos_[i]] = val2[i];
+                if (a.grp) a.grp[bi.pbase + pos_[i]] = nrk_[i];
+            }
             if (BOOT) {
                 a.rank[val2[i]] = nrk_[i];
                 if (single) atomicOr(a.single + (val2[i] >> 5), 1u << (val2[i] & 31));
@@ -785,6 +833,261 @@ __global__ void k_round_end(u32* __restrict__ newcls, u32* __restrict__ done, co
     if (b >= nblocks) return;
     if (cyclic && !done[b] && active[b] && newcls[b] == 0) done[b] = 1;   // partition stable: equal rotations remain
     newcls[b] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Local refinement rounds (Larsson–Sadakane form).  After a rerank the order `sa` is grouped: the records of an unsettled group
+// are consecutive, and doubling the depth only permutes every group inside its own range by rank[succ_h(.)].  Groups are short
+// (text at depth 12: a third of the records sit in groups of weighted mean size 38, 0.8 % in groups above 256), so instead of
+// streaming the whole order to emit the unsettled records, sorting them globally by their group start (three radix passes over
+// 8-byte records) and re-ranking, ONE CTA per static tile of the order
+//   * reads grp[] (group start of every order index) for its 4096 indices + LR_GCAP look-ahead: a group belongs to the tile its
+//     start lies in; a group longer than LR_GCAP ("big") is left to the global path (its members are flagged in F[]),
+//   * fetches rank[succ_h(.)] of the unsettled records of its groups into shared memory,
+//   * lets every record count, inside its group, the keys below its own and the equal keys before it: that is its new place,
+//     its new group start and whether it is now alone — no sort, no scan, no barrier besides the one after the key fetch,
+//   * writes the new order in place and the new group starts to nr[] (by order index).
+// k_apply_local publishes nr -> grp / rank after the kernel boundary (every CTA must order against the same snapshot of the
+// ranks).  No ticket, no look-back; tiles without unsettled records retire (live[] = 0) and cost one byte load afterwards.
+// ------------------------------------------------------------------------------------------------
+#define LR_GCAP 256
+#define LR_CAP (KOLM_TILE + LR_GCAP)
+#define LR_RPT (LR_CAP / KOLM_THREADS)                   // 17 order indices per thread
+#define LR_FOREIGN 0xffffu
+#define LR_SMEM (2 * (LR_CAP + 8) + 2 * LR_CAP + 4 * LR_CAP + 4 * LR_CAP + 2 * LR_CAP + LR_CAP)
+
+struct RefineArgs {
+    u32* sa; const u32* rank; const u32* grp; u32* list; u32* list2; u32* lcount; u32* F; const TileDesc* tiles; const BlockInfo* binfo;
+    const u32* fstart; const u32* nfac; const u32* done; u8* live; u32* lact; u32* newcls; u32* stats; u32 h;
+};
+
+template <bool CYCLIC>
+__global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) {
+    extern __shared__ __align__(16) u8 lr_smem[];
+    u32* K2c = reinterpret_cast<u32*>(lr_smem);            // successor rank of compact record i
+    u32* CP = K2c + LR_CAP;                                // its position
+    u16* G16 = reinterpret_cast<u16*>(CP + LR_CAP);        // grp[] window minus t0 (LR_FOREIGN: the group starts before the tile)   [LR_CAP + 8]
+    u16* E = G16 + LR_CAP + 8;                             // end (exclusive, window index) of the group that starts at this window index
+    u16* CX = E + LR_CAP;                                  // window index of compact record i
+    u8* COFF = reinterpret_cast<u8*>(CX + LR_CAP);         // its offset inside its group
+    __shared__ u32 s_wcnt[NWARPS];
+    __shared__ u32 s_flag[4];                              // [0] unsettled in the nominal range, [1] big in the nominal range, [2] straddling-in group is big, [3] changed records
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const u32 tile = blockIdx.x;
+    if (!a.live[tile]) return;
+    const TileDesc td = a.tiles[tile];
+    const BlockInfo bi = a.binfo[td.block];
+    if (a.done[td.block]) { if (tid == 0) a.live[tile] = 0; return; }
+    const u32 nrec = bi.len, t0 = td.start - bi.pbase, cnt = td.count;
+    const u32 navail = min((u32)LR_CAP, nrec - t0);        // order indices this CTA may refine
+    const u32 nG = min((u32)LR_CAP + 1, nrec - t0);        // grp[] entries staged
+    const u32* grp = a.grp + td.start;
+    for (u32 x = tid; x < nG; x += KOLM_THREADS) { const u32 g = grp[x]; G16[x] = g >= t0 ? (u16)(g - t0) : (u16)LR_FOREIGN; }
+    if (tid == 0) {
+        const u32 g0 = grp[0];
+        s_flag[0] = 0; s_flag[1] = 0; s_flag[3] = 0;
+        s_flag[2] = (g0 < t0 && g0 + LR_GCAP < nrec && a.grp[bi.pbase + g0 + LR_GCAP] == g0) ? 1u : 0u;
+    }
+    __syncthreads();
+    const bool big_in = s_flag[2] != 0;
+    // ---- classify: warp w looks at window indices [w*LR_RPT*32, (w+1)*LR_RPT*32), iteration k at 32 consecutive ones
+    u32 procbits = 0, bigbits = 0, nuns = 0, nbig = 0, nproc = 0;
+#pragma unroll
+    for (int k = 0; k < LR_RPT; ++k) {
+        const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
+        bool proc = false;
+        if (x < nG) {
+            const u32 g = G16[x];
+            const bool head = g == x;
+            if (head && x > 0) { const u32 ps = G16[x - 1]; if (ps != LR_FOREIGN) E[ps] = (u16)x; }       // the group before me ends here
+            if (x + 1 == nG && t0 + nG == nrec && g != LR_FOREIGN) E[g] = (u16)nG;                        // the block's last group
+            if (x < navail) {
+                const bool own = g != LR_FOREIGN && g < cnt;
+                const bool single = head && (t0 + x + 1 == nrec || G16[x + 1] == x + 1);
+                bool big;
+                if (own) big = g + LR_GCAP < nG && G16[g + LR_GCAP] == g;
+                else big = x < cnt && g == LR_FOREIGN && big_in;
+                proc = own && !big && !single;
+                if (x < cnt) { nuns += single ? 0u : 1u; if (big) { ++nbig; bigbits |= 1u << k; } }
+            }
+        }
+        if (proc) procbits |= 1u << k;
+        nproc += __popc(__ballot_sync(FULL, proc));        // warp total (the same in every lane)
+    }
+    for (int o = 16; o > 0; o >>= 1) { nuns += __shfl_xor_sync(FULL, nuns, o); nbig += __shfl_xor_sync(FULL, nbig, o); }
+    if (lane == 0) { s_wcnt[w] = nproc; if (nuns) atomicAdd(&s_flag[0], nuns); if (nbig) atomicAdd(&s_flag[1], nbig); }
+    u32 pp[LR_RPT];                                        // positions of my records: in flight across the barrier
+#pragma unroll
+    for (int k = 0; k < LR_RPT; ++k) pp[k] = ((procbits >> k) & 1u) ? a.sa[td.start + w * (LR_RPT * 32) + k * 32 + lane] : 0u;
+    __syncthreads();
+    const u32 tot_uns = s_flag[0], tot_big = s_flag[1];
+    if (!tot_uns) { if (tid == 0) { a.live[tile] = 0; a.lcount[tile] = 0; } return; }
+    if (tid == 0) {
+        atomicAdd(a.lact + td.block, tot_uns); atomicAdd(a.stats + 6, tot_uns);
+        if (tot_big) atomicAdd(a.stats + 5, tot_big);
+        a.live[tile] = tot_big ? 3 : 1;                    // bit 1: k_big_emit has work here
+    }
+    if (tot_big) {                                         // only such tiles are read by k_big_emit
+#pragma unroll
+        for (int k = 0; k < LR_RPT; ++k) {
+            const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
+            if (x < cnt) a.F[td.start + x] = ((bigbits >> k) & 1u) ? 0u : 0x80000000u;
+        }
+    }
+    u32 wbase = 0, m = 0;
+#pragma unroll
+    for (int i = 0; i < NWARPS; ++i) { const u32 c_ = s_wcnt[i]; if ((u32)i < w) wbase += c_; m += c_; }
+    if (!m) { if (tid == 0) a.lcount[tile] = 0; return; }  // only big or foreign groups here
+    // ---- compact my records
+    {
+        u32 run = wbase;
+#pragma unroll
+        for (int k = 0; k < LR_RPT; ++k) {
+            const bool proc = (procbits >> k) & 1u;
+            const u32 pm = __ballot_sync(FULL, proc);
+            if (proc) {
+                const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
+                const u32 slot = run + __popc(pm & lanemask_lt());
+                CX[slot] = (u16)x; COFF[slot] = (u8)(x - G16[x]); CP[slot] = pp[k];
+            }
+            run += __popc(pm);
+        }
+    }
+    __syncthreads();
+    // ---- successor ranks, four gathers in flight per thread
+    {
+        const u32 nf = CYCLIC ? a.nfac[td.block] : 0;
+        const u32* fst = a.fstart + bi.pbase;
+        for (u32 i0 = tid; i0 < m; i0 += 4 * KOLM_THREADS) {
+            u32 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const u32 i = i0 + u * KOLM_THREADS;
+                q[u] = 0xffffffffu;
+                if (i < m) {
+                    u32 lp = CP[i] - bi.pbase, sp;
+                    if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
+                    else sp = lp + a.h;
+                    q[u] = bi.pbase + sp;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (q[u] != 0xffffffffu) q[u] = a.rank[q[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const u32 i = i0 + u * KOLM_THREADS; if (i < m) K2c[i] = q[u]; }
+        }
+    }
+    __syncthreads();
+    // ---- every record finds its place inside its group: keys below mine, equal keys before me
+    u32 nnew = 0, nsurv = 0;
+    for (u32 i = tid; i < m; i += KOLM_THREADS) {
+        const u32 x = CX[i], off = COFF[i], cs = i - off, gs = x - off, n = (u32)E[gs] - gs, mine = K2c[i];
+        const u32* kp = K2c + cs;
+        u32 lt = 0, eq = 0, eqb = 0, j = 0;
+        for (; j + 4 <= n; j += 4) {
+            const u32 k0 = kp[j], k1 = kp[j + 1], k2 = kp[j + 2], k3 = kp[j + 3];
+            lt += (k0 < mine) + (k1 < mine) + (k2 < mine) + (k3 < mine);
+            eq += (k0 == mine) + (k1 == mine) + (k2 == mine) + (k3 == mine);
+            eqb += (k0 == mine && j < off) + (k1 == mine && j + 1 < off) + (k2 == mine && j + 2 < off) + (k3 == mine && j + 3 < off);
+        }
+        for (; j < n; ++j) { const u32 kj = kp[j]; lt += kj < mine; eq += kj == mine; eqb += (kj == mine && j < off); }
+        const u32 np = gs + lt + eqb;
+        a.sa[td.start + np] = CP[i];
+        if (lt) {                                          // group start moved: k_apply_local publishes it
+            const u32 idx = atomicAdd(&s_flag[3], 1u);
+            const u32 e = np | ((gs + lt) << 16);
+            if (idx < KOLM_TILE) a.list[td.start + idx] = e; else a.list2[td.start + idx - KOLM_TILE] = e;
+        }
+        nnew += (eqb == 0 && lt > 0) ? 1u : 0u;           // a new group start that was none before
+        nsurv += eq > 1 ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) { nnew += __shfl_xor_sync(FULL, nnew, o); nsurv += __shfl_xor_sync(FULL, nsurv, o); }
+    if (lane == 0) { if (nnew) atomicAdd(a.newcls + td.block, nnew); if (nsurv) atomicAdd(a.stats + 4, nsurv); }
+    __syncthreads();
+    if (tid == 0) a.lcount[tile] = s_flag[3];
+}
+
+// records of the tiles k_refine_local marked, appended to the block's record list as (rank[succ_h(v)], v) in any order (the LS
+// path sorts by both keys); runs after k_apply_local so that all keys of the global path come from one snapshot.
+//   ALL = false: members of big groups (F == 0) in tiles with live == 3;  ALL = true: every unsettled record of every live tile
+//   (hand-over to the compacted LS rounds once few records are left).
+template <bool CYCLIC, bool ALL>
+__global__ void __launch_bounds__(KOLM_THREADS) k_big_emit(const u32* __restrict__ sa, const u32* __restrict__ rank, const u32* __restrict__ F, const u32* __restrict__ grp,
+                                                           const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo, const u32* __restrict__ fstart,
+                                                           const u32* __restrict__ nfac, const u32* __restrict__ done, const u8* __restrict__ live, u32* __restrict__ active,
+                                                           u32* __restrict__ K2, u32* __restrict__ V2, u32 h) {
+    __shared__ u32 s_w[NWARPS];
+    __shared__ u32 s_base;
+    const u8 lv = live[blockIdx.x];
+    if (ALL ? lv == 0 : lv != 3) return;
+    const TileDesc td = tiles[blockIdx.x];
+    if (done[td.block]) return;
+    const BlockInfo bi = binfo[td.block];
+    const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const u32 t0 = td.start - bi.pbase;
+    u32 bits = 0, mycnt = 0;
+#pragma unroll
+    for (int k = 0; k < KOLM_IPT; ++k) {
+        const u32 x = w * (KOLM_IPT * 32) + k * 32 + lane;
+        bool take = false;
+        if (x < td.count) {
+            if (ALL) {
+                const u32 g = grp[td.start + x];
+                take = !(g == t0 + x && (t0 + x + 1 == bi.len || grp[td.start + x + 1] == t0 + x + 1));
+            } else take = F[td.start + x] == 0u;
+        }
+        if (take) bits |= 1u << k;
+        mycnt += __popc(__ballot_sync(FULL, take));        // warp total so far (same in every lane)
+    }
+    if (lane == 0) s_w[w] = mycnt;
+    __syncthreads();
+    if (tid == 0) { u32 t = 0; for (int i = 0; i < NWARPS; ++i) { const u32 c_ = s_w[i]; s_w[i] = t; t += c_; } s_base = t ? atomicAdd(active + td.block, t) : 0u; }
+    __syncthreads();
+    u32 run = bi.pbase + s_base + s_w[w];
+    const u32 nf = CYCLIC ? nfac[td.block] : 0;
+#pragma unroll 1
+    for (int k = 0; k < KOLM_IPT; ++k) {
+        const bool take = (bits >> k) & 1u;
+        const u32 bm = __ballot_sync(FULL, take);
+        if (take) {
+            const u32 x = w * (KOLM_IPT * 32) + k * 32 + lane;
+            const u32 p = sa[td.start + x];
+            u32 lp = p - bi.pbase, sp;
+            if (CYCLIC) { u32 fs, fl; find_factor(fstart + bi.pbase, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + h % fl; sp = fs + (o >= fl ? o - fl : o); } }
+            else sp = lp + h;
+            const u32 d = run + __popc(bm & lanemask_lt());
+            K2[d] = rank[bi.pbase + sp]; V2[d] = p;
+        }
+        run += __popc(bm);
+    }
+}
+
+// publish a local round: grp / rank take the new group starts of the records k_refine_local listed
+__global__ void __launch_bounds__(KOLM_THREADS) k_apply_local(const u32* __restrict__ sa, const u32* __restrict__ list, const u32* __restrict__ list2,
+                                                              const u32* __restrict__ lcount, u32* __restrict__ grp, u32* __restrict__ rank,
+                                                              const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo, const u8* __restrict__ live) {
+    if (!live[blockIdx.x]) return;
+    const u32 n = lcount[blockIdx.x];
+    if (!n) return;
+    const TileDesc td = tiles[blockIdx.x];
+    const u32 t0 = td.start - binfo[td.block].pbase;
+    for (u32 i0 = threadIdx.x; i0 < n; i0 += 4 * KOLM_THREADS) {
+        u32 e[4], v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const u32 i = i0 + u * KOLM_THREADS; e[u] = i < n ? (i < KOLM_TILE ? list[td.start + i] : list2[td.start + i - KOLM_TILE]) : 0xffffffffu; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = e[u] != 0xffffffffu ? sa[td.start + (e[u] & 0xffffu)] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (e[u] != 0xffffffffu) { const u32 g = t0 + (e[u] >> 16); grp[td.start + (e[u] & 0xffffu)] = g; rank[v[u]] = g; }
+    }
+}
+
+// local rounds: a block whose unsettled groups produced no new class in a whole round is stable (equal rotations)
+__global__ void k_round_end_local(u32* __restrict__ newcls, u32* __restrict__ done, u32* __restrict__ lact, int nblocks, int cyclic) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    if (cyclic && !done[b] && lact[b] && newcls[b] == 0) done[b] = 1;
+    newcls[b] = 0; lact[b] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1140,7 +1443,7 @@ static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, i64 nrec, 
     for (int p = 0; p < passes; ++p) {
         int shift = p * dbits;
         KL(c, KC_HIST, nrec * 4 + (i64)ntiles * 1024, s, k_radix_hist<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, tiles, c->d_thist, shift, mask));
-        KL(c, KC_SCAN, (i64)ntiles * 2048, s, k_radix_scan<<<sgrid, 256, 0, s>>>(c->d_thist, tile0, tilen, c->nblocks));
+        KL(c, KC_SCAN, (i64)ntiles * 2048, s, k_radix_scan<<<sgrid, 256 * RSCAN_GROUPS, 0, s>>>(c->d_thist, tile0, tilen, c->nblocks));
         KL(c, KC_SCATTER, nrec * 16 + (i64)ntiles * 1024, s, k_radix_scatter<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, Va, Kb, Vb, tiles, c->d_binfo, c->d_thist, shift, mask));
         u32* t = Ka; Ka = Kb; Kb = t; t = Va; Va = Vb; Vb = t;
     }
@@ -1225,7 +1528,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
     RerankArgs ra;
     ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
-    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0; ra.lo = c->d_lo;
+    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0; ra.lo = c->d_lo; ra.grp = c->d_grp;
     if (deep) { KL(c, KC_RERANK, N * 20, s, k_rerank<2, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra)); h0 *= 2; c->counters[4] += N; }   // second full sort
     else if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<1, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
     else KL(c, KC_RERANK, N * 16, s, k_rerank<1, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
@@ -1238,9 +1541,103 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     ra.survivors = c->d_stats + 4;
     bool use_ls = false;
     u32 *Kprev = nullptr, *Vprev = nullptr;                  // sorted records of the previous round (aligned with d_nr)
-    for (u64 h = h0; rounds < 40; h <<= 1) {
+    static int local_rounds = -1;
+    if (local_rounds < 0) { const char* e = getenv("KOLM_LOCAL_ROUNDS"); local_rounds = e ? atoi(e) : 1; }
+    u64 hstart = h0;
+    bool prebuilt = false;                                   // the first global round finds its (second key, position) records already emitted
+    if (local_rounds) {
+        // ---- local refinement rounds (k_refine_local) while the unsettled records are dense; groups longer than LR_GCAP go
+        //      through the global LS path of the same round; once few records are left the compacted LS rounds below take over
+        static bool attr_done = false;
+        if (!attr_done) {
+            CUDA_TRY(cudaFuncSetAttribute(k_refine_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LR_SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(k_refine_local<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LR_SMEM));
+            attr_done = true;
+        }
+        CUDA_TRY(cudaMemsetAsync(c->d_live, 1, (size_t)nt, s));
+        CUDA_TRY(cudaMemsetAsync(c->d_lact, 0, (size_t)nb * 4, s));
+        RefineArgs fa;
+        fa.sa = c->d_sa; fa.rank = c->d_rank; fa.grp = c->d_grp; fa.list = c->d_nr; fa.list2 = c->d_k0; fa.lcount = c->d_thist; fa.F = c->d_lo;
+        fa.tiles = c->d_tiles; fa.binfo = c->d_binfo; fa.fstart = c->d_fstart; fa.nfac = c->d_nfac; fa.done = c->d_done; fa.live = c->d_live;
+        fa.lact = c->d_lact; fa.newcls = c->d_newcls; fa.stats = c->d_stats;
+        static int trace = -1;
+        if (trace < 0) { const char* e = getenv("KOLM_TRACE_ROUNDS"); trace = e ? atoi(e) : 0; }
+        bool finished = false;
+        u64 h = h0;
+        for (; rounds < 64; h <<= 1) {
+            if (h > 0x7fffffffull) h = 0x7fffffffull;
+            fa.h = (u32)h;
+            CUDA_TRY(cudaMemsetAsync(c->d_stats + 4, 0, 12, s));      // [4] survivors, [5] members of big groups, [6] unsettled at the start
+            if (cyclic) KL(c, KC_RERANK, N * 4, s, k_refine_local<true><<<nt, KOLM_THREADS, LR_SMEM, s>>>(fa));
+            else KL(c, KC_RERANK, N * 4, s, k_refine_local<false><<<nt, KOLM_THREADS, LR_SMEM, s>>>(fa));
+            KL(c, KC_APPLY, N / 2, s, k_apply_local<<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_nr, c->d_k0, c->d_thist, c->d_grp, c->d_rank, c->d_tiles, c->d_binfo, c->d_live));
+            CUDA_TRY(cudaMemcpyAsync(c->h_stats + 4, c->d_stats + 4, 12, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            const u64 uns = c->h_stats[6], big = c->h_stats[5];
+            if (trace) fprintf(stderr, "[kolm sort] %s local round %d h=%llu unsettled=%llu of %lld (%.3f) big=%llu survivors(local)=%u\n", cyclic ? "cyclic" : "plain",
+                               rounds + 1, (unsigned long long)h, (unsigned long long)uns, (long long)N, (double)uns / (double)N, (unsigned long long)big, c->h_stats[4]);
+            if (uns == 0) { finished = true; break; }
+            ++rounds;
+            c->counters[4] += (i64)uns;
+            if (big) {
+                // members of big groups (flagged in d_lo): (rank[succ_h(v)], v) per block -> sort -> (rank[v], v) -> stable sort -> rerank
+                CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
+                if (cyclic) KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<true, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
+                else KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<false, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
+                KL(c, KC_PLAN, (i64)nb * 16, s, k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb));
+                CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 12, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                const int ant = (int)c->h_stats[0];
+                const i64 M = (i64)c->h_stats[1];
+                c->active_rows = c->h_stats[2];
+                if (ant) {
+                    KL(c, KC_TILES, (i64)ant * 16, s, k_build_tiles<<<bgrid, 128, 0, s>>>(c->d_binfo, c->d_atile0, c->d_atilen, c->d_active, c->d_atiles, nb));
+                    u32 *K1, *V1;
+                    KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K1, &V1, s));
+                    KL(c, KC_GATHER, M * 12, s, k_ls_key1<<<ant, KOLM_THREADS, 0, s>>>(K1, V1, c->d_atiles, c->d_rank));
+                    u32* K1o = (K1 == c->d_k0) ? c->d_k1 : c->d_k0;
+                    u32* V1o = (V1 == c->d_v0) ? c->d_v1 : c->d_v0;
+                    KOLM_TRY(radix_sort(c, c->d_atiles, ant, M, c->d_atile0, c->d_atilen, kbits, K1, V1, K1o, V1o, &K, &V, s));
+                    KOLM_TRY(kolm_lb_reset(c, true, ant, &lgrid, s));
+                    ra.K = K; ra.V = V; ra.tiles = c->d_atiles; ra.h = (u32)h;
+                    if (cyclic) KL(c, KC_RERANK, M * 20, s, k_rerank<0, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
+                    else KL(c, KC_RERANK, M * 20, s, k_rerank<0, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
+                    KL(c, KC_APPLY, M * 12, s, k_apply<<<ant, KOLM_THREADS, 0, s>>>(V, c->d_nr, c->d_atiles, c->d_rank, c->d_single));
+                }
+            }
+            KL(c, KC_PLAN, (i64)nb * 12, s, k_round_end_local<<<(nb + 255) / 256, 256, 0, s>>>(c->d_newcls, c->d_done, c->d_lact, nb, cyclic ? 1 : 0));
+            CUDA_TRY(cudaGetLastError());
+            if (h >= 0x7fffffffull) { finished = true; break; }
+            u64 surv = c->h_stats[4];
+            if (big) {
+                CUDA_TRY(cudaMemcpyAsync(c->h_stats + 4, c->d_stats + 4, 4, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                surv = c->h_stats[4];
+            }
+            if (surv == 0) { finished = true; break; }
+            if (ls_div > 0 && surv * (u64)ls_div < (u64)N) {
+                // few records left, spread over most tiles: hand the unsettled records (read off grp[]) to the compacted LS rounds
+                h <<= 1;
+                if (h > 0x7fffffffull) h = 0x7fffffffull;
+                CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
+                if (cyclic) KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<true, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
+                else KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<false, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
+                prebuilt = true; use_ls = true; Kprev = c->d_k1; Vprev = c->d_v1;      // "the other pair" of the LS branch is (d_k0, d_v0)
+                break;
+            }
+        }
+        if (finished || rounds >= 64) {
+            if (rounds_out) *rounds_out = rounds + (deep ? 1 : 0);
+            return KOLM_OK;
+        }
+        hstart = h;
+        ra.grp = nullptr;                                    // the compacted rounds do not keep grp[] up to date (nothing reads it any more)
+    }
+    for (u64 h = hstart; rounds < 80; h <<= 1) {
         if (h > 0x7fffffffull) h = 0x7fffffffull;
-        if (!use_ls) {
+        if (prebuilt) {
+            // records emitted by k_big_emit<.., true>
+        } else if (!use_ls) {
             // ---- Manber–Myers gather: stream the order, emit unsettled predecessors
             KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
             GatherArgs ga;
@@ -1302,6 +1699,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         const u64 surv = c->h_stats[4];
         if (surv == 0) break;
         Kprev = K; Vprev = V;
+        prebuilt = false;
         use_ls = ls_div > 0 && surv * (u64)ls_div < (u64)N;
     }
     if (rounds_out) *rounds_out = rounds + (deep ? 1 : 0);    // doublings of the sorted depth: the deep bootstrap is one (h0 -> 2*h0)

@@ -79,7 +79,10 @@ struct kolm_ctx {
     u32 *d_sa;               // current order
     u32 *d_rank;             // rank by position (block-local group start)
     u32 *d_nr;               // new ranks aligned with sorted records
-    u32 *d_lo;               // deep bootstrap: low key half by position (k_boot_lo -> k_rerank<2>)
+    u32 *d_lo;               // deep bootstrap: low key half by position (k_boot_lo -> k_rerank<2>); local rounds: fallback flags by order index
+    u32 *d_grp;              // group start of every order index (block-local), the local refinement rounds' view of the partition
+    u8  *d_live;             // [max_tiles] static tile still holds unsettled records
+    u32 *d_lact;             // [max_blocks] unsettled records at the start of a local round
     u32 *d_single;           // bitmap by position: rank is final and unique
     u32 *d_fstart;           // Lyndon factor starts, front-packed per block (block-local positions)
     u8  *d_tmp8a, *d_tmp8b;  // byte staging (bbwt out -> mtf -> rice)
