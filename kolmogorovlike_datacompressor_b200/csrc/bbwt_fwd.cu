@@ -854,11 +854,14 @@ __global__ void k_round_end(u32* __restrict__ newcls, u32* __restrict__ done, co
 #define LR_CAP (KOLM_TILE + LR_GCAP)
 #define LR_RPT (LR_CAP / KOLM_THREADS)                   // 17 order indices per thread
 #define LR_FOREIGN 0xffffu
+#define LR_NOHEAD 0xfffeu
+#define LR_UNIFORM_MIN 24                                 // groups at least this long are tested for "all keys equal" before the quadratic count
 #define LR_SMEM (2 * (LR_CAP + 8) + 2 * LR_CAP + 4 * LR_CAP + 4 * LR_CAP + 2 * LR_CAP + LR_CAP)
 
 struct RefineArgs {
     u32* sa; const u32* rank; const u32* grp; u32* list; u32* list2; u32* lcount; u32* F; const TileDesc* tiles; const BlockInfo* binfo;
     const u32* fstart; const u32* nfac; const u32* done; u8* live; u32* lact; u32* newcls; u32* stats; u32 h;
+    u32* gflag; u32 stamp;              // gflag[group start] == stamp: that big group's members do not all carry the same successor rank
 };
 
 template <bool CYCLIC>
@@ -870,7 +873,8 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     u16* E = G16 + LR_CAP + 8;                             // end (exclusive, window index) of the group that starts at this window index
     u16* CX = E + LR_CAP;                                  // window index of compact record i
     u8* COFF = reinterpret_cast<u8*>(CX + LR_CAP);         // its offset inside its group
-    __shared__ u32 s_wcnt[NWARPS];
+    __shared__ u32 s_wcnt[NWARPS], s_wbig[NWARPS];
+    __shared__ u32 s_g0, s_keyprev, s_nchg;
     __shared__ u32 s_flag[4];                              // [0] unsettled in the nominal range, [1] big in the nominal range, [2] straddling-in group is big, [3] changed records
     const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const u32 tile = blockIdx.x;
@@ -882,49 +886,51 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     const u32 navail = min((u32)LR_CAP, nrec - t0);        // order indices this CTA may refine
     const u32 nG = min((u32)LR_CAP + 1, nrec - t0);        // grp[] entries staged
     const u32* grp = a.grp + td.start;
-    for (u32 x = tid; x < nG; x += KOLM_THREADS) { const u32 g = grp[x]; G16[x] = g >= t0 ? (u16)(g - t0) : (u16)LR_FOREIGN; }
+    // window entries past the staged ones: "a head" right after the block's last record, "not a head" otherwise (LR_NOHEAD never
+    // equals a window index or a group start), so the classify loop needs no bounds checks
+    for (u32 x = tid; x < LR_CAP + 8; x += KOLM_THREADS) {
+        u32 v = LR_NOHEAD;
+        if (x < nG) { const u32 g = grp[x]; v = g >= t0 ? g - t0 : LR_FOREIGN; }
+        else if (x == nG && t0 + nG == nrec) v = nG;
+        G16[x] = (u16)v;
+    }
     if (tid == 0) {
         const u32 g0 = grp[0];
-        s_flag[0] = 0; s_flag[1] = 0; s_flag[3] = 0;
+        s_flag[0] = 0; s_flag[1] = 0; s_flag[3] = 0; s_g0 = g0; s_nchg = 0;
         s_flag[2] = (g0 < t0 && g0 + LR_GCAP < nrec && a.grp[bi.pbase + g0 + LR_GCAP] == g0) ? 1u : 0u;
     }
     __syncthreads();
     const bool big_in = s_flag[2] != 0;
     // ---- classify: warp w looks at window indices [w*LR_RPT*32, (w+1)*LR_RPT*32), iteration k at 32 consecutive ones
-    u32 procbits = 0, bigbits = 0, nuns = 0, nbig = 0, nproc = 0;
+    u32 procbits = 0, bigbits = 0, nuns = 0, nbig = 0, nproc = 0, nbigw = 0;
 #pragma unroll
     for (int k = 0; k < LR_RPT; ++k) {
         const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
-        bool proc = false;
-        if (x < nG) {
-            const u32 g = G16[x];
-            const bool head = g == x;
-            if (head && x > 0) { const u32 ps = G16[x - 1]; if (ps != LR_FOREIGN) E[ps] = (u16)x; }       // the group before me ends here
-            if (x + 1 == nG && t0 + nG == nrec && g != LR_FOREIGN) E[g] = (u16)nG;                        // the block's last group
-            if (x < navail) {
-                const bool own = g != LR_FOREIGN && g < cnt;
-                const bool single = head && (t0 + x + 1 == nrec || G16[x + 1] == x + 1);
-                bool big;
-                if (own) big = g + LR_GCAP < nG && G16[g + LR_GCAP] == g;
-                else big = x < cnt && g == LR_FOREIGN && big_in;
-                proc = own && !big && !single;
-                if (x < cnt) { nuns += single ? 0u : 1u; if (big) { ++nbig; bigbits |= 1u << k; } }
-            }
-        }
+        const u32 g = G16[x], gn = G16[x + 1];
+        const bool ends = gn == x + 1;                     // my group ends with me
+        const bool own = g < cnt;                          // its start lies in the nominal range (LR_FOREIGN / LR_NOHEAD are larger)
+        if (ends && g < LR_CAP) { E[g] = (u16)(x + 1); if (own && x + 1 - g >= LR_UNIFORM_MIN) s_flag[3] = 1; }
+        const bool single = ends && g == x;
+        const bool big = own ? G16[g + LR_GCAP] == g : (g == LR_FOREIGN && big_in);
+        const bool proc = own && !big && !single;
+        const bool nb = big && x < cnt;                    // member of a big group in the nominal range
+        if (x < cnt) nuns += single ? 0u : 1u;
+        if (nb) { ++nbig; bigbits |= 1u << k; }
         if (proc) procbits |= 1u << k;
-        nproc += __popc(__ballot_sync(FULL, proc));        // warp total (the same in every lane)
+        nproc += __popc(__ballot_sync(FULL, proc));        // warp totals (the same in every lane)
+        nbigw += __popc(__ballot_sync(FULL, nb));
     }
     for (int o = 16; o > 0; o >>= 1) { nuns += __shfl_xor_sync(FULL, nuns, o); nbig += __shfl_xor_sync(FULL, nbig, o); }
-    if (lane == 0) { s_wcnt[w] = nproc; if (nuns) atomicAdd(&s_flag[0], nuns); if (nbig) atomicAdd(&s_flag[1], nbig); }
+    if (lane == 0) { s_wcnt[w] = nproc; s_wbig[w] = nbigw; if (nuns) atomicAdd(&s_flag[0], nuns); if (nbig) atomicAdd(&s_flag[1], nbig); }
     u32 pp[LR_RPT];                                        // positions of my records: in flight across the barrier
 #pragma unroll
-    for (int k = 0; k < LR_RPT; ++k) pp[k] = ((procbits >> k) & 1u) ? a.sa[td.start + w * (LR_RPT * 32) + k * 32 + lane] : 0u;
+    for (int k = 0; k < LR_RPT; ++k) pp[k] = (((procbits | bigbits) >> k) & 1u) ? a.sa[td.start + w * (LR_RPT * 32) + k * 32 + lane] : 0u;
     __syncthreads();
     const u32 tot_uns = s_flag[0], tot_big = s_flag[1];
     if (!tot_uns) { if (tid == 0) { a.live[tile] = 0; a.lcount[tile] = 0; } return; }
     if (tid == 0) {
         atomicAdd(a.lact + td.block, tot_uns); atomicAdd(a.stats + 6, tot_uns);
-        if (tot_big) atomicAdd(a.stats + 5, tot_big);
+        if (tot_big) { atomicAdd(a.stats + 5, tot_big); atomicAdd(a.stats + 4, tot_big); }    // big members stay unsettled unless the global path splits them
         a.live[tile] = tot_big ? 3 : 1;                    // bit 1: k_big_emit has work here
     }
     if (tot_big) {                                         // only such tiles are read by k_big_emit
@@ -934,23 +940,28 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
             if (x < cnt) a.F[td.start + x] = ((bigbits >> k) & 1u) ? 0u : 0x80000000u;
         }
     }
-    u32 wbase = 0, m = 0;
+    u32 wbase = 0, m = 0, bbase = 0;
 #pragma unroll
-    for (int i = 0; i < NWARPS; ++i) { const u32 c_ = s_wcnt[i]; if ((u32)i < w) wbase += c_; m += c_; }
-    if (!m) { if (tid == 0) a.lcount[tile] = 0; return; }  // only big or foreign groups here
-    // ---- compact my records
+    for (int i = 0; i < NWARPS; ++i) { const u32 c_ = s_wcnt[i], b_ = s_wbig[i]; if ((u32)i < w) { wbase += c_; bbase += b_; } m += c_; }
+    const u32 mall = m + tot_big;
+    if (!mall) { if (tid == 0) a.lcount[tile] = 0; return; }     // only a foreign small group here
+    // ---- compact: my records at [0, m), then the nominal members of big groups at [m, mall) (only their keys are looked at)
     {
-        u32 run = wbase;
+        u32 run = wbase, brun = m + bbase;
 #pragma unroll
         for (int k = 0; k < LR_RPT; ++k) {
-            const bool proc = (procbits >> k) & 1u;
-            const u32 pm = __ballot_sync(FULL, proc);
+            const bool proc = (procbits >> k) & 1u, nb = (bigbits >> k) & 1u;
+            const u32 pm = __ballot_sync(FULL, proc), bm = __ballot_sync(FULL, nb);
+            const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
             if (proc) {
-                const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
                 const u32 slot = run + __popc(pm & lanemask_lt());
                 CX[slot] = (u16)x; COFF[slot] = (u8)(x - G16[x]); CP[slot] = pp[k];
             }
-            run += __popc(pm);
+            if (nb) {
+                const u32 slot = brun + __popc(bm & lanemask_lt());
+                CX[slot] = (u16)x; CP[slot] = pp[k];
+            }
+            run += __popc(pm); brun += __popc(bm);
         }
     }
     __syncthreads();
@@ -958,13 +969,19 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     {
         const u32 nf = CYCLIC ? a.nfac[td.block] : 0;
         const u32* fst = a.fstart + bi.pbase;
-        for (u32 i0 = tid; i0 < m; i0 += 4 * KOLM_THREADS) {
+        if (tid == KOLM_THREADS - 1 && big_in && t0 > 0) {         // the key of the order index before the tile: left neighbour of a big group's member at x = 0
+            u32 lp = a.sa[td.start - 1] - bi.pbase, sp;
+            if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
+            else sp = lp + a.h;
+            s_keyprev = a.rank[bi.pbase + sp];
+        }
+        for (u32 i0 = tid; i0 < mall; i0 += 4 * KOLM_THREADS) {
             u32 q[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const u32 i = i0 + u * KOLM_THREADS;
                 q[u] = 0xffffffffu;
-                if (i < m) {
+                if (i < mall) {
                     u32 lp = CP[i] - bi.pbase, sp;
                     if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
                     else sp = lp + a.h;
@@ -974,27 +991,54 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (q[u] != 0xffffffffu) q[u] = a.rank[q[u]];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const u32 i = i0 + u * KOLM_THREADS; if (i < m) K2c[i] = q[u]; }
+            for (int u = 0; u < 4; ++u) { const u32 i = i0 + u * KOLM_THREADS; if (i < mall) K2c[i] = q[u]; }
         }
     }
     __syncthreads();
+    // ---- groups whose members all carry the same key stay as they are (periodic data: most groups, for many rounds).  Small
+    //      groups: bit 15 of E[group start]; big groups: gflag[group start] = stamp, read by k_big_emit
+    const bool utest = s_flag[3] != 0;                     // (read after the barriers that follow its writers)
+    for (u32 i = utest ? tid : m + tid; i < mall; i += KOLM_THREADS) {
+        if (i < m) {
+            const u32 off = COFF[i];
+            if (off && K2c[i] != K2c[i - off]) { const u32 gs = (u32)CX[i] - off; atomicOr(reinterpret_cast<u32*>(E) + (gs >> 1), 0x8000u << (16 * (gs & 1u))); }
+        } else {
+            const u32 x = CX[i], g = G16[x];
+            if (g != x) {                                  // not the group's first member: slot i - 1 holds order index x - 1 (same group) unless x = 0
+                const u32 left = x ? K2c[i - 1] : s_keyprev;
+                if (K2c[i] != left) a.gflag[bi.pbase + (g == LR_FOREIGN ? s_g0 : t0 + g)] = a.stamp;
+            }
+        }
+    }
+    __syncthreads();
+    if (!m) { if (tid == 0) a.lcount[tile] = 0; return; }
     // ---- every record finds its place inside its group: keys below mine, equal keys before me
     u32 nnew = 0, nsurv = 0;
     for (u32 i = tid; i < m; i += KOLM_THREADS) {
-        const u32 x = CX[i], off = COFF[i], cs = i - off, gs = x - off, n = (u32)E[gs] - gs, mine = K2c[i];
+        const u32 x = CX[i], off = COFF[i], cs = i - off, gs = x - off, eg = E[gs], n = (eg & 0x7fffu) - gs, mine = K2c[i];
+        if (utest && !(eg >> 15)) { ++nsurv; continue; }   // all keys of the group equal: nothing moves
+        // keys are below 2^30: (k - mine) >> 31 counts "k < mine", (k - mine - 1) >> 31 counts "k <= mine" — two adds per key
+        // and count; the keys before me and the ones from me on are counted apart, their "<=" minus "<" are the equal ones
         const u32* kp = K2c + cs;
-        u32 lt = 0, eq = 0, eqb = 0, j = 0;
+        const u32 m1 = mine + 1u;
+        u32 ltb = 0, leb = 0, lta = 0, lea = 0, j = 0;
+        for (; j + 4 <= off; j += 4) {
+            const u32 k0 = kp[j], k1 = kp[j + 1], k2 = kp[j + 2], k3 = kp[j + 3];
+            ltb += ((k0 - mine) >> 31) + ((k1 - mine) >> 31) + ((k2 - mine) >> 31) + ((k3 - mine) >> 31);
+            leb += ((k0 - m1) >> 31) + ((k1 - m1) >> 31) + ((k2 - m1) >> 31) + ((k3 - m1) >> 31);
+        }
+        for (; j < off; ++j) { const u32 kj = kp[j]; ltb += (kj - mine) >> 31; leb += (kj - m1) >> 31; }
         for (; j + 4 <= n; j += 4) {
             const u32 k0 = kp[j], k1 = kp[j + 1], k2 = kp[j + 2], k3 = kp[j + 3];
-            lt += (k0 < mine) + (k1 < mine) + (k2 < mine) + (k3 < mine);
-            eq += (k0 == mine) + (k1 == mine) + (k2 == mine) + (k3 == mine);
-            eqb += (k0 == mine && j < off) + (k1 == mine && j + 1 < off) + (k2 == mine && j + 2 < off) + (k3 == mine && j + 3 < off);
+            lta += ((k0 - mine) >> 31) + ((k1 - mine) >> 31) + ((k2 - mine) >> 31) + ((k3 - mine) >> 31);
+            lea += ((k0 - m1) >> 31) + ((k1 - m1) >> 31) + ((k2 - m1) >> 31) + ((k3 - m1) >> 31);
         }
-        for (; j < n; ++j) { const u32 kj = kp[j]; lt += kj < mine; eq += kj == mine; eqb += (kj == mine && j < off); }
+        for (; j < n; ++j) { const u32 kj = kp[j]; lta += (kj - mine) >> 31; lea += (kj - m1) >> 31; }
+        const u32 lt = ltb + lta, eqb = leb - ltb, eq = eqb + (lea - lta);
         const u32 np = gs + lt + eqb;
         a.sa[td.start + np] = CP[i];
         if (lt) {                                          // group start moved: k_apply_local publishes it
-            const u32 idx = atomicAdd(&s_flag[3], 1u);
+            const u32 idx = atomicAdd(&s_nchg, 1u);
             const u32 e = np | ((gs + lt) << 16);
             if (idx < KOLM_TILE) a.list[td.start + idx] = e; else a.list2[td.start + idx - KOLM_TILE] = e;
         }
@@ -1004,7 +1048,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     for (int o = 16; o > 0; o >>= 1) { nnew += __shfl_xor_sync(FULL, nnew, o); nsurv += __shfl_xor_sync(FULL, nsurv, o); }
     if (lane == 0) { if (nnew) atomicAdd(a.newcls + td.block, nnew); if (nsurv) atomicAdd(a.stats + 4, nsurv); }
     __syncthreads();
-    if (tid == 0) a.lcount[tile] = s_flag[3];
+    if (tid == 0) a.lcount[tile] = s_nchg;
 }
 
 // records of the tiles k_refine_local marked, appended to the block's record list as (rank[succ_h(v)], v) in any order (the LS
@@ -1015,7 +1059,7 @@ template <bool CYCLIC, bool ALL>
 __global__ void __launch_bounds__(KOLM_THREADS) k_big_emit(const u32* __restrict__ sa, const u32* __restrict__ rank, const u32* __restrict__ F, const u32* __restrict__ grp,
                                                            const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo, const u32* __restrict__ fstart,
                                                            const u32* __restrict__ nfac, const u32* __restrict__ done, const u8* __restrict__ live, u32* __restrict__ active,
-                                                           u32* __restrict__ K2, u32* __restrict__ V2, u32 h) {
+                                                           u32* __restrict__ K2, u32* __restrict__ V2, u32 h, const u32* __restrict__ gflag, u32 stamp) {
     __shared__ u32 s_w[NWARPS];
     __shared__ u32 s_base;
     const u8 lv = live[blockIdx.x];
@@ -1034,7 +1078,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_big_emit(const u32* __restrict
             if (ALL) {
                 const u32 g = grp[td.start + x];
                 take = !(g == t0 + x && (t0 + x + 1 == bi.len || grp[td.start + x + 1] == t0 + x + 1));
-            } else take = F[td.start + x] == 0u;
+            } else take = F[td.start + x] == 0u && gflag[bi.pbase + grp[td.start + x]] == stamp;   // a big group some of whose keys differ
         }
         if (take) bits |= 1u << k;
         mycnt += __popc(__ballot_sync(FULL, take));        // warp total so far (same in every lane)
@@ -1559,7 +1603,8 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         RefineArgs fa;
         fa.sa = c->d_sa; fa.rank = c->d_rank; fa.grp = c->d_grp; fa.list = c->d_nr; fa.list2 = c->d_k0; fa.lcount = c->d_thist; fa.F = c->d_lo;
         fa.tiles = c->d_tiles; fa.binfo = c->d_binfo; fa.fstart = c->d_fstart; fa.nfac = c->d_nfac; fa.done = c->d_done; fa.live = c->d_live;
-        fa.lact = c->d_lact; fa.newcls = c->d_newcls; fa.stats = c->d_stats;
+        fa.lact = c->d_lact; fa.newcls = c->d_newcls; fa.stats = c->d_stats; fa.gflag = c->d_v1;
+        const u32 serial = ++c->sort_serial;
         static int trace = -1;
         if (trace < 0) { const char* e = getenv("KOLM_TRACE_ROUNDS"); trace = e ? atoi(e) : 0; }
         bool finished = false;
@@ -1567,6 +1612,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         for (; rounds < 64; h <<= 1) {
             if (h > 0x7fffffffull) h = 0x7fffffffull;
             fa.h = (u32)h;
+            fa.stamp = 0x80000000u | ((serial & 0xffffffu) << 7) | (u32)(rounds & 127);   // never a value a sort leaves in d_v1 (positions < 2^31); a stale hit only costs work
             CUDA_TRY(cudaMemsetAsync(c->d_stats + 4, 0, 12, s));      // [4] survivors, [5] members of big groups, [6] unsettled at the start
             if (cyclic) KL(c, KC_RERANK, N * 4, s, k_refine_local<true><<<nt, KOLM_THREADS, LR_SMEM, s>>>(fa));
             else KL(c, KC_RERANK, N * 4, s, k_refine_local<false><<<nt, KOLM_THREADS, LR_SMEM, s>>>(fa));
@@ -1582,8 +1628,8 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
             if (big) {
                 // members of big groups (flagged in d_lo): (rank[succ_h(v)], v) per block -> sort -> (rank[v], v) -> stable sort -> rerank
                 CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
-                if (cyclic) KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<true, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
-                else KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<false, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
+                if (cyclic) KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<true, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
+                else KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<false, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
                 KL(c, KC_PLAN, (i64)nb * 16, s, k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb));
                 CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 12, cudaMemcpyDeviceToHost, s));
                 CUDA_TRY(cudaStreamSynchronize(s));
@@ -1620,8 +1666,8 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
                 h <<= 1;
                 if (h > 0x7fffffffull) h = 0x7fffffffull;
                 CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
-                if (cyclic) KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<true, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
-                else KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<false, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h));
+                if (cyclic) KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<true, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
+                else KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<false, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
                 prebuilt = true; use_ls = true; Kprev = c->d_k1; Vprev = c->d_v1;      // "the other pair" of the LS branch is (d_k0, d_v0)
                 break;
             }

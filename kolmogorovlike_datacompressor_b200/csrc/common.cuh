@@ -100,6 +100,7 @@ struct kolm_ctx {
     i64 launches[32]; i64 algbytes[32];
     int prof_on; int prof_n; int prof_cat[8192]; cudaEvent_t* prof_ev;
     i64 counters[8];
+    u32 sort_serial;         // sorts run on this context (stamps of the local rounds' per-group flags)
 };
 
 // ------------------------------------------------------------------------------------------------
