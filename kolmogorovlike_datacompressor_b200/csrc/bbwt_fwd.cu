@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256 * RSCAN_GROUPS) k_radix_scan(u32* __restri
 __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __restrict__ Kin, const u32* __restrict__ Vin,
                                                                 u32* __restrict__ Kout, u32* __restrict__ Vout,
                                                                 const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
-                                                                const u32* __restrict__ thist, int shift, u32 mask) {
+                                                                const u32* __restrict__ thist, int shift, u32 mask, const u32* __restrict__ rekey) {
     __shared__ __align__(128) u32 sk[KOLM_TILE];
     __shared__ __align__(128) u32 sv[KOLM_TILE];
     __shared__ u32 whist[NWARPS][256];
@@ -513,6 +513,18 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_radix_scatter(const u32* __res
     }
     __syncthreads();
     // ---- coalesced digit runs to global
+    if (rekey) {                                            // last pass of the deep bootstrap's first sort: the key column leaves as rekey[value]
+        for (u32 s0 = tid; s0 < td.count; s0 += 4 * KOLM_THREADS) {
+            u32 g[4], v[4], nk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const u32 s = s0 + u * KOLM_THREADS; g[u] = 0xffffffffu; if (s < td.count) { g[u] = gofs[(sk[s] >> shift) & mask] + s; v[u] = sv[s]; } }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (g[u] != 0xffffffffu) nk[u] = rekey[v[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (g[u] != 0xffffffffu) { Kout[g[u]] = nk[u]; Vout[g[u]] = v[u]; }
+        }
+        return;
+    }
     for (u32 s = tid; s < td.count; s += KOLM_THREADS) {
         const u32 kk = sk[s];
         const u32 g = gofs[(kk >> shift) & mask] + s;
@@ -1479,7 +1491,7 @@ static inline int ceil_log2_u32(u32 v) { int b = 0; while ((1ull << b) < v) ++b;
 
 // stable LSD radix sort of (K,V) records over `ntiles` tiles; result pointers returned in *Kr,*Vr.
 static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, i64 nrec, const u32* tile0, const u32* tilen, int bits,
-                      u32* Ka, u32* Va, u32* Kb, u32* Vb, u32** Kr, u32** Vr, cudaStream_t s) {
+                      u32* Ka, u32* Va, u32* Kb, u32* Vb, u32** Kr, u32** Vr, cudaStream_t s, const u32* rekey_last = nullptr) {
     int passes = (bits + 7) / 8; if (passes < 1) passes = 1;
     int dbits = (bits + passes - 1) / passes; if (dbits < 1) dbits = 1;
     u32 mask = (1u << dbits) - 1;
@@ -1488,7 +1500,7 @@ static int radix_sort(kolm_ctx* c, const TileDesc* tiles, int ntiles, i64 nrec, 
         int shift = p * dbits;
         KL(c, KC_HIST, nrec * 4 + (i64)ntiles * 1024, s, k_radix_hist<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, tiles, c->d_thist, shift, mask));
         KL(c, KC_SCAN, (i64)ntiles * 2048, s, k_radix_scan<<<sgrid, 256 * RSCAN_GROUPS, 0, s>>>(c->d_thist, tile0, tilen, c->nblocks));
-        KL(c, KC_SCATTER, nrec * 16 + (i64)ntiles * 1024, s, k_radix_scatter<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, Va, Kb, Vb, tiles, c->d_binfo, c->d_thist, shift, mask));
+        KL(c, KC_SCATTER, nrec * 16 + (i64)ntiles * 1024, s, k_radix_scatter<<<ntiles, KOLM_THREADS, 0, s>>>(Ka, Va, Kb, Vb, tiles, c->d_binfo, c->d_thist, shift, mask, p + 1 == passes ? rekey_last : nullptr));
         u32* t = Ka; Ka = Kb; Kb = t; t = Va; Va = Vb; Vb = t;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1560,8 +1572,8 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     u32 *K, *V;
     if (deep) {
         KL(c, KC_BOOT, N * 12, s, k_boot_lo<<<nt, KOLM_THREADS, 0, s>>>(c->d_nr, c->d_binfo, c->d_tiles, c->d_fstart, c->d_nfac, h0, c->d_k0, c->d_lo));
-        KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, 32, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s));
-        KL(c, KC_BOOT, N * 12, s, k_boot_rekey<<<nt, KOLM_THREADS, 0, s>>>(c->d_nr, V, c->d_tiles, K));
+        // the last pass writes KH[V[j]] as its key column (k_boot_rekey fused into the scatter: one read of V and one write of K less)
+        KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, 32, c->d_k0, c->d_v0, c->d_k1, c->d_v1, &K, &V, s, c->d_nr));
         u32* Ko = (K == c->d_k0) ? c->d_k1 : c->d_k0;
         u32* Vo = (V == c->d_v0) ? c->d_v1 : c->d_v0;
         KOLM_TRY(radix_sort(c, c->d_tiles, nt, N, c->d_btile0, c->d_btilen, 32, K, V, Ko, Vo, &K, &V, s));

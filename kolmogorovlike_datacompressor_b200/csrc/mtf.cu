@@ -626,12 +626,12 @@ __global__ void __launch_bounds__(MTF_WARPS * 32) k_mtf_dec_perm(const u8* __res
 }
 
 // pass B (decode): entry list of every tile = composition of the previous tiles' permutations
-__global__ void __launch_bounds__(256) k_mtf_dec_compose(u8* __restrict__ tperm, const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks) {
+__global__ void __launch_bounds__(256) k_mtf_dec_compose(u8* __restrict__ tperm, const u32* __restrict__ tile0, const u32* __restrict__ tilen, int nblocks, u32 ss) {
     __shared__ u8 cur[256];
     __shared__ u8 nxt[256];
     for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        u32 nt = tilen[b];
-        u8* base = tperm + (size_t)tile0[b] * 256;
+        u32 nt = tilen[b] << ss;                           // rows = pieces of 4096 >> ss bytes
+        u8* base = tperm + ((size_t)tile0[b] << ss) * 256;
         cur[threadIdx.x] = (u8)threadIdx.x;
         __syncthreads();
         for (u32 t = 0; t < nt; ++t) {
@@ -718,6 +718,90 @@ __global__ void __launch_bounds__(MTF2_THREADS) k_mtf_dec2(const u8* __restrict_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// decode, v3 (default): ONE walk instead of two.  The list operations of a piece depend on the index stream only, so the
+// walk from the identity list yields, besides the piece's permutation, for every byte the SLOT of the entry list its symbol
+// sits in (what the identity start "decodes" to).  After the per-block composition of the permutations has produced the
+// true entry lists, the symbols are a table lookup — no second serial walk.  Pieces of 1 KiB (four per tile) instead of whole
+// tiles: four times the independent walks for a kernel that is bound by the latency of its serial chain.
+//   k_mtf_dec3_walk   thread per piece: identity-start replay (packed list as in k_mtf_dec2), slots to `out`, permutation to tperm
+//   k_mtf_dec_compose per block: entry list of every piece (tperm rewritten in place)
+//   k_mtf_dec3_map    CTA per tile: out[i] = entry_list[piece(i)][out[i]]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MTF2_THREADS) k_mtf_dec3_walk(const u8* __restrict__ in, u8* __restrict__ out, const TileDesc* __restrict__ tiles,
+                                                                const BlockInfo* __restrict__ binfo, u8* __restrict__ tperm, int np) {
+    __shared__ u32 lst[64][MTF2_THREADS];
+    const u32 tid = threadIdx.x;
+    const int piece = blockIdx.x * MTF2_THREADS + tid;
+    if (piece >= np) return;
+#pragma unroll 8
+    for (u32 k = 0; k < 64; ++k) lst[k][tid] = 0x03020100u + 0x04040404u * k;
+    const TileDesc td = tiles[(u32)piece >> 2];
+    const BlockInfo bi = binfo[td.block];
+    u32 pstart, pcount;
+    mtf_piece(td, (u32)piece, 2u, pstart, pcount);
+    const u32 t0 = pstart - bi.pbase;
+    const u8* src = in + bi.ioff + t0;
+    u8* dst = out + bi.ioff + t0;
+    u32 w0 = lst[0][tid];
+    const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    for (u32 x0 = 0; x0 < pcount; x0 += 16) {
+        u32 inw[4], outw[4] = {0, 0, 0, 0};
+        const u32 nb = min(16u, pcount - x0);
+        if (aligned && nb == 16) { uint4 v = *reinterpret_cast<const uint4*>(src + x0); inw[0] = v.x; inw[1] = v.y; inw[2] = v.z; inw[3] = v.w; }
+        else { inw[0] = inw[1] = inw[2] = inw[3] = 0; for (u32 i = 0; i < nb; ++i) inw[i >> 2] |= (u32)src[x0 + i] << (8 * (i & 3)); }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((u32)i < nb) {
+                const u32 idx = (inw[i >> 2] >> (8 * (i & 3))) & 0xFF;
+                u32 sym;
+                if (idx < 4) {
+                    sym = (w0 >> (8 * idx)) & 0xFF;
+                    if (idx) w0 = __byte_perm(w0, sym, idx == 1 ? 0x3204 : idx == 2 ? 0x3104 : 0x2104);
+                } else {
+                    const u32 k = idx >> 2, j = idx & 3;
+                    const u32 wk = lst[k][tid];
+                    sym = (wk >> (8 * j)) & 0xFF;
+                    u32 carry = w0 >> 24;
+                    w0 = (w0 << 8) | sym;
+                    for (u32 q = 1; q < k; ++q) { u32 w = lst[q][tid]; lst[q][tid] = (w << 8) | carry; carry = w >> 24; }
+                    lst[k][tid] = __byte_perm(wk, carry, j == 0 ? 0x3214 : j == 1 ? 0x3204 : j == 2 ? 0x3104 : 0x2104);
+                }
+                outw[i >> 2] |= sym << (8 * (i & 3));
+            }
+        }
+        if (aligned && nb == 16) *reinterpret_cast<uint4*>(dst + x0) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+        else for (u32 i = 0; i < nb; ++i) dst[x0 + i] = (u8)(outw[i >> 2] >> (8 * (i & 3)));
+    }
+    u32* orow = reinterpret_cast<u32*>(tperm + (size_t)piece * 256);
+    orow[0] = w0;
+    for (u32 k = 1; k < 64; ++k) orow[k] = lst[k][tid];
+}
+
+__global__ void __launch_bounds__(KOLM_THREADS) k_mtf_dec3_map(u8* __restrict__ out, const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
+                                                               const u8* __restrict__ tperm) {
+    __shared__ u32 E[4][64];                               // entry lists of the tile's four pieces
+    const u32 tid = threadIdx.x;
+    const TileDesc td = tiles[blockIdx.x];
+    const BlockInfo bi = binfo[td.block];
+    (&E[0][0])[tid] = reinterpret_cast<const u32*>(tperm + (size_t)blockIdx.x * 1024)[tid];
+    __syncthreads();
+    const u8* e = reinterpret_cast<const u8*>(&E[tid >> 6][0]);   // 16 bytes per thread: thread t sits in piece t / 64
+    u8* dst = out + bi.ioff + (td.start - bi.pbase) + 16 * tid;
+    const u32 x = 16 * tid;
+    if (x >= td.count) return;
+    if (x + 16 <= td.count && (((uintptr_t)dst) & 15) == 0) {
+        uint4 v = *reinterpret_cast<const uint4*>(dst);
+        u32 wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[i] = (u32)e[wv[i] & 0xFF] | ((u32)e[(wv[i] >> 8) & 0xFF] << 8) | ((u32)e[(wv[i] >> 16) & 0xFF] << 16) | ((u32)e[wv[i] >> 24] << 24);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    } else {
+        const u32 nb = min(16u, td.count - x);
+        for (u32 i = 0; i < nb; ++i) dst[i] = e[dst[i]];
+    }
+}
 
 // KOLM_MTF3_DBG=2: host re-computation of every intermediate of the v3 encode (pieces' local lists and misses, group lists,
 // group entry lists) compared with what the kernels left in scratch — a debugging aid, never on in production.
@@ -838,9 +922,19 @@ int kolm_mtf_impl(kolm_ctx* c, const u8* in, u8* out, bool decode, cudaStream_t 
         static int v2 = -1;
         if (v2 < 0) { const char* e = getenv("KOLM_MTF_V2"); v2 = e ? atoi(e) : 1; }
         const int g2 = (nt + MTF2_THREADS - 1) / MTF2_THREADS;
+        static int v3 = -1;
+        if (v3 < 0) { const char* e = getenv("KOLM_MTF_DEC_V3"); v3 = e ? atoi(e) : 1; }
+        if (v3 && v2) {
+            const int np = nt * 4;
+            KL(c, KC_MTF_MAIN, 2 * N + (i64)np * 256, s, k_mtf_dec3_walk<<<(np + MTF2_THREADS - 1) / MTF2_THREADS, MTF2_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, np));
+            KL(c, KC_MTF_SCAN, (i64)np * 512, s, k_mtf_dec_compose<<<sgrid, 256, 0, s>>>(tperm, c->d_btile0, c->d_btilen, nb, 2u));
+            KL(c, KC_MTF_PRE, 2 * N + (i64)np * 256, s, k_mtf_dec3_map<<<nt, KOLM_THREADS, 0, s>>>(out, c->d_tiles, c->d_binfo, tperm));
+            CUDA_TRY(cudaGetLastError());
+            return KOLM_OK;
+        }
         if (v2) KL(c, KC_MTF_PRE, N + (i64)nt * 256, s, k_mtf_dec2<true><<<g2, MTF2_THREADS, 0, s>>>(in, nullptr, c->d_tiles, c->d_binfo, tperm, nt));
         else KL(c, KC_MTF_PRE, N + (i64)nt * 256, s, k_mtf_dec_perm<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, c->d_tiles, c->d_binfo, tperm, nt));
-        KL(c, KC_MTF_SCAN, (i64)nt * 512, s, k_mtf_dec_compose<<<sgrid, 256, 0, s>>>(tperm, c->d_btile0, c->d_btilen, nb));
+        KL(c, KC_MTF_SCAN, (i64)nt * 512, s, k_mtf_dec_compose<<<sgrid, 256, 0, s>>>(tperm, c->d_btile0, c->d_btilen, nb, 0u));
         if (v2) KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 256, s, k_mtf_dec2<false><<<g2, MTF2_THREADS, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt));
         else KL(c, KC_MTF_MAIN, 2 * N + (i64)nt * 256, s, k_mtf_dec<<<wgrid, MTF_WARPS * 32, 0, s>>>(in, out, c->d_tiles, c->d_binfo, tperm, nt));
     }
