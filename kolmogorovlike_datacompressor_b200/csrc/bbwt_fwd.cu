@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 4) k_rerank(RerankArgs a) {
             }
             if (BOOT) {
                 a.rank[val2[i]] = nrk_[i];
-                if (single) atomicOr(a.single + (val2[i] >> 5), 1u << (val2[i] & 31));
+                if (single && a.single) atomicOr(a.single + (val2[i] >> 5), 1u << (val2[i] & 31));
             } else { a.nr[td.start + r] = nrk_[i] | (single ? 0x80000000u : 0u); nsurv += single ? 0u : 1u; }
         }
     }
@@ -900,11 +900,19 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     const u32* grp = a.grp + td.start;
     // window entries past the staged ones: "a head" right after the block's last record, "not a head" otherwise (LR_NOHEAD never
     // equals a window index or a group start), so the classify loop needs no bounds checks
-    for (u32 x = tid; x < LR_CAP + 8; x += KOLM_THREADS) {
-        u32 v = LR_NOHEAD;
-        if (x < nG) { const u32 g = grp[x]; v = g >= t0 ? g - t0 : LR_FOREIGN; }
-        else if (x == nG && t0 + nG == nrec) v = nG;
-        G16[x] = (u16)v;
+    {
+        constexpr int NI = (LR_CAP + 8 + KOLM_THREADS - 1) / KOLM_THREADS;
+        u32 gv[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { const u32 x = tid + i * KOLM_THREADS; gv[i] = x < nG ? grp[x] : 0u; }     // all loads in flight at once
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const u32 x = tid + i * KOLM_THREADS;
+            u32 v = LR_NOHEAD;
+            if (x < nG) v = gv[i] >= t0 ? gv[i] - t0 : LR_FOREIGN;
+            else if (x == nG && t0 + nG == nrec) v = nG;
+            if (x < LR_CAP + 8) G16[x] = (u16)v;
+        }
     }
     if (tid == 0) {
         const u32 g0 = grp[0];
@@ -1034,12 +1042,22 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
         const u32* kp = K2c + cs;
         const u32 m1 = mine + 1u;
         u32 ltb = 0, leb = 0, lta = 0, lea = 0, j = 0;
-        for (; j + 4 <= off; j += 4) {
+        if (n <= 4) {                                      // most groups of text: no loops (slots past the group are masked out)
+            const u32 k0 = kp[0], k1 = kp[1], k2 = n > 2 ? kp[2] : 0x7fffffffu, k3 = n > 3 ? kp[3] : 0x7fffffffu;
+            const u32 l0 = (k0 - mine) >> 31, l1 = (k1 - mine) >> 31, l2 = (k2 - mine) >> 31, l3 = (k3 - mine) >> 31;
+            const u32 e0 = (k0 - m1) >> 31, e1 = (k1 - m1) >> 31, e2 = (k2 - m1) >> 31, e3 = (k3 - m1) >> 31;
+            lta = l0 + l1 + l2 + l3; lea = e0 + e1 + e2 + e3;
+            ltb = (off > 0 ? l0 : 0u) + (off > 1 ? l1 : 0u) + (off > 2 ? l2 : 0u);
+            leb = (off > 0 ? e0 : 0u) + (off > 1 ? e1 : 0u) + (off > 2 ? e2 : 0u);
+            lta -= ltb; lea -= leb;
+            j = n;
+        }
+        for (; j + 4 <= off && j < n; j += 4) {
             const u32 k0 = kp[j], k1 = kp[j + 1], k2 = kp[j + 2], k3 = kp[j + 3];
             ltb += ((k0 - mine) >> 31) + ((k1 - mine) >> 31) + ((k2 - mine) >> 31) + ((k3 - mine) >> 31);
             leb += ((k0 - m1) >> 31) + ((k1 - m1) >> 31) + ((k2 - m1) >> 31) + ((k3 - m1) >> 31);
         }
-        for (; j < off; ++j) { const u32 kj = kp[j]; ltb += (kj - mine) >> 31; leb += (kj - m1) >> 31; }
+        for (; j < off && j < n; ++j) { const u32 kj = kp[j]; ltb += (kj - mine) >> 31; leb += (kj - m1) >> 31; }
         for (; j + 4 <= n; j += 4) {
             const u32 k0 = kp[j], k1 = kp[j + 1], k2 = kp[j + 2], k3 = kp[j + 3];
             lta += ((k0 - mine) >> 31) + ((k1 - mine) >> 31) + ((k2 - mine) >> 31) + ((k3 - mine) >> 31);
@@ -1127,14 +1145,14 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_apply_local(const u32* __restr
     if (!n) return;
     const TileDesc td = tiles[blockIdx.x];
     const u32 t0 = td.start - binfo[td.block].pbase;
-    for (u32 i0 = threadIdx.x; i0 < n; i0 += 4 * KOLM_THREADS) {
-        u32 e[4], v[4];
+    for (u32 i0 = threadIdx.x; i0 < n; i0 += 8 * KOLM_THREADS) {
+        u32 e[8], v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const u32 i = i0 + u * KOLM_THREADS; e[u] = i < n ? (i < KOLM_TILE ? list[td.start + i] : list2[td.start + i - KOLM_TILE]) : 0xffffffffu; }
+        for (int u = 0; u < 8; ++u) { const u32 i = i0 + u * KOLM_THREADS; e[u] = i < n ? (i < KOLM_TILE ? list[td.start + i] : list2[td.start + i - KOLM_TILE]) : 0xffffffffu; }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = e[u] != 0xffffffffu ? sa[td.start + (e[u] & 0xffffu)] : 0u;
+        for (int u = 0; u < 8; ++u) v[u] = e[u] != 0xffffffffu ? sa[td.start + (e[u] & 0xffffu)] : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (e[u] != 0xffffffffu) { const u32 g = t0 + (e[u] >> 16); grp[td.start + (e[u] & 0xffffu)] = g; rank[v[u]] = g; }
+        for (int u = 0; u < 8; ++u) if (e[u] != 0xffffffffu) { const u32 g = t0 + (e[u] >> 16); grp[td.start + (e[u] & 0xffffu)] = g; rank[v[u]] = g; }
     }
 }
 
@@ -1582,9 +1600,12 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     }
     int lgrid = nt;
     KOLM_TRY(kolm_lb_reset(c, false, nt, &lgrid, s));
+    static int local_rounds = -1;
+    if (local_rounds < 0) { const char* e = getenv("KOLM_LOCAL_ROUNDS"); local_rounds = e ? atoi(e) : 1; }
     RerankArgs ra;
     ra.K = K; ra.V = V; ra.tiles = c->d_tiles; ra.binfo = c->d_binfo; ra.active = c->d_active; ra.fstart = c->d_fstart; ra.nfac = c->d_nfac;
-    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0; ra.lo = c->d_lo; ra.grp = c->d_grp;
+    ra.lb = c->d_lb; ra.sa = c->d_sa; ra.rank = c->d_rank; ra.nr = c->d_nr; ra.single = c->d_single; ra.newcls = c->d_newcls; ra.h = deep ? h0 : 0; ra.lo = c->d_lo; ra.grp = local_rounds ? c->d_grp : nullptr;
+    if (local_rounds) ra.single = nullptr;                   // the settled-bit map is read by k_gather only, which the local rounds never run
     if (deep) { KL(c, KC_RERANK, N * 20, s, k_rerank<2, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra)); h0 *= 2; c->counters[4] += N; }   // second full sort
     else if (cyclic) KL(c, KC_RERANK, N * 16, s, k_rerank<1, true><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
     else KL(c, KC_RERANK, N * 16, s, k_rerank<1, false><<<lgrid, KOLM_THREADS, 0, s>>>(ra));
@@ -1597,8 +1618,6 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
     ra.survivors = c->d_stats + 4;
     bool use_ls = false;
     u32 *Kprev = nullptr, *Vprev = nullptr;                  // sorted records of the previous round (aligned with d_nr)
-    static int local_rounds = -1;
-    if (local_rounds < 0) { const char* e = getenv("KOLM_LOCAL_ROUNDS"); local_rounds = e ? atoi(e) : 1; }
     u64 hstart = h0;
     bool prebuilt = false;                                   // the first global round finds its (second key, position) records already emitted
     if (local_rounds) {
@@ -1758,7 +1777,7 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         if (surv == 0) break;
         Kprev = K; Vprev = V;
         prebuilt = false;
-        use_ls = ls_div > 0 && surv * (u64)ls_div < (u64)N;
+        use_ls = local_rounds ? true : (ls_div > 0 && surv * (u64)ls_div < (u64)N);   // after local rounds there is no settled-bit map for k_gather
     }
     if (rounds_out) *rounds_out = rounds + (deep ? 1 : 0);    // doublings of the sorted depth: the deep bootstrap is one (h0 -> 2*h0)
     return KOLM_OK;

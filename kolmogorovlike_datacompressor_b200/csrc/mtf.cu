@@ -256,12 +256,15 @@ __global__ void __launch_bounds__(MTF2_THREADS) k_mtf_enc2(const u8* __restrict_
 //
 //   k_mtf3_walk   one THREAD per 1 KiB piece walks its bytes from the EMPTY list.  A symbol already seen in the piece has its true
 //                 MTF index (everything between its two occurrences lies inside the piece); a first occurrence ("miss") is
-//                 recorded (symbol, position) and patched later.  The walk alternates two warp-uniform phases per 32 bytes:
-//                   A  all lanes run the same branch-free code on the four front entries (one register): the entry is found
-//                      there (index 0..3) or not; either way the register word is final — a symbol not found in front is pushed
-//                      on the front and the fourth entry drops into the deep part — so the phase never waits for a deep search;
-//                   B  the deep searches of the group (packed words in shared memory, [word][thread]) are drained in order.
-//                 The divergence of the old walk (every byte step cost the warp its slowest lane) is confined to phase B.
+//                 recorded (symbol, position) and patched later.  The walk alternates three warp-uniform phases per 32 bytes:
+//                   A   all lanes run the same branch-free code on the four front entries (one register): the entry is found
+//                       there (index 0..3) or not; either way the register word is final — a symbol not found in front is pushed
+//                       on the front and the fourth entry drops to the next level — so the phase never waits for a search;
+//                   A2  the bytes that missed the front (19 % on BWT of text) are drained in order against entries 4..15, three
+//                       more register words searched and rotated branch-free by all lanes (the loop runs as often as the lane
+//                       with the most such bytes needs); what drops out of entry 15 goes on;
+//                   B   the rest (3 %) searches the deep part (packed words in shared memory, [word][thread]) in order.
+//                 The divergence of the old walk (every byte step cost the warp its slowest lane's search) is confined to phase B.
 //   k_mtf3_agg    one warp per group of 32 pieces: the group's list = fold of its pieces' final lists under
 //                 later (+) earlier = later, then earlier without the symbols of later.
 //   k_mtf3_prefix one warp per block: entry list of every group (identity list at the block start).
