@@ -804,7 +804,7 @@ def ncu_traffic(category, args):
     not measured by this run."""
     kname = {"rerank": "k_rerank", "radix_scatter": "k_radix_scatter", "gather": "k_gather"}.get(category)
     pdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
-    path = next((os.path.join(pdir, t + "_traffic.json") for t in ("r2b", "r2a", "r1d", "r1c") if os.path.isfile(os.path.join(pdir, t + "_traffic.json"))), "")
+    path = next((os.path.join(pdir, t + "_traffic.json") for t in ("r2z", "r2b", "r2a", "r1d", "r1c") if os.path.isfile(os.path.join(pdir, t + "_traffic.json"))), "")
     if kname is None or not path or args.mib != 256 or args.block_kib != 1024:
         return None, "no ncu capture for this kernel/workload"
     doc = json.load(open(path))
