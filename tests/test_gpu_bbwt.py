@@ -109,3 +109,25 @@ def test_bbwt_forward_deep_bootstrap_forced():
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_bbwt.py"), "-k",
                         "ragged_batch or single_blocks or fixture_blocks"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("knobs", [
+    {"KOLM_LOCAL_ROUNDS": "0"},                          # the round-1 engine (gather + global passes every round)
+    {"KOLM_LS_DIV": "0"},                                # local refinement rounds to the end, no hand-over to the compacted rounds
+    {"KOLM_LS_DIV": "1"},                                # hand-over right after the first local round
+    {"KOLM_LYNDON_FAST": "0"},                           # plain-suffix sort (ISA -> Lyndon starts) through the local rounds as well
+    {"KOLM_LYNDON_FAST": "0", "KOLM_LOCAL_ROUNDS": "0"},
+    {"KOLM_DEEP_BOOT": "0"},                             # first local round at depth 4..6: most records unsettled, many big groups
+], ids=lambda k: ",".join("%s=%s" % kv for kv in sorted(k.items())))
+def test_sort_engine_variants_agree_with_the_oracle(knobs):
+    """Every way through the rotation / suffix sort (knobs are read once per process, hence the child process) on the ragged,
+    periodic and fixture batches, Lyndon flags included."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, **knobs)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_bbwt.py"), "-k",
+                        "lyndon_flags or ragged_batch or fixture_blocks or deep_bootstrap_batch"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
