@@ -1473,33 +1473,71 @@ __global__ void __launch_bounds__(128) k_lyn_duval(const u8* __restrict__ in, co
     if (lane == 0) nfac[b] = nf;
 }
 
-// out[j] = byte preceding rotation sa[j] inside its factor  (kolm_final.py:321)
-__global__ void __launch_bounds__(KOLM_THREADS) k_bbwt_emit(const u8* __restrict__ in, u8* __restrict__ out, const u32* __restrict__ sa,
-                                                            const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo,
-                                                            const u32* __restrict__ fstart, const u32* __restrict__ nfac) {
-    TileDesc td = tiles[blockIdx.x];
-    BlockInfo bi = binfo[td.block];
-    const u8* src = in + bi.ioff;
-    u32 nf = nfac[td.block];
-    // four consecutive outputs per thread: one 16-byte load of the order, four independent byte gathers in flight, one word store
-    // (td.start is a multiple of 32 elements, so the order is 16-byte aligned; the output is word aligned when the block is)
-    u8* const dst = out + bi.ioff + (td.start - bi.pbase);
-    const u32 n4 = (((uintptr_t)dst & 3) == 0) ? (td.count & ~3u) : 0u;
-    for (u32 x = threadIdx.x * 4; x < n4; x += KOLM_THREADS * 4) {
-        const uint4 s4 = *reinterpret_cast<const uint4*>(sa + td.start + x);
-        const u32 lp[4] = {s4.x - bi.pbase, s4.y - bi.pbase, s4.z - bi.pbase, s4.w - bi.pbase};
-        u32 pp[4];
+// out[j] = byte preceding rotation sa[j] inside its factor  (kolm_final.py:321).  Three kernels: prevb[p] = in[p - 1] for every
+// position (streaming; indexed like sa's values, i.e. by padded position), the factor starts patched to their factor's last byte
+// (one thread per factor), then the emit is one byte gather per order index — no factor search in the 268 M-record kernel.
+__global__ void __launch_bounds__(KOLM_THREADS) k_prev_bytes(const u8* __restrict__ in, u8* __restrict__ prevb, const TileDesc* __restrict__ tiles,
+                                                             const BlockInfo* __restrict__ binfo) {
+    const TileDesc td = tiles[blockIdx.x];
+    const BlockInfo bi = binfo[td.block];
+    const u32 t0 = td.start - bi.pbase;
+    const u8* src = in + bi.ioff + t0;                     // src[x - 1] is the predecessor of tile index x (x = 0 at t0 = 0: patched below)
+    u8* dst = prevb + td.start;                            // 128-byte aligned
+    const bool al = (((uintptr_t)src) & 3) == 0;
+    for (u32 x = threadIdx.x * 16; x < td.count; x += KOLM_THREADS * 16) {
+        u32 w[4] = {0, 0, 0, 0};
+        const u32 nb = min(16u, td.count - x);
+        if (al && nb == 16) {                               // five aligned words in[x-4 .. x+15], shifted down by three bytes
+            const u32* sw = reinterpret_cast<const u32*>(src + x);
+            u32 v[5];
+            v[0] = (t0 + x) ? sw[-1] : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { u32 fs, fl; find_factor(fstart + bi.pbase, nf, bi.len, lp[k], fs, fl); pp[k] = (lp[k] == fs) ? fs + fl - 1 : lp[k] - 1; }
-        const u32 b0 = src[pp[0]], b1 = src[pp[1]], b2 = src[pp[2]], b3 = src[pp[3]];
-        *reinterpret_cast<u32*>(dst + x) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            for (int i = 0; i < 4; ++i) v[i + 1] = sw[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = __funnelshift_r(v[i], v[i + 1], 24);
+        } else
+        for (u32 i = 0; i < nb; ++i) { const u32 q = x + i; const u32 b = (t0 + q) ? src[(int)q - 1] : 0u; w[i >> 2] |= b << (8 * (i & 3)); }
+        if (nb == 16) *reinterpret_cast<uint4*>(dst + x) = make_uint4(w[0], w[1], w[2], w[3]);
+        else for (u32 i = 0; i < nb; ++i) dst[x + i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
     }
-    for (u32 x = n4 + threadIdx.x; x < td.count; x += KOLM_THREADS) {
-        u32 lp = sa[td.start + x] - bi.pbase, fs, fl;
-        find_factor(fstart + bi.pbase, nf, bi.len, lp, fs, fl);
-        u32 pp = (lp == fs) ? fs + fl - 1 : lp - 1;
-        dst[x] = src[pp];
+}
+
+__global__ void __launch_bounds__(256) k_prev_patch(const u8* __restrict__ in, u8* __restrict__ prevb, const BlockInfo* __restrict__ binfo,
+                                                    const u32* __restrict__ fstart, const u32* __restrict__ nfac, int nblocks) {
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const BlockInfo bi = binfo[b];
+        const u32 nf = nfac[b];
+        const u32* fst = fstart + bi.pbase;
+        const u8* src = in + bi.ioff;
+        for (u32 f = threadIdx.x; f < nf; f += blockDim.x) {
+            const u32 fs = fst[f], fe = f + 1 < nf ? fst[f + 1] : bi.len;
+            prevb[bi.pbase + fs] = src[fe - 1];
+        }
     }
+}
+
+__global__ void __launch_bounds__(KOLM_THREADS) k_bbwt_emit(const u8* __restrict__ prevb, u8* __restrict__ out, const u32* __restrict__ sa,
+                                                            const TileDesc* __restrict__ tiles, const BlockInfo* __restrict__ binfo) {
+    const TileDesc td = tiles[blockIdx.x];
+    const BlockInfo bi = binfo[td.block];
+    // sixteen consecutive outputs per thread: four 16-byte loads of the order, sixteen byte gathers in flight, one 16-byte store
+    // (td.start is a multiple of 32 elements, so the order is 16-byte aligned; the output is when the block is)
+    u8* const dst = out + bi.ioff + (td.start - bi.pbase);
+    const u32 n16 = (((uintptr_t)dst & 15) == 0) ? (td.count & ~15u) : 0u;
+    for (u32 x = threadIdx.x * 16; x < n16; x += KOLM_THREADS * 16) {
+        const uint4* sp = reinterpret_cast<const uint4*>(sa + td.start + x);
+        uint4 s4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = sp[k];
+        u32 w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 b0 = prevb[s4[k].x], b1 = prevb[s4[k].y], b2 = prevb[s4[k].z], b3 = prevb[s4[k].w];
+            w[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        *reinterpret_cast<uint4*>(dst + x) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (u32 x = n16 + threadIdx.x; x < td.count; x += KOLM_THREADS) dst[x] = prevb[sa[td.start + x]];
 }
 
 // ================================================================================================
@@ -1831,7 +1869,10 @@ int kolm_bbwt_fwd_impl(kolm_ctx* c, const u8* in, u8* out, int* rounds_plain, in
     if (!c->ntiles) return KOLM_OK;
     KOLM_TRY(kolm_lyndon_impl(c, in, nullptr, rounds_plain, s));
     KOLM_TRY(sort_batch(c, in, true, rounds_cyclic, s));
-    KL(c, KC_EMIT, c->total_bytes * 6, s, k_bbwt_emit<<<c->ntiles, KOLM_THREADS, 0, s>>>(in, out, c->d_sa, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac));
+    u8* prevb = reinterpret_cast<u8*>(c->d_k1);              // the sort buffers are idle again
+    KL(c, KC_EMIT, c->total_bytes * 2, s, k_prev_bytes<<<c->ntiles, KOLM_THREADS, 0, s>>>(in, prevb, c->d_tiles, c->d_binfo));
+    KL(c, KC_EMIT, (i64)c->nblocks * 64, s, k_prev_patch<<<c->nblocks < 1024 ? c->nblocks : 1024, 256, 0, s>>>(in, prevb, c->d_binfo, c->d_fstart, c->d_nfac, c->nblocks));
+    KL(c, KC_EMIT, c->total_bytes * 6, s, k_bbwt_emit<<<c->ntiles, KOLM_THREADS, 0, s>>>(prevb, out, c->d_sa, c->d_tiles, c->d_binfo));
     CUDA_TRY(cudaGetLastError());
     return KOLM_OK;
 }
