@@ -102,6 +102,82 @@ __device__ __forceinline__ KfHdr kf_header(const BitWin& bw) {
     return r;
 }
 
+// Register bit window for the common case.  peek32 costs two dependent loads per token (~4 bits of payload); the cursor keeps
+// 33..64 upcoming bits in a 64-bit register and refills with one aligned word per 32 bits consumed, so the token-to-token
+// dependency is arithmetic only.  It is used while at least 64 bits of payload lie ahead (no end-of-stream cases inside) and for
+// tokens that fit 33 bits (unary part up to 16, gamma width up to 15); everything else goes through kf_token / k2_token above,
+// whose results define the format, and the cursor is re-seated behind that token.
+struct BitCur {
+    const u32* wbase; u64 buf; u32 avail, widx;
+    __device__ __forceinline__ void seat(const BitWin& bw, u64 pos) {
+        const uintptr_t a = (uintptr_t)(bw.p + (pos >> 3));
+        wbase = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+        const u32 skip = ((u32)a & 3u) * 8u + ((u32)pos & 7u);
+        buf = (u64)__byte_perm(wbase[0], 0, 0x0123) << (32 + skip);
+        avail = 32 - skip; widx = 1;
+    }
+    __device__ __forceinline__ void refill() {
+        if (avail <= 32) { buf |= (u64)__byte_perm(wbase[widx++], 0, 0x0123) << (32 - avail); avail += 32; }
+    }
+    __device__ __forceinline__ u32 top() const { return (u32)(buf >> 32); }
+    __device__ __forceinline__ void skip(u32 n) { buf <<= n; avail -= n; }
+};
+
+// fast KF token from the cursor: returns the number of bits consumed, 0 if the token needs the general path
+__device__ __forceinline__ u32 kf_token_fast(BitCur& cu, u32 k0, u32 k1, bool urz, bool urn, u64& nsym, u32& val) {
+    cu.refill();
+    const u32 t = cu.top();
+    const u32 tag = t >> 31;
+    const bool rice = tag ? urn : urz; const u32 k = tag ? k1 : k0;
+    const u32 body = t << 1;                               // the 31 bits after the tag
+    u32 n; u64 v;
+    if (rice) {
+        const u32 q = __clz(~body);                        // leading ones
+        if (q > 16) return 0;
+        n = 1 + q + 1 + k;                                 // <= 33
+        const u64 rest = cu.buf << (q + 2);                // bits after the terminating 0
+        const u32 r = k ? (u32)(rest >> (64 - k)) : 0u;
+        v = ((u64)q << k) | r;
+    } else {
+        const u32 z = __clz(body);                         // leading zeros before the 1 (body == 0 -> 32)
+        if (z > 15) return 0;
+        n = 1 + z + 1 + z;                                 // <= 32
+        const u64 rest = cu.buf << (z + 2);
+        const u32 r = z ? (u32)(rest >> (64 - z)) : 0u;
+        v = (1ull << z) | r;
+    }
+    if (tag) { const u64 x = v - (rice ? 0 : 1) + 1; if (x > 255) return 0; val = (u32)x; nsym = 1; }
+    else { val = 0; nsym = v; }
+    cu.skip(n);
+    return n;
+}
+
+__device__ __forceinline__ u32 k2_token_fast(BitCur& cu, u32& val) {
+    cu.refill();
+    const u32 q = __clz(~cu.top());
+    if (q > 24) return 0;
+    const u32 r = (u32)((cu.buf << (q + 1)) >> 62);
+    const u32 v = q * 4 + r;
+    if (v > 255) return 0;
+    val = v;
+    cu.skip(q + 3);
+    return q + 3;
+}
+
+// one token at pos through the cursor when it applies, else through the general parser (cursor re-seated afterwards)
+template <bool KF>
+__device__ __forceinline__ bool rd_token(const BitWin& bw, BitCur& cu, bool& seated, u64 pos, const KfHdr& h, u64& npos, u64& nsym, u32& val, bool& bad) {
+    if (pos + 64 <= bw.nbits) {
+        if (!seated) { cu.seat(bw, pos); seated = true; }
+        nsym = 1;
+        const u32 n = KF ? kf_token_fast(cu, h.k0, h.k1, h.urz, h.urn, nsym, val) : k2_token_fast(cu, val);
+        if (n) { npos = pos + n; return true; }
+    }
+    seated = false;
+    nsym = 1;
+    return KF ? kf_token(bw, pos, h.k0, h.k1, h.urz, h.urn, npos, nsym, val, bad) : k2_token(bw, pos, npos, val, bad);
+}
+
 template <bool KF>
 __global__ void __launch_bounds__(128) k_rdec_iter(RdecArgs a, int first_iter) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,9 +198,10 @@ __global__ void __launch_bounds__(128) k_rdec_iter(RdecArgs a, int first_iter) {
     for (u32 walked = 0;; ++walked) {
         const u64 cend = (u64)(lc + 1) * RD_CHUNK;
         u64 pos = e, cnt = 0; bool bad = false;
+        BitCur cu; bool seated = false;
         while (pos < cend) {
             u64 np, ns = 1; u32 val;
-            bool ok = KF ? kf_token(bw, pos, h.k0, h.k1, h.urz, h.urn, np, ns, val, bad) : k2_token(bw, pos, np, val, bad);
+            bool ok = rd_token<KF>(bw, cu, seated, pos, h, np, ns, val, bad);
             if (!ok) { pos = bw.nbits > cend ? bw.nbits : cend; break; }      // truncated token: nothing more starts in this block
             cnt += ns; pos = np;
         }
@@ -180,9 +257,10 @@ __global__ void __launch_bounds__(128) k_rdec_write(RdecArgs a) {
     u8* dst = a.out + bi.ioff;
     bool bad = false;
     const bool last = cend >= bw.nbits;
+    BitCur cu; bool seated = false;
     while (pos < cend && o < bi.len) {
         u64 np, ns = 1; u32 val;
-        bool ok = KF ? kf_token(bw, pos, h.k0, h.k1, h.urz, h.urn, np, ns, val, bad) : k2_token(bw, pos, np, val, bad);
+        bool ok = rd_token<KF>(bw, cu, seated, pos, h, np, ns, val, bad);
         if (!ok) { atomicMax((unsigned int*)(a.err + b), 1u); break; }    // stream ends inside a token before orig_len symbols
         if (KF) { if (val) { if (bad) break; dst[o] = (u8)val; } }
         else {
