@@ -874,6 +874,7 @@ struct RefineArgs {
     u32* sa; const u32* rank; const u32* grp; u32* list; u32* list2; u32* lcount; u32* F; const TileDesc* tiles; const BlockInfo* binfo;
     const u32* fstart; const u32* nfac; const u32* done; u8* live; u32* lact; u32* newcls; u32* stats; u32 h;
     u32* gflag; u32 stamp;              // gflag[group start] == stamp: that big group's members do not all carry the same successor rank
+    int big_uniform;                    // 1: fetch the keys of big groups' members too and let k_big_emit skip groups without a difference
 };
 
 template <bool CYCLIC>
@@ -944,8 +945,9 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     for (int o = 16; o > 0; o >>= 1) { nuns += __shfl_xor_sync(FULL, nuns, o); nbig += __shfl_xor_sync(FULL, nbig, o); }
     if (lane == 0) { s_wcnt[w] = nproc; s_wbig[w] = nbigw; if (nuns) atomicAdd(&s_flag[0], nuns); if (nbig) atomicAdd(&s_flag[1], nbig); }
     u32 pp[LR_RPT];                                        // positions of my records: in flight across the barrier
+    const u32 loadbits = a.big_uniform ? (procbits | bigbits) : procbits;
 #pragma unroll
-    for (int k = 0; k < LR_RPT; ++k) pp[k] = (((procbits | bigbits) >> k) & 1u) ? a.sa[td.start + w * (LR_RPT * 32) + k * 32 + lane] : 0u;
+    for (int k = 0; k < LR_RPT; ++k) pp[k] = ((loadbits >> k) & 1u) ? a.sa[td.start + w * (LR_RPT * 32) + k * 32 + lane] : 0u;
     __syncthreads();
     const u32 tot_uns = s_flag[0], tot_big = s_flag[1];
     if (!tot_uns) { if (tid == 0) { a.live[tile] = 0; a.lcount[tile] = 0; } return; }
@@ -964,14 +966,14 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     u32 wbase = 0, m = 0, bbase = 0;
 #pragma unroll
     for (int i = 0; i < NWARPS; ++i) { const u32 c_ = s_wcnt[i], b_ = s_wbig[i]; if ((u32)i < w) { wbase += c_; bbase += b_; } m += c_; }
-    const u32 mall = m + tot_big;
+    const u32 mall = m + (a.big_uniform ? tot_big : 0u);
     if (!mall) { if (tid == 0) a.lcount[tile] = 0; return; }     // only a foreign small group here
     // ---- compact: my records at [0, m), then the nominal members of big groups at [m, mall) (only their keys are looked at)
     {
         u32 run = wbase, brun = m + bbase;
 #pragma unroll
         for (int k = 0; k < LR_RPT; ++k) {
-            const bool proc = (procbits >> k) & 1u, nb = (bigbits >> k) & 1u;
+            const bool proc = (procbits >> k) & 1u, nb = a.big_uniform && ((bigbits >> k) & 1u);
             const u32 pm = __ballot_sync(FULL, proc), bm = __ballot_sync(FULL, nb);
             const u32 x = w * (LR_RPT * 32) + k * 32 + lane;
             if (proc) {
@@ -990,7 +992,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     {
         const u32 nf = CYCLIC ? a.nfac[td.block] : 0;
         const u32* fst = a.fstart + bi.pbase;
-        if (tid == KOLM_THREADS - 1 && big_in && t0 > 0) {         // the key of the order index before the tile: left neighbour of a big group's member at x = 0
+        if (tid == KOLM_THREADS - 1 && big_in && t0 > 0 && a.big_uniform) {         // the key of the order index before the tile: left neighbour of a big group's member at x = 0
             u32 lp = a.sa[td.start - 1] - bi.pbase, sp;
             if (CYCLIC) { u32 fs, fl; find_factor(fst, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + a.h % fl; sp = fs + (o >= fl ? o - fl : o); } }
             else sp = lp + a.h;
@@ -1145,7 +1147,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_big_emit(const u32* __restrict
             if (ALL) {
                 const u32 g = grp[td.start + x];
                 take = !(g == t0 + x && (t0 + x + 1 == bi.len || grp[td.start + x + 1] == t0 + x + 1));
-            } else take = F[td.start + x] == 0u && gflag[bi.pbase + grp[td.start + x]] == stamp;   // a big group some of whose keys differ
+            } else take = F[td.start + x] == 0u && (!gflag || gflag[bi.pbase + grp[td.start + x]] == stamp);   // gflag: only big groups some of whose keys differ
         }
         if (take) bits |= 1u << k;
         mycnt += __popc(__ballot_sync(FULL, take));        // warp total so far (same in every lane)
@@ -1543,6 +1545,7 @@ __global__ void __launch_bounds__(256) k_prev_patch(const u8* __restrict__ in, u
                                                     const u32* __restrict__ fstart, const u32* __restrict__ nfac, int nblocks) {
     for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const BlockInfo bi = binfo[b];
+        if (!bi.len) continue;                             // an empty block has no tiles: nothing wrote its factor count
         const u32 nf = nfac[b];
         const u32* fst = fstart + bi.pbase;
         const u8* src = in + bi.ioff;
@@ -1710,6 +1713,9 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
         fa.sa = c->d_sa; fa.rank = c->d_rank; fa.grp = c->d_grp; fa.list = c->d_nr; fa.list2 = c->d_k0; fa.lcount = c->d_thist; fa.F = c->d_lo;
         fa.tiles = c->d_tiles; fa.binfo = c->d_binfo; fa.fstart = c->d_fstart; fa.nfac = c->d_nfac; fa.done = c->d_done; fa.live = c->d_live;
         fa.lact = c->d_lact; fa.newcls = c->d_newcls; fa.stats = c->d_stats; fa.gflag = c->d_v1;
+        static int big_uniform = -1;
+        if (big_uniform < 0) { const char* e = getenv("KOLM_BIG_UNIFORM"); big_uniform = e ? atoi(e) : 0; }
+        fa.big_uniform = big_uniform;
         const u32 serial = ++c->sort_serial;
         static int trace = -1;
         if (trace < 0) { const char* e = getenv("KOLM_TRACE_ROUNDS"); trace = e ? atoi(e) : 0; }
@@ -1734,8 +1740,8 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
             if (big) {
                 // members of big groups (flagged in d_lo): (rank[succ_h(v)], v) per block -> sort -> (rank[v], v) -> stable sort -> rerank
                 CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
-                if (cyclic) KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<true, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
-                else KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<false, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
+                if (cyclic) KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<true, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, fa.big_uniform ? c->d_v1 : nullptr, fa.stamp));
+                else KL(c, KC_GATHER, (i64)big * 16, s, k_big_emit<false, false><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, fa.big_uniform ? c->d_v1 : nullptr, fa.stamp));
                 KL(c, KC_PLAN, (i64)nb * 16, s, k_plan_active<<<1, 1024, 0, s>>>(c->d_active, c->d_done, c->d_atile0, c->d_atilen, c->d_stats, nb));
                 CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, 12, cudaMemcpyDeviceToHost, s));
                 CUDA_TRY(cudaStreamSynchronize(s));
@@ -1772,8 +1778,8 @@ static int sort_batch(kolm_ctx* c, const u8* in, bool cyclic, int* rounds_out, c
                 h <<= 1;
                 if (h > 0x7fffffffull) h = 0x7fffffffull;
                 CUDA_TRY(cudaMemsetAsync(c->d_active, 0, (size_t)nb * 4, s));
-                if (cyclic) KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<true, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
-                else KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<false, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, c->d_v1, fa.stamp));
+                if (cyclic) KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<true, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, fa.big_uniform ? c->d_v1 : nullptr, fa.stamp));
+                else KL(c, KC_GATHER, N * 4 + (i64)surv * 16, s, k_big_emit<false, true><<<nt, KOLM_THREADS, 0, s>>>(c->d_sa, c->d_rank, c->d_lo, c->d_grp, c->d_tiles, c->d_binfo, c->d_fstart, c->d_nfac, c->d_done, c->d_live, c->d_active, c->d_k0, c->d_v0, (u32)h, fa.big_uniform ? c->d_v1 : nullptr, fa.stamp));
                 prebuilt = true; use_ls = true; Kprev = c->d_k1; Vprev = c->d_v1;      // "the other pair" of the LS branch is (d_k0, d_v0)
                 break;
             }
