@@ -117,10 +117,11 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_inv_emit(const u8* __restrict_
 #define RULER_MAXWALK (1u << 22)
 struct __align__(16) RulerNode { u32 nxt, mn, dmn, wlen; };     // nxt = ruler slot (padded position >> 5)
 
-__global__ void __launch_bounds__(256) k_inv_walk(const u32* __restrict__ pi, const BlockInfo* __restrict__ binfo, const TileDesc* __restrict__ tiles,
+__global__ void __launch_bounds__(KOLM_TILE >> RULER_SHIFT) k_inv_walk(const u32* __restrict__ pi, const BlockInfo* __restrict__ binfo, const TileDesc* __restrict__ tiles,
                                                   RulerNode* __restrict__ seg, RulerNode* __restrict__ node, u32* __restrict__ visited,
                                                   u32* __restrict__ fallback) {
-    // one tile = 4096 positions = 128 rulers; 256 threads -> first 128 work
+    // one tile = 4096 positions = 128 rulers = 128 threads (with 256-thread CTAs half of the resident threads idled, and these
+    // pointer-chasing kernels are bound by the number of dependent loads in flight)
     const TileDesc td = tiles[blockIdx.x];
     const u32 k = threadIdx.x;
     const u32 r = td.start + (k << RULER_SHIFT);
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_inv_orphan_emit(const u8* __re
     }
 }
 
-__global__ void __launch_bounds__(256) k_inv_rjump(const RulerNode* __restrict__ a, RulerNode* __restrict__ b, const TileDesc* __restrict__ tiles) {
+__global__ void __launch_bounds__(KOLM_TILE >> RULER_SHIFT) k_inv_rjump(const RulerNode* __restrict__ a, RulerNode* __restrict__ b, const TileDesc* __restrict__ tiles) {
     const TileDesc td = tiles[blockIdx.x];
     const u32 k = threadIdx.x;
     if (k >= (KOLM_TILE >> RULER_SHIFT) || (k << RULER_SHIFT) >= td.count) return;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) k_inv_rjump(const RulerNode* __restrict__
 }
 
 // cycle length at the cycle minimum M: the ruler whose segment contains M closes the loop
-__global__ void __launch_bounds__(256) k_inv_rlen(const RulerNode* __restrict__ seg, const RulerNode* __restrict__ node, const TileDesc* __restrict__ tiles,
+__global__ void __launch_bounds__(KOLM_TILE >> RULER_SHIFT) k_inv_rlen(const RulerNode* __restrict__ seg, const RulerNode* __restrict__ node, const TileDesc* __restrict__ tiles,
                                                   u32* __restrict__ cyc_len) {
     const TileDesc td = tiles[blockIdx.x];
     const u32 k = threadIdx.x;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_inv_roffsets(const TileDesc* _
     for (int k = 0; k < KOLM_IPT; ++k) { u32 r = tid * KOLM_IPT + k; if (r < td.count) { run += d[k]; if (d[k]) cyc_off[td.start + r] = bi.len - (u32)run; } }
 }
 
-__global__ void __launch_bounds__(256) k_inv_remit(const u8* __restrict__ in, u8* __restrict__ out, const u32* __restrict__ pi,
+__global__ void __launch_bounds__(KOLM_TILE >> RULER_SHIFT) k_inv_remit(const u8* __restrict__ in, u8* __restrict__ out, const u32* __restrict__ pi,
                                                    const RulerNode* __restrict__ node, const TileDesc* __restrict__ tiles,
                                                    const BlockInfo* __restrict__ binfo, const u32* __restrict__ cyc_len, const u32* __restrict__ cyc_off) {
     const TileDesc td = tiles[blockIdx.x];
@@ -270,21 +271,21 @@ int kolm_bbwt_inv_impl(kolm_ctx* c, const u8* in, u8* out, cudaStream_t s) {
         CUDA_TRY(cudaMemsetAsync(visited, 0, ((size_t)c->total_elems / 32 + 2) * 4, s));
         CUDA_TRY(cudaMemsetAsync(c->d_stats + 8, 0, 4, s));
         CUDA_TRY(cudaMemsetAsync(c->d_sa, 0, (size_t)c->total_elems * 4, s));                 // cyc_len: non-zero only at cycle minima
-        KL(c, KC_INV, N * 5, s, k_inv_walk<<<nt, 256, 0, s>>>(V, c->d_binfo, c->d_tiles, seg, RA, visited, c->d_stats + 8));
+        KL(c, KC_INV, N * 5, s, k_inv_walk<<<nt, KOLM_TILE >> RULER_SHIFT, 0, s>>>(V, c->d_binfo, c->d_tiles, seg, RA, visited, c->d_stats + 8));
         KL(c, KC_INV, N / 8, s, k_inv_orphan_len<<<nt, KOLM_THREADS, 0, s>>>(V, c->d_tiles, visited, c->d_sa, c->d_stats + 8));
         CUDA_TRY(cudaMemcpyAsync(c->h_stats + 8, c->d_stats + 8, 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c->h_stats[8] == 0) {                            // no walk hit its cap (else: element-level pointer jumping below)
             u32 nr = (c->max_len >> RULER_SHIFT) + 2;
             for (u32 span = 1; span < nr; span <<= 1) {
-                KL(c, KC_INV, (N >> RULER_SHIFT) * 48, s, k_inv_rjump<<<nt, 256, 0, s>>>(RA, RB, c->d_tiles));
+                KL(c, KC_INV, (N >> RULER_SHIFT) * 48, s, k_inv_rjump<<<nt, KOLM_TILE >> RULER_SHIFT, 0, s>>>(RA, RB, c->d_tiles));
                 RulerNode* t = RA; RA = RB; RB = t;
             }
-            KL(c, KC_INV, (N >> RULER_SHIFT) * 40, s, k_inv_rlen<<<nt, 256, 0, s>>>(seg, RA, c->d_tiles, c->d_sa));
+            KL(c, KC_INV, (N >> RULER_SHIFT) * 40, s, k_inv_rlen<<<nt, KOLM_TILE >> RULER_SHIFT, 0, s>>>(seg, RA, c->d_tiles, c->d_sa));
             int lgrid = nt;
             KOLM_TRY(kolm_lb_reset_mode(c, false, nt, &lgrid, 1, s));
             KL(c, KC_INV, N * 8, s, k_inv_roffsets<<<lgrid, KOLM_THREADS, 0, s>>>(c->d_tiles, c->d_binfo, c->d_lb, c->d_sa, c->d_rank));
-            KL(c, KC_INV, N * 6, s, k_inv_remit<<<nt, 256, 0, s>>>(in, out, V, RA, c->d_tiles, c->d_binfo, c->d_sa, c->d_rank));
+            KL(c, KC_INV, N * 6, s, k_inv_remit<<<nt, KOLM_TILE >> RULER_SHIFT, 0, s>>>(in, out, V, RA, c->d_tiles, c->d_binfo, c->d_sa, c->d_rank));
             KL(c, KC_INV, N / 8, s, k_inv_orphan_emit<<<nt, KOLM_THREADS, 0, s>>>(in, out, V, c->d_tiles, c->d_binfo, visited, c->d_sa, c->d_rank));
             CUDA_TRY(cudaGetLastError());
             return KOLM_OK;
