@@ -20,26 +20,36 @@
 #define REPAIR_HASH 16384          // slots; load factor <= 0.5
 #define REPAIR_EMPTY 0xffffffffu
 
-struct RepairSmem {
-    u16 seq[2][REPAIR_MAX];
-    u32 hkey[REPAIR_HASH];
-    u32 hcnt[REPAIR_HASH];
-    u32 scan[REPAIR_THREADS / 32];
+// Two shapes of the same kernel: blocks of up to REPAIR_MAX symbols on 1024 threads and 160 KB (one CTA per SM), and blocks of up
+// to REPAIR_SMALL symbols — the reference's default 2 KiB blocks — on 256 threads and 41 KB, five CTAs per SM: the rounds are
+// bound by their dozen block barriers and the table sweeps, which shrink with the CTA, and five times as many blocks are in
+// flight (61 440 blocks of 2 KiB: 131 -> 30 ms per 32 MiB, KOLR compress at the default block size 107 -> 330 MB/s).
+#define REPAIR_SMALL 2048
+template <int MAXLEN, int THREADS, int HASH>
+struct RepairSmemT {
+    u16 seq[2][MAXLEN];
+    u32 hkey[HASH];
+    u32 hcnt[HASH];
+    u32 scan[THREADS / 32];
+    u32 wlast[THREADS / 32];
+    u32 wt[THREADS / 32];
     unsigned long long best;
-    u32 replaced, m;
+    u32 replaced, m, hdr;
 };
+typedef RepairSmemT<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH> RepairSmem;
 
-__device__ __forceinline__ u32 rp_hash(u32 k) { k *= 2654435761u; return (k >> 15) & (REPAIR_HASH - 1); }
+template <int HASH>
+__device__ __forceinline__ u32 rp_hash(u32 k) { k *= 2654435761u; return (k >> 15) & (HASH - 1); }
 
 // block-wide inclusive scan (sum or max) of one u32 per thread
-template <bool MAXOP>
+template <bool MAXOP, int THREADS>
 __device__ __forceinline__ u32 rp_scan(u32 v, u32* s_w, u32* total) {
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v = MAXOP ? max(v, n) : v + n; }
     if (lane == 31) s_w[w] = v;
     __syncthreads();
     u32 pre = 0, tot = 0;
-    for (int i = 0; i < REPAIR_THREADS / 32; ++i) { u32 x = s_w[i]; if ((u32)i < w) pre = MAXOP ? max(pre, x) : pre + x; tot = MAXOP ? max(tot, x) : tot + x; }
+    for (int i = 0; i < THREADS / 32; ++i) { u32 x = s_w[i]; if ((u32)i < w) pre = MAXOP ? max(pre, x) : pre + x; tot = MAXOP ? max(tot, x) : tot + x; }
     __syncthreads();
     if (total) *total = tot;
     return MAXOP ? max(pre, v) : pre + v;
@@ -49,39 +59,42 @@ __device__ __forceinline__ u32 rp_uleb_size(u32 v) { return v < 128u ? 1u : v < 
 __device__ __forceinline__ u8* rp_put_uleb(u8* p, u32 v) { while (v >= 128) { *p++ = (u8)(v | 0x80); v >>= 7; } *p++ = (u8)v; return p; }
 
 // out_tmp: per block a staging region of 4*len+64 bytes at tmp + 4*pbase; sizes[b] = payload bytes
-__global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
-                                                                  u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err) {
+template <int MAXLEN, int THREADS, int HASH, int MINLEN>
+__global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
+                                                        u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err) {
     extern __shared__ __align__(16) u8 smem_raw[];
-    RepairSmem& S = *reinterpret_cast<RepairSmem*>(smem_raw);
+    typedef RepairSmemT<MAXLEN, THREADS, HASH> SM;
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
     const u32 tid = threadIdx.x, b = blockIdx.x;
     const BlockInfo bi = binfo[b];
-    if (bi.len > REPAIR_MAX) { if (tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }
+    if (bi.len <= MINLEN && MINLEN) return;                 // the small shape of this kernel takes these
+    if (bi.len > MAXLEN) { if (MAXLEN == REPAIR_MAX && tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }
     const u8* src = in + bi.ioff;
     u32* rules = rules_scratch + bi.pbase;                  // up to len/2 rules, (a<<16|b)
-    for (u32 i = tid; i < bi.len; i += REPAIR_THREADS) S.seq[0][i] = src[i];
+    for (u32 i = tid; i < bi.len; i += THREADS) S.seq[0][i] = src[i];
     if (tid == 0) S.m = bi.len;
     __syncthreads();
     u32 cur = 0, nrules = 0;
-    constexpr u32 IPT = REPAIR_MAX / REPAIR_THREADS;        // 8 consecutive positions per thread
+    constexpr u32 IPT = MAXLEN / THREADS;        // 8 consecutive positions per thread
     for (;;) {
         const u32 m = S.m;
         if (m < 2) break;
         // ---- pair histogram
-        for (u32 i = tid; i < REPAIR_HASH; i += REPAIR_THREADS) { S.hkey[i] = REPAIR_EMPTY; S.hcnt[i] = 0; }
+        for (u32 i = tid; i < HASH; i += THREADS) { S.hkey[i] = REPAIR_EMPTY; S.hcnt[i] = 0; }
         if (tid == 0) { S.best = 0; S.replaced = 0; }
         __syncthreads();
         const u16* q = S.seq[cur];
-        for (u32 i = tid; i + 1 < m; i += REPAIR_THREADS) {
+        for (u32 i = tid; i + 1 < m; i += THREADS) {
             u32 key = ((u32)q[i] << 16) | q[i + 1];
-            u32 h = rp_hash(key);
+            u32 h = rp_hash<HASH>(key);
             for (;;) {
                 u32 old = atomicCAS(&S.hkey[h], REPAIR_EMPTY, key);
                 if (old == REPAIR_EMPTY || old == key) { atomicAdd(&S.hcnt[h], 1u); break; }
-                h = (h + 1) & (REPAIR_HASH - 1);
+                h = (h + 1) & (HASH - 1);
             }
         }
         __syncthreads();
-        for (u32 i = tid; i < REPAIR_HASH; i += REPAIR_THREADS) {
+        for (u32 i = tid; i < HASH; i += THREADS) {
             u32 k = S.hkey[i];
             if (k != REPAIR_EMPTY && S.hcnt[i] >= 2) atomicMax(&S.best, ((unsigned long long)S.hcnt[i] << 32) | (unsigned long long)(~k));
         }
@@ -99,11 +112,11 @@ __global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __re
             bool f = (i + 1 < m) && ((((u32)q[i] << 16) | q[i + 1]) == bkey);
             if (f) flags |= 1u << k; else lastun = i + 1;
         }
-        u32 incl = rp_scan<true>(lastun, S.scan, nullptr);
+        u32 incl = rp_scan<true, THREADS>(lastun, S.scan, nullptr);
         u32 prevun = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive: last unflagged before my first item
         if ((tid & 31) == 0) prevun = 0;
         // cross-warp exclusive: recompute from the scan array is gone; do it with a second tiny scan on warp leaders
-        __shared__ u32 s_wlast[REPAIR_THREADS / 32];
+        u32* s_wlast = S.wlast;
         if ((tid & 31) == 31) s_wlast[tid >> 5] = incl;
         __syncthreads();
         if ((tid & 31) == 0 && tid) prevun = s_wlast[(tid >> 5) - 1];
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __re
         }
         // removed(i) = taken(i-1): the second symbol of a replaced pair disappears
         u32 tprev = __shfl_up_sync(0xffffffffu, taken >> (IPT - 1), 1) & 1u;
-        __shared__ u32 s_wt[REPAIR_THREADS / 32];
+        u32* s_wt = S.wt;
         if ((tid & 31) == 31) s_wt[tid >> 5] = (taken >> (IPT - 1)) & 1u;
         __syncthreads();
         if ((tid & 31) == 0) tprev = tid ? s_wt[(tid >> 5) - 1] : 0;
@@ -127,11 +140,11 @@ __global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __re
 #pragma unroll
         for (u32 k = 0; k < IPT; ++k) { u32 i = tid * IPT + k; if (i < m && !((removed >> k) & 1u)) ++keep; }
         u32 tot_taken;
-        u32 tincl = rp_scan<false>(ntaken, S.scan, &tot_taken);
+        u32 tincl = rp_scan<false, THREADS>(ntaken, S.scan, &tot_taken);
         (void)tincl;
         if (tot_taken < 2) break;                            // V22.py:1880-1882: rule not recorded, sequence unchanged
         u32 newm;
-        u32 kincl = rp_scan<false>(keep, S.scan, &newm);
+        u32 kincl = rp_scan<false, THREADS>(keep, S.scan, &newm);
         u32 o = kincl - keep;
         u16* nq = S.seq[cur ^ 1];
 #pragma unroll
@@ -148,11 +161,11 @@ __global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __re
     const u32 m = S.m;
     const u16* q = S.seq[cur];
     u8* dst = tmp + (size_t)bi.pbase * 4;
-    __shared__ u32 s_hdr;
+    u32& s_hdr = S.hdr;
     u32 rbytes = 0;
-    for (u32 r = tid; r < nrules; r += REPAIR_THREADS) { u32 k = rules[r]; rbytes += rp_uleb_size(k >> 16) + rp_uleb_size(k & 0xffff); }
+    for (u32 r = tid; r < nrules; r += THREADS) { u32 k = rules[r]; rbytes += rp_uleb_size(k >> 16) + rp_uleb_size(k & 0xffff); }
     u32 rtot;
-    rp_scan<false>(rbytes, S.scan, &rtot);
+    rp_scan<false, THREADS>(rbytes, S.scan, &rtot);
     // rules are few thousand at most: thread 0 writes header + rules sequentially, everyone writes symbols
     if (tid == 0) {
         u8* p = dst; *p++ = 'R'; *p++ = 'P'; p = rp_put_uleb(p, 256); p = rp_put_uleb(p, nrules);
@@ -164,7 +177,7 @@ __global__ void __launch_bounds__(REPAIR_THREADS, 1) k_repair_enc(const u8* __re
 #pragma unroll
     for (u32 k = 0; k < IPT; ++k) { u32 i = tid * IPT + k; if (i < m) sb += rp_uleb_size(q[i]); }
     u32 stot;
-    u32 sincl = rp_scan<false>(sb, S.scan, &stot);
+    u32 sincl = rp_scan<false, THREADS>(sb, S.scan, &stot);
     __syncthreads();
     u8* p = dst + s_hdr + (sincl - sb);
 #pragma unroll
@@ -362,14 +375,24 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     static long long big_max = -1;                            // KOLM_REPAIR_BIG_MAX: largest block (bytes) the incremental kernel takes (0: none)
     if (big_max < 0) { const char* e = getenv("KOLM_REPAIR_BIG_MAX"); big_max = e ? atoll(e) : (1ll << 30); }
     if (c->max_len > REPAIR_MAX && (long long)c->max_len > big_max) return KOLM_E_UNSUPPORTED;
+    typedef RepairSmemT<REPAIR_SMALL, 256, 4096> RepairSmemSmall;
     static bool attr_set[64];
     if (c->device < 64 && !attr_set[c->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_SMALL, 256, 4096, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmemSmall)));
         attr_set[c->device] = true;
     }
+    static int small_on = -1;
+    if (small_on < 0) { const char* e = getenv("KOLM_REPAIR_SMALL"); small_on = e ? atoi(e) : 1; }
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * 64 * 8, s));
     u8* tmp = (u8*)c->d_k0;                                   // 4 bytes per padded element
-    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+    if (small_on) {
+        // blocks of up to 2 KiB on the small shape (five CTAs per SM), the others (if any) on the 160 KB shape
+        KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_SMALL, 256, 4096, 0><<<nb, 256, sizeof(RepairSmemSmall), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+        if (c->max_len > REPAIR_SMALL) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_SMALL><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+    } else
+    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
     if (c->max_len > REPAIR_MAX) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));
