@@ -349,6 +349,143 @@ __global__ void __launch_bounds__(128) k_lz_dec_warp(const u8* __restrict__ pay,
     if (lane == 0) err[b] = e;
 }
 
+// decode, v2: the same warp-per-block decoder with the token stream read through a REGISTER window — lane l holds four
+// bytes of a 128-byte window of the payload, a byte is one shuffle away — instead of one dependent global load per header byte
+// (the serial token chain was ~500 cycles per token: 53 ms for a 1 MiB block of short tokens, 88 % of KOLR decompress at 1 MiB
+// blocks), runs of literal tokens (flag 0, byte) decoded up to sixteen at a time (their layout is fixed, so a ballot over the
+// even offsets finds the run), and no modulo in the copy of a non-overlapping match.  The last 8 KiB of the output are mirrored
+// in a shared-memory ring per warp: a match reads what the previous tokens just stored, and through global memory that is an
+// L2 round trip per token (~600 cycles on blocks of short matches: 50 ms per MiB); matches of up to 2 KiB at distances of up to
+// 6 KiB — all of them with the reference's windows of 255 and 4096 — read the ring instead.  The window path runs while at least
+// 160 payload bytes lie ahead; the block's tail goes through the byte-wise code of v1, whose error behaviour is the reference's.
+#define LZ_RING 8192u
+#define LZ_RING_MAXLEN 2048u
+__global__ void __launch_bounds__(128) k_lz_dec_warp2(const u8* __restrict__ pay, const i64* __restrict__ pay_off, const BlockInfo* __restrict__ binfo,
+                                                      u8* __restrict__ out, int* __restrict__ err, int nblocks, u32 window_check) {
+    const u32 lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const BlockInfo bi = binfo[b];
+    const u8* d = pay + pay_off[b];
+    const i64 n = pay_off[b + 1] - pay_off[b];
+    u8* dst = out + bi.ioff;
+    i64 i = 0; u32 o = 0; int e = KOLM_OK;
+    __shared__ u8 s_ring[4][LZ_RING];
+    u8* ring = s_ring[threadIdx.x >> 5];
+    // window: 32 aligned words starting at payload index wbase (wbase + misalignment of d is a multiple of 4)
+    const u32 mis = (u32)((uintptr_t)d & 3u);
+    i64 wbase = -(i64)mis - 256;                             // "no window"
+    u32 wword = 0;
+    while (i + 160 <= n && o < bi.len) {
+        if (i - wbase > 88) {                                // refill so that 40 bytes from i on are inside the window
+            wbase = ((i + mis) & ~(i64)3) - mis;
+            wword = *reinterpret_cast<const u32*>(d + wbase + 4 * lane);     // aligned; at most 128 + 3 bytes past i, inside the payload
+        }
+#define LZ_GB(j) ((__shfl_sync(0xffffffffu, wword, (u32)((j) - wbase) >> 2) >> (8u * ((u32)((j) - wbase) & 3u))) & 0xFFu)
+        const u32 flag = LZ_GB(i);
+        if (flag == 0) {
+            // literal tokens: (0, byte) pairs; lanes 0..15 look at the even offsets
+            const u32 fb = LZ_GB(i + 2 * (i64)(lane & 15));
+            const u32 vb = LZ_GB(i + 2 * (i64)(lane & 15) + 1);
+            const u32 zm = __ballot_sync(0xffffffffu, lane < 16 && fb == 0);
+            u32 t = __ffs(~zm) - 1;                          // consecutive literal tokens from i (>= 1, <= 16)
+            const u32 room = bi.len - o;
+            if (t > room) t = room;
+            if (lane < t) { dst[o + lane] = (u8)vb; ring[(o + lane) & (LZ_RING - 1)] = (u8)vb; }
+            i += 2 * (i64)t; o += t;
+        } else if (flag == 1) {
+            u64 v[2]; i64 p = i + 1;
+            bool longv = false;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                u64 r = 0; int sh = 0;
+                for (;;) {
+                    if (p - i >= 36) { longv = true; break; }               // absurdly padded value: let v1's code deal with it
+                    const u32 x = LZ_GB(p); ++p;
+                    if (sh < 64) r |= (u64)(x & 0x7F) << sh;
+                    if (!(x & 0x80)) break;
+                    sh += 7;
+                }
+                v[q] = r;
+                if (longv) break;
+            }
+            if (longv) break;                                // (i unchanged)
+            i = p;
+            const u64 len = v[0], dist = v[1];
+            const u32 avail = window_check ? min(o, window_check) : o;
+            const u64 room = (u64)(bi.len - o);
+            const u32 cnt = (u32)(len < room ? len : room);
+            if (dist == 0) {                                                // see k_lz_dec: V22 rejects, KF repeats out[0] (IndexError on empty output)
+                if (window_check) { e = KOLM_E_CORRUPT; break; }
+                if (cnt && o == 0) { e = KOLM_E_INDEX; break; }
+                __syncwarp();
+                const u8 first = dst[0];
+                for (u32 k = lane; k < cnt; k += 32) { dst[o + k] = first; ring[(o + k) & (LZ_RING - 1)] = first; }
+                o += cnt;
+                __syncwarp();
+                continue;
+            }
+            if (cnt && dist > avail) { e = KOLM_E_CORRUPT; break; }
+            __syncwarp();                                                  // earlier literal / match stores are visible to all lanes
+            const u32 dd = (u32)dist;
+            if (cnt <= LZ_RING_MAXLEN && dd <= LZ_RING - LZ_RING_MAXLEN) {
+                // source and destination both inside the ring and disjoint there (dd + cnt <= LZ_RING): shared-memory latency only
+                const u32 sb = o - dd;
+                if (dd >= cnt) { for (u32 k = lane; k < cnt; k += 32) { const u8 v = ring[(sb + k) & (LZ_RING - 1)]; dst[o + k] = v; ring[(o + k) & (LZ_RING - 1)] = v; } }
+                else { for (u32 k = lane; k < cnt; k += 32) { const u8 v = ring[(sb + k % dd) & (LZ_RING - 1)]; dst[o + k] = v; ring[(o + k) & (LZ_RING - 1)] = v; } }
+            } else {
+                const u8* srcp = dst + o - dd;
+                if (dd >= cnt) { for (u32 k = lane; k < cnt; k += 32) { const u8 v = srcp[k]; dst[o + k] = v; ring[(o + k) & (LZ_RING - 1)] = v; } }
+                else { for (u32 k = lane; k < cnt; k += 32) { const u8 v = srcp[k % dd]; dst[o + k] = v; ring[(o + k) & (LZ_RING - 1)] = v; } }
+            }
+            o += cnt;
+            __syncwarp();
+        } else { e = KOLM_E_CORRUPT; break; }
+#undef LZ_GB
+    }
+    __syncwarp();
+    // ---- tail (and anything unusual): v1's byte-wise token loop
+    while (!e && i < n && o < bi.len) {
+        u8 flag = d[i++];
+        if (flag == 0) {
+            if (i >= n) { e = KOLM_E_TRUNCATED; break; }
+            if (lane == 0) dst[o] = d[i];
+            ++i; ++o;
+        } else if (flag == 1) {
+            u64 v[2];
+            for (int q = 0; q < 2 && !e; ++q) {
+                u64 r = 0; int sh = 0;
+                for (;;) { if (i >= n) { e = KOLM_E_TRUNCATED; break; } u8 x = d[i++]; if (sh < 64) r |= (u64)(x & 0x7F) << sh; if (!(x & 0x80)) break; sh += 7; }
+                v[q] = r;
+            }
+            if (e) break;
+            u64 len = v[0], dist = v[1];
+            u32 avail = window_check ? min(o, window_check) : o;
+            u64 room = (u64)(bi.len - o);
+            u32 cnt = (u32)(len < room ? len : room);
+            if (dist == 0) {
+                if (window_check) { e = KOLM_E_CORRUPT; break; }
+                if (cnt && o == 0) { e = KOLM_E_INDEX; break; }
+                __syncwarp();
+                const u8 first = dst[0];
+                for (u32 k = lane; k < cnt; k += 32) dst[o + k] = first;
+                o += cnt;
+                __syncwarp();
+                continue;
+            }
+            if (cnt && dist > avail) { e = KOLM_E_CORRUPT; break; }
+            __syncwarp();
+            const u32 dd = (u32)dist;
+            const u8* srcp = dst + o - dd;
+            for (u32 k = lane; k < cnt; k += 32) dst[o + k] = srcp[k % dd];
+            o += cnt;
+            __syncwarp();
+        } else { e = KOLM_E_CORRUPT; break; }
+    }
+    if (!e && o != bi.len) e = KOLM_E_CORRUPT;
+    if (lane == 0) err[b] = e;
+}
+
 // out_off == nullptr: device mode (kolm_encode_blocks) — the offsets stay in c->d_poff, nothing comes home, no synchronisation
 int kolm_lz77_enc_impl(kolm_ctx* c, const u8* in, u32 window, u32 maxlen, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
     const int nb = c->nblocks, nt = c->ntiles;
@@ -405,8 +542,9 @@ int kolm_lz77_dec_impl(kolm_ctx* c, const u8* pay, const i64* pay_off, u32 windo
     memcpy(c->h_poff, pay_off, (size_t)(nb + 1) * 8);
     CUDA_TRY(cudaMemcpyAsync(c->d_poff, c->h_poff, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
     static int warpdec = -1;
-    if (warpdec < 0) { const char* e = getenv("KOLM_LZ_DEC_WARP"); warpdec = e ? atoi(e) : 1; }
-    if (warpdec) KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec_warp<<<(nb + 3) / 4, 128, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
+    if (warpdec < 0) { const char* e = getenv("KOLM_LZ_DEC_WARP"); warpdec = e ? atoi(e) : 2; }
+    if (warpdec >= 2) KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec_warp2<<<(nb + 3) / 4, 128, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
+    else if (warpdec) KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec_warp<<<(nb + 3) / 4, 128, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
     else KL(c, KC_MISC, c->total_bytes * 2, s, k_lz_dec<<<(nb + 63) / 64, 64, 0, s>>>(pay, c->d_poff, c->d_binfo, out, c->d_err, nb, window_check));
     CUDA_TRY(cudaGetLastError());
     return rice_dec_finish(c, s);
