@@ -377,11 +377,91 @@ __global__ void __launch_bounds__(128) k_lz_dec_warp2(const u8* __restrict__ pay
     i64 wbase = -(i64)mis - 256;                             // "no window"
     u32 wword = 0;
     while (i + 160 <= n && o < bi.len) {
-        if (i - wbase > 88) {                                // refill so that 40 bytes from i on are inside the window
+        if (i - wbase > 60) {                                // refill so that 68 bytes from i on are inside the window
             wbase = ((i + mis) & ~(i64)3) - mis;
             wword = *reinterpret_cast<const u32*>(d + wbase + 4 * lane);     // aligned; at most 128 + 3 bytes past i, inside the payload
         }
 #define LZ_GB(j) ((__shfl_sync(0xffffffffu, wword, (u32)((j) - wbase) >> 2) >> (8u * ((u32)((j) - wbase) & 3u))) & 0xFFu)
+        // ---- all tokens that start in the next 32 payload bytes at once.  Lane l assumes a token starts at byte i + l: a literal
+        //      is two bytes, a match 1 + the two ULEB lengths, which are runs of continuation bits in a 64-bit ballot.  The real
+        //      starts are the lanes reachable from lane 0 by "next = l + token length" (five doubling steps); their output
+        //      lengths are scanned, the literals stored in one step and the matches copied in order.  Anything unusual (bad
+        //      flag, value over four bytes, distance 0 or beyond the window, output nearly full) leaves the window to the
+        //      token-at-a-time code below, whose checks are the reference's.
+        // (a run of eight or more literal tokens ahead is cheaper through the literal path below: one ballot instead of ~30 collectives)
+        bool litrun;
+        {
+            const u32 fb = LZ_GB(i + 2 * (i64)(lane & 15));
+            const u32 zm = __ballot_sync(0xffffffffu, lane < 16 && fb == 0);
+            litrun = (u32)(__ffs(~zm) - 1) >= 8u;
+        }
+        if (!litrun) {
+            const u32 b0 = LZ_GB(i + (i64)lane), b1 = LZ_GB(i + 32 + (i64)lane);
+            const u64 C = (u64)__ballot_sync(0xffffffffu, (b0 & 0x80u) != 0) | ((u64)__ballot_sync(0xffffffffu, (b1 & 0x80u) != 0) << 32);
+            u32 tl = 1, kind = 2, l1 = 0, l2 = 0;
+            if (b0 == 0) { tl = 2; kind = 0; }
+            else if (b0 == 1) {
+                l1 = (u32)__ffsll((long long)~(C >> (lane + 1)));
+                l2 = l1 <= 4 ? (u32)__ffsll((long long)~(C >> (lane + 1 + l1))) : 9u;
+                if (l1 > 4 || l2 > 4) { l1 = 0; l2 = 0; tl = 1; }                    // kind stays 2: a value of more than four bytes
+                else { tl = 1 + l1 + l2; kind = 1u; }
+            }
+            const u32 nx1 = lane + tl;
+            u32 R = 1u, j = nx1;
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+                const u32 tgt = (((R >> lane) & 1u) && j < 32) ? (1u << j) : 0u;
+                R |= __reduce_or_sync(0xffffffffu, tgt);
+                const u32 jj = __shfl_sync(0xffffffffu, j, j & 31u);
+                j = j < 32 ? jj : j;
+            }
+            const bool start = (R >> lane) & 1u;
+            // values of my token (bytes through the register window; four shuffles per value, executed by every lane)
+            u32 mlen = 0, mdist = 0;
+            {
+                const i64 p1 = i + lane + 1, p2 = p1 + l1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const u32 x1 = LZ_GB(p1 + ((u32)q < l1 ? q : 0)), x2 = LZ_GB(p2 + ((u32)q < l2 ? q : 0));
+                    if ((u32)q < l1) mlen |= (x1 & 0x7Fu) << (7 * q);
+                    if ((u32)q < l2) mdist |= (x2 & 0x7Fu) << (7 * q);
+                }
+            }
+            const u32 outlen = !start ? 0u : kind == 0 ? 1u : mlen;
+            u32 incl = outlen;
+#pragma unroll
+            for (int sh = 1; sh < 32; sh <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, sh); if (lane >= (u32)sh) incl += t; }
+            const u32 excl = incl - outlen, total = __shfl_sync(0xffffffffu, incl, 31);
+            const u32 om = o + excl;
+            const u32 avail = window_check ? min(om, window_check) : om;
+            const bool odd = start && (kind == 2 || (kind == 1 && (mdist == 0 || (mlen && mdist > avail))));
+            // (total <= 2 KiB: every match takes the ring path below, and no store of this window can reach a ring slot that one of
+            //  its matches still reads — sources lie at most 6 KiB behind, the ring holds 8)
+            if (!__any_sync(0xffffffffu, odd) && (u64)o + total <= (u64)bi.len && total <= LZ_RING_MAXLEN) {
+                const u32 vnext = __shfl_down_sync(0xffffffffu, b0, 1), v0 = __shfl_sync(0xffffffffu, b1, 0);
+                if (start && kind == 0) { const u8 v = (u8)(lane < 31 ? vnext : v0); dst[om] = v; ring[om & (LZ_RING - 1)] = v; }
+                u32 mm = __ballot_sync(0xffffffffu, start && kind == 1 && mlen);
+                while (mm) {
+                    const u32 l = __ffs(mm) - 1; mm &= mm - 1;
+                    const u32 cnt = __shfl_sync(0xffffffffu, mlen, l), dd = __shfl_sync(0xffffffffu, mdist, l), oo = __shfl_sync(0xffffffffu, om, l);
+                    __syncwarp();
+                    if (cnt <= LZ_RING_MAXLEN && dd <= LZ_RING - LZ_RING_MAXLEN) {
+                        const u32 sb = oo - dd;
+                        if (dd >= cnt) { for (u32 k = lane; k < cnt; k += 32) { const u8 v = ring[(sb + k) & (LZ_RING - 1)]; dst[oo + k] = v; ring[(oo + k) & (LZ_RING - 1)] = v; } }
+                        else { for (u32 k = lane; k < cnt; k += 32) { const u8 v = ring[(sb + k % dd) & (LZ_RING - 1)]; dst[oo + k] = v; ring[(oo + k) & (LZ_RING - 1)] = v; } }
+                    } else {
+                        const u8* srcp = dst + oo - dd;
+                        if (dd >= cnt) { for (u32 k = lane; k < cnt; k += 32) { const u8 v = srcp[k]; dst[oo + k] = v; ring[(oo + k) & (LZ_RING - 1)] = v; } }
+                        else { for (u32 k = lane; k < cnt; k += 32) { const u8 v = srcp[k % dd]; dst[oo + k] = v; ring[(oo + k) & (LZ_RING - 1)] = v; } }
+                    }
+                }
+                __syncwarp();
+                const u32 last = 31u - __clz(R);             // the last token that starts in the window
+                i += (i64)__shfl_sync(0xffffffffu, nx1, last);
+                o += total;
+                continue;
+            }
+        }
         const u32 flag = LZ_GB(i);
         if (flag == 0) {
             // literal tokens: (0, byte) pairs; lanes 0..15 look at the even offsets
