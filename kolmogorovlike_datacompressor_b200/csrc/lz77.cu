@@ -396,37 +396,45 @@ __global__ void __launch_bounds__(128) k_lz_dec_warp2(const u8* __restrict__ pay
             litrun = (u32)(__ffs(~zm) - 1) >= 8u;
         }
         if (!litrun) {
-            const u32 b0 = LZ_GB(i + (i64)lane), b1 = LZ_GB(i + 32 + (i64)lane);
-            const u64 C = (u64)__ballot_sync(0xffffffffu, (b0 & 0x80u) != 0) | ((u64)__ballot_sync(0xffffffffu, (b1 & 0x80u) != 0) << 32);
-            u32 tl = 1, kind = 2, l1 = 0, l2 = 0;
+            // my nine bytes (payload i + lane .. i + lane + 8) from three words of the register window: everything about "the
+            // token that would start at my byte" is then lane-local arithmetic
+            u32 blo, bhi, b8;
+            {
+                const u32 off = (u32)(i - wbase) + lane, wi = off >> 2, sh = 8u * (off & 3u);
+                const u32 w0 = __shfl_sync(0xffffffffu, wword, wi), w1 = __shfl_sync(0xffffffffu, wword, wi + 1), w2 = __shfl_sync(0xffffffffu, wword, wi + 2);
+                blo = __funnelshift_r(w0, w1, sh); bhi = __funnelshift_r(w1, w2, sh); b8 = (sh ? (w2 >> sh) : w2) & 0xFFu;   // wi + 2 <= 31: off <= 60 + 31
+            }
+            const u32 b0 = blo & 0xFFu;
+            u32 tl = 1, kind = 2, mlen = 0, mdist = 0;
             if (b0 == 0) { tl = 2; kind = 0; }
             else if (b0 == 1) {
-                l1 = (u32)__ffsll((long long)~(C >> (lane + 1)));
-                l2 = l1 <= 4 ? (u32)__ffsll((long long)~(C >> (lane + 1 + l1))) : 9u;
-                if (l1 > 4 || l2 > 4) { l1 = 0; l2 = 0; tl = 1; }                    // kind stays 2: a value of more than four bytes
-                else { tl = 1 + l1 + l2; kind = 1u; }
+                // bytes 1..8 as one 64-bit word; a ULEB value ends at its first byte without the continuation bit
+                const u64 v8 = ((u64)(blo >> 8)) | ((u64)bhi << 24) | ((u64)b8 << 56);
+                const u64 stop = ~v8 & 0x8080808080808080ull;
+                const u32 l1 = stop ? (u32)(__ffsll((long long)stop) >> 3) : 9u;               // bytes of the first value
+                if (l1 <= 4) {
+                    const u64 v2 = v8 >> (8 * l1), stop2 = stop >> (8 * l1);
+                    const u32 l2 = stop2 ? (u32)(__ffsll((long long)stop2) >> 3) : 9u;
+                    if (l2 <= 4) {
+                        tl = 1 + l1 + l2; kind = 1;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if ((u32)q < l1) mlen |= ((u32)(v8 >> (8 * q)) & 0x7Fu) << (7 * q);
+                            if ((u32)q < l2) mdist |= ((u32)(v2 >> (8 * q)) & 0x7Fu) << (7 * q);
+                        }
+                    }
+                }
             }
             const u32 nx1 = lane + tl;
             u32 R = 1u, j = nx1;
 #pragma unroll
-            for (int st = 0; st < 5; ++st) {
+            for (int st = 0; st < 4; ++st) {                 // valid tokens are at least two bytes: at most sixteen start in the window, and a chain that meets a bad one stops there
                 const u32 tgt = (((R >> lane) & 1u) && j < 32) ? (1u << j) : 0u;
                 R |= __reduce_or_sync(0xffffffffu, tgt);
                 const u32 jj = __shfl_sync(0xffffffffu, j, j & 31u);
                 j = j < 32 ? jj : j;
             }
             const bool start = (R >> lane) & 1u;
-            // values of my token (bytes through the register window; four shuffles per value, executed by every lane)
-            u32 mlen = 0, mdist = 0;
-            {
-                const i64 p1 = i + lane + 1, p2 = p1 + l1;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const u32 x1 = LZ_GB(p1 + ((u32)q < l1 ? q : 0)), x2 = LZ_GB(p2 + ((u32)q < l2 ? q : 0));
-                    if ((u32)q < l1) mlen |= (x1 & 0x7Fu) << (7 * q);
-                    if ((u32)q < l2) mdist |= (x2 & 0x7Fu) << (7 * q);
-                }
-            }
             const u32 outlen = !start ? 0u : kind == 0 ? 1u : mlen;
             u32 incl = outlen;
 #pragma unroll
@@ -438,8 +446,7 @@ __global__ void __launch_bounds__(128) k_lz_dec_warp2(const u8* __restrict__ pay
             // (total <= 2 KiB: every match takes the ring path below, and no store of this window can reach a ring slot that one of
             //  its matches still reads — sources lie at most 6 KiB behind, the ring holds 8)
             if (!__any_sync(0xffffffffu, odd) && (u64)o + total <= (u64)bi.len && total <= LZ_RING_MAXLEN) {
-                const u32 vnext = __shfl_down_sync(0xffffffffu, b0, 1), v0 = __shfl_sync(0xffffffffu, b1, 0);
-                if (start && kind == 0) { const u8 v = (u8)(lane < 31 ? vnext : v0); dst[om] = v; ring[om & (LZ_RING - 1)] = v; }
+                if (start && kind == 0) { const u8 v = (u8)(blo >> 8); dst[om] = v; ring[om & (LZ_RING - 1)] = v; }
                 u32 mm = __ballot_sync(0xffffffffu, start && kind == 1 && mlen);
                 while (mm) {
                     const u32 l = __ffs(mm) - 1; mm &= mm - 1;
