@@ -559,7 +559,8 @@ def leg_cfg4(env, args):
     futs = [pool.submit(O.encode_block, O.PROFILE_KOLR, corp.get(0)[blocks[i][1]:blocks[i][2]].tobytes(), None, True) for i in range(nchk)]
     # warm-up on a small corpus: contexts, the Re-Pair slab pool, NCCL connections
     kfirst = blocks[b0][0] if b1 > b0 else 0
-    kd.compress_kolr_fixed_corpus([min(cbytes, 16 * env.world * MIB)], lambda k, a, b: corp.get(kfirst)[a:b], bs)
+    wconts = kd.compress_kolr_fixed_corpus([min(cbytes, 16 * env.world * MIB)], lambda k, a, b: corp.get(kfirst)[a:b], bs)
+    kd.decompress_kolr_corpus(wconts, gather=False)                  # ... and the rank 0 -> rank r connections of the payload scatter
     env.barrier()
     st = {}
     e0, e1 = ev_pair(torch)
