@@ -106,3 +106,15 @@ def test_kolm_container_1mib_target_equals_oracle_selection():
             assert ids[names[i]] == mid, i
             assert blob[starts[i]:starts[i] + plens[i]] == payload, i
     assert KF.decompress(blob) == data
+
+
+def test_chain_1mib_blocks_of_the_s3_mix_every_segment_kind():
+    """The S3 mix (cfg 4 / cfg 5 data) at 1 MiB blocks, one block of each of its eight segment kinds: long repeats (fills, ramps,
+    checker rows) keep the rotation sort in its rounds for 15-20 doublings with groups far above the local kernel's limit, so
+    k_refine_local, the big-group path, the hand-over to the compacted rounds and the stable-partition exit all run."""
+    import gpu_util as G
+    from kolmogorovlike_datacompressor_b200 import synth
+    mib = 1 << 20
+    data = synth.s3_mix(8 * mib)
+    off = np.arange(0, 8 * mib + 1, mib, dtype=np.int64)
+    _chain_vs_oracle(G.ctx(max_bytes=16 << 20, max_blocks=64), data, off, range(8))
