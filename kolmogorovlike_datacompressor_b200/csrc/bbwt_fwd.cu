@@ -868,7 +868,7 @@ __global__ void k_round_end(u32* __restrict__ newcls, u32* __restrict__ done, co
 #define LR_FOREIGN 0xffffu
 #define LR_NOHEAD 0xfffeu
 #define LR_UNIFORM_MIN 24                                 // groups at least this long are tested for "all keys equal" before the quadratic count
-#define LR_SMEM (2 * (LR_CAP + 8) + 4 * LR_CAP + 4 * LR_CAP + 4 * LR_CAP + 2 * LR_CAP + LR_CAP)
+#define LR_SMEM (2 * (LR_CAP + 8) + 2 * LR_CAP + 4 * LR_CAP + 4 * LR_CAP + 2 * LR_CAP + LR_CAP)
 
 struct RefineArgs {
     u32* sa; const u32* rank; const u32* grp; u32* list; u32* list2; u32* lcount; u32* F; const TileDesc* tiles; const BlockInfo* binfo;
@@ -882,10 +882,9 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     extern __shared__ __align__(16) u8 lr_smem[];
     u32* K2c = reinterpret_cast<u32*>(lr_smem);            // successor rank of compact record i
     u32* CP = K2c + LR_CAP;                                // its position
-    u32* E = CP + LR_CAP;                                  // by the window index a group starts at: [12:0] its end (exclusive), [15] its keys differ, [31:16] keys below its first member's
-    u16* G16 = reinterpret_cast<u16*>(E + LR_CAP);         // grp[] window minus t0 (LR_FOREIGN: the group starts before the tile)   [LR_CAP + 8]
-    u16* CPRE = G16;                                       // later: records before compact slot i whose key equals their group's first key   [m + 1]
-    u16* CX = G16 + LR_CAP + 8;                            // window index of compact record i
+    u16* G16 = reinterpret_cast<u16*>(CP + LR_CAP);        // grp[] window minus t0 (LR_FOREIGN: the group starts before the tile)   [LR_CAP + 8]
+    u16* E = G16 + LR_CAP + 8;                             // end (exclusive, window index) of the group that starts at this window index
+    u16* CX = E + LR_CAP;                                  // window index of compact record i
     u8* COFF = reinterpret_cast<u8*>(CX + LR_CAP);         // its offset inside its group
     __shared__ u32 s_wcnt[NWARPS], s_wbig[NWARPS];
     __shared__ u32 s_g0, s_keyprev, s_nchg;
@@ -931,7 +930,7 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
         const u32 g = G16[x], gn = G16[x + 1];
         const bool ends = gn == x + 1;                     // my group ends with me
         const bool own = g < cnt;                          // its start lies in the nominal range (LR_FOREIGN / LR_NOHEAD are larger)
-        if (ends && g < LR_CAP) { E[g] = x + 1; if (own && x + 1 - g >= LR_UNIFORM_MIN) s_flag[3] = 1; }
+        if (ends && g < LR_CAP) { E[g] = (u16)(x + 1); if (own && x + 1 - g >= LR_UNIFORM_MIN) s_flag[3] = 1; }
         const bool single = ends && g == x;
         const bool big = own ? G16[g + LR_GCAP] == g : (g == LR_FOREIGN && big_in);
         const bool proc = own && !big && !single;
@@ -1018,19 +1017,13 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
         }
     }
     __syncthreads();
-    // ---- long repeats (periodic data, fills): most members of a group carry the same key for many rounds and only a tail splits
-    //      off.  Small groups: every record is compared with its group's first member — keys differ: bit 15 of E[group start],
-    //      keys below that first key are counted in E's high half; the records that share the first key ("core") then find their
-    //      place by a prefix count over the compact slots instead of the quadratic in-group count, groups without any difference
-    //      are left alone.  Big groups: gflag[group start] = stamp when neighbours differ, read by k_big_emit.
+    // ---- groups whose members all carry the same key stay as they are (periodic data: most groups, for many rounds).  Small
+    //      groups: bit 15 of E[group start]; big groups: gflag[group start] = stamp, read by k_big_emit
     const bool utest = s_flag[3] != 0;                     // (read after the barriers that follow its writers)
     for (u32 i = utest ? tid : m + tid; i < mall; i += KOLM_THREADS) {
         if (i < m) {
             const u32 off = COFF[i];
-            if (off) {
-                const u32 mine = K2c[i], c = K2c[i - off];
-                if (mine != c) { const u32 gs = (u32)CX[i] - off; atomicOr(&E[gs], 0x8000u); if (mine < c) atomicAdd(&E[gs], 0x10000u); }
-            }
+            if (off && K2c[i] != K2c[i - off]) { const u32 gs = (u32)CX[i] - off; atomicOr(reinterpret_cast<u32*>(E) + (gs >> 1), 0x8000u << (16 * (gs & 1u))); }
         } else {
             const u32 x = CX[i], g = G16[x];
             if (g != x) {                                  // not the group's first member: slot i - 1 holds order index x - 1 (same group) unless x = 0
@@ -1041,46 +1034,16 @@ __global__ void __launch_bounds__(KOLM_THREADS, 3) k_refine_local(RefineArgs a) 
     }
     __syncthreads();
     if (!m) { if (tid == 0) a.lcount[tile] = 0; return; }
-    if (utest) {
-        // CPRE[i] = core records of long groups among the compact slots before i (warp w scans a contiguous range of slots)
-        const u32 kmax = (m + KOLM_THREADS - 1) / KOLM_THREADS, w0 = w * kmax * 32;
-        u32 tot = 0;
-        for (u32 k = 0; k < kmax; ++k) {
-            const u32 i = w0 + k * 32 + lane;
-            bool core = false;
-            if (i < m) { const u32 off = COFF[i], gs = (u32)CX[i] - off; core = ((E[gs] & 0x1fffu) - gs >= LR_UNIFORM_MIN) && K2c[i] == K2c[i - off]; }
-            tot += __popc(__ballot_sync(FULL, core));
-        }
-        if (lane == 0) s_wcnt[w] = tot;
-        __syncthreads();                                   // (also: the last reader of G16 above is done, CPRE takes its place)
-        u32 run = 0;
-        for (u32 q = 0; q < w; ++q) run += s_wcnt[q];
-        for (u32 k = 0; k < kmax; ++k) {
-            const u32 i = w0 + k * 32 + lane;
-            bool core = false;
-            if (i < m) { const u32 off = COFF[i], gs = (u32)CX[i] - off; core = ((E[gs] & 0x1fffu) - gs >= LR_UNIFORM_MIN) && K2c[i] == K2c[i - off]; }
-            const u32 bm = __ballot_sync(FULL, core);
-            if (i <= m) CPRE[i] = (u16)(run + __popc(bm & lanemask_lt()));
-            run += __popc(bm);
-        }
-        if (w == NWARPS - 1 && lane == 0 && w0 + kmax * 32 <= m) CPRE[m] = (u16)run;   // (m a multiple of the scanned range: the loop above did not reach slot m)
-        __syncthreads();
-    }
     // ---- every record finds its place inside its group: keys below mine, equal keys before me
     u32 nnew = 0, nsurv = 0;
     for (u32 i = tid; i < m; i += KOLM_THREADS) {
-        const u32 x = CX[i], off = COFF[i], cs = i - off, gs = x - off, eg = E[gs], n = (eg & 0x1fffu) - gs, mine = K2c[i];
-        if (utest && !(eg & 0x8000u)) { ++nsurv; continue; }   // all keys of the group equal: nothing moves
+        const u32 x = CX[i], off = COFF[i], cs = i - off, gs = x - off, eg = E[gs], n = (eg & 0x7fffu) - gs, mine = K2c[i];
+        if (utest && !(eg >> 15)) { ++nsurv; continue; }   // all keys of the group equal: nothing moves
         // keys are below 2^30: (k - mine) >> 31 counts "k < mine", (k - mine - 1) >> 31 counts "k <= mine" — two adds per key
         // and count; the keys before me and the ones from me on are counted apart, their "<=" minus "<" are the equal ones
         const u32* kp = K2c + cs;
         const u32 m1 = mine + 1u;
         u32 ltb = 0, leb = 0, lta = 0, lea = 0, j = 0;
-        if (utest && n >= LR_UNIFORM_MIN && mine == kp[0]) {  // core record of a long group: counts from the prefix scan
-            ltb = eg >> 16; leb = ltb + ((u32)CPRE[i] - (u32)CPRE[cs]);
-            lea = (u32)CPRE[cs + n] - (u32)CPRE[i];        // equal keys from me on (lta = 0)
-            j = n;
-        } else
         if (n <= 4) {                                      // most groups of text: no loops (slots past the group are masked out)
             const u32 k0 = kp[0], k1 = kp[1], k2 = n > 2 ? kp[2] : 0x7fffffffu, k3 = n > 3 ? kp[3] : 0x7fffffffu;
             const u32 l0 = (k0 - mine) >> 31, l1 = (k1 - mine) >> 31, l2 = (k2 - mine) >> 31, l3 = (k3 - mine) >> 31;
