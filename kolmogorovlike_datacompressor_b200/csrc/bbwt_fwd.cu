@@ -1101,6 +1101,48 @@ __global__ void __launch_bounds__(KOLM_THREADS) k_big_emit(const u32* __restrict
     const BlockInfo bi = binfo[td.block];
     const u32 tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const u32 t0 = td.start - bi.pbase;
+    if (ALL) {
+        // sixteen consecutive order indices per thread: four 16-byte loads of grp[] (+ the next thread's first value), the
+        // unsettled ones read off in registers; any order inside the block's list will do (the LS path sorts by both keys)
+        const u32 x0 = tid * KOLM_IPT;
+        u32 g[KOLM_IPT + 1];
+        if (x0 + KOLM_IPT <= td.count) {
+            const uint4* gp = reinterpret_cast<const uint4*>(grp + td.start + x0);
+#pragma unroll
+            for (int q = 0; q < KOLM_IPT / 4; ++q) { const uint4 v = gp[q]; g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KOLM_IPT; ++k) g[k] = x0 + k < td.count ? grp[td.start + x0 + k] : 0u;
+        }
+        g[KOLM_IPT] = (x0 + KOLM_IPT < td.count || t0 + x0 + KOLM_IPT < bi.len) && x0 + KOLM_IPT <= td.count ? grp[td.start + x0 + KOLM_IPT] : 0xffffffffu;
+        u32 bits = 0;
+#pragma unroll
+        for (int k = 0; k < KOLM_IPT; ++k) {
+            const u32 j = t0 + x0 + k;                           // block-local order index
+            const bool single = g[k] == j && (j + 1 == bi.len || g[k + 1] == j + 1);
+            if (x0 + k < td.count && !single) bits |= 1u << k;
+        }
+        const u32 c = __popc(bits);
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(FULL, incl, o); if (lane >= (u32)o) incl += t; }
+        if (lane == 31) s_w[w] = incl;
+        __syncthreads();
+        if (tid == 0) { u32 t = 0; for (int i = 0; i < NWARPS; ++i) { const u32 c_ = s_w[i]; s_w[i] = t; t += c_; } s_base = t ? atomicAdd(active + td.block, t) : 0u; }
+        __syncthreads();
+        u32 d = bi.pbase + s_base + s_w[w] + incl - c;
+        const u32 nf = CYCLIC ? nfac[td.block] : 0;
+        u32 b = bits;
+        while (b) {
+            const u32 k = __ffs(b) - 1; b &= b - 1;
+            const u32 p = sa[td.start + x0 + k];
+            u32 lp = p - bi.pbase, sp;
+            if (CYCLIC) { u32 fs, fl; find_factor(fstart + bi.pbase, nf, bi.len, lp, fs, fl); { u32 o = lp - fs + h % fl; sp = fs + (o >= fl ? o - fl : o); } }
+            else sp = lp + h;
+            K2[d] = rank[bi.pbase + sp]; V2[d] = p; ++d;
+        }
+        return;
+    }
     u32 bits = 0, mycnt = 0;
 #pragma unroll
     for (int k = 0; k < KOLM_IPT; ++k) {
