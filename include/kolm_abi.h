@@ -202,12 +202,18 @@ int kolm_copy_blocks(kolm_ctx* ctx, const uint64_t* src_addr, const uint64_t* ds
  *   scratch (DEVICE, 256-byte aligned, kolm_encode_blocks_scratch(profile, batch bytes, nblocks) bytes).
  *   payload_out (DEVICE, cap bytes, 8 bytes of slack wanted): the winners' payloads back to back in block order (KF.py:896-901;
  *                V22.py:2443-2444); payload_off (HOST, nblocks+1); method_ids (HOST u8[nblocks]); sizes_out (HOST, may be NULL):
- *                every candidate's size, row-major [nblocks][4 or 10], 2^62-1 for a candidate that was not offered. */
+ *                every candidate's size, row-major [nblocks][4 or 10], 2^62-1 for a candidate that was not offered.
+ *   Re-Pair (V22.py:1841-1911, the last candidate of the list) of blocks of up to 8 KiB is evaluated after all the others and, when
+ *   sizes_out is NULL, only as far as it can still win: a block's rounds stop once a lower bound on the final payload (the rules
+ *   made so far + one left symbol per distinct adjacent pair of the current sequence + 7) reaches the best other size.  The
+ *   selection is unchanged — the reference picks Re-Pair on a strictly smaller payload only; KOLM_REPAIR_STOP=0 runs every block
+ *   to the end.  kolm_encode_blocks_stats: out2[0] = blocks of the last call whose Re-Pair candidate stopped early. */
 size_t kolm_encode_blocks_scratch(int profile, size_t batch_bytes, int nblocks);
 int kolm_encode_blocks(kolm_ctx* ctx, int profile, const uint8_t* in, const int64_t* off, int nblocks, uint32_t cand_mask,
                        int ext_id, const int64_t* ext_sizes, const uint64_t* ext_addr, uint8_t* scratch, size_t scratch_bytes,
                        uint8_t* payload_out, size_t cap, int64_t* payload_off, uint8_t* method_ids, int64_t* sizes_out,
                        kolm_stream_t stream);
+int kolm_encode_blocks_stats(kolm_ctx* ctx, int64_t* out2);
 /* The decode loops of decompress (KF.py:925-949 over _DECODERS; V22.py:2530-2540 over _select_decoders()): block b's payload is
  * payload[payload_start[b] .. + payload_len[b]) (DEVICE buffer, HOST arrays — KOLM containers interleave 9-byte block headers with
  * the payloads, so starts and lengths are separate), its method method_ids[b], and it decodes to

@@ -18,7 +18,7 @@ EXPORTS = [
     "kolm_rice_kf_enc", "kolm_rice_kf_dec", "kolm_rice_k2_enc", "kolm_rice_k2_dec", "kolm_last_counters",
     "kolm_lz77_enc", "kolm_lz77_dec", "kolm_residual_sizes", "kolm_residual_enc", "kolm_residual_dec",
     "kolm_repair_enc", "kolm_repair_dec", "kolm_repair_max_block", "kolm_v2new_enc", "kolm_v2new_dec", "kolm_cdc_kf", "kolm_cdc_v22", "kolm_cdc_candidates", "kolm_cdc_walk_kf", "kolm_cdc_walk_v22", "kolm_select_blocks", "kolm_gather_payloads", "kolm_copy_blocks",
-    "kolm_rice_dual_enc", "kolm_encode_blocks_scratch", "kolm_encode_blocks", "kolm_decode_blocks_scratch", "kolm_decode_blocks",
+    "kolm_rice_dual_enc", "kolm_encode_blocks_scratch", "kolm_encode_blocks", "kolm_encode_blocks_stats", "kolm_decode_blocks_scratch", "kolm_decode_blocks",
     "kolm_profile_categories", "kolm_profile_name", "kolm_profile_enable", "kolm_profile_reset", "kolm_profile_read",
 ]
 
@@ -72,6 +72,7 @@ def lib():
     L.kolm_decode_blocks.argtypes = [p, C.c_int, p, i64p, i64p, p, i64p, C.c_int, p, C.c_size_t, p, ip, p]
     L.kolm_rice_dual_enc.argtypes = [p, p, i64p, C.c_int, C.c_int, p, C.c_size_t, i64p, ip, p, C.c_size_t, i64p, i64p, p]
     L.kolm_last_counters.argtypes = [p, i64p]
+    L.kolm_encode_blocks_stats.argtypes = [p, i64p]
     L.kolm_lz77_enc.argtypes = [p, p, i64p, C.c_int, C.c_uint32, C.c_uint32, p, C.c_size_t, i64p, p]
     L.kolm_lz77_dec.argtypes = [p, p, i64p, i64p, C.c_int, C.c_uint32, p, p]
     for f in ("kolm_cdc_kf", "kolm_cdc_v22"):

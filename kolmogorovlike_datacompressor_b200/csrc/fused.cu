@@ -31,6 +31,22 @@ __global__ void k_fe_diff(const i64* __restrict__ poff, i64* __restrict__ row, i
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < nb) row[b] = poff[b + 1] - poff[b];
 }
+// Re-Pair row: blocks whose candidate stopped early (accumulator slot 34, see k_repair_enc) count as not evaluated
+__global__ void k_fe_diff_rp(const i64* __restrict__ poff, const u64* __restrict__ acc, i64* __restrict__ row, int nb, u32* __restrict__ nstopped) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const bool st = acc[(size_t)b * 64 + 34] != 0;
+    row[b] = st ? FE_BIG : poff[b + 1] - poff[b];
+    if (st) atomicAdd(nstopped, 1u);
+}
+// limit[b] = the smallest size among the candidates other than `skip` (what Re-Pair has to beat)
+__global__ void k_fe_limit(const i64* __restrict__ cs, int nb, int ncand, int skip, i64* __restrict__ limit) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    i64 v = FE_BIG;
+    for (int m = 0; m < ncand; ++m) if (m != skip) { const i64 x = cs[(size_t)m * nb + b]; if (x < v) v = x; }
+    limit[b] = v;
+}
 __global__ void k_fe_kf(const u64* __restrict__ bacc, i64* __restrict__ row, int nb) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < nb) row[b] = (i64)bacc[(size_t)b * RB_STRIDE + RB_BYTES];
@@ -96,7 +112,7 @@ __global__ void __launch_bounds__(256) k_fe_copy(const u8* __restrict__ base, co
 static inline size_t fe_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct FeLayout {
-    size_t cs, foff, method, lzoff, rpoff, extaddr, L, M, lzpay, rppay, total, lzcap, rpcap;
+    size_t cs, foff, method, lzoff, rpoff, extaddr, L, M, lzpay, rppay, rpacc, rplim, misc, total, lzcap, rpcap;
 };
 static FeLayout fe_layout(int profile, size_t n, int nb, bool rp_inline) {
     FeLayout l; size_t p = 0;
@@ -106,6 +122,8 @@ static FeLayout fe_layout(int profile, size_t n, int nb, bool rp_inline) {
     l.L = take(n + 64); l.M = take(n + 64);
     l.lzcap = 2 * n + 16 * (size_t)nb + 64; l.lzpay = take(l.lzcap);
     l.rpcap = (profile == KOLM_PROFILE_KOLR && rp_inline) ? 5 * n + 16 * (size_t)nb + 64 : 0; l.rppay = take(l.rpcap);
+    const bool rp = l.rpcap != 0;                            // Re-Pair runs last, beside the Rice state: its own accumulators and limits
+    l.rpacc = take(rp ? (size_t)nb * 64 * 8 : 0); l.rplim = take(rp ? (size_t)nb * 8 : 0); l.misc = take(64);
     l.total = p;
     return l;
 }
@@ -168,11 +186,6 @@ extern "C" int kolm_encode_blocks(kolm_ctx* c, int profile, const uint8_t* in, c
         CUDA_TRY(cudaMemcpyAsync(lzoff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToDevice, s));
         k_fe_diff<<<g1, 256, 0, s>>>(lzoff, row(id_lz), nb);
     }
-    if (rp_inline) {
-        KOLM_TRY(kolm_repair_enc_impl(c, in, rppay, L.rpcap, nullptr, s));
-        CUDA_TRY(cudaMemcpyAsync(rpoff, c->d_poff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToDevice, s));
-        k_fe_diff<<<g1, 256, 0, s>>>(rpoff, row(id_rp), nb);
-    }
     // ---- BBWT -> MTF -> exact sizes of the Rice coders
     const u32 k2mask = kolm ? 0u : (mask & 0x7Cu);
     const bool kf = kolm && ((mask >> 2) & 1u);
@@ -185,6 +198,26 @@ extern "C" int kolm_encode_blocks(kolm_ctx* c, int profile, const uint8_t* in, c
         KL(c, KC_RICE_PLAN, (i64)nb * 256, s, k_rice_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_binfo, c->d_poff, c->d_params, c->d_sizes, nb, kf ? 1 : 2, 0));
         if (kf) k_fe_kf<<<g1, 256, 0, s>>>(c->d_bacc, row(2), nb);
         else k_fe_k2<<<g1, 256, 0, s>>>(c->d_sizes, cs, nb, 2, k2mask);
+    }
+    // ---- Re-Pair last: every other size is in the table, so the shared-memory kernel can stop a block as soon as its lower
+    //      bound reaches the best of them (k_repair_enc).  A caller that asks for the size table gets every candidate in full.
+    //      The Rice state (d_bacc, d_poff) stays untouched: accumulators and offsets of this candidate live in the scratch.
+    u32* nstopped = (u32*)(scratch + L.misc);
+    CUDA_TRY(cudaMemsetAsync(nstopped, 0, 64, s));
+    if (rp_inline) {
+        static int stop_on = -1;
+        if (stop_on < 0) { const char* e = getenv("KOLM_REPAIR_STOP"); stop_on = e ? atoi(e) : 1; }
+        i64* rplim = nullptr;
+        if (stop_on && !sizes_out) {
+            rplim = (i64*)(scratch + L.rplim);
+            k_fe_limit<<<g1, 256, 0, s>>>(cs, nb, ncand, id_rp, rplim);
+        }
+        u64* const bacc0 = c->d_bacc; i64* const poff0 = c->d_poff;
+        c->d_bacc = (u64*)(scratch + L.rpacc); c->d_poff = rpoff;
+        const int rc = kolm_repair_enc_impl(c, in, rppay, L.rpcap, nullptr, s, rplim);
+        c->d_bacc = bacc0; c->d_poff = poff0;
+        if (rc != KOLM_OK) return rc;
+        k_fe_diff_rp<<<g1, 256, 0, s>>>(rpoff, (const u64*)(scratch + L.rpacc), row(id_rp), nb, nstopped);
     }
     // ---- selection and final offsets, on the device
     KL(c, KC_PLAN, (i64)nb * ncand * 8, s, k_fe_select<<<1, 1024, 0, s>>>(cs, nb, ncand, method, foff));
@@ -229,11 +262,20 @@ extern "C" int kolm_encode_blocks(kolm_ctx* c, int profile, const uint8_t* in, c
     CUDA_TRY(cudaMemcpyAsync(h_foff, foff, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(h_m, method, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
     if (sizes_out) CUDA_TRY(cudaMemcpyAsync(h_cs, cs, (size_t)ncand * nb * 8, cudaMemcpyDeviceToHost, s));
+    u32* h_st = (u32*)(h_cs + (size_t)ncand * nb);
+    CUDA_TRY(cudaMemcpyAsync(h_st, nstopped, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    c->counters[5] = (i64)*h_st;
     memcpy(payload_off, h_foff, (size_t)(nb + 1) * 8);
     for (int b = 0; b < nb; ++b) method_ids[b] = (uint8_t)h_m[b];
     if (sizes_out) for (int b = 0; b < nb; ++b) for (int m = 0; m < ncand; ++m) sizes_out[(size_t)b * ncand + m] = h_cs[(size_t)m * nb + b];
     if ((size_t)payload_off[nb] + 8 > cap) return KOLM_E_CAPACITY;
+    return KOLM_OK;
+}
+
+extern "C" int kolm_encode_blocks_stats(kolm_ctx* c, int64_t* out2) {
+    if (!c || !out2) return KOLM_E_ARG;
+    out2[0] = c->counters[5]; out2[1] = 0;
     return KOLM_OK;
 }
 

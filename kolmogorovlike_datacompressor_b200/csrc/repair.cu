@@ -34,7 +34,7 @@ struct RepairSmemT {
     u32 wlast[THREADS / 32];
     u32 wt[THREADS / 32];
     unsigned long long best;
-    u32 replaced, m, hdr;
+    u32 replaced, m, hdr, wsum;
 };
 typedef RepairSmemT<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH> RepairSmem;
 
@@ -61,7 +61,8 @@ __device__ __forceinline__ u8* rp_put_uleb(u8* p, u32 v) { while (v >= 128) { *p
 // out_tmp: per block a staging region of 4*len+64 bytes at tmp + 4*pbase; sizes[b] = payload bytes
 template <int MAXLEN, int THREADS, int HASH, int MINLEN>
 __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
-                                                        u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err) {
+                                                        u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err,
+                                                        const i64* __restrict__ limit) {
     extern __shared__ __align__(16) u8 smem_raw[];
     typedef RepairSmemT<MAXLEN, THREADS, HASH> SM;
     SM& S = *reinterpret_cast<SM*>(smem_raw);
@@ -75,13 +76,26 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
     if (tid == 0) S.m = bi.len;
     __syncthreads();
     u32 cur = 0, nrules = 0;
+    // Early stop (kolm_encode_blocks, limit != nullptr): limit[b] = the smallest size among the block's other candidates, all of
+    // which precede Re-Pair in the list, so Re-Pair is selected only if its payload is SMALLER.  Whatever the remaining rounds do,
+    //   payload >= 6 + (bytes of the rules made so far) + sum over the DISTINCT adjacent pairs (x, y) of the current sequence of
+    //              uleb(x) + 1:
+    // in the final grammar every adjacency of the current sequence sits at one boundary — between two neighbours of the final
+    // sequence or between the two sides of a later rule — and a boundary determines its pair (last symbol of the left expansion,
+    // first of the right), so distinct pairs have distinct boundaries; the left symbol of a boundary is x itself or a later
+    // nonterminal (a larger id: at least as many ULEB bytes), each such symbol is written once per boundary, the last symbol of the
+    // final sequence costs a byte more, and 'RP', ULEB(256) and the two counts take at least 6.  Once the bound reaches limit[b]
+    // the candidate cannot win: the block is marked (bacc slot 34) and its size reported as "not evaluated".
+    const i64 lim = limit ? limit[b] : (i64)0x7fffffffffffffffll;
+    u32 rule_bytes = 0;
+    bool stopped = false;
     constexpr u32 IPT = MAXLEN / THREADS;        // 8 consecutive positions per thread
     for (;;) {
         const u32 m = S.m;
         if (m < 2) break;
         // ---- pair histogram
         for (u32 i = tid; i < HASH; i += THREADS) { S.hkey[i] = REPAIR_EMPTY; S.hcnt[i] = 0; }
-        if (tid == 0) { S.best = 0; S.replaced = 0; }
+        if (tid == 0) { S.best = 0; S.replaced = 0; S.wsum = 0; }
         __syncthreads();
         const u16* q = S.seq[cur];
         for (u32 i = tid; i + 1 < m; i += THREADS) {
@@ -94,13 +108,22 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
             }
         }
         __syncthreads();
+        u32 wloc = 0;                                        // ULEB bytes of the left symbols of my distinct pairs
         for (u32 i = tid; i < HASH; i += THREADS) {
             u32 k = S.hkey[i];
-            if (k != REPAIR_EMPTY && S.hcnt[i] >= 2) atomicMax(&S.best, ((unsigned long long)S.hcnt[i] << 32) | (unsigned long long)(~k));
+            if (k != REPAIR_EMPTY) {
+                wloc += 1u + ((k >> 16) >= 128u ? 1u : 0u);
+                if (S.hcnt[i] >= 2) atomicMax(&S.best, ((unsigned long long)S.hcnt[i] << 32) | (unsigned long long)(~k));
+            }
+        }
+        if (limit) {
+            wloc = __reduce_add_sync(0xffffffffu, wloc);
+            if ((tid & 31) == 0 && wloc) atomicAdd(&S.wsum, wloc);
         }
         __syncthreads();
         const unsigned long long best = S.best;
         if ((u32)(best >> 32) < 2) break;                    // V22.py:1875-1876
+        if (limit && (i64)(7u + rule_bytes + S.wsum) >= lim) { stopped = true; break; }
         const u32 bkey = ~(u32)best;
         const u32 newsym = 256 + nrules;
         // ---- which occurrences are replaced: position i is "flagged" if pair(i) == best
@@ -153,10 +176,15 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
             if (i < m && !((removed >> k) & 1u)) nq[o++] = ((taken >> k) & 1u) ? (u16)newsym : q[i];
         }
         if (tid == 0) { rules[nrules] = bkey; S.m = newm; }
+        rule_bytes += rp_uleb_size(bkey >> 16) + rp_uleb_size(bkey & 0xffff);
         ++nrules; cur ^= 1;
         __syncthreads();
     }
     __syncthreads();
+    if (stopped) {
+        if (tid == 0) { bacc[(size_t)b * 64 + 32] = 0; bacc[(size_t)b * 64 + 34] = 1; err[b] = KOLM_OK; }
+        return;
+    }
     // ---- serialise: 'R','P', ULEB 256, ULEB nrules, rules, ULEB len, symbols   (V22.py:1889-1903)
     const u32 m = S.m;
     const u16* q = S.seq[cur];
@@ -369,7 +397,9 @@ __global__ void __launch_bounds__(RD2_THREADS) k_repair_dec2(const u8* __restric
 }
 
 // out_off == nullptr: device mode (kolm_encode_blocks) — the offsets stay in c->d_poff, nothing comes home
-int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64* out_off, cudaStream_t s) {
+// limit (device, one entry per block, or nullptr): see k_repair_enc — blocks whose lower bound reaches limit[b] stop early, get
+// size 0 here and a 1 in accumulator slot 34; only the shared-memory kernel looks at it (the incremental one always finishes).
+int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64* out_off, cudaStream_t s, const i64* limit = nullptr) {
     const int nb = c->nblocks;
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     static long long big_max = -1;                            // KOLM_REPAIR_BIG_MAX: largest block (bytes) the incremental kernel takes (0: none)
@@ -389,10 +419,10 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     u8* tmp = (u8*)c->d_k0;                                   // 4 bytes per padded element
     if (small_on) {
         // blocks of up to 2 KiB on the small shape (five CTAs per SM), the others (if any) on the 160 KB shape
-        KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_SMALL, 256, 4096, 0><<<nb, 256, sizeof(RepairSmemSmall), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
-        if (c->max_len > REPAIR_SMALL) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_SMALL><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+        KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_SMALL, 256, 4096, 0><<<nb, 256, sizeof(RepairSmemSmall), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
+        if (c->max_len > REPAIR_SMALL) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_SMALL><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
     } else
-    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err));
+    KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
     if (c->max_len > REPAIR_MAX) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));

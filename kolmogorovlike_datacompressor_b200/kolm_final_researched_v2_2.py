@@ -136,29 +136,78 @@ def _select_decoders() -> List[Callable[[bytes, int, Dict[str, Any]], bytes]]:
 
 # ---- TOC coders (host; O(nblocks)) ---------------------------------------------------------------------
 class _Bits:
-    """MSB-first bit accumulator (== _BitWriter.getvalue_bits)."""
+    """MSB-first bit accumulator (== _BitWriter.getvalue_bits).  Whole bytes leave the integer accumulator as soon as a few
+    thousand bits are pending, so a TOC of n blocks costs O(n) (one growing big integer made it quadratic: 0.8 s of host time per
+    61 440 blocks, more than the GPU spent on encoding them)."""
+    _FLUSH = 4096
 
     def __init__(self):
-        self.acc = 0
-        self.n = 0
+        self.acc = 0                               # the pending bits (fewer than _FLUSH + the last value's width)
+        self.pend = 0
+        self.n = 0                                 # all bits so far
+        self.done: List[bytes] = []
+
+    def _spill(self):
+        r = self.pend % 8                          # whole bytes out, fewer than 8 bits stay
+        if self.pend > r:
+            self.done.append((self.acc >> r).to_bytes((self.pend - r) // 8, "big"))
+            self.acc &= (1 << r) - 1
+            self.pend = r
 
     def put(self, val: int, k: int):
         if k:
             self.acc = (self.acc << k) | (val & ((1 << k) - 1))
+            self.pend += k
             self.n += k
+            if self.pend >= self._FLUSH:
+                self._spill()
 
     def unary(self, q: int):
         self.acc = (self.acc << (q + 1)) | (((1 << q) - 1) << 1)
+        self.pend += q + 1
         self.n += q + 1
+        if self.pend >= self._FLUSH:
+            self._spill()
 
     def rice(self, seq, k: int):
         for v in seq:
             self.unary(v >> k)
             self.put(v, k)
 
+    def put_array(self, bits: "np.ndarray"):
+        """append a 0/1 uint8 array (MSB first = array order)"""
+        nb = int(bits.size)
+        if not nb:
+            return
+        self._spill()
+        r = self.pend                              # < 8 bits wait in acc: they lead the array
+        if r:
+            lead = np.array([(self.acc >> (r - 1 - i)) & 1 for i in range(r)], dtype=np.uint8)
+            bits = np.concatenate((lead, bits.astype(np.uint8, copy=False)))
+        whole = (bits.size // 8) * 8
+        if whole:
+            self.done.append(np.packbits(bits[:whole]).tobytes())
+        tail = bits[whole:]
+        self.acc = 0
+        for b in tail.tolist():
+            self.acc = (self.acc << 1) | int(b)
+        self.pend = int(tail.size)
+        self.n += nb
+
+    def put_fixed(self, vals: "np.ndarray", k: int):
+        """put(v, k) for every v of an integer array (k <= 63)"""
+        if k <= 0 or not vals.size:
+            return
+        v = vals.astype(np.uint64, copy=False)
+        sh = np.arange(k - 1, -1, -1, dtype=np.uint64)
+        self.put_array(((v[:, None] >> sh[None, :]) & np.uint64(1)).astype(np.uint8).reshape(-1))
+
     def value(self) -> Tuple[bytes, int]:
-        nbytes = (self.n + 7) // 8
-        return (self.acc << (nbytes * 8 - self.n)).to_bytes(nbytes, "big"), self.n
+        tail = b""
+        if self.pend:
+            nbytes = (self.pend + 7) // 8
+            tail = (self.acc << (nbytes * 8 - self.pend)).to_bytes(nbytes, "big")
+        return b"".join(self.done) + tail, self.n
 
 
 class _BitsIn:
@@ -342,19 +391,29 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
         bw.rice(deltas, best_k2)
     n = len(payload_lens)
     l = _ef_choose_l(total_payload, n)
-    P, s = [], 0
-    for L in payload_lens:
-        s += L
-        P.append(s)
-    for x in P:
-        bw.put(x, l)
     m = (total_payload + ((1 << l) - 1)) >> l
     total = m + n
-    if total:
-        bitmap = 0
-        for i, x in enumerate(P):
-            bitmap |= 1 << (total - 1 - ((x >> l) + i))
-        bw.put(bitmap, total)
+    if n and total_payload < (1 << 62) and l <= 62:
+        # Elias-Fano of the cumulative payload ends: low l bits of every end, then the unary bitmap with bit (end >> l) + i set,
+        # written MSB first into `total` bits — as bit arrays (the per-block big-integer shifts were quadratic in the block count)
+        P = np.cumsum(np.asarray(payload_lens, dtype=np.int64))
+        bw.put_fixed(P & ((1 << l) - 1) if l else P, l)
+        hi = (P >> l) + np.arange(n, dtype=np.int64)
+        bitmap = np.zeros(total, dtype=np.uint8)
+        bitmap[hi] = 1
+        bw.put_array(bitmap)
+    else:
+        P, s = [], 0
+        for L in payload_lens:
+            s += L
+            P.append(s)
+        for x in P:
+            bw.put(x, l)
+        if total:
+            bitmap = 0
+            for i, x in enumerate(P):
+                bitmap |= 1 << (total - 1 - ((x >> l) + i))
+            bw.put(bitmap, total)
     toc_bits, toc_bitlen = bw.value()
     out += uleb128_encode(len(toc_header))
     out += uleb128_encode(toc_bitlen)
@@ -367,7 +426,6 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
         return b"".join((head, memoryview(area)))       # one copy of the payload area
     # large payload areas: the container is filled in place by several threads (one copy, page faults spread over the cores)
     from .engine import _new_bytes, _par_copy
-    import numpy as np
     blob, sink = _new_bytes(len(head) + n_area)
     sink[:len(head)] = np.frombuffer(head, dtype=np.uint8)
     _par_copy(sink[len(head):], np.frombuffer(memoryview(area), dtype=np.uint8))

@@ -246,6 +246,12 @@ class Context:
         res = (out, poff, mids[:nb])
         return res + (sizes.reshape(-1, ncand)[:nb],) if want_sizes else res
 
+    def encode_blocks_stats(self):
+        """kolm_encode_blocks_stats: about the last encode_blocks call of this context"""
+        a = (C.c_int64 * 2)()
+        _lib.check(_lib.lib().kolm_encode_blocks_stats(self._h, a), "kolm_encode_blocks_stats")
+        return dict(repair_stopped_early=int(a[0]))
+
     def decode_blocks(self, profile: int, payload: torch.Tensor, pay_start, pay_len, method_ids, out_off, out: Optional[torch.Tensor] = None):
         """kolm_decode_blocks: the decode loop of decompress (KF.py:925-949 / V22.py:2530-2540) for a whole batch; block b's payload is
         payload[pay_start[b] : pay_start[b] + pay_len[b]].  Raises KolmError with .block = the lowest failing block index."""

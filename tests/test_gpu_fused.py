@@ -132,3 +132,39 @@ def test_dropins_fused_and_stagewise_paths_agree():
                 eng.fused = old
     assert res[(KF.__name__, True)] == res[(KF.__name__, False)] == O.kf_compress(data, 4096)
     assert res[(V.__name__, True)] == res[(V.__name__, False)]
+
+
+def test_repair_early_stop_leaves_the_selection_unchanged():
+    """kolm_encode_blocks without the size table stops the Re-Pair rounds of a block once a lower bound on the final payload
+    reaches the best other candidate (csrc/repair.cu; tests/test_repair_bound.py checks the bound itself): method ids, offsets and
+    payload bytes equal the call that runs every candidate to the end, and the oracle's selection; many blocks do stop early."""
+    import gpu_util as G
+    from kolmogorovlike_datacompressor_b200 import synth
+    mix = synth.s3_mix(8 << 20)
+    blocks = [b for b in _blocks() if b]
+    for kind in range(8):                                     # 2 KiB (the reference's default block size) ... 8 KiB blocks of every segment kind
+        seg = mix[kind << 20:(kind + 1) << 20].tobytes()
+        for k in range(24):
+            n = (2048, 2048, 2048, 1000, 4096, 8192)[k % 6]
+            blocks.append(seg[k * 40960:k * 40960 + n])
+    import random
+    rnd = random.Random(3)                                    # "word soup": a dozen random words repeated — Re-Pair beats LZ77 by a few bytes
+    for n in (2048, 3000, 5000, 8192, 2048, 6000):
+        words = [bytes(rnd.getrandbits(8) for _ in range(rnd.randint(3, 9))) for _ in range(12)]
+        blocks.append(b"".join(rnd.choice(words) for _ in range(n))[:n])
+    t, off = G.batch(blocks)
+    c = G.ctx()
+    full = c.encode_blocks(2, t, off, want_sizes=True)
+    assert c.encode_blocks_stats()["repair_stopped_early"] == 0
+    fast = c.encode_blocks(2, t, off)
+    stopped = c.encode_blocks_stats()["repair_stopped_early"]
+    assert np.array_equal(full[1], fast[1]) and np.array_equal(full[2], fast[2])
+    n = int(full[1][-1])
+    got = fast[0][:n].cpu().numpy().tobytes()
+    assert full[0][:n].cpu().numpy().tobytes() == got
+    assert stopped >= len(blocks) // 3, stopped
+    assert (np.asarray(fast[2]) == 9).any()                  # and Re-Pair still wins where it should
+    poff, mids = fast[1], fast[2]
+    for b in list(range(0, len(blocks), 5)) + list(range(len(blocks) - 6, len(blocks))):
+        mid, payload, _ = O.encode_block(2, blocks[b])
+        assert int(mids[b]) == mid and got[poff[b]:poff[b + 1]] == payload, b

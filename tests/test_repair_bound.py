@@ -1,0 +1,97 @@
+"""The lower bound behind the early stop of the Re-Pair candidate in kolm_encode_blocks (csrc/repair.cu, k_repair_enc):
+
+    final payload >= 7 + bytes of the rules made so far + sum over the DISTINCT adjacent pairs (x, y) of the current sequence of uleb(x)
+
+checked round by round on a plain restatement of repair_compress (kolm_final_researched_v2-2.py:1841-1911) whose payload must
+equal the oracle's.  CPU only: this is the arithmetic the kernel relies on, not the kernel."""
+import random
+
+import pytest
+
+import datasets
+from oracle import oracle as O
+
+
+def _uleb(v):
+    return 1 if v < 128 else 2 if v < 16384 else 3 if v < (1 << 21) else 4
+
+
+def _uleb_bytes(v):
+    out = bytearray()
+    while v >= 128:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def repair_with_bounds(block: bytes):
+    """-> (payload, [bound before every round, and before the final break])"""
+    seq = list(block)
+    rules = []
+    bounds = []
+    while True:
+        freq = {}
+        for i in range(len(seq) - 1):                       # _count_pairs: overlapping adjacencies
+            p = (seq[i], seq[i + 1])
+            freq[p] = freq.get(p, 0) + 1
+        if seq:
+            bounds.append(7 + sum(_uleb(a) + _uleb(b) for a, b in rules) + sum(_uleb(x) for x, _ in freq))
+        best, bf = None, 1
+        for p, f in freq.items():
+            if f > bf or (f == bf and best is not None and p < best):
+                best, bf = p, f
+        if best is None or bf < 2:
+            break
+        new, out, i, rep = 256 + len(rules), [], 0, 0
+        while i < len(seq):
+            if i + 1 < len(seq) and (seq[i], seq[i + 1]) == best:
+                out.append(new)
+                i += 2
+                rep += 1
+            else:
+                out.append(seq[i])
+                i += 1
+        if rep < 2:
+            break
+        rules.append(best)
+        seq = out
+    pay = bytearray(b"RP") + _uleb_bytes(256) + _uleb_bytes(len(rules))
+    for a, b in rules:
+        pay += _uleb_bytes(a) + _uleb_bytes(b)
+    pay += _uleb_bytes(len(seq))
+    for s in seq:
+        pay += _uleb_bytes(s)
+    return bytes(pay), bounds
+
+
+def _cases():
+    c = datasets.small_cases()
+    rnd = random.Random(11)
+    out = [v[:600] for k, v in sorted(c.items()) if v]
+    for n in (1, 2, 3, 17, 200, 700):
+        out.append(bytes(rnd.getrandbits(8) for _ in range(n)))
+        out.append(bytes(rnd.choice(b"ab") for _ in range(n)))
+        out.append(bytes(rnd.choice(b"\x80\x81\xfe\xff") for _ in range(n)))
+        out.append(bytes((i * 7) & 0xFF for i in range(n)))
+        out.append(b"\xaa" * n)
+    return out
+
+
+def test_bound_never_exceeds_the_final_payload():
+    checked = 0
+    for blk in _cases():
+        pay, bounds = repair_with_bounds(blk)
+        assert pay == O.repair_compress(blk), len(blk)
+        assert bounds and all(b <= len(pay) for b in bounds), (len(blk), max(bounds), len(pay))
+        checked += len(bounds)
+    assert checked > 1000
+
+
+def test_bound_is_tight_enough_to_matter():
+    """on incompressible bytes the bound passes the raw size long before the last round"""
+    rnd = random.Random(5)
+    blk = bytes(rnd.getrandbits(8) for _ in range(2048))
+    pay, bounds = repair_with_bounds(blk)
+    first = next(i for i, b in enumerate(bounds) if b >= len(blk))
+    assert first == 0 and len(bounds) > 20 and len(pay) > len(blk)
