@@ -733,7 +733,17 @@ def leg_default_blocks(env, args):
     # first call at this size: the engine's contexts, scratch and pinned buffers grow inside it (reported as *_cold); the second is the steady state
     tc = time.perf_counter(); V.compress_blocks_fixed(d_r, 2048); torch.cuda.synchronize(); cold_r = time.perf_counter() - tc
     t0 = time.perf_counter(); blob = V.compress_blocks_fixed(d_r, 2048); torch.cuda.synchronize(); t1 = time.perf_counter()
+    stopped = V._engine().ctx.encode_blocks_stats()["repair_stopped_early"]      # blocks whose Re-Pair rounds ended at the lower bound
     back = V.decompress(blob); t2 = time.perf_counter()
+    # the same bytes through the stage-by-stage path, where every candidate (Re-Pair included) runs to the end
+    eng = V._engine()
+    was, pre = eng.fused, d_r[:min(n_r, 8 * MIB)]
+    try:
+        part = V.compress_blocks_fixed(pre, 2048)
+        eng.fused = False
+        same_r = V.compress_blocks_fixed(pre, 2048) == part
+    finally:
+        eng.fused = was
     names, starts, plens, olens, _, _ = V._parse(blob)
     bad = [i for i, f in zip(picks, futs) if V.KOLR_NAMES[f.result()[0]] != names[i] or blob[starts[i]:starts[i] + plens[i]] != f.result()[1]]
     hist = {}
@@ -741,7 +751,8 @@ def leg_default_blocks(env, args):
         hist[nme] = hist.get(nme, 0) + 1
     out["kolr_2KiB"] = {"bytes": n_r, "blocks": len(names), "compress_MBps": round(n_r / (t1 - t0) / 1e6, 1), "compress_cold_MBps": round(n_r / cold_r / 1e6, 1),
                         "decompress_MBps": round(n_r / (t2 - t1) / 1e6, 1),
-                        "roundtrip_bit_exact": back == d_r, "container_bytes": len(blob), "methods": hist, "oracle_blocks": len(picks), "oracle_blocks_identical": not bad}
+                        "roundtrip_bit_exact": back == d_r, "container_bytes": len(blob), "methods": hist, "oracle_blocks": len(picks), "oracle_blocks_identical": not bad,
+                        "repair_stopped_early_blocks": int(stopped), "container_8MiB_equals_full_repair_path": bool(same_r)}
     d_m = data[:args.default_mib * MIB].tobytes()
     small = d_m[:2 * MIB]
     fut_c = pool.submit(O.kf_compress, small, 8192)                  # the oracle's whole container for a 2 MiB prefix
@@ -754,7 +765,7 @@ def leg_default_blocks(env, args):
                         "compress_cold_MBps": round(len(d_m) / cold_m / 1e6, 1),
                         "decompress_MBps": round(len(d_m) / (t2 - t1) / 1e6, 1), "roundtrip_bit_exact": back == d_m, "container_bytes": len(blob),
                         "oracle_container_2MiB_identical": bool(same)}
-    out["ok"] = bool(out["kolr_2KiB"]["roundtrip_bit_exact"] and not bad and out["kolm_8KiB"]["roundtrip_bit_exact"] and same)
+    out["ok"] = bool(out["kolr_2KiB"]["roundtrip_bit_exact"] and not bad and same_r and out["kolm_8KiB"]["roundtrip_bit_exact"] and same)
     return out
 
 

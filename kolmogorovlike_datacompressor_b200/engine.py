@@ -663,19 +663,22 @@ class Engine:
         if sink is None and on_batch is None and not lazy:           # 0 or 1 byte: CPython shares these objects, build them the ordinary way
             sink = np.zeros(int(ends[-1]), dtype=np.uint8)
         i = 0
-        while i < nb:                                                # output batches of <= batch_bytes
-            j, tot = i, 0
-            while j < nb and (j == i or tot + int(ols[j]) <= self.batch_bytes):
-                tot += int(ols[j])
-                j += 1
+        uniq = set(names)                                            # 61 440 blocks at the default block size: no per-block Python here
+        any_kf = any(nm.startswith("kf_") for nm in uniq)
+        any_v2 = "v2_new" in uniq
+        ends_l = np.asarray(ends, dtype=np.int64)
+        while i < nb:                                                # output batches of <= batch_bytes (at least one block)
+            done = int(ends_l[i - 1]) if i else 0
+            j = max(i + 1, int(np.searchsorted(ends_l, done + self.batch_bytes, side="right")))
+            tot = int(ends_l[j - 1]) - done
             base_off = int(ends[i] - ols[i])
             span0, span1 = int(starts[i]), int((starts[i:j] + plens[i:j]).max())
             with torch.cuda.device(self.device):
                 dev_out = torch.empty(max(tot, 4) + 16, dtype=torch.uint8, device=torch.device("cuda", self.device))
                 span = self._upload(blob, span0, max(span0, span1))
-                if self.fused and "v2_new" not in names[i:j]:
+                if self.fused and not (any_v2 and "v2_new" in names[i:j]):
                     # one kolm_decode_blocks call for the output batch (groups by method inside)
-                    kolm_prof = any(nm.startswith("kf_") for nm in names[i:j])
+                    kolm_prof = any_kf and any(nm.startswith("kf_") for nm in names[i:j])
                     ids = _KOLM_IDS if kolm_prof else _KOLR_IDS
                     try:
                         mids = np.array([ids[nm] for nm in names[i:j]], dtype=np.uint8)
