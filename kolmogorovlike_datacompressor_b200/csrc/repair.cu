@@ -20,16 +20,19 @@
 #define REPAIR_HASH 16384          // slots; load factor <= 0.5
 #define REPAIR_EMPTY 0xffffffffu
 
-// Two shapes of the same kernel: blocks of up to REPAIR_MAX symbols on 1024 threads and 160 KB (one CTA per SM), and blocks of up
-// to REPAIR_SMALL symbols — the reference's default 2 KiB blocks — on 256 threads and 41 KB, five CTAs per SM: the rounds are
-// bound by their dozen block barriers and the table sweeps, which shrink with the CTA, and five times as many blocks are in
-// flight (61 440 blocks of 2 KiB: 131 -> 30 ms per 32 MiB, KOLR compress at the default block size 107 -> 330 MB/s).
+// Three shapes of the same kernel, eight symbols per thread, 6 bytes of table per slot + 2 per symbol, 32 registers:
+//   up to 8192 symbols   1024 threads, 115 KB   two CTAs per SM
+//   up to 4096 symbols    512 threads,  58 KB   three
+//   up to 2048 symbols    256 threads,  29 KB   seven   (the reference's default block size)
+// The rounds are bound by their block barriers and the table sweep, which shrink with the CTA, and more blocks are in flight
+// (61 440 blocks of 2 KiB: 131 ms per 32 MiB on the one-CTA shape, 30 on the first small shape, 7 with the early stop).
 #define REPAIR_SMALL 2048
+#define REPAIR_MID 4096
 template <int MAXLEN, int THREADS, int HASH>
 struct RepairSmemT {
-    u16 seq[2][MAXLEN];
+    u16 seq[MAXLEN];                 // compacted in place (a thread's symbols wait in registers across the scan's barriers)
     u32 hkey[HASH];
-    u32 hcnt[HASH];
+    u32 hcnt2[HASH / 2];             // 16-bit counts (<= MAXLEN - 1), two per word: 6 bytes per slot let two 8 KiB CTAs share an SM
     u32 scan[THREADS / 32];
     u32 wlast[THREADS / 32];
     u32 wt[THREADS / 32];
@@ -60,7 +63,7 @@ __device__ __forceinline__ u8* rp_put_uleb(u8* p, u32 v) { while (v >= 128) { *p
 
 // out_tmp: per block a staging region of 4*len+64 bytes at tmp + 4*pbase; sizes[b] = payload bytes
 template <int MAXLEN, int THREADS, int HASH, int MINLEN>
-__global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
                                                         u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err,
                                                         const i64* __restrict__ limit) {
     extern __shared__ __align__(16) u8 smem_raw[];
@@ -72,10 +75,9 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
     if (bi.len > MAXLEN) { if (MAXLEN == REPAIR_MAX && tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }
     const u8* src = in + bi.ioff;
     u32* rules = rules_scratch + bi.pbase;                  // up to len/2 rules, (a<<16|b)
-    for (u32 i = tid; i < bi.len; i += THREADS) S.seq[0][i] = src[i];
+    for (u32 i = tid; i < bi.len; i += THREADS) S.seq[i] = src[i];
     if (tid == 0) S.m = bi.len;
-    __syncthreads();
-    u32 cur = 0, nrules = 0;
+    u32 nrules = 0;
     // Early stop (kolm_encode_blocks, limit != nullptr): limit[b] = the smallest size among the block's other candidates, all of
     // which precede Re-Pair in the list, so Re-Pair is selected only if its payload is SMALLER.  Whatever the remaining rounds do,
     //   payload >= 6 + (bytes of the rules made so far) + sum over the DISTINCT adjacent pairs (x, y) of the current sequence of
@@ -90,32 +92,46 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
     u32 rule_bytes = 0;
     bool stopped = false;
     constexpr u32 IPT = MAXLEN / THREADS;        // 8 consecutive positions per thread
+    // The pair table is emptied by the sweep that reads it (one pass and one barrier less per round than clearing it up front).
+    for (u32 i = tid; i < HASH; i += THREADS) { S.hkey[i] = REPAIR_EMPTY; if (i < HASH / 2) S.hcnt2[i] = 0; }
+    __syncthreads();
+    u16* const q = S.seq;
     for (;;) {
         const u32 m = S.m;
         if (m < 2) break;
-        // ---- pair histogram
-        for (u32 i = tid; i < HASH; i += THREADS) { S.hkey[i] = REPAIR_EMPTY; S.hcnt[i] = 0; }
+        // ---- pair histogram (every reader of last round's S.best is past a barrier; the barrier below publishes the reset)
         if (tid == 0) { S.best = 0; S.replaced = 0; S.wsum = 0; }
-        __syncthreads();
-        const u16* q = S.seq[cur];
         for (u32 i = tid; i + 1 < m; i += THREADS) {
             u32 key = ((u32)q[i] << 16) | q[i + 1];
             u32 h = rp_hash<HASH>(key);
             for (;;) {
                 u32 old = atomicCAS(&S.hkey[h], REPAIR_EMPTY, key);
-                if (old == REPAIR_EMPTY || old == key) { atomicAdd(&S.hcnt[h], 1u); break; }
+                if (old == REPAIR_EMPTY || old == key) { atomicAdd(&S.hcnt2[h >> 1], (h & 1u) ? 0x10000u : 1u); break; }
                 h = (h + 1) & (HASH - 1);
             }
         }
         __syncthreads();
+        // ---- best pair = max of (count << 32 | ~pair): per thread, per warp, one shared atomic per warp (one per qualifying slot
+        //      serialised thousands of 64-bit atomics on one address per round); the slots are emptied on the way
         u32 wloc = 0;                                        // ULEB bytes of the left symbols of my distinct pairs
-        for (u32 i = tid; i < HASH; i += THREADS) {
-            u32 k = S.hkey[i];
-            if (k != REPAIR_EMPTY) {
+        unsigned long long lbest = 0;
+        for (u32 j = tid; j < HASH / 2; j += THREADS) {      // slots 2j and 2j + 1: one 8-byte key load, one count word
+            const uint2 kk = reinterpret_cast<const uint2*>(S.hkey)[j];
+            if ((kk.x & kk.y) == REPAIR_EMPTY) continue;
+            const u32 cc = S.hcnt2[j];
+            reinterpret_cast<uint2*>(S.hkey)[j] = make_uint2(REPAIR_EMPTY, REPAIR_EMPTY); S.hcnt2[j] = 0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const u32 k = hh ? kk.y : kk.x, cnt = hh ? cc >> 16 : cc & 0xffffu;
+                if (k == REPAIR_EMPTY) continue;
                 wloc += 1u + ((k >> 16) >= 128u ? 1u : 0u);
-                if (S.hcnt[i] >= 2) atomicMax(&S.best, ((unsigned long long)S.hcnt[i] << 32) | (unsigned long long)(~k));
+                const unsigned long long v = ((unsigned long long)cnt << 32) | (unsigned long long)(~k);
+                if (cnt >= 2 && v > lbest) lbest = v;
             }
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, lbest, o); if (t > lbest) lbest = t; }
+        if ((tid & 31) == 0 && lbest) atomicMax(&S.best, lbest);
         if (limit) {
             wloc = __reduce_add_sync(0xffffffffu, wloc);
             if ((tid & 31) == 0 && wloc) atomicAdd(&S.wsum, wloc);
@@ -129,28 +145,35 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
         // ---- which occurrences are replaced: position i is "flagged" if pair(i) == best
         //      taken(i) = flagged(i) and (i - start of its maximal flagged run) is even
         u32 flags = 0, lastun = 0;                           // lastun: 1 + index of the last unflagged position among mine
+        u32 mine[IPT + 1];                                   // my IPT symbols and the next thread's first: the sequence is rewritten in place below
+#pragma unroll
+        for (u32 k = 0; k <= IPT; ++k) { const u32 i = tid * IPT + k; mine[k] = i < m ? (u32)q[i] : 0xffffu; }
 #pragma unroll
         for (u32 k = 0; k < IPT; ++k) {
             u32 i = tid * IPT + k;
-            bool f = (i + 1 < m) && ((((u32)q[i] << 16) | q[i + 1]) == bkey);
+            bool f = (i + 1 < m) && (((mine[k] << 16) | mine[k + 1]) == bkey);
             if (f) flags |= 1u << k; else lastun = i + 1;
         }
-        u32 incl = rp_scan<true, THREADS>(lastun, S.scan, nullptr);
-        u32 prevun = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive: last unflagged before my first item
-        if ((tid & 31) == 0) prevun = 0;
-        // cross-warp exclusive: recompute from the scan array is gone; do it with a second tiny scan on warp leaders
-        u32* s_wlast = S.wlast;
-        if ((tid & 31) == 31) s_wlast[tid >> 5] = incl;
-        __syncthreads();
-        if ((tid & 31) == 0 && tid) prevun = s_wlast[(tid >> 5) - 1];
-        __syncthreads();
-        u32 taken = 0, run0 = prevun;                        // run0 = first index of the current flagged run
-        u32 ntaken = 0;
+        u32 taken = 0, ntaken = 0;
+        if ((bkey >> 16) != (bkey & 0xffffu)) {              // a != b: two occurrences cannot overlap, every one is taken (no run bookkeeping, four barriers less)
+            taken = flags; ntaken = (u32)__popc(flags);
+        } else {
+            u32 incl = rp_scan<true, THREADS>(lastun, S.scan, nullptr);
+            u32 prevun = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive: last unflagged before my first item
+            if ((tid & 31) == 0) prevun = 0;
+            // cross-warp exclusive: recompute from the scan array is gone; do it with a second tiny scan on warp leaders
+            u32* s_wlast = S.wlast;
+            if ((tid & 31) == 31) s_wlast[tid >> 5] = incl;
+            __syncthreads();
+            if ((tid & 31) == 0 && tid) prevun = s_wlast[(tid >> 5) - 1];
+            __syncthreads();
+            u32 run0 = prevun;                               // run0 = first index of the current flagged run
 #pragma unroll
-        for (u32 k = 0; k < IPT; ++k) {
-            u32 i = tid * IPT + k;
-            if ((flags >> k) & 1u) { if (((i - run0) & 1u) == 0) { taken |= 1u << k; ++ntaken; } }
-            else run0 = i + 1;
+            for (u32 k = 0; k < IPT; ++k) {
+                u32 i = tid * IPT + k;
+                if ((flags >> k) & 1u) { if (((i - run0) & 1u) == 0) { taken |= 1u << k; ++ntaken; } }
+                else run0 = i + 1;
+            }
         }
         // removed(i) = taken(i-1): the second symbol of a replaced pair disappears
         u32 tprev = __shfl_up_sync(0xffffffffu, taken >> (IPT - 1), 1) & 1u;
@@ -162,22 +185,19 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
         u32 keep = 0;
 #pragma unroll
         for (u32 k = 0; k < IPT; ++k) { u32 i = tid * IPT + k; if (i < m && !((removed >> k) & 1u)) ++keep; }
-        u32 tot_taken;
-        u32 tincl = rp_scan<false, THREADS>(ntaken, S.scan, &tot_taken);
-        (void)tincl;
-        if (tot_taken < 2) break;                            // V22.py:1880-1882: rule not recorded, sequence unchanged
-        u32 newm;
-        u32 kincl = rp_scan<false, THREADS>(keep, S.scan, &newm);
-        u32 o = kincl - keep;
-        u16* nq = S.seq[cur ^ 1];
+        u32 tot;                                             // one scan for both counts: taken in the upper half, kept below (<= MAXLEN < 2^16)
+        const u32 pincl = rp_scan<false, THREADS>((ntaken << 16) | keep, S.scan, &tot);
+        if ((tot >> 16) < 2) break;                          // V22.py:1880-1882: rule not recorded, sequence unchanged
+        const u32 newm = tot & 0xffffu;
+        u32 o = (pincl & 0xffffu) - keep;
 #pragma unroll
-        for (u32 k = 0; k < IPT; ++k) {
+        for (u32 k = 0; k < IPT; ++k) {                      // in place: every thread read its symbols before the scan's barriers
             u32 i = tid * IPT + k;
-            if (i < m && !((removed >> k) & 1u)) nq[o++] = ((taken >> k) & 1u) ? (u16)newsym : q[i];
+            if (i < m && !((removed >> k) & 1u)) q[o++] = ((taken >> k) & 1u) ? (u16)newsym : (u16)mine[k];
         }
         if (tid == 0) { rules[nrules] = bkey; S.m = newm; }
         rule_bytes += rp_uleb_size(bkey >> 16) + rp_uleb_size(bkey & 0xffff);
-        ++nrules; cur ^= 1;
+        ++nrules;
         __syncthreads();
     }
     __syncthreads();
@@ -187,7 +207,6 @@ __global__ void __launch_bounds__(THREADS) k_repair_enc(const u8* __restrict__ i
     }
     // ---- serialise: 'R','P', ULEB 256, ULEB nrules, rules, ULEB len, symbols   (V22.py:1889-1903)
     const u32 m = S.m;
-    const u16* q = S.seq[cur];
     u8* dst = tmp + (size_t)bi.pbase * 4;
     u32& s_hdr = S.hdr;
     u32 rbytes = 0;
@@ -406,11 +425,18 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     if (big_max < 0) { const char* e = getenv("KOLM_REPAIR_BIG_MAX"); big_max = e ? atoll(e) : (1ll << 30); }
     if (c->max_len > REPAIR_MAX && (long long)c->max_len > big_max) return KOLM_E_UNSUPPORTED;
     typedef RepairSmemT<REPAIR_SMALL, 256, 4096> RepairSmemSmall;
+    typedef RepairSmemT<REPAIR_MID, 512, 8192> RepairSmemMid;
     static bool attr_set[64];
     if (c->device < 64 && !attr_set[c->device]) {
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
-        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MID, 512, 8192, REPAIR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmemMid)));
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_SMALL, 256, 4096, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmemSmall)));
+        // all of the SM's shared memory for these kernels: two CTAs of the 115 KB shape only fit the largest carve-out
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_MID>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MID, 512, 8192, REPAIR_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_SMALL, 256, 4096, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[c->device] = true;
     }
     static int small_on = -1;
@@ -418,9 +444,10 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     CUDA_TRY(cudaMemsetAsync(c->d_bacc, 0, (size_t)nb * 64 * 8, s));
     u8* tmp = (u8*)c->d_k0;                                   // 4 bytes per padded element
     if (small_on) {
-        // blocks of up to 2 KiB on the small shape (five CTAs per SM), the others (if any) on the 160 KB shape
+        // blocks of up to 2 KiB on the small shape (five CTAs per SM), up to 4 KiB on the middle one (two), the others (if any) on the 160 KB shape
         KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_SMALL, 256, 4096, 0><<<nb, 256, sizeof(RepairSmemSmall), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
-        if (c->max_len > REPAIR_SMALL) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_SMALL><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
+        if (c->max_len > REPAIR_SMALL) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MID, 512, 8192, REPAIR_SMALL><<<nb, 512, sizeof(RepairSmemMid), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
+        if (c->max_len > REPAIR_MID) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_MID><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
     } else
     KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
     if (c->max_len > REPAIR_MAX) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
