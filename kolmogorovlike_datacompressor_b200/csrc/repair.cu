@@ -37,7 +37,7 @@ struct RepairSmemT {
     u32 wlast[THREADS / 32];
     u32 wt[THREADS / 32];
     unsigned long long best;
-    u32 replaced, m, hdr, wsum;
+    u32 nhigh, m, hdr, wsum;
 };
 typedef RepairSmemT<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH> RepairSmem;
 
@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     if (bi.len > MAXLEN) { if (MAXLEN == REPAIR_MAX && tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }
     const u8* src = in + bi.ioff;
     u32* rules = rules_scratch + bi.pbase;                  // up to len/2 rules, (a<<16|b)
-    for (u32 i = tid; i < bi.len; i += THREADS) S.seq[i] = src[i];
-    if (tid == 0) S.m = bi.len;
+    u32 high = 0;                                            // bytes >= 128: two ULEB bytes each
+    for (u32 i = tid; i < bi.len; i += THREADS) { const u8 v = src[i]; S.seq[i] = v; high += v >> 7; }
+    if (tid == 0) { S.m = bi.len; S.nhigh = 0; }
     u32 nrules = 0;
     // Early stop (kolm_encode_blocks, limit != nullptr): limit[b] = the smallest size among the block's other candidates, all of
     // which precede Re-Pair in the list, so Re-Pair is selected only if its payload is SMALLER.  Whatever the remaining rounds do,
@@ -88,6 +89,15 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     // nonterminal (a larger id: at least as many ULEB bytes), each such symbol is written once per boundary, the last symbol of the
     // final sequence costs a byte more, and 'RP', ULEB(256) and the two counts take at least 6.  Once the bound reaches limit[b]
     // the candidate cannot win: the block is marked (bacc slot 34) and its size reported as "not evaluated".
+    // A second bound from the byte count itself.  With n1 one-byte and n2 two-byte symbols in the sequence (every nonterminal of a
+    // block of <= 8 KiB has a two-byte id) the payload is 6 + rules + n1 + 2 n2 + what the counts need, and a round that replaces
+    // r occurrences of (a, b) changes it by -(r (ca + cb - 2) - (ca + cb)): nothing is gained on (1,1) pairs, r - 3 on mixed ones,
+    // 2r - 4 on (2,2) pairs.  The largest pair count f never rises (new adjacencies contain the new symbol, which occurs r <= f
+    // times), so every later round has r <= f; one-byte symbols are never created (x replacements of (1,1) pairs and y of mixed
+    // pairs use 2x + y <= n1 of them) and z replacements of (2,2) pairs need z <= n2 + x two-byte symbols; each round pays for its
+    // rule.  Maximising y (1 - 3/f) + z (2 - 4/f) - x 2/f under these constraints gives at most n1 (1 - 3/f) + n2 (2 - 4/f), i.e.
+    //   payload >= 6 + rules + (3 n1 + 4 n2) / f   for f >= 3   (f = 2: 6 + rules + n1 + 2 n2)
+    // which ends blocks of high bytes (sine waves, noise) long before the pair bound does.
     const i64 lim = limit ? limit[b] : (i64)0x7fffffffffffffffll;
     u32 rule_bytes = 0;
     bool stopped = false;
@@ -95,12 +105,16 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     // The pair table is emptied by the sweep that reads it (one pass and one barrier less per round than clearing it up front).
     for (u32 i = tid; i < HASH; i += THREADS) { S.hkey[i] = REPAIR_EMPTY; if (i < HASH / 2) S.hcnt2[i] = 0; }
     __syncthreads();
+    high = __reduce_add_sync(0xffffffffu, high);
+    if ((tid & 31) == 0 && high) atomicAdd(&S.nhigh, high);
+    __syncthreads();
+    u32 n2 = S.nhigh, n1 = bi.len - n2;                      // one- and two-byte symbols of the sequence (kept by every thread)
     u16* const q = S.seq;
     for (;;) {
         const u32 m = S.m;
         if (m < 2) break;
         // ---- pair histogram (every reader of last round's S.best is past a barrier; the barrier below publishes the reset)
-        if (tid == 0) { S.best = 0; S.replaced = 0; S.wsum = 0; }
+        if (tid == 0) { S.best = 0; S.wsum = 0; }
         for (u32 i = tid; i + 1 < m; i += THREADS) {
             u32 key = ((u32)q[i] << 16) | q[i + 1];
             u32 h = rp_hash<HASH>(key);
@@ -139,7 +153,10 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
         __syncthreads();
         const unsigned long long best = S.best;
         if ((u32)(best >> 32) < 2) break;                    // V22.py:1875-1876
-        if (limit && (i64)(7u + rule_bytes + S.wsum) >= lim) { stopped = true; break; }
+        if (limit) {
+            const i64 f = (i64)(best >> 32), gain = (i64)n1 * (f > 3 ? f - 3 : 0) + (i64)n2 * (2 * f - 4);
+            if ((i64)(7u + rule_bytes + S.wsum) >= lim || f * (i64)(6u + rule_bytes + n1 + 2u * n2) - gain >= f * lim) { stopped = true; break; }
+        }
         const u32 bkey = ~(u32)best;
         const u32 newsym = 256 + nrules;
         // ---- which occurrences are replaced: position i is "flagged" if pair(i) == best
@@ -196,7 +213,12 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
             if (i < m && !((removed >> k) & 1u)) q[o++] = ((taken >> k) & 1u) ? (u16)newsym : (u16)mine[k];
         }
         if (tid == 0) { rules[nrules] = bkey; S.m = newm; }
-        rule_bytes += rp_uleb_size(bkey >> 16) + rp_uleb_size(bkey & 0xffff);
+        {
+            const u32 ca = rp_uleb_size(bkey >> 16), cb = rp_uleb_size(bkey & 0xffff), r = tot >> 16;
+            rule_bytes += ca + cb;
+            n1 -= r * ((ca == 1u) + (cb == 1u));
+            n2 = n2 + r - r * ((ca == 2u) + (cb == 2u));
+        }
         ++nrules;
         __syncthreads();
     }

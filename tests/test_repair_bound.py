@@ -1,6 +1,8 @@
-"""The lower bound behind the early stop of the Re-Pair candidate in kolm_encode_blocks (csrc/repair.cu, k_repair_enc):
+"""The lower bounds behind the early stop of the Re-Pair candidate in kolm_encode_blocks (csrc/repair.cu, k_repair_enc):
 
     final payload >= 7 + bytes of the rules made so far + sum over the DISTINCT adjacent pairs (x, y) of the current sequence of uleb(x)
+    final payload >= 6 + bytes of the rules made so far + (3 n1 + 4 n2) / f     (n1 / n2 one- / two-byte symbols in the sequence,
+                                                                                 f = the largest pair count, f >= 3; blocks <= 8 KiB)
 
 checked round by round on a plain restatement of repair_compress (kolm_final_researched_v2-2.py:1841-1911) whose payload must
 equal the oracle's.  CPU only: this is the arithmetic the kernel relies on, not the kernel."""
@@ -26,10 +28,11 @@ def _uleb_bytes(v):
 
 
 def repair_with_bounds(block: bytes):
-    """-> (payload, [bound before every round, and before the final break])"""
+    """-> (payload, [pair bound before every round, and before the final break], [(f, f * payload bound 2) before every round])"""
     seq = list(block)
     rules = []
     bounds = []
+    bounds2 = []
     while True:
         freq = {}
         for i in range(len(seq) - 1):                       # _count_pairs: overlapping adjacencies
@@ -43,6 +46,10 @@ def repair_with_bounds(block: bytes):
                 best, bf = p, f
         if best is None or bf < 2:
             break
+        n1 = sum(1 for v in seq if v < 128)
+        n2 = len(seq) - n1
+        gain = n1 * max(bf - 3, 0) + n2 * (2 * bf - 4)
+        bounds2.append((bf, bf * (6 + sum(_uleb(a) + _uleb(b) for a, b in rules) + n1 + 2 * n2) - gain))
         new, out, i, rep = 256 + len(rules), [], 0, 0
         while i < len(seq):
             if i + 1 < len(seq) and (seq[i], seq[i + 1]) == best:
@@ -62,7 +69,7 @@ def repair_with_bounds(block: bytes):
     pay += _uleb_bytes(len(seq))
     for s in seq:
         pay += _uleb_bytes(s)
-    return bytes(pay), bounds
+    return bytes(pay), bounds, bounds2
 
 
 def _cases():
@@ -81,9 +88,11 @@ def _cases():
 def test_bound_never_exceeds_the_final_payload():
     checked = 0
     for blk in _cases():
-        pay, bounds = repair_with_bounds(blk)
+        pay, bounds, bounds2 = repair_with_bounds(blk)
         assert pay == O.repair_compress(blk), len(blk)
         assert bounds and all(b <= len(pay) for b in bounds), (len(blk), max(bounds), len(pay))
+        assert all(fb <= f * len(pay) for f, fb in bounds2), (len(blk), len(pay))
+        assert all(bounds2[i][0] >= bounds2[i + 1][0] for i in range(len(bounds2) - 1))      # the largest count never rises
         checked += len(bounds)
     assert checked > 1000
 
@@ -92,6 +101,16 @@ def test_bound_is_tight_enough_to_matter():
     """on incompressible bytes the bound passes the raw size long before the last round"""
     rnd = random.Random(5)
     blk = bytes(rnd.getrandbits(8) for _ in range(2048))
-    pay, bounds = repair_with_bounds(blk)
+    pay, bounds, bounds2 = repair_with_bounds(blk)
     first = next(i for i, b in enumerate(bounds) if b >= len(blk))
     assert first == 0 and len(bounds) > 20 and len(pay) > len(blk)
+    # 8 KiB of the S3 mix's sine segment (high bytes, few distinct pairs at first): the pair bound needs 848 of the 3696 rounds,
+    # the byte-count bound under a hundred
+    from kolmogorovlike_datacompressor_b200 import synth
+    blk = synth.s3_mix(8 << 20)[3 << 20:(3 << 20) + 8192].tobytes()
+    pay, bounds, bounds2 = repair_with_bounds(blk)
+    assert pay == O.repair_compress(blk) and len(pay) > len(blk)
+    assert all(b <= len(pay) for b in bounds) and all(fb <= f * len(pay) for f, fb in bounds2)
+    t1 = next((i for i, b in enumerate(bounds) if b >= len(blk)), len(bounds))
+    t2 = next((i for i, (f, fb) in enumerate(bounds2) if fb >= f * len(blk)), len(bounds2))
+    assert t2 < len(bounds2) and t2 * 4 < t1, (t1, t2, len(bounds))
