@@ -534,47 +534,45 @@ class S3Corpus:
         return self.get(k)[a:b]                                      # a view: the engine uploads straight from it
 
 
-def leg_cfg4(env, args):
-    """BASELINE cfg 4: the full kolm_final_researched_v2-2 pipeline (compress_blocks_fixed + decompress, all ten candidates exact, TOC
-    on the host) on a corpus of 1 GiB S3 containers at 1 MiB blocks, block-sharded over the N GPUs of the run.  Strong scaling: the
-    corpus is the same at every N; the timed region holds each rank's load of its own bytes, the encode, the NCCL table all_gather and
-    payload gather, rank 0's D2H and container assembly."""
-    import numpy as np
-    torch, dist = env.torch, env.dist
+def _cfg4_pass(env, sizes, load, get, bs, what):
+    """One compress + decompress of the corpus (sizes[k] bytes of container k from load(k, a, b) / get(k)) at block size bs, sharded by
+    blocks over the ranks of the run; see leg_cfg4."""
+    torch = env.torch
     from kolmogorovlike_datacompressor_b200 import dist as kd
     from kolmogorovlike_datacompressor_b200 import kolm_final_researched_v2_2 as V
     from oracle import oracle as O
-    ncont, cbytes, bs = args.cfg4_containers, args.cfg4_container_mib * MIB, MIB
-    corp = S3Corpus(ncont, cbytes)
-    blocks = kd.corpus_blocks(corp.sizes, bs)
+    ncont, cbytes = len(sizes), sizes[0]
+    blocks = kd.corpus_blocks(sizes, bs)
     parts = kd.partition_blocks(kd._virtual_bounds(blocks), env.world)
     b0, b1 = parts[env.rank]
     for k in sorted({blocks[i][0] for i in range(b0, b1)}):          # generation is not part of the path: before the clock
-        corp.get(k)
-    total = sum(corp.sizes)
-    # sampled oracle expectation (rank 0): the first eight blocks of container 0 = one of every S3 segment kind
+        get(k)
+    total = sum(sizes)
+    # sampled oracle expectation (rank 0): 1 MiB blocks: the first eight blocks of container 0 = one of every S3 segment kind;
+    # smaller blocks: one block out of each of the first eight MiB
     import concurrent.futures as cf
     pool = cf.ThreadPoolExecutor(max_workers=8)
-    nchk = min(8, len(blocks)) if env.rank == 0 else 0
-    futs = [pool.submit(O.encode_block, O.PROFILE_KOLR, corp.get(0)[blocks[i][1]:blocks[i][2]].tobytes(), None, True) for i in range(nchk)]
+    step = max(1, MIB // bs)
+    picks = [i * step + (5 if step > 1 else 0) for i in range(8) if i * step + 5 < len(blocks) and blocks[i * step + 5][0] == 0] if env.rank == 0 else []
+    futs = [pool.submit(O.encode_block, O.PROFILE_KOLR, get(0)[blocks[i][1]:blocks[i][2]].tobytes(), None, True) for i in picks]
     # warm-up on a small corpus: contexts, the Re-Pair slab pool, NCCL connections
     kfirst = blocks[b0][0] if b1 > b0 else 0
-    wconts = kd.compress_kolr_fixed_corpus([min(cbytes, 16 * env.world * MIB)], lambda k, a, b: corp.get(kfirst)[a:b], bs)
+    wconts = kd.compress_kolr_fixed_corpus([min(cbytes, 16 * env.world * MIB)], lambda k, a, b: get(kfirst)[a:b], bs)
     kd.decompress_kolr_corpus(wconts, gather=False)                  # ... and the rank 0 -> rank r connections of the payload scatter
     env.barrier()
     st = {}
     e0, e1 = ev_pair(torch)
     t0 = time.perf_counter()
     e0.record()
-    conts = kd.compress_kolr_fixed_corpus(corp.sizes, corp.load, bs, stats=st)
+    conts = kd.compress_kolr_fixed_corpus(sizes, load, bs, stats=st)
     e1.record()
     env.barrier()
     wall = env.gmax(time.perf_counter() - t0)
     ev_s = env.gmax(e0.elapsed_time(e1) / 1e3)
     # the same keys on every rank (each gmax is a collective): ranks other than 0 have no D2H / assembly phase
     phases = {k: round(env.gmax(st.get(k, 0.0)), 4) for k in ("load_s", "encode_s", "table_allgather_s", "payload_exchange_s", "d2h_s", "assemble_s")}
-    out = {"workload": f"{ncont} containers x {cbytes // MIB} MiB of the S3 mix, fixed 1 MiB blocks, all ten candidates exact; one corpus "
-                       f"sharded by blocks over {env.world} GPU(s) (strong scaling)", "n_gpus": env.world, "scaling": "strong",
+    out = {"workload": f"{ncont} containers x {cbytes // MIB} MiB of the S3 mix, {what}, all ten candidates exact; one corpus "
+                       f"sharded by blocks over {env.world} GPU(s) (strong scaling)", "n_gpus": env.world, "scaling": "strong", "block_bytes": bs,
            "corpus_bytes": total, "compress_MBps": round(total / wall / 1e6, 1), "compress_s": round(wall, 3), "compress_s_cuda_events_max_over_ranks": round(ev_s, 3),
            "compress_phases_s_max_over_ranks": phases, "nccl_exchanged_bytes": int(st.get("exchanged_bytes", 0)) if env.rank == 0 else None}
     # decompress: containers live on rank 0; payload spans are scattered over NCCL, every rank decodes its block range (sharded output)
@@ -586,9 +584,10 @@ def leg_cfg4(env, args):
     dwall = env.gmax(time.perf_counter() - t0)
     ok = True
     for k, a, b, y in pieces:
-        ref = torch.from_numpy(corp.get(k)[a:b]).cuda()
+        ref = torch.from_numpy(get(k)[a:b]).cuda()
         ok = ok and bool(torch.equal(ref, y[:b - a]))
         del ref
+    del pieces
     out.update({"decompress_MBps": round(total / dwall / 1e6, 1), "decompress_s": round(dwall, 3), "decompress_output": "sharded (each rank keeps its block range on its GPU)",
                 "decompress_phases_s_max_over_ranks": {k: round(env.gmax(dst_.get(k, 0.0)), 4) for k in ("toc_s", "h2d_s", "payload_scatter_s", "decode_s")},
                 "roundtrip_bit_exact": env.gall(ok)})
@@ -608,16 +607,43 @@ def leg_cfg4(env, args):
             hist[nme] = hist.get(nme, 0) + 1
         out["container0_methods"] = hist
         bad = []
-        for i, f in enumerate(futs):
+        for i, f in zip(picks, futs):
             mid, payload, _sizes = f.result()
             if V.KOLR_NAMES[mid] != names[i] or conts[0][starts[i]:starts[i] + plens[i]] != payload:
                 bad.append(i)
-        out["oracle_blocks"] = nchk
+        out["oracle_blocks"] = len(picks)
         out["oracle_blocks_identical"] = not bad
         if bad:
             out["oracle_mismatch_blocks"] = bad
         out["limiting_phase"] = max(phases.items(), key=lambda kv: kv[1])[0] if phases else None
     out["ok"] = bool(out["roundtrip_bit_exact"]) and (env.rank != 0 or (out.get("oracle_blocks_identical", True) and out.get("sha_equals_single_gpu") is not False))
+    return out
+
+
+def leg_cfg4(env, args):
+    """BASELINE cfg 4: the full kolm_final_researched_v2-2 pipeline (compress_blocks_fixed + decompress, all ten candidates exact, TOC
+    on the host) on a corpus of 1 GiB S3 containers, block-sharded over the N GPUs of the run — at 1 MiB blocks and, on the same bytes
+    cut into 256 MiB containers, at the block size compress_blocks_fixed defaults to (8 KiB, V22.py:2332).  Strong scaling: the
+    corpus is the same at every N; the timed region holds each rank's load of its own bytes, the encode, the NCCL table all_gather and
+    payload gather, rank 0's D2H and container assembly."""
+    torch = env.torch
+    from oracle import oracle as O
+    import concurrent.futures as cf
+    pool = cf.ThreadPoolExecutor(max_workers=8)
+    ncont, cbytes = args.cfg4_containers, args.cfg4_container_mib * MIB
+    corp = S3Corpus(ncont, cbytes)
+    out = _cfg4_pass(env, corp.sizes, corp.load, corp.get, MIB, "fixed 1 MiB blocks")
+    if args.cfg4_default_block > 0:
+        # the same corpus as containers of at most 256 MiB (a KOLR container holds at most 65 535 blocks)
+        sub = min(cbytes, 256 * MIB)
+        per = (cbytes + sub - 1) // sub
+        sizes2 = [min(sub, cbytes - (j % per) * sub) for j in range(ncont * per)]
+        get2 = lambda j: corp.get(j // per)[(j % per) * sub:(j % per) * sub + sizes2[j]]
+        env.torch.cuda.empty_cache()
+        small = _cfg4_pass(env, sizes2, lambda j, a, b: get2(j)[a:b], get2, args.cfg4_default_block,
+                           "fixed %d-byte blocks (the default of compress_blocks_fixed)" % args.cfg4_default_block)
+        out["default_block"] = small
+        out["ok"] = out["ok"] and small["ok"]
     # KOLM (kolm_final.compress / decompress) on one GPU: N = 1 only
     if env.world == 1 and args.kolm_mib > 0:
         from kolmogorovlike_datacompressor_b200 import kolm_final as KF
@@ -854,6 +880,7 @@ def main():
     ap.add_argument("--cfg3-mib", type=int, default=256)
     ap.add_argument("--cfg4-containers", type=int, default=4, help="containers of the sharded S3 corpus (BASELINE cfg 4: 4 x 1 GiB)")
     ap.add_argument("--cfg4-container-mib", type=int, default=1024)
+    ap.add_argument("--cfg4-default-block", type=int, default=8192, help="second pass of the cfg-4 leg at this block size (0 = skip)")
     ap.add_argument("--kolm-mib", type=int, default=256, help="KOLM drop-in leg on this many MiB (N = 1; 0 = skip)")
     ap.add_argument("--cfg5-mib", type=int, default=512, help="cfg 5 corpus MiB per GPU")
     ap.add_argument("--default-mib", type=int, default=120, help="corpus MiB of the default-block-size leg (N = 1)")

@@ -64,3 +64,74 @@ def test_truncated_toc_raises_like_the_scalar_walk():
         bad[i] = 0
     with pytest.raises((ValueError, IndexError, KeyError)):
         V._parse(bytes(bad))
+
+
+class _SlowBits:
+    """the TOC bit writer as one growing integer (what _BitWriter.getvalue_bits of the reference amounts to): the linear-time
+    writer and its array appends must produce the same bytes"""
+
+    def __init__(self):
+        self.acc, self.n = 0, 0
+
+    def put(self, val, k):
+        if k:
+            self.acc = (self.acc << k) | (val & ((1 << k) - 1))
+            self.n += k
+
+    def unary(self, q):
+        self.acc = (self.acc << (q + 1)) | (((1 << q) - 1) << 1)
+        self.n += q + 1
+
+    def rice(self, seq, k):
+        for v in seq:
+            self.unary(v >> k)
+            self.put(v, k)
+
+    def put_array(self, bits):
+        for b in np.asarray(bits).tolist():
+            self.put(int(b), 1)
+
+    def put_fixed(self, vals, k):
+        for v in np.asarray(vals).tolist():
+            self.put(int(v), k)
+
+    def value(self):
+        nbytes = (self.n + 7) // 8
+        return (self.acc << (nbytes * 8 - self.n)).to_bytes(nbytes, "big"), self.n
+
+
+@pytest.mark.parametrize("mode", [V.MODE_FIXED, V.MODE_CDC])
+@pytest.mark.parametrize("nblocks,spread", [(1, 1), (2, 70000), (65, 3), (700, 1), (700, 4000), (3000, 300)])
+def test_linear_time_toc_writer_equals_big_integer_writer(mode, nblocks, spread, monkeypatch):
+    rnd = random.Random(nblocks * 11 + spread + mode)
+    fast, mids, plens, lens = _container(rnd, nblocks, mode, spread)
+    rnd = random.Random(nblocks * 11 + spread + mode)
+    monkeypatch.setattr(V, "_Bits", _SlowBits)
+    slow, mids2, plens2, lens2 = _container(rnd, nblocks, mode, spread)
+    assert (mids, plens, lens) == (mids2, plens2, lens2)
+    assert fast == slow
+
+
+def test_bit_writer_pieces():
+    rnd = random.Random(9)
+    for _ in range(200):
+        a, b = _SlowBits(), V._Bits()
+        b._FLUSH = rnd.choice([8, 64, 4096])
+        for _ in range(rnd.randint(0, 40)):
+            op = rnd.randrange(5)
+            if op == 0:
+                k = rnd.choice([0, 1, 7, 8, 13, 64, 300, 5000]); v = rnd.getrandbits(k + 2)
+                a.put(v, k); b.put(v, k)
+            elif op == 1:
+                q = rnd.choice([0, 1, 9, 70, 9000]); a.unary(q); b.unary(q)
+            elif op == 2:
+                seq = [rnd.randrange(300) for _ in range(rnd.randrange(20))]; k = rnd.randrange(8)
+                a.rice(seq, k); b.rice(seq, k)
+            elif op == 3:
+                bits = np.array([rnd.randrange(2) for _ in range(rnd.choice([0, 1, 5, 8, 9, 64, 1001]))], dtype=np.uint8)
+                a.put_array(bits); b.put_array(bits)
+            else:
+                k = rnd.choice([0, 1, 5, 13, 40, 62])
+                vals = np.array([rnd.getrandbits(max(k, 1)) for _ in range(rnd.randrange(30))], dtype=np.int64)
+                a.put_fixed(vals, k); b.put_fixed(vals, k)
+        assert a.value() == b.value()
