@@ -671,7 +671,8 @@ def leg_cfg4(env, args):
 
 # sha256 of the concatenated containers of leg_cfg4 produced on ONE GPU, keyed by (containers, bytes per container, block bytes):
 # recorded from single-GPU runs of this same code; the N-GPU runs must reproduce them byte for byte.
-KNOWN_SHA = {(4, 1024 * MIB, MIB): "191da9d501138af8f8d8dfe557c959b7e8456eb42f3770621f73c18d69386ce0"}
+KNOWN_SHA = {(4, 1024 * MIB, MIB): "191da9d501138af8f8d8dfe557c959b7e8456eb42f3770621f73c18d69386ce0",
+             (16, 256 * MIB, 8192): "8d8c5c53063db0f5a2c523aa59e2d0653ac8b784ce7d5b28edb424d5aed6dcdc"}
 
 
 def leg_cfg5(env, args):
@@ -758,10 +759,31 @@ def leg_default_blocks(env, args):
     V.compress_blocks_fixed(d_r[:4 * MIB], 2048)
     # first call at this size: the engine's contexts, scratch and pinned buffers grow inside it (reported as *_cold); the second is the steady state
     tc = time.perf_counter(); V.compress_blocks_fixed(d_r, 2048); torch.cuda.synchronize(); cold_r = time.perf_counter() - tc
-    t0 = time.perf_counter(); blob = V.compress_blocks_fixed(d_r, 2048); torch.cuda.synchronize(); t1 = time.perf_counter()
+    runs_r = []
+    for _ in range(2):                                               # steady state: the faster of two calls (host-side noise is one-sided)
+        t0 = time.perf_counter(); blob = V.compress_blocks_fixed(d_r, 2048); torch.cuda.synchronize(); runs_r.append(time.perf_counter() - t0)
     stopped = V._engine().ctx.encode_blocks_stats()["repair_stopped_early"]      # blocks whose Re-Pair rounds ended at the lower bound
-    back = V.decompress(blob); t2 = time.perf_counter()
-    # the same bytes through the stage-by-stage path, where every candidate (Re-Pair included) runs to the end
+    t1 = time.perf_counter(); back = V.decompress(blob); t2 = time.perf_counter()
+    names, starts, plens, olens, _, _ = V._parse(blob)
+    bad = [i for i, f in zip(picks, futs) if V.KOLR_NAMES[f.result()[0]] != names[i] or blob[starts[i]:starts[i] + plens[i]] != f.result()[1]]
+    hist = {}
+    for nme in names:
+        hist[nme] = hist.get(nme, 0) + 1
+    out["kolr_2KiB"] = {"bytes": n_r, "blocks": len(names), "compress_MBps": round(n_r / min(runs_r) / 1e6, 1), "compress_runs_MBps": [round(n_r / t / 1e6, 1) for t in runs_r],
+                        "compress_cold_MBps": round(n_r / cold_r / 1e6, 1), "decompress_MBps": round(n_r / (t2 - t1) / 1e6, 1),
+                        "roundtrip_bit_exact": back == d_r, "container_bytes": len(blob), "methods": hist, "oracle_blocks": len(picks), "oracle_blocks_identical": not bad,
+                        "repair_stopped_early_blocks": int(stopped)}
+    d_m = data[:args.default_mib * MIB].tobytes()
+    small = d_m[:2 * MIB]
+    fut_c = pool.submit(O.kf_compress, small, 8192)                  # the oracle's whole container for a 2 MiB prefix
+    KF.compress(d_m[:4 * MIB], 8192)
+    tc = time.perf_counter(); KF.compress(d_m, 8192); torch.cuda.synchronize(); cold_m = time.perf_counter() - tc
+    runs_m = []
+    for _ in range(2):
+        t0 = time.perf_counter(); blob = KF.compress(d_m, 8192); torch.cuda.synchronize(); runs_m.append(time.perf_counter() - t0)
+    t1 = time.perf_counter(); back = KF.decompress(blob); t2 = time.perf_counter()
+    same = KF.compress(small, 8192) == fut_c.result()
+    # KOLR again on an 8 MiB prefix: the fused call (Re-Pair stops early) against the stage-by-stage path (every candidate to the end)
     eng = V._engine()
     was, pre = eng.fused, d_r[:min(n_r, 8 * MIB)]
     try:
@@ -770,25 +792,9 @@ def leg_default_blocks(env, args):
         same_r = V.compress_blocks_fixed(pre, 2048) == part
     finally:
         eng.fused = was
-    names, starts, plens, olens, _, _ = V._parse(blob)
-    bad = [i for i, f in zip(picks, futs) if V.KOLR_NAMES[f.result()[0]] != names[i] or blob[starts[i]:starts[i] + plens[i]] != f.result()[1]]
-    hist = {}
-    for nme in names:
-        hist[nme] = hist.get(nme, 0) + 1
-    out["kolr_2KiB"] = {"bytes": n_r, "blocks": len(names), "compress_MBps": round(n_r / (t1 - t0) / 1e6, 1), "compress_cold_MBps": round(n_r / cold_r / 1e6, 1),
-                        "decompress_MBps": round(n_r / (t2 - t1) / 1e6, 1),
-                        "roundtrip_bit_exact": back == d_r, "container_bytes": len(blob), "methods": hist, "oracle_blocks": len(picks), "oracle_blocks_identical": not bad,
-                        "repair_stopped_early_blocks": int(stopped), "container_8MiB_equals_full_repair_path": bool(same_r)}
-    d_m = data[:args.default_mib * MIB].tobytes()
-    small = d_m[:2 * MIB]
-    fut_c = pool.submit(O.kf_compress, small, 8192)                  # the oracle's whole container for a 2 MiB prefix
-    KF.compress(d_m[:4 * MIB], 8192)
-    tc = time.perf_counter(); KF.compress(d_m, 8192); torch.cuda.synchronize(); cold_m = time.perf_counter() - tc
-    t0 = time.perf_counter(); blob = KF.compress(d_m, 8192); torch.cuda.synchronize(); t1 = time.perf_counter()
-    back = KF.decompress(blob); t2 = time.perf_counter()
-    same = KF.compress(small, 8192) == fut_c.result()
-    out["kolm_8KiB"] = {"bytes": len(d_m), "blocks": int.from_bytes(blob[16:18], "little"), "compress_MBps": round(len(d_m) / (t1 - t0) / 1e6, 1),
-                        "compress_cold_MBps": round(len(d_m) / cold_m / 1e6, 1),
+    out["kolr_2KiB"]["container_8MiB_equals_full_repair_path"] = bool(same_r)
+    out["kolm_8KiB"] = {"bytes": len(d_m), "blocks": int.from_bytes(blob[16:18], "little"), "compress_MBps": round(len(d_m) / min(runs_m) / 1e6, 1),
+                        "compress_runs_MBps": [round(len(d_m) / t / 1e6, 1) for t in runs_m], "compress_cold_MBps": round(len(d_m) / cold_m / 1e6, 1),
                         "decompress_MBps": round(len(d_m) / (t2 - t1) / 1e6, 1), "roundtrip_bit_exact": back == d_m, "container_bytes": len(blob),
                         "oracle_container_2MiB_identical": bool(same)}
     out["ok"] = bool(out["kolr_2KiB"]["roundtrip_bit_exact"] and not bad and same_r and out["kolm_8KiB"]["roundtrip_bit_exact"] and same)
