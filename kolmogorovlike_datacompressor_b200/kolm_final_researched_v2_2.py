@@ -345,24 +345,21 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
     label = "FIXED" if mode == MODE_FIXED else "Fast CDC"
     _print_progress(label, 0, nblocks)
     if nblocks and encoded is not None:
-        method_ids, payload_lens, area = [int(x) for x in encoded[0]], [int(x) for x in encoded[1]], encoded[2]
+        mids_np, lens_np, area = np.asarray(encoded[0], dtype=np.int64), np.asarray(encoded[1], dtype=np.int64), encoded[2]
     elif nblocks:
         mids_np, lens_np, area = _engine().encode_kolr_area(data, boundaries, names)
-        method_ids, payload_lens = mids_np.tolist(), lens_np.tolist()
+        mids_np, lens_np = np.asarray(mids_np, dtype=np.int64), np.asarray(lens_np, dtype=np.int64)
     else:
-        method_ids, payload_lens, area = [], [], b""
+        mids_np, lens_np, area = np.zeros(0, np.int64), np.zeros(0, np.int64), b""
     _print_progress(label + " COMPRESS", nblocks, nblocks, final=True)
-    orig_lens = [b - a for a, b in boundaries]
-    total_payload = sum(payload_lens)
-    # ---- TOC header
-    run_syms: List[int] = []
-    run_lens: List[int] = []
-    for x in method_ids:
-        if run_syms and x == run_syms[-1]:
-            run_lens[-1] += 1
-        else:
-            run_syms.append(x)
-            run_lens.append(1)
+    total_payload = int(lens_np.sum())
+    # ---- TOC header (no per-block Python: a container holds up to 65 535 blocks)
+    if nblocks:
+        first = np.concatenate(([0], np.flatnonzero(np.diff(mids_np)) + 1))          # where a run of equal method ids starts
+        run_syms: List[int] = mids_np[first].tolist()
+        run_lens: List[int] = np.diff(np.concatenate((first, [nblocks]))).tolist()
+    else:
+        run_syms, run_lens = [], []
     lengths = _huff_lengths(Counter(run_syms))
     enc_tbl, _, _ = _huff_canonical(lengths)
     best_k = _best_rice_k(run_lens)
@@ -376,9 +373,9 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
     deltas: List[int] = []
     best_k2 = 0
     if mode == MODE_FIXED:
-        toc_header += uleb128_encode(orig_lens[-1] if nblocks > 0 else 0)
+        toc_header += uleb128_encode(boundaries[-1][1] - boundaries[-1][0] if nblocks > 0 else 0)
     else:
-        deltas = [_zz_enc(ol - size_field) for ol in orig_lens]
+        deltas = [_zz_enc((b - a) - size_field) for a, b in boundaries]
         best_k2 = _best_rice_k(deltas)
         toc_header += uleb128_encode(best_k2)
     # ---- TOC bitstream
@@ -389,14 +386,14 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
     bw.rice(run_lens, best_k)
     if mode == MODE_CDC:
         bw.rice(deltas, best_k2)
-    n = len(payload_lens)
+    n = nblocks
     l = _ef_choose_l(total_payload, n)
     m = (total_payload + ((1 << l) - 1)) >> l
     total = m + n
     if n and total_payload < (1 << 62) and l <= 62:
         # Elias-Fano of the cumulative payload ends: low l bits of every end, then the unary bitmap with bit (end >> l) + i set,
         # written MSB first into `total` bits — as bit arrays (the per-block big-integer shifts were quadratic in the block count)
-        P = np.cumsum(np.asarray(payload_lens, dtype=np.int64))
+        P = np.cumsum(lens_np)
         bw.put_fixed(P & ((1 << l) - 1) if l else P, l)
         hi = (P >> l) + np.arange(n, dtype=np.int64)
         bitmap = np.zeros(total, dtype=np.uint8)
@@ -404,7 +401,7 @@ def _assemble(data: bytes, boundaries, mode: int, size_field: int, encoded=None)
         bw.put_array(bitmap)
     else:
         P, s = [], 0
-        for L in payload_lens:
+        for L in lens_np.tolist():
             s += L
             P.append(s)
         for x in P:
