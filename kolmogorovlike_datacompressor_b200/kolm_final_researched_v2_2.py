@@ -502,6 +502,7 @@ def _parse(container: bytes):
     l = _ef_choose_l(total_payload, nblocks)
     m = (total_payload + ((1 << l) - 1)) >> l
     P = None
+    P_np = None
     if nblocks > 64 and l <= 62 and br.pos + nblocks * l + 1 <= br.total:
         # well-formed TOCs: low bits as one reshape, the upper-bit unary code as one flatnonzero (same values as the loops below,
         # which stay for short or damaged TOCs so that their errors are the reference's)
@@ -516,7 +517,8 @@ def _parse(container: bytes):
                 lows_np = a[p0:hi0].reshape(nblocks, l).astype(np.int64) @ w
             else:
                 lows_np = np.zeros(nblocks, dtype=np.int64)
-            P = (((ones_np.astype(np.int64) - np.arange(nblocks, dtype=np.int64)) << l) | lows_np).tolist()
+            P_np = ((ones_np.astype(np.int64) - np.arange(nblocks, dtype=np.int64)) << l) | lows_np
+            P = P_np.tolist()
             br.pos = hi0 + int(ones_np[-1]) + 1
     if P is None:
         lows = [br.bits(l) for _ in range(nblocks)]
@@ -533,6 +535,17 @@ def _parse(container: bytes):
         raise ValueError("Truncated payload area")
     area0 = pos
     pos += total_payload
+    if P_np is not None:                                             # many blocks: the per-block lists come out of numpy in one go
+        mids_np = np.asarray(method_ids, dtype=np.int64)
+        bad_id = np.flatnonzero((mids_np < 0) | (mids_np >= len(KOLR_NAMES)))
+        if len(bad_id):
+            raise ValueError(f"Unknown method_id {int(mids_np[bad_id[0]])}")
+        names = np.array(KOLR_NAMES, dtype=object)[mids_np].tolist()
+        starts = (area0 + np.concatenate(([0], P_np[:-1]))).tolist()
+        plens_np = np.diff(P_np, prepend=0)
+        if bool((plens_np < 0).any()):
+            raise ValueError("Payload EF offsets not monotone")
+        return names, starts, plens_np.tolist(), orig_lens, total_len, pos
     names = []
     for i in range(nblocks):
         mid = method_ids[i]
