@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     // first of the right), so distinct pairs have distinct boundaries; the left symbol of a boundary is x itself or a later
     // nonterminal (a larger id: at least as many ULEB bytes), each such symbol is written once per boundary, the last symbol of the
     // final sequence costs a byte more, and 'RP', ULEB(256) and the two counts take at least 6.  Once the bound reaches limit[b]
-    // the candidate cannot win: the block is marked (bacc slot 34) and its size reported as "not evaluated".
+    // the candidate cannot win: the block is marked (bacc slot 34) and its size reported as "not evaluated".  (The code adds
+    // (m - 1 - D) / (f - 1) for the rules that are still needed when only D of the m - 1 adjacencies are distinct: see the test.)
     // A second bound from the byte count itself.  With n1 one-byte and n2 two-byte symbols in the sequence (every nonterminal of a
     // block of <= 8 KiB has a two-byte id) the payload is 6 + rules + n1 + 2 n2 + what the counts need, and a round that replaces
     // r occurrences of (a, b) changes it by -(r (ca + cb - 2) - (ca + cb)): nothing is gained on (1,1) pairs, r - 3 on mixed ones,
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
             for (int hh = 0; hh < 2; ++hh) {
                 const u32 k = hh ? kk.y : kk.x, cnt = hh ? cc >> 16 : cc & 0xffffu;
                 if (k == REPAIR_EMPTY) continue;
-                wloc += 1u + ((k >> 16) >= 128u ? 1u : 0u);
+                wloc += 0x10001u + ((k >> 16) >= 128u ? 1u : 0u);      // distinct pairs in the upper half, their left symbols' bytes below
                 const unsigned long long v = ((unsigned long long)cnt << 32) | (unsigned long long)(~k);
                 if (cnt >= 2 && v > lbest) lbest = v;
             }
@@ -155,7 +156,12 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
         if ((u32)(best >> 32) < 2) break;                    // V22.py:1875-1876
         if (limit) {
             const i64 f = (i64)(best >> 32), gain = (i64)n1 * (f > 3 ? f - 3 : 0) + (i64)n2 * (2 * f - 4);
-            if ((i64)(7u + rule_bytes + S.wsum) >= lim || f * (i64)(6u + rule_bytes + n1 + 2u * n2) - gain >= f * lim) { stopped = true; break; }
+            // pair bound, sharpened by the rules still needed: D distinct pairs need D boundaries, K later rules and a final
+            // sequence of F symbols have K + F - 1, the rules shorten the sequence by at most f each (F >= m - f K), every boundary
+            // costs at least a byte on its left and a rule one more on its right: payload >= 7 + rules + W + (m - 1 - D) / (f - 1)
+            const u32 W = S.wsum & 0xffffu, D = S.wsum >> 16;
+            const i64 more = (i64)(m - 1u - D + (u32)f - 2u) / (f - 1);
+            if ((i64)(7u + rule_bytes + W) + more >= lim || f * (i64)(6u + rule_bytes + n1 + 2u * n2) - gain >= f * lim) { stopped = true; break; }
         }
         const u32 bkey = ~(u32)best;
         const u32 newsym = 256 + nrules;

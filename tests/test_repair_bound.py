@@ -1,6 +1,7 @@
 """The lower bounds behind the early stop of the Re-Pair candidate in kolm_encode_blocks (csrc/repair.cu, k_repair_enc):
 
     final payload >= 7 + bytes of the rules made so far + sum over the DISTINCT adjacent pairs (x, y) of the current sequence of uleb(x)
+                     + (m - 1 - D) / (f - 1)   (m symbols, D distinct pairs, f the largest pair count)
     final payload >= 6 + bytes of the rules made so far + (3 n1 + 4 n2) / f     (n1 / n2 one- / two-byte symbols in the sequence,
                                                                                  f = the largest pair count, f >= 3; blocks <= 8 KiB)
 
@@ -39,7 +40,12 @@ def repair_with_bounds(block: bytes):
             p = (seq[i], seq[i + 1])
             freq[p] = freq.get(p, 0) + 1
         if seq:
-            bounds.append(7 + sum(_uleb(a) + _uleb(b) for a, b in rules) + sum(_uleb(x) for x, _ in freq))
+            # the kernel's sharpened form: D distinct pairs need D boundaries; K later rules and a final sequence of F symbols have
+            # K + F - 1 of them, every rule shortens the sequence by at most f (the largest count now, which never rises), every
+            # boundary costs a byte or more on its left and a rule one more on its right
+            f = max(freq.values(), default=0)
+            more = -(-(len(seq) - 1 - len(freq)) // (f - 1)) if f >= 2 else 0
+            bounds.append(7 + sum(_uleb(a) + _uleb(b) for a, b in rules) + sum(_uleb(x) for x, _ in freq) + more)
         best, bf = None, 1
         for p, f in freq.items():
             if f > bf or (f == bf and best is not None and p < best):
@@ -104,8 +110,8 @@ def test_bound_is_tight_enough_to_matter():
     pay, bounds, bounds2 = repair_with_bounds(blk)
     first = next(i for i, b in enumerate(bounds) if b >= len(blk))
     assert first == 0 and len(bounds) > 20 and len(pay) > len(blk)
-    # 8 KiB of the S3 mix's sine segment (high bytes, few distinct pairs at first): the pair bound needs 848 of the 3696 rounds,
-    # the byte-count bound under a hundred
+    # 8 KiB of the S3 mix's sine segment (high bytes, few distinct pairs at first): the plain pair bound needs 848 of the 3696
+    # rounds; its sharpened form and the byte-count bound under a hundred
     from kolmogorovlike_datacompressor_b200 import synth
     blk = synth.s3_mix(8 << 20)[3 << 20:(3 << 20) + 8192].tobytes()
     pay, bounds, bounds2 = repair_with_bounds(blk)
@@ -113,4 +119,4 @@ def test_bound_is_tight_enough_to_matter():
     assert all(b <= len(pay) for b in bounds) and all(fb <= f * len(pay) for f, fb in bounds2)
     t1 = next((i for i, b in enumerate(bounds) if b >= len(blk)), len(bounds))
     t2 = next((i for i, (f, fb) in enumerate(bounds2) if fb >= f * len(blk)), len(bounds2))
-    assert t2 < len(bounds2) and t2 * 4 < t1, (t1, t2, len(bounds))
+    assert t2 < 100 and t1 < 100 and len(bounds) > 3000, (t1, t2, len(bounds))
