@@ -20,7 +20,7 @@ def partition_blocks(bounds: Bounds, world: int) -> List[Tuple[int, int]]:
     n = len(bounds)
     if n == 0:
         return [(0, 0)] * world
-    ends = np.array([b for _, b in bounds], dtype=np.int64)
+    ends = np.fromiter((b for _, b in bounds), dtype=np.int64, count=n)
     total = int(ends[-1]) - int(bounds[0][0])
     cuts = [0]
     for r in range(1, world):
@@ -336,17 +336,17 @@ def decompress_kolr(container: bytes, group=None) -> Optional[bytes]:
 def corpus_blocks(sizes: Sequence[int], block_size: int) -> List[Tuple[int, int, int]]:
     """[(container, start, end)] of the fixed-size blocks of every container (V22.py:314-320), container-major."""
     out = []
-    for k, n in enumerate(sizes):
-        out.extend((k, a, min(n, a + block_size)) for a in range(0, n, block_size))
+    for k, n in enumerate(sizes):                                    # per container in numpy: a 4 GiB corpus has 524 288 blocks of 8 KiB
+        a = np.arange(0, n, block_size, dtype=np.int64)
+        out.extend(zip([k] * len(a), a.tolist(), np.minimum(a + block_size, n).tolist()))
     return out
 
 
 def _virtual_bounds(blocks):
-    out, p = [], 0
-    for _, a, b in blocks:
-        out.append((p, p + (b - a)))
-        p += b - a
-    return out
+    from itertools import accumulate
+    lens = [b - a for _, a, b in blocks]
+    ends = list(accumulate(lens))
+    return list(zip([e - n for e, n in zip(ends, lens)], ends))
 
 
 def _my_runs(blocks, b0, b1):
