@@ -17,7 +17,8 @@ variants' exact costs + one packed variant (kolm_final_researched_v2-2.py models
     cfg4_full_pipeline   kolm_final_researched_v2-2 compress_blocks_fixed + decompress with per-block model selection, all ten
                          candidates exact, S3 corpus of 1 GiB containers at 1 MiB blocks, BLOCK-SHARDED over the N GPUs with the NCCL
                          gather of the compressed stream inside the timed region (strong scaling: the corpus does not grow with N);
-                         at N = 1 also kolm_final compress/decompress (KOLM)
+                         `default_block`: the same corpus, sharded the same way, at the default block size of compress_blocks_fixed
+                         (8 KiB; 16 containers of 256 MiB); at N = 1 also kolm_final compress/decompress (KOLM)
     cfg5_block_sweep     block sizes 64 KiB .. 16 MiB, encode and decode, S3 mix, per GPU (weak)
     default_block_sizes  the reference's default block sizes (2 KiB KOLR, 8 KiB KOLM) through the drop-ins' fused per-batch call (N = 1)
 """
