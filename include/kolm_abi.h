@@ -203,7 +203,7 @@ int kolm_copy_blocks(kolm_ctx* ctx, const uint64_t* src_addr, const uint64_t* ds
  *   payload_out (DEVICE, cap bytes, 8 bytes of slack wanted): the winners' payloads back to back in block order (KF.py:896-901;
  *                V22.py:2443-2444); payload_off (HOST, nblocks+1); method_ids (HOST u8[nblocks]); sizes_out (HOST, may be NULL):
  *                every candidate's size, row-major [nblocks][4 or 10], 2^62-1 for a candidate that was not offered.
- *   Re-Pair (V22.py:1841-1911, the last candidate of the list) of blocks of up to 8 KiB is evaluated after all the others and, when
+ *   Re-Pair (V22.py:1841-1911, the last candidate of the list) of blocks of up to 16 KiB is evaluated after all the others and, when
  *   sizes_out is NULL, only as far as it can still win: a block's rounds stop once a lower bound on the final payload (the rules
  *   made so far + one left symbol per distinct adjacent pair of the current sequence + 7) reaches the best other size.  The
  *   selection is unchanged — the reference picks Re-Pair on a strictly smaller payload only; KOLM_REPAIR_STOP=0 runs every block

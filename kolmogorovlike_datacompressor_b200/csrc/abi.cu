@@ -307,7 +307,7 @@ int kolm_repair_dec(kolm_ctx* c, const uint8_t* payload, const int64_t* pay_off,
     return kolm_repair_dec_impl(c, payload, pay_off, out, s);
 }
 
-int kolm_repair_max_block(void) { return REPAIR_MAX; }          // shared-memory kernel; longer blocks take the incremental kernel (repair_big.cu)
+int kolm_repair_max_block(void) { return REPAIR_XL; }          // shared-memory kernel; longer blocks take the incremental kernel (repair_big.cu)
 
 int kolm_v2new_enc(kolm_ctx* c, const uint8_t* in, const int64_t* off, int nblocks, uint8_t* out, size_t out_cap, int64_t* out_off,
                    kolm_stream_t stream) {

@@ -21,6 +21,7 @@
 #define REPAIR_EMPTY 0xffffffffu
 
 // Three shapes of the same kernel, eight symbols per thread, 6 bytes of table per slot + 2 per symbol, 32 registers:
+//   up to 16384 symbols  1024 threads, 224 KB   one CTA per SM (sixteen symbols per thread)
 //   up to 8192 symbols   1024 threads, 115 KB   two CTAs per SM
 //   up to 4096 symbols    512 threads,  58 KB   three
 //   up to 2048 symbols    256 threads,  29 KB   seven   (the reference's default block size)
@@ -28,6 +29,8 @@
 // (61 440 blocks of 2 KiB: 131 ms per 32 MiB on the one-CTA shape, 30 on the first small shape, 7 with the early stop).
 #define REPAIR_SMALL 2048
 #define REPAIR_MID 4096
+#define REPAIR_XL 16384             // the largest shape: 16 symbols per thread, 32 768 slots, 224 KB — the CDC default's longest block
+#define REPAIR_XL_HASH 32768
 template <int MAXLEN, int THREADS, int HASH>
 struct RepairSmemT {
     u16 seq[MAXLEN];                 // compacted in place (a thread's symbols wait in registers across the scan's barriers)
@@ -40,6 +43,7 @@ struct RepairSmemT {
     u32 nhigh, m, hdr, wsum;
 };
 typedef RepairSmemT<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH> RepairSmem;
+static_assert(sizeof(RepairSmemT<16384, 1024, 32768>) <= 227 * 1024, "the 16 KiB shape must fit one CTA's shared memory");
 
 template <int HASH>
 __device__ __forceinline__ u32 rp_hash(u32 k) { k *= 2654435761u; return (k >> 15) & (HASH - 1); }
@@ -63,7 +67,7 @@ __device__ __forceinline__ u8* rp_put_uleb(u8* p, u32 v) { while (v >= 128) { *p
 
 // out_tmp: per block a staging region of 4*len+64 bytes at tmp + 4*pbase; sizes[b] = payload bytes
 template <int MAXLEN, int THREADS, int HASH, int MINLEN>
-__global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
+__global__ void __launch_bounds__(THREADS, MAXLEN > REPAIR_MAX ? 1 : 2048 / THREADS) k_repair_enc(const u8* __restrict__ in, const BlockInfo* __restrict__ binfo, u8* __restrict__ tmp,
                                                         u32* __restrict__ rules_scratch, u64* __restrict__ bacc, int* __restrict__ err,
                                                         const i64* __restrict__ limit) {
     extern __shared__ __align__(16) u8 smem_raw[];
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     const u32 tid = threadIdx.x, b = blockIdx.x;
     const BlockInfo bi = binfo[b];
     if (bi.len <= MINLEN && MINLEN) return;                 // the small shape of this kernel takes these
-    if (bi.len > MAXLEN) { if (MAXLEN == REPAIR_MAX && tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }
+    if (bi.len > MAXLEN) { if (MAXLEN == REPAIR_XL && tid == 0) { err[b] = KOLM_E_UNSUPPORTED; bacc[(size_t)b * 64 + 32] = 0; } return; }   // the incremental kernel's
     const u8* src = in + bi.ioff;
     u32* rules = rules_scratch + bi.pbase;                  // up to len/2 rules, (a<<16|b)
     u32 high = 0;                                            // bytes >= 128: two ULEB bytes each
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     // the candidate cannot win: the block is marked (bacc slot 34) and its size reported as "not evaluated".  (The code adds
     // (m - 1 - D) / (f - 1) for the rules that are still needed when only D of the m - 1 adjacencies are distinct: see the test.)
     // A second bound from the byte count itself.  With n1 one-byte and n2 two-byte symbols in the sequence (every nonterminal of a
-    // block of <= 8 KiB has a two-byte id) the payload is 6 + rules + n1 + 2 n2 + what the counts need, and a round that replaces
+    // block of <= 16 KiB has a two-byte id) the payload is 6 + rules + n1 + 2 n2 + what the counts need, and a round that replaces
     // r occurrences of (a, b) changes it by -(r (ca + cb - 2) - (ca + cb)): nothing is gained on (1,1) pairs, r - 3 on mixed ones,
     // 2r - 4 on (2,2) pairs.  The largest pair count f never rises (new adjacencies contain the new symbol, which occurs r <= f
     // times), so every later round has r <= f; one-byte symbols are never created (x replacements of (1,1) pairs and y of mixed
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS) k_repair_enc(const u8
     const i64 lim = limit ? limit[b] : (i64)0x7fffffffffffffffll;
     u32 rule_bytes = 0;
     bool stopped = false;
-    constexpr u32 IPT = MAXLEN / THREADS;        // 8 consecutive positions per thread
+    constexpr u32 IPT = MAXLEN / THREADS;        // 8 (16 on the largest shape) consecutive positions per thread
     // The pair table is emptied by the sweep that reads it (one pass and one barrier less per round than clearing it up front).
     for (u32 i = tid; i < HASH; i += THREADS) { S.hkey[i] = REPAIR_EMPTY; if (i < HASH / 2) S.hcnt2[i] = 0; }
     __syncthreads();
@@ -451,15 +455,18 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
     if (!nb) { if (out_off) out_off[0] = 0; return KOLM_OK; }
     static long long big_max = -1;                            // KOLM_REPAIR_BIG_MAX: largest block (bytes) the incremental kernel takes (0: none)
     if (big_max < 0) { const char* e = getenv("KOLM_REPAIR_BIG_MAX"); big_max = e ? atoll(e) : (1ll << 30); }
-    if (c->max_len > REPAIR_MAX && (long long)c->max_len > big_max) return KOLM_E_UNSUPPORTED;
+    if (c->max_len > REPAIR_XL && (long long)c->max_len > big_max) return KOLM_E_UNSUPPORTED;
     typedef RepairSmemT<REPAIR_SMALL, 256, 4096> RepairSmemSmall;
     typedef RepairSmemT<REPAIR_MID, 512, 8192> RepairSmemMid;
+    typedef RepairSmemT<REPAIR_XL, REPAIR_THREADS, REPAIR_XL_HASH> RepairSmemXL;
     static bool attr_set[64];
     if (c->device < 64 && !attr_set[c->device]) {
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmem)));
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MID, 512, 8192, REPAIR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmemMid)));
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_SMALL, 256, 4096, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmemSmall)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_XL, REPAIR_THREADS, REPAIR_XL_HASH, REPAIR_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RepairSmemXL)));
+        CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_XL, REPAIR_THREADS, REPAIR_XL_HASH, REPAIR_MAX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         // all of the SM's shared memory for these kernels: two CTAs of the 115 KB shape only fit the largest carve-out
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_MID>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -478,7 +485,8 @@ int kolm_repair_enc_impl(kolm_ctx* c, const u8* in, u8* out, size_t out_cap, i64
         if (c->max_len > REPAIR_MID) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, REPAIR_MID><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
     } else
     KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_MAX, REPAIR_THREADS, REPAIR_HASH, 0><<<nb, REPAIR_THREADS, sizeof(RepairSmem), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
-    if (c->max_len > REPAIR_MAX) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
+    if (c->max_len > REPAIR_MAX) KL(c, KC_MISC, c->total_bytes * 2, s, k_repair_enc<REPAIR_XL, REPAIR_THREADS, REPAIR_XL_HASH, REPAIR_MAX><<<nb, REPAIR_THREADS, sizeof(RepairSmemXL), s>>>(in, c->d_binfo, tmp, c->d_v0, c->d_bacc, c->d_err, limit));
+    if (c->max_len > REPAIR_XL) KOLM_TRY(kolm_repair_big_impl(c, in, tmp, s));    // blocks the shared-memory kernel passed over
     KL(c, KC_RICE_PLAN, (i64)nb * 16, s, k_lz_plan<<<1, 1024, 0, s>>>(c->d_bacc, c->d_poff, nb));
     KL(c, KC_MISC, c->total_bytes, s, k_repair_gather<<<nb, 256, 0, s>>>(tmp, c->d_binfo, c->d_bacc, out, c->d_poff + nb, (u64)out_cap));
     CUDA_TRY(cudaGetLastError());

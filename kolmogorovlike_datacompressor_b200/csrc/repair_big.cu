@@ -519,11 +519,11 @@ int kolm_repair_big_impl(kolm_ctx* c, const u8* in, u8* tmp, cudaStream_t s) {
     const int nb = c->nblocks;
     u32* list = c->h_u32;
     int nbig = 0; u64 maxn = 0;
-    for (int b = 0; b < nb; ++b) if (c->h_binfo[b].len > 8192u) { ++nbig; if (c->h_binfo[b].len > maxn) maxn = c->h_binfo[b].len; }
+    for (int b = 0; b < nb; ++b) if (c->h_binfo[b].len > (u32)REPAIR_XL) { ++nbig; if (c->h_binfo[b].len > maxn) maxn = c->h_binfo[b].len; }
     if (!nbig) return KOLM_OK;
     CUDA_TRY(cudaStreamSynchronize(s));                      // `list` is pinned staging that earlier copies of this call may still read
     nbig = 0;
-    for (int b = 0; b < nb; ++b) if (c->h_binfo[b].len > 8192u) list[nbig++] = (u32)b;
+    for (int b = 0; b < nb; ++b) if (c->h_binfo[b].len > (u32)REPAIR_XL) list[nbig++] = (u32)b;
     const size_t need = rpb_need(maxn);
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));

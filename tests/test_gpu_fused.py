@@ -147,6 +147,7 @@ def test_repair_early_stop_leaves_the_selection_unchanged():
         for k in range(24):
             n = (2048, 2048, 2048, 1000, 4096, 8192)[k % 6]
             blocks.append(seg[k * 40960:k * 40960 + n])
+        blocks.append(seg[600000:600000 + (12000, 16384, 9001, 16383)[kind % 4]])      # the 16 KiB shape of the Re-Pair kernel
     import random
     rnd = random.Random(3)                                    # "word soup": a dozen random words repeated — Re-Pair beats LZ77 by a few bytes
     for n in (2048, 3000, 5000, 8192, 2048, 6000):

@@ -65,7 +65,7 @@ def _big_cases():
 
 
 def test_repair_large_blocks_incremental_kernel():
-    """Blocks beyond the shared-memory kernel (> 8192 bytes) take the incremental kernel: payloads equal the literal oracle's."""
+    """Blocks of 9 .. 24 KB: the 16 KiB shape of the shared-memory kernel and, beyond it, the incremental kernel: payloads equal the literal oracle's."""
     import gpu_util as G
     cases = _big_cases()
     cases["small_mixed_in"] = b"abracadabra" * 50               # small and large blocks in one batch
@@ -102,7 +102,7 @@ def test_kolr_selection_with_repair_ahead_of_the_batches(monkeypatch):
     from kolmogorovlike_datacompressor_b200.engine import Engine
     from kolmogorovlike_datacompressor_b200.kolm_final_researched_v2_2 import KOLR_NAMES
     rnd = random.Random(5)
-    bs = 12 << 10
+    bs = 20 << 10                                               # beyond the largest shape of the shared-memory kernel (16 KiB)
     parts = [synth.s1_text(3 * bs).tobytes(), bytes(rnd.randrange(4) for _ in range(bs)), b"abcabcabd" * (2 * bs // 9),
              synth.s2_mixed(2 * bs).tobytes(), bytes(rnd.randrange(256) for _ in range(bs // 2))]
     data = b"".join(parts)
