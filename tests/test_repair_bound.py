@@ -88,6 +88,24 @@ def _cases():
         out.append(bytes(rnd.choice(b"\x80\x81\xfe\xff") for _ in range(n)))
         out.append(bytes((i * 7) & 0xFF for i in range(n)))
         out.append(b"\xaa" * n)
+    # compressible structure, where a wrong bound would show first: word soups, periodic strings with defects, nested repeats,
+    # runs of one symbol (a == b rounds), high bytes only (two-byte terminals)
+    for k in range(40):
+        words = [bytes(rnd.getrandbits(8) | (0x80 if k % 3 == 0 else 0) for _ in range(rnd.randint(1, 7))) for _ in range(rnd.randint(2, 10))]
+        out.append(b"".join(rnd.choice(words) for _ in range(rnd.randint(5, 300)))[:1200])
+    for k in range(20):
+        unit = bytes(rnd.getrandbits(8) for _ in range(rnd.randint(1, 12)))
+        s = bytearray(unit * rnd.randint(2, 120))[:1000]
+        for _ in range(rnd.randint(0, 4)):
+            s[rnd.randrange(len(s))] ^= 1 << rnd.randrange(8)
+        out.append(bytes(s))
+    for k in range(10):
+        a, b = bytes([rnd.getrandbits(8)]), bytes([rnd.getrandbits(8)])
+        out.append((a * rnd.randint(1, 40) + b * rnd.randint(1, 40)) * rnd.randint(1, 12))
+        x = bytes(rnd.getrandbits(8) for _ in range(3))
+        for _ in range(rnd.randint(2, 6)):
+            x = x + x[:rnd.randint(1, len(x))] + x
+        out.append(x[:1500])
     return out
 
 
