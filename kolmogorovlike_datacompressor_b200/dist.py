@@ -425,12 +425,11 @@ def compress_kolr_fixed_corpus(sizes: Sequence[int], load: Callable[[int, int, i
     ends = np.cumsum(alll)
     out, i = [], 0
     for k, n in enumerate(sizes):
-        j = i
-        while j < len(blocks) and blocks[j][0] == k:
-            j += 1
+        bounds_k = V._FixedBounds(int(n), block_size)                # container k's blocks, in corpus_blocks order, without the list
+        j = i + len(bounds_k)
         a0 = int(ends[i] - alll[i]) if j > i else 0
         a1 = int(ends[j - 1]) if j > i else 0
-        out.append(V._assemble(int(n), [(a, b) for _, a, b in blocks[i:j]], V.MODE_FIXED, block_size,
+        out.append(V._assemble(int(n), bounds_k, V.MODE_FIXED, block_size,
                                encoded=(allm[i:j], alll[i:j], area[a0:a1]) if j > i else None))
         i = j
     clk.lap("assemble_s")

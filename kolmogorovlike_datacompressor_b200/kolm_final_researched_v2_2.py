@@ -93,6 +93,33 @@ def fixed_boundaries(data: bytes, block_size: int = 8192) -> List[Tuple[int, int
     return [(i, min(n, i + block_size)) for i in range(0, n, block_size)]
 
 
+class _FixedBounds:
+    """fixed_boundaries(data of n bytes, block_size) as a read-only sequence without the list: what _assemble needs of it in FIXED
+    mode is the length and the last block (dist.compress_kolr_fixed_corpus assembles containers of tens of thousands of blocks
+    that were encoded elsewhere)."""
+
+    def __init__(self, n: int, block_size: int):
+        if block_size <= 0:
+            raise ValueError("block_size must be positive")
+        self.n, self.bs = int(n), int(block_size)
+        self.count = (self.n + self.bs - 1) // self.bs
+
+    def __len__(self) -> int:
+        return self.count
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(self.count))]
+        if i < 0:
+            i += self.count
+        if not 0 <= i < self.count:
+            raise IndexError("block index out of range")
+        return (i * self.bs, min(self.n, (i + 1) * self.bs))
+
+    def __iter__(self):
+        return ((a, min(self.n, a + self.bs)) for a in range(0, self.n, self.bs))
+
+
 def cdc_fast_boundaries_strict(data: bytes, min_size: int = 4096, avg_size: int = 8192, max_size: int = 16384,
                                merge_orphan_tail: bool = True) -> List[Tuple[int, int]]:
     if len(data) == 0:
