@@ -20,18 +20,53 @@ def partition_blocks(bounds: Bounds, world: int) -> List[Tuple[int, int]]:
     n = len(bounds)
     if n == 0:
         return [(0, 0)] * world
-    ends = np.fromiter((b for _, b in bounds), dtype=np.int64, count=n)
-    total = int(ends[-1]) - int(bounds[0][0])
+    return _partition_ends(np.fromiter((b for _, b in bounds), dtype=np.int64, count=n), int(bounds[0][0]), world)
+
+
+def _partition_ends(ends: np.ndarray, start0: int, world: int) -> List[Tuple[int, int]]:
+    """partition_blocks on the blocks' end offsets alone (block i = [ends[i-1], ends[i]), the first one starts at start0)."""
+    n = len(ends)
+    if n == 0:
+        return [(0, 0)] * world
+    total = int(ends[-1]) - start0
     cuts = [0]
     for r in range(1, world):
-        target = bounds[0][0] + (total * r) // world
+        target = start0 + (total * r) // world
         k = int(np.searchsorted(ends, target, side="left"))
         # block k straddles the target: give it to the side that keeps the split closer to the target
-        if k < n and (ends[k] - target) <= (target - (ends[k - 1] if k else bounds[0][0])):
+        if k < n and (ends[k] - target) <= (target - (ends[k - 1] if k else start0)):
             k += 1
         cuts.append(min(max(k, cuts[-1]), n))
     cuts.append(n)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def _fixed_plan(sizes: Sequence[int], block_size: int, world: int, rank: int):
+    """The block table of a corpus of fixed-size blocks by arithmetic — the same ranges partition_blocks(_virtual_bounds(
+    corpus_blocks(sizes, block_size)), world) gives, without the per-block lists (a 4 GiB corpus has 524 288 blocks of 8 KiB):
+    -> (parts [(first block, end block) per rank], total number of blocks, runs of `rank`: [(container, lo, hi, [(a - lo, b - lo)
+    of its blocks])] with [lo, hi) the byte range of the container this rank encodes)."""
+    bs = int(block_size)
+    counts = [(int(n) + bs - 1) // bs for n in sizes]
+    cum = np.concatenate(([0], np.cumsum(np.asarray(counts, dtype=np.int64)))).astype(np.int64)
+    nblocks = int(cum[-1])
+    ends = np.empty(nblocks, dtype=np.int64)
+    base = 0
+    for k, n in enumerate(sizes):
+        c = counts[k]
+        if c:
+            ends[cum[k]:cum[k + 1]] = np.minimum(np.arange(1, c + 1, dtype=np.int64) * bs, int(n)) + base
+        base += int(n)
+    parts = _partition_ends(ends, 0, world)
+    b0, b1 = parts[rank]
+    runs = []
+    for k, n in enumerate(sizes):
+        i, j = max(b0, int(cum[k])), min(b1, int(cum[k + 1]))
+        if i >= j:
+            continue
+        lo, hi = (i - int(cum[k])) * bs, min(int(n), (j - int(cum[k])) * bs)
+        runs.append((k, lo, hi, [(a - lo, min(hi, a + bs) - lo) for a in range(lo, hi, bs)]))
+    return parts, nblocks, runs
 
 
 def _dev(group) -> torch.device:
@@ -372,18 +407,16 @@ def compress_kolr_fixed_corpus(sizes: Sequence[int], load: Callable[[int, int, i
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = _dev(group)
     clk = _Clock(stats, dev)
-    blocks = corpus_blocks(sizes, block_size)
-    parts = partition_blocks(_virtual_bounds(blocks), world)
+    parts, nblocks_all, runs = _fixed_plan(sizes, block_size, world, rank)
     b0, b1 = parts[rank]
     if area_fn is None:
         eng, names = V._engine(), V._candidate_names()
         area_fn = _engine_area(eng, lambda d, b: eng.encode_kolr_area(d, b, names))
     mids_l, lens_l, areas = [], [], []
-    for k, i, j in _my_runs(blocks, b0, b1):
-        lo, hi = blocks[i][1], blocks[j - 1][2]
+    for k, lo, hi, local in runs:
         d = load(k, lo, hi)
         clk.lap("load_s")
-        m, l, ar = area_fn(d, [(a - lo, b - lo) for _, a, b in blocks[i:j]])
+        m, l, ar = area_fn(d, local)
         if not isinstance(ar, torch.Tensor):
             ar = torch.from_numpy(np.ascontiguousarray(np.frombuffer(memoryview(ar), dtype=np.uint8)).copy())
         mids_l.append(np.asarray(m, dtype=np.int64)); lens_l.append(np.asarray(l, dtype=np.int64)); areas.append(ar.to(dev))
@@ -420,8 +453,8 @@ def compress_kolr_fixed_corpus(sizes: Sequence[int], load: Callable[[int, int, i
     clk.lap("payload_exchange_s")
     area = _home_area(buf, total) if buf.is_cuda else buf[:total].numpy()
     clk.lap("d2h_s")
-    allm = np.concatenate([t[:, 0] for t in tabs]) if blocks else np.zeros(0, np.int64)
-    alll = np.concatenate([t[:, 1] for t in tabs]) if blocks else np.zeros(0, np.int64)
+    allm = np.concatenate([t[:, 0] for t in tabs]) if nblocks_all else np.zeros(0, np.int64)
+    alll = np.concatenate([t[:, 1] for t in tabs]) if nblocks_all else np.zeros(0, np.int64)
     ends = np.cumsum(alll)
     out, i = [], 0
     for k, n in enumerate(sizes):

@@ -22,3 +22,28 @@ def test_spans_examples():
     assert container_spans(10, 4, max_bytes=9, max_blocks=100) == [(0, 8), (8, 10)]
     with pytest.raises(ValueError):
         container_spans(10, 8, max_bytes=7)
+
+
+def test_fixed_plan_equals_the_block_lists():
+    """dist._fixed_plan (block ranges, partition and per-rank runs of a corpus of fixed-size blocks by arithmetic) against the
+    per-block lists it replaces: corpus_blocks -> _virtual_bounds -> partition_blocks -> _my_runs."""
+    import random
+    from kolmogorovlike_datacompressor_b200 import dist as kd
+    rnd = random.Random(12)
+    for _ in range(400):
+        sizes = [rnd.choice([0, 0, 1, 5, 100, 2047, 2048, 2049, 8192, 30000, 70001]) for _ in range(rnd.randint(0, 6))]
+        bs = rnd.choice([1, 7, 100, 2048, 8192])
+        if sum(sizes) // bs > 30000:
+            continue
+        blocks = kd.corpus_blocks(sizes, bs)
+        for world in (1, 2, 3, 8):
+            want_parts = kd.partition_blocks(kd._virtual_bounds(blocks), world)
+            for rank in range(world):
+                parts, nblocks, runs = kd._fixed_plan(sizes, bs, world, rank)
+                assert parts == want_parts and nblocks == len(blocks), (sizes, bs, world)
+                b0, b1 = want_parts[rank]
+                want = []
+                for k, i, j in kd._my_runs(blocks, b0, b1):
+                    lo, hi = blocks[i][1], blocks[j - 1][2]
+                    want.append((k, lo, hi, [(a - lo, b - lo) for _, a, b in blocks[i:j]]))
+                assert runs == want, (sizes, bs, world, rank)
