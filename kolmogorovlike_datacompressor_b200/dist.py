@@ -499,17 +499,25 @@ def decompress_kolr_corpus(containers: Optional[Sequence[bytes]], group=None, sr
     dist.broadcast_object_list(box, src=src, group=group)
     table = box[0]
     clk.lap("toc_s")
-    blocks, gstart, plen, olen, names = [], [], [], [], []           # flat, container-major
-    for k, m in enumerate(table):
-        o = 0
-        for i, ol in enumerate(m["olens"]):
-            blocks.append((k, o, o + ol)); o += ol
-            gstart.append(m["gbase"] + m["rel"][i]); plen.append(m["plens"][i]); olen.append(ol); names.append(m["names"][i])
-    parts = partition_blocks(_virtual_bounds(blocks), world)
+    # flat, container-major block table as arrays (a 4 GiB corpus at 8 KiB blocks has 524 288 rows: no per-block Python)
+    counts = [len(m["olens"]) for m in table]
+    cum = np.concatenate(([0], np.cumsum(np.asarray(counts, dtype=np.int64)))).astype(np.int64)
+    nall = int(cum[-1])
+
+    def _flat(key, add=None):
+        if not nall:
+            return np.zeros(0, dtype=np.int64)
+        return np.concatenate([np.asarray(m[key], dtype=np.int64) + (m[add] if add else 0) for m in table])
+    olen, plen, gstart = _flat("olens"), _flat("plens"), _flat("rel", "gbase")
+    ostart = np.concatenate([np.cumsum(np.asarray(m["olens"], dtype=np.int64)) - np.asarray(m["olens"], dtype=np.int64) for m in table]) if nall else olen
+    names: List[str] = []
+    for m in table:
+        names.extend(m["names"])
+    parts = _partition_ends(np.cumsum(olen), 0, world)
     spans = []
     for s0, s1 in parts:                                             # payload span (in the concatenated areas) of every rank's range
         if s1 > s0:
-            spans.append((min(gstart[s0:s1]), max(g + l for g, l in zip(gstart[s0:s1], plen[s0:s1]))))
+            spans.append((int(gstart[s0:s1].min()), int((gstart[s0:s1] + plen[s0:s1]).max())))
         else:
             spans.append((0, 0))
     b0, b1 = parts[rank]
@@ -532,14 +540,16 @@ def decompress_kolr_corpus(containers: Optional[Sequence[bytes]], group=None, sr
     if decode_fn is None:
         decode_fn = V._engine().decode_to_device
     pieces = []
-    for k, i, j in _my_runs(blocks, b0, b1):
-        st = [g - lo for g in gstart[i:j]]
-        y = decode_fn(span, names[i:j], st, plen[i:j], olen[i:j])
-        pieces.append((k, blocks[i][1], blocks[j - 1][2], y))
+    for k in range(len(table)):                                      # my blocks, one run per container
+        i, j = max(b0, int(cum[k])), min(b1, int(cum[k + 1]))
+        if i >= j:
+            continue
+        y = decode_fn(span, names[i:j], (gstart[i:j] - lo).tolist(), plen[i:j].tolist(), olen[i:j].tolist())
+        pieces.append((k, int(ostart[i]), int(ostart[j - 1] + olen[j - 1]), y))
     clk.lap("decode_s")
     if not gather:
         return pieces
-    nbytes = [sum(olen[s0:s1]) for s0, s1 in parts]
+    nbytes = [int(olen[s0:s1].sum()) for s0, s1 in parts]
     mine = torch.cat([y for *_, y in pieces]) if len(pieces) > 1 else (pieces[0][3] if pieces else torch.empty(0, dtype=torch.uint8, device=dev))
     if rank != src:
         _exchange([(mine[:nbytes[rank]].contiguous(), src)] if nbytes[rank] else [], [], group)
